@@ -1,0 +1,187 @@
+/* nexoclom_b200 -- C ABI of the B200-native nexoclom hot path.
+ *
+ * The reference (mburger-stsci/nexoclom v3.7.4) is pure Python and has no FFI
+ * layer; each entry point below replaces the body of a Python function that
+ * takes plain ndarrays, and is bound from Python with ctypes
+ * (nexoclom_b200/_lib.py; the stub a reference maintainer would add is shown
+ * in INTEGRATION.md).  Citations are relative to the reference tree.
+ *
+ * Conventions
+ *   - every function returns 0 on success; < 0 = CUDA error (message via
+ *     nx_last_error); > 0 = violated numerical invariant (bit mask, see
+ *     NX_INV_*), mirroring the reference's bare `assert`s.
+ *   - host buffers are caller-owned, contiguous, little-endian f64 / i64 / u8;
+ *     packet tables are structure-of-arrays: one pointer per column.
+ *   - `*_dev` variants take DEVICE pointers (e.g. torch tensors' data_ptr())
+ *     for results that stay on the GPU for a following NCCL all-reduce.
+ *   - one nx_ctx per (process, GPU); calls on a ctx are serialised by the
+ *     caller; the library keeps no global mutable state.
+ *   - units: length = planet radii, time = s, GM < 0, Sun at -y.
+ */
+#ifndef NEXOCLOM_B200_H
+#define NEXOCLOM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nx_ctx nx_ctx;
+
+/* invariant bits (positive return values / nx_status) */
+#define NX_INV_BAD_ERRMAX 4   /* non-finite errmax        (Output.py:284)      */
+#define NX_INV_NEG_FRAC   8   /* accepted negative frac   (Output.py:287-288)  */
+#define NX_INV_BAD_STEP   16  /* non-finite step size     (Output.py:337-339)  */
+#define NX_INV_BAD_STATE  32  /* non-finite packet state  (Output.py:388-389)  */
+
+/* packet-state columns (Output.py:247, :370) */
+enum { NX_COL_TIME = 0, NX_COL_X, NX_COL_Y, NX_COL_Z, NX_COL_VX, NX_COL_VY, NX_COL_VZ,
+       NX_COL_FRAC, NX_NCOL_STATE };
+/* X0 columns (Output.py:180-182) */
+enum { NX_X0_TIME = 0, NX_X0_X, NX_X0_Y, NX_X0_Z, NX_X0_VX, NX_X0_VY, NX_X0_VZ, NX_X0_FRAC,
+       NX_X0_V, NX_X0_LONGITUDE, NX_X0_LATITUDE, NX_X0_LOCAL_TIME, NX_X0_ALTITUDE,
+       NX_X0_AZIMUTH, NX_NCOL_X0 };
+
+/* Per-run scalars (what Output.__init__ builds, Output.py:102-133). */
+typedef struct nx_run_params {
+  double GM;               /* R_p^3/s^2, negative (SSObject.py:53)                 */
+  double vrplanet;         /* R_p/s (planet_dist.py:67)                            */
+  double loss_rate;        /* loss_mode 1: 1/lifetime; 2: photo rate (LossInfo.py) */
+  double outeredge;        /* Options.outeredge                                    */
+  double resolution;       /* Options.resolution (adaptive)                        */
+  double step_size;        /* Options.step_size; 0 = adaptive                      */
+  double endtime;          /* Options.endtime [s]                                  */
+  double stickcoef;        /* SurfaceInteraction.stickcoef                         */
+  double accomfactor;      /* SurfaceInteraction.accomfactor                       */
+  double stick_A[3];       /* SurfaceInteraction.A (temperature dependent)         */
+  double surf_t1;          /* 600+125(cos taa-1)/2 (surface_temperature.py:9)      */
+  double planet_radius_km;
+  int32_t gravity, radpres;
+  int32_t loss_mode;       /* 0 none, 1 constant lifetime, 2 photo x sunlit        */
+  int32_t sticktype;       /* 0 constant, 1 temperature dependent                  */
+  int32_t strict_math;     /* 1: NumPy operation order without FMA contraction     */
+  int32_t reserved;
+} nx_run_params;
+
+/* Initial-state distributions (source_distribution.py:37-283). */
+enum { NX_SPATIAL_UNIFORM = 0, NX_SPATIAL_MAP = 1 };
+enum { NX_SPEED_FLAT = 0, NX_SPEED_GAUSSIAN = 1, NX_SPEED_TABLE = 2 };
+enum { NX_ANGULAR_RADIAL = 0, NX_ANGULAR_ISOTROPIC = 1 };
+typedef struct nx_source_params {
+  int32_t spatial_type, speed_type, angular_type, is_planet;
+  double exobase;
+  double sinlat0, sinlat1;   /* uniform: sin(latitude) range                        */
+  double lon0, lon1;         /* uniform: longitude range (lon1 > lon0, may be > 2pi) */
+  double vprob, vsigma, delv;/* km/s                                                */
+  double v_scale;            /* km/s -> R_p/s  (1/R_km)                             */
+  double sinalt0, sinalt1;   /* isotropic: sin(altitude) range                      */
+  double az0, az1;           /* isotropic: azimuth range                            */
+  double endtime;
+  int32_t random_time;       /* 1: time = U*endtime (adaptive); 0: time = endtime   */
+  int32_t map_nx, map_ny;    /* source map grid (surface map / surface spot)        */
+  int32_t map_lat_is_sin;    /* 1: y-axis is sin(lat) (surface map); 0: lat (spot)  */
+  double map_fmax;
+} nx_source_params;
+
+/* Image accumulation (ModelImage.py:229-274). */
+typedef struct nx_image_params {
+  double M[9];               /* row-major rotation Sun frame -> observer frame      */
+  double x0, x1, z0, z1;     /* image range [R_p]                                   */
+  double apix;               /* pixel area [cm^2]; weights are divided by it        */
+  double vrplanet;           /* R_p/s                                               */
+  int32_t nx, nz;
+  int32_t quantity;          /* 0 column, 1 radiance                                */
+  int32_t round_f32;         /* 1: round x,y,z,vy,frac to f32 first (Output.save)   */
+  int32_t skip_dead;         /* 1: ignore frac == 0 packets (compress=True)         */
+  int32_t reserved;
+} nx_image_params;
+
+/* Line-of-sight accumulation (compute_iteration.py:90-240). */
+typedef struct nx_los_params {
+  double dphi;               /* cone half-angle [rad]                               */
+  double outeredge;          /* R_p                                                 */
+  double vrplanet;           /* R_p/s                                               */
+  double rp_cm;              /* planet radius [cm]                                  */
+  int32_t quantity;          /* 1 radiance (only one the reference supports)        */
+  int32_t round_f32;
+  int32_t skip_dead;
+  int32_t reserved;
+} nx_los_params;
+
+/* ---- context ---------------------------------------------------------------- */
+int nx_ctx_create(int device, nx_ctx** out);
+int nx_ctx_destroy(nx_ctx* ctx);
+/* adopt a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) */
+int nx_ctx_set_stream(nx_ctx* ctx, void* cuda_stream);
+int nx_ctx_sync(nx_ctx* ctx);
+const char* nx_last_error(nx_ctx* ctx);
+int nx_status(nx_ctx* ctx, int* invariant_bits);
+
+/* ---- tables (replaces the table objects Output.__init__ attaches:
+ *      self.radpres, self.loss_info, self.surfaceint; Output.py:113-133) ------- */
+int nx_tables_upload(nx_ctx* ctx, const nx_run_params* p,
+                     const double* radpres_v, const double* radpres_a, int n_radpres,
+                     const double* spl_tx, int ntx, const double* spl_ty, int nty,
+                     const double* spl_c);
+/* g-value tables for radiance weighting (ModelResult.py:152-161): `ntables`
+ * tables concatenated in v[] / g[] with lengths sizes[]; v in R_p/s.            */
+int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes,
+                      const double* v, const double* g);
+
+/* ---- packets ------------------------------------------------------------------ */
+int nx_packets_resize(nx_ctx* ctx, long long n);
+/* import mode: reference-generated initial state, cols[8] = time,x,y,z,vx,vy,vz,frac */
+int nx_import_state(nx_ctx* ctx, long long n, const double* const* cols);
+int nx_export_state(nx_ctx* ctx, long long n, double* const* cols);
+int nx_export_x0(nx_ctx* ctx, long long n, double* const* cols /* NX_NCOL_X0 */);
+int nx_export_stats(nx_ctx* ctx, long long n, uint32_t* attempted, uint32_t* accepted);
+int nx_export_step(nx_ctx* ctx, long long n, double* step_size);
+int nx_state_device_ptr(nx_ctx* ctx, int column, void** dev_ptr);
+
+/* ---- K1: initial state (source_distribution.py:37-283, Output.py:136-147) ---- */
+int nx_sourcemap_upload(nx_ctx* ctx, const double* fmap, int nx, int ny,
+                        const double* xaxis, const double* yaxis);
+int nx_speedtable_upload(nx_ctx* ctx, const double* cdf, const double* v, int n);
+int nx_init_state(nx_ctx* ctx, const nx_source_params* sp, uint64_t seed,
+                  uint64_t first_id, long long n);
+
+/* ---- K2: adaptive driver (Output.py:221-366 + rk5.py + state.py) ------------- */
+int nx_integrate_adaptive(nx_ctx* ctx, long long n,
+                          unsigned long long* attempted_steps,
+                          unsigned long long* accepted_steps);
+
+/* ---- K3: constant-step driver with bounce (Output.py:368-455, bouncepackets.py)
+ * Optional fused per-step image accumulation (image_dev / counts_dev device
+ * pointers, may be NULL) and optional dense trajectory sink traj_host
+ * [n][8][nsteps] (small n only; NULL otherwise).                                 */
+int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
+                          const nx_image_params* img, void* image_dev, void* counts_dev,
+                          double* traj_host, unsigned long long* packet_steps);
+
+/* ---- K4: image (ModelImage.create_image + packet_weighting + Histogram2d) ---- */
+int nx_image_accumulate(nx_ctx* ctx, long long n, const nx_image_params* ip,
+                        double* image /* nx*nz */, long long* counts /* nx*nz */);
+int nx_image_accumulate_dev(nx_ctx* ctx, long long n, const nx_image_params* ip,
+                            void* image_dev, void* counts_dev);
+
+/* ---- K5: lines of sight (compute_iteration.py:151-222) ------------------------
+ * los[6*nlos] SoA: x,y,z,xbore,ybore,zbore; dist_from_plan[nlos] as computed at
+ * compute_iteration.py:105-115.                                                  */
+int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                      const double* dist_from_plan, const nx_los_params* lp,
+                      double* radiance, long long* npackets, uint8_t* included);
+int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_dev,
+                          void* dist_dev, const nx_los_params* lp,
+                          void* radiance_dev, void* npackets_dev, void* included_dev);
+
+/* ---- measurement --------------------------------------------------------------- */
+int nx_last_kernel_ms(nx_ctx* ctx, float* ms);          /* CUDA-event time of last K* */
+int nx_kernel_launches(nx_ctx* ctx, unsigned long long* count);
+int nx_measure_fp64_peak(nx_ctx* ctx, double* tflops);  /* DFMA-chain microbenchmark  */
+int nx_measure_copy_bw(nx_ctx* ctx, long long bytes, double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEXOCLOM_B200_H */

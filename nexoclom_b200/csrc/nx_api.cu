@@ -1,0 +1,649 @@
+// nexoclom_b200 -- C ABI (include/nexoclom_b200.h) over the kernels.
+// Host code only: context, device memory, table preparation, H2D/D2H copies,
+// launches and CUDA-event timing.  No torch types, no global mutable state.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/nexoclom_b200.h"
+#include "nx_kernels.h"
+#include "nx_tables.h"
+
+using namespace nx;
+
+static_assert(sizeof(nx_run_params) == sizeof(RunParams), "RunParams layout");
+static_assert(sizeof(nx_source_params) == sizeof(SourceParams), "SourceParams layout");
+static_assert(sizeof(nx_image_params) == sizeof(ImageParams), "ImageParams layout");
+static_assert(sizeof(nx_los_params) == sizeof(LosParams), "LosParams layout");
+
+struct DevInterp {
+  double *x = nullptr, *f = nullptr, *slope = nullptr;
+  unsigned short* bucket = nullptr;
+  InterpTable view{};
+};
+
+struct nx_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  unsigned long long launches = 0;
+  std::string err;
+
+  RunParams params{};
+  bool have_params = false;
+  DevInterp radpres;
+  DevInterp speed;
+  DevInterp gtab[NX_MAX_GTABLES];
+  GTables gtables{};
+  double *spl_tx = nullptr, *spl_ty = nullptr, *spl_c = nullptr;
+  Spline2D spline{};
+  double* srcmap = nullptr;
+  SourceMap map{};
+
+  long long cap = 0;           // column stride (multiple of 32)
+  double* state = nullptr;     // 9 columns
+  double* x0 = nullptr;        // 14 columns
+  unsigned *att = nullptr, *acc = nullptr;
+  unsigned long long* scalars = nullptr;   // [0] queue, [1] total attempted, [2] total accepted
+  int* status = nullptr;
+  int status_host = 0;
+};
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+      return -(int)e_;                                                                 \
+    }                                                                                  \
+  } while (0)
+
+static void free_interp(DevInterp& d) {
+  cudaFree(d.x); cudaFree(d.f); cudaFree(d.slope); cudaFree(d.bucket);
+  d = DevInterp{};
+}
+
+static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const double* f, int n) {
+  free_interp(d);
+  if (n <= 0) return 0;
+  HostInterp h = make_interp(x, f, n);
+  CK(cudaMalloc(&d.x, n * sizeof(double)));
+  CK(cudaMalloc(&d.f, n * sizeof(double)));
+  CK(cudaMalloc(&d.slope, n * sizeof(double)));
+  CK(cudaMalloc(&d.bucket, h.nbucket * sizeof(unsigned short)));
+  CK(cudaMemcpyAsync(d.x, h.x.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d.f, h.f.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d.slope, h.slope.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d.bucket, h.bucket.data(), h.nbucket * sizeof(unsigned short),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  d.view.x = d.x; d.view.f = d.f; d.view.slope = d.slope; d.view.bucket = d.bucket;
+  d.view.n = n; d.view.nbucket = h.nbucket; d.view.blo = h.blo; d.view.binvw = h.binvw;
+  return 0;
+}
+
+static StateCols state_cols(nx_ctx* ctx) {
+  StateCols P;
+  for (int k = 0; k < 9; ++k) P.c[k] = ctx->state + (size_t)k * ctx->cap;
+  return P;
+}
+static X0Cols x0_cols(nx_ctx* ctx) {
+  X0Cols X;
+  for (int k = 0; k < 14; ++k) X.c[k] = ctx->x0 + (size_t)k * ctx->cap;
+  return X;
+}
+
+static int begin_timed(nx_ctx* ctx) { CK(cudaEventRecord(ctx->ev0, ctx->stream)); return 0; }
+static int end_timed(nx_ctx* ctx, int nlaunch) {
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->launches += nlaunch;
+  return 0;
+}
+
+extern "C" {
+
+int nx_ctx_create(int device, nx_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) {
+    fprintf(stderr, "nexoclom_b200: no usable CUDA device %d (%s); there is no CPU fallback\n",
+            device, e == cudaSuccess ? "index out of range" : cudaGetErrorString(e));
+    return e == cudaSuccess ? -(int)cudaErrorInvalidDevice : -(int)e;
+  }
+  nx_ctx* ctx = new nx_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaMalloc(&ctx->scalars, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->status, sizeof(int)) != cudaSuccess ||
+      cudaMemset(ctx->status, 0, sizeof(int)) != cudaSuccess) {
+    fprintf(stderr, "nexoclom_b200: context setup failed: %s\n",
+            cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return -2;
+  }
+  *out = ctx;
+  return 0;
+}
+
+int nx_ctx_destroy(nx_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_interp(ctx->radpres);
+  free_interp(ctx->speed);
+  for (auto& g : ctx->gtab) free_interp(g);
+  cudaFree(ctx->spl_tx); cudaFree(ctx->spl_ty); cudaFree(ctx->spl_c);
+  cudaFree(ctx->srcmap);
+  cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
+  cudaFree(ctx->scalars); cudaFree(ctx->status);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+int nx_ctx_set_stream(nx_ctx* ctx, void* cuda_stream) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) CK(cudaStreamDestroy(ctx->stream));
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return 0;
+}
+
+int nx_ctx_sync(nx_ctx* ctx) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+const char* nx_last_error(nx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nx_status(nx_ctx* ctx, int* bits) {
+  CK(cudaSetDevice(ctx->device));
+  int v = 0;
+  CK(cudaMemcpyAsync(&v, ctx->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bits) *bits = v;
+  return 0;
+}
+
+int nx_tables_upload(nx_ctx* ctx, const nx_run_params* p, const double* rv, const double* ra,
+                     int nrp, const double* tx, int ntx, const double* ty, int nty,
+                     const double* c) {
+  CK(cudaSetDevice(ctx->device));
+  std::memcpy(&ctx->params, p, sizeof(RunParams));
+  ctx->have_params = true;
+  if (ctx->params.radpres && nrp < 2) {
+    ctx->err = "radpres enabled but no radiation-pressure table given";
+    return -1;
+  }
+  int r = upload_interp(ctx, ctx->radpres, rv, ra, ctx->params.radpres ? nrp : 0);
+  if (r) return r;
+  cudaFree(ctx->spl_tx); cudaFree(ctx->spl_ty); cudaFree(ctx->spl_c);
+  ctx->spl_tx = ctx->spl_ty = ctx->spl_c = nullptr;
+  ctx->spline = Spline2D{};
+  if (tx && ty && c && ntx > 8 && nty > 8) {
+    const size_t nc = (size_t)(ntx - 4) * (nty - 4);
+    CK(cudaMalloc(&ctx->spl_tx, ntx * sizeof(double)));
+    CK(cudaMalloc(&ctx->spl_ty, nty * sizeof(double)));
+    CK(cudaMalloc(&ctx->spl_c, nc * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->spl_tx, tx, ntx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->spl_ty, ty, nty * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->spl_c, c, nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->spline = Spline2D{ctx->spl_tx, ctx->spl_ty, ctx->spl_c, ntx, nty};
+  }
+  return 0;
+}
+
+int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* v,
+                      const double* g) {
+  CK(cudaSetDevice(ctx->device));
+  if (ntables < 0 || ntables > NX_MAX_GTABLES) { ctx->err = "too many g-value tables"; return -1; }
+  ctx->gtables.n = 0;
+  size_t off = 0;
+  for (int t = 0; t < ntables; ++t) {
+    int r = upload_interp(ctx, ctx->gtab[t], v + off, g + off, sizes[t]);
+    if (r) return r;
+    ctx->gtables.t[t] = ctx->gtab[t].view;
+    off += sizes[t];
+  }
+  ctx->gtables.n = ntables;
+  return 0;
+}
+
+int nx_packets_resize(nx_ctx* ctx, long long n) {
+  CK(cudaSetDevice(ctx->device));
+  if (n <= ctx->cap) return 0;
+  const long long cap = ((n + 31) / 32) * 32;
+  cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
+  ctx->state = ctx->x0 = nullptr; ctx->att = ctx->acc = nullptr; ctx->cap = 0;
+  CK(cudaMalloc(&ctx->state, (size_t)9 * cap * sizeof(double)));
+  CK(cudaMalloc(&ctx->x0, (size_t)14 * cap * sizeof(double)));
+  CK(cudaMalloc(&ctx->att, (size_t)cap * sizeof(unsigned)));
+  CK(cudaMalloc(&ctx->acc, (size_t)cap * sizeof(unsigned)));
+  CK(cudaMemsetAsync(ctx->att, 0, (size_t)cap * sizeof(unsigned), ctx->stream));
+  CK(cudaMemsetAsync(ctx->acc, 0, (size_t)cap * sizeof(unsigned), ctx->stream));
+  ctx->cap = cap;
+  return 0;
+}
+
+int nx_import_state(nx_ctx* ctx, long long n, const double* const* cols) {
+  int r = nx_packets_resize(ctx, n);
+  if (r) return r;
+  StateCols P = state_cols(ctx);
+  for (int k = 0; k < 8; ++k)
+    CK(cudaMemcpyAsync(P.c[k], cols[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  CK(launch_fill(ctx->stream, P.c[8], n, 1000.0));       // Output.py:246
+  ctx->launches += 1;
+  return 0;
+}
+
+int nx_export_state(nx_ctx* ctx, long long n, double* const* cols) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "export: n exceeds resident packets"; return -1; }
+  StateCols P = state_cols(ctx);
+  for (int k = 0; k < 8; ++k)
+    CK(cudaMemcpyAsync(cols[k], P.c[k], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int nx_export_x0(nx_ctx* ctx, long long n, double* const* cols) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "export: n exceeds resident packets"; return -1; }
+  X0Cols X = x0_cols(ctx);
+  for (int k = 0; k < 14; ++k)
+    CK(cudaMemcpyAsync(cols[k], X.c[k], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int nx_export_stats(nx_ctx* ctx, long long n, uint32_t* attempted, uint32_t* accepted) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "export: n exceeds resident packets"; return -1; }
+  CK(cudaMemcpyAsync(attempted, ctx->att, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(accepted, ctx->acc, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int nx_export_step(nx_ctx* ctx, long long n, double* step) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "export: n exceeds resident packets"; return -1; }
+  CK(cudaMemcpyAsync(step, state_cols(ctx).c[8], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int nx_state_device_ptr(nx_ctx* ctx, int column, void** dev_ptr) {
+  if (column < 0 || column >= 9 || !ctx->state) { ctx->err = "bad column / no packets"; return -1; }
+  *dev_ptr = state_cols(ctx).c[column];
+  return 0;
+}
+
+int nx_sourcemap_upload(nx_ctx* ctx, const double* fmap, int nx_, int ny_, const double* xaxis,
+                        const double* yaxis) {
+  CK(cudaSetDevice(ctx->device));
+  cudaFree(ctx->srcmap); ctx->srcmap = nullptr;
+  CK(cudaMalloc(&ctx->srcmap, (size_t)nx_ * ny_ * sizeof(double)));
+  CK(cudaMemcpyAsync(ctx->srcmap, fmap, (size_t)nx_ * ny_ * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->map.f = ctx->srcmap;
+  ctx->map.x_lo = xaxis[0]; ctx->map.x_hi = xaxis[nx_ - 1];
+  ctx->map.y_lo = yaxis[0]; ctx->map.y_hi = yaxis[ny_ - 1];
+  return 0;
+}
+
+int nx_speedtable_upload(nx_ctx* ctx, const double* cdf, const double* v, int n) {
+  CK(cudaSetDevice(ctx->device));
+  return upload_interp(ctx, ctx->speed, cdf, v, n);
+}
+
+int nx_init_state(nx_ctx* ctx, const nx_source_params* sp_, uint64_t seed, uint64_t first_id,
+                  long long n) {
+  int r = nx_packets_resize(ctx, n);
+  if (r) return r;
+  SourceParams sp;
+  std::memcpy(&sp, sp_, sizeof(sp));
+  if (sp.spatial_type == SPATIAL_MAP && !ctx->srcmap) { ctx->err = "no source map uploaded"; return -1; }
+  if (sp.speed_type == SPEED_TABLE && ctx->speed.view.n == 0) { ctx->err = "no speed table uploaded"; return -1; }
+  if (n == 0) return 0;
+  if ((r = begin_timed(ctx))) return r;
+  CK(launch_init_state(ctx->stream, state_cols(ctx), x0_cols(ctx), n, sp, ctx->map,
+                       ctx->speed.view, seed, first_id));
+  return end_timed(ctx, 1);
+}
+
+static int check_status(nx_ctx* ctx) {
+  int v = 0;
+  CK(cudaMemcpyAsync(&v, ctx->status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->status_host = v;
+  if (v) {
+    ctx->err = "numerical invariant violated on device (bits " + std::to_string(v) + ")";
+    CK(cudaMemsetAsync(ctx->status, 0, sizeof(int), ctx->stream));
+  }
+  return v;
+}
+
+int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempted,
+                          unsigned long long* accepted) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_params) { ctx->err = "nx_tables_upload not called"; return -1; }
+  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  if (!(ctx->params.sticktype == STICK_CONSTANT && ctx->params.stickcoef == 1.0)) {
+    ctx->err = "Not set up";      // reference Output.py:315 (adaptive needs stickcoef == 1)
+    return -1;
+  }
+  CK(cudaMemsetAsync(ctx->scalars, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  int r;
+  if (n > 0) {
+    if ((r = begin_timed(ctx))) return r;
+    CK(launch_integrate_adaptive(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
+                                 ctx->radpres.view, ctx->scalars, ctx->scalars + 1, ctx->att,
+                                 ctx->acc, ctx->status));
+    if ((r = end_timed(ctx, 1))) return r;
+  }
+  unsigned long long h[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  r = check_status(ctx);
+  if (r < 0) return r;
+  if (attempted) *attempted = h[1];
+  if (accepted) *accepted = h[2];
+  return r;
+}
+
+int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
+                          const nx_image_params* img, void* image_dev, void* counts_dev,
+                          double* traj_host, unsigned long long* packet_steps) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->have_params) { ctx->err = "nx_tables_upload not called"; return -1; }
+  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  const RunParams& p = ctx->params;
+  if (!(p.step_size > 0.0)) { ctx->err = "constant driver needs step_size > 0"; return -1; }
+  const bool simple = (p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0);
+  if (!simple && p.accomfactor != 0.0 && !ctx->spl_c) {
+    ctx->err = "accommodation enabled but no speed spline uploaded";
+    return -1;
+  }
+  const int nsteps = (int)std::ceil(p.endtime / p.step_size + 1);
+  ImageParams ip{};
+  if (img) std::memcpy(&ip, img, sizeof(ip));
+  else { ip.nx = ip.nz = 1; ip.x1 = ip.z1 = 1.0; }
+  if (image_dev && ip.quantity == 1 && ctx->gtables.n == 0) {
+    ctx->err = "radiance image requested but no g-value tables uploaded";
+    return -1;
+  }
+  double* traj = nullptr;
+  const size_t traj_bytes = (size_t)n * 8 * nsteps * sizeof(double);
+  if (traj_host) {
+    CK(cudaMalloc(&traj, traj_bytes));
+    CK(cudaMemsetAsync(traj, 0, traj_bytes, ctx->stream));
+  }
+  CK(cudaMemsetAsync(ctx->scalars, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  int r;
+  if (n > 0) {
+    if ((r = begin_timed(ctx))) return r;
+    CK(launch_integrate_constant(ctx->stream, ctx->device, state_cols(ctx), n, p,
+                                 ctx->radpres.view, ctx->spline, seed, first_id, nsteps, ip,
+                                 ctx->gtables, (double*)image_dev,
+                                 (unsigned long long*)counts_dev, traj, ctx->scalars,
+                                 ctx->scalars + 1, ctx->status));
+    if ((r = end_timed(ctx, 1))) return r;
+  }
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  if (traj_host) {
+    CK(cudaMemcpyAsync(traj_host, traj, traj_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  r = check_status(ctx);
+  if (traj) cudaFree(traj);
+  if (r < 0) return r;
+  if (packet_steps) *packet_steps = h[1];
+  return r;
+}
+
+int nx_image_accumulate_dev(nx_ctx* ctx, long long n, const nx_image_params* ip_, void* image_dev,
+                            void* counts_dev) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  ImageParams ip;
+  std::memcpy(&ip, ip_, sizeof(ip));
+  if (ip.quantity == 1 && ctx->gtables.n == 0) {
+    ctx->err = "radiance image requested but no g-value tables uploaded";
+    return -1;
+  }
+  if (n == 0) return 0;
+  int r;
+  if ((r = begin_timed(ctx))) return r;
+  CK(launch_image_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, ip, ctx->gtables,
+                             (double*)image_dev, (unsigned long long*)counts_dev));
+  return end_timed(ctx, 1);
+}
+
+int nx_image_accumulate(nx_ctx* ctx, long long n, const nx_image_params* ip, double* image,
+                        long long* counts) {
+  CK(cudaSetDevice(ctx->device));
+  const size_t npix = (size_t)ip->nx * ip->nz;
+  double* d_img = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  CK(cudaMalloc(&d_img, npix * sizeof(double)));
+  CK(cudaMalloc(&d_cnt, npix * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_img, 0, npix * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(d_cnt, 0, npix * sizeof(unsigned long long), ctx->stream));
+  int r = nx_image_accumulate_dev(ctx, n, ip, d_img, d_cnt);
+  if (r == 0) {
+    cudaMemcpyAsync(image, d_img, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(counts, d_cnt, npix * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  }
+  cudaFree(d_img); cudaFree(d_cnt);
+  return r;
+}
+
+// Per-LOS ladder length and the shared geometric ladder (compute_iteration.py:158-171).
+static void los_prepare(const double* los, long long nlos, const LosParams& lp,
+                        std::vector<int>& nball, std::vector<double>& ladder,
+                        std::vector<double>& wid2, LosConsts& lc) {
+  const double s = std::sin(lp.dphi);
+  const double s2 = std::sin(lp.dphi * 2);
+  std::vector<double> dd(nlos);
+  double ddmax = 0.0;
+  for (long long i = 0; i < nlos; ++i) {
+    const double x = los[i], y = los[nlos + i], z = los[2 * nlos + i];
+    const double bx = los[3 * nlos + i], by = los[4 * nlos + i], bz = los[5 * nlos + i];
+    const double b = 2 * ((x * bx + y * by) + z * bz);
+    const double nrm = std::sqrt((x * x + y * y) + z * z);
+    const double c = nrm * nrm - lp.outeredge * lp.outeredge;
+    dd[i] = (-b + std::sqrt(b * b - 4 * 1 * c)) / 2;
+    if (dd[i] > ddmax) ddmax = dd[i];
+  }
+  ladder.clear();
+  ladder.push_back(s);
+  while (ladder.back() < ddmax && ladder.size() < (1u << 20)) {
+    const double t = ladder.back();
+    ladder.push_back(t + t * s);
+  }
+  wid2.resize(ladder.size());
+  for (size_t k = 0; k < ladder.size(); ++k) { const double w = ladder[k] * s2; wid2[k] = w * w; }
+  nball.resize(nlos);
+  for (long long i = 0; i < nlos; ++i) {
+    // first k with t_k >= dd is the last ladder entry; NaN dd -> single entry
+    int k = 0;
+    if (dd[i] == dd[i]) {
+      k = (int)(std::lower_bound(ladder.begin(), ladder.end(), dd[i]) - ladder.begin());
+      if (k >= (int)ladder.size()) k = (int)ladder.size() - 1;
+    }
+    nball[i] = k + 1;
+  }
+  lc.sin_dphi = s;
+  const double cd = std::cos(lp.dphi);
+  lc.cos_margin2 = (cd * (1 - 1e-9)) * (cd * (1 - 1e-9));
+  lc.cos_loose2 = (cd * (1 - 1e-6)) * (cd * (1 - 1e-6));
+  lc.inv_log_ratio = 1.0 / std::log1p(s);
+  lc.log_t0 = std::log(s);
+  const double w1 = std::log1p(s2) * lc.inv_log_ratio;
+  const double w2 = -std::log1p(-s2) * lc.inv_log_ratio;
+  lc.kwin = (int)std::ceil(w1 > w2 ? w1 : w2) + 2;
+  lc.nladder = (int)ladder.size();
+}
+
+static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_host,
+                   const double* los_dev, const double* dist_dev, const LosParams& lp,
+                   double* rad_dev, unsigned long long* np_dev, unsigned char* inc_dev) {
+  std::vector<int> nball;
+  std::vector<double> ladder, wid2;
+  LosConsts lc;
+  los_prepare(los_host, nlos, lp, nball, ladder, wid2, lc);
+  int* d_nball = nullptr;
+  double *d_ladder = nullptr, *d_wid2 = nullptr;
+  CK(cudaMalloc(&d_nball, nlos * sizeof(int)));
+  CK(cudaMalloc(&d_ladder, ladder.size() * sizeof(double)));
+  CK(cudaMalloc(&d_wid2, wid2.size() * sizeof(double)));
+  CK(cudaMemcpyAsync(d_nball, nball.data(), nlos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ladder, ladder.data(), ladder.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_wid2, wid2.data(), wid2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int r = begin_timed(ctx);
+  if (r == 0) {
+    cudaError_t e = launch_los_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, nlos,
+                                          los_dev, dist_dev, d_nball, d_ladder, d_wid2, lp, lc,
+                                          ctx->gtables, rad_dev, np_dev, inc_dev);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  }
+  if (r == 0) r = end_timed(ctx, 1);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (r == 0 && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2);
+  return r;
+}
+
+int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_dev, void* dist_dev,
+                          const nx_los_params* lp_, void* radiance_dev, void* npackets_dev,
+                          void* included_dev) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  LosParams lp;
+  std::memcpy(&lp, lp_, sizeof(lp));
+  if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }   // compute_iteration.py:213
+  if (ctx->gtables.n == 0) { ctx->err = "no g-value tables uploaded"; return -1; }
+  if (n == 0 || nlos == 0) return 0;
+  std::vector<double> los_host((size_t)6 * nlos);
+  CK(cudaMemcpyAsync(los_host.data(), los_dev, los_host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return los_run(ctx, n, nlos, los_host.data(), (const double*)los_dev, (const double*)dist_dev,
+                 lp, (double*)radiance_dev, (unsigned long long*)npackets_dev,
+                 (unsigned char*)included_dev);
+}
+
+int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                      const double* dist_from_plan, const nx_los_params* lp_, double* radiance,
+                      long long* npackets, uint8_t* included) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  LosParams lp;
+  std::memcpy(&lp, lp_, sizeof(lp));
+  if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }
+  if (ctx->gtables.n == 0) { ctx->err = "no g-value tables uploaded"; return -1; }
+  double *d_los = nullptr, *d_dist = nullptr, *d_rad = nullptr;
+  unsigned long long* d_np = nullptr;
+  unsigned char* d_inc = nullptr;
+  const size_t nl = (size_t)(nlos > 0 ? nlos : 1), nn = (size_t)(n > 0 ? n : 1);
+  CK(cudaMalloc(&d_los, 6 * nl * sizeof(double)));
+  CK(cudaMalloc(&d_dist, nl * sizeof(double)));
+  CK(cudaMalloc(&d_rad, nl * sizeof(double)));
+  CK(cudaMalloc(&d_np, nl * sizeof(unsigned long long)));
+  CK(cudaMalloc(&d_inc, nn));
+  CK(cudaMemcpyAsync(d_los, los, 6 * (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_dist, dist_from_plan, (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_rad, 0, nl * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(d_np, 0, nl * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(d_inc, 0, nn, ctx->stream));
+  int r = 0;
+  if (n > 0 && nlos > 0) r = los_run(ctx, n, nlos, los, d_los, d_dist, lp, d_rad, d_np, d_inc);
+  if (r == 0) {
+    cudaMemcpyAsync(radiance, d_rad, (size_t)nlos * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(npackets, d_np, (size_t)nlos * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (included) cudaMemcpyAsync(included, d_inc, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  }
+  cudaFree(d_los); cudaFree(d_dist); cudaFree(d_rad); cudaFree(d_np); cudaFree(d_inc);
+  return r;
+}
+
+int nx_last_kernel_ms(nx_ctx* ctx, float* ms) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  if (ms) *ms = ctx->last_ms;
+  return 0;
+}
+
+int nx_kernel_launches(nx_ctx* ctx, unsigned long long* count) {
+  if (count) *count = ctx->launches;
+  return 0;
+}
+
+int nx_measure_fp64_peak(nx_ctx* ctx, double* tflops) {
+  CK(cudaSetDevice(ctx->device));
+  int blocks = 0, threads = 0;
+  const int iters = 1 << 15;
+  double* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)148 * 64 * 256 * sizeof(double)));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_fp64_peak(ctx->stream, ctx->device, out, iters, &blocks, &threads));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best) best = ms;
+    ctx->launches += 1;
+  }
+  cudaFree(out);
+  const double flops = 2.0 * 8.0 * iters * (double)blocks * threads;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+}
+
+int nx_measure_copy_bw(nx_ctx* ctx, long long bytes, double* gbs) {
+  CK(cudaSetDevice(ctx->device));
+  const long long n = bytes / 8 / 2 * 2;
+  double *a = nullptr, *b = nullptr;
+  CK(cudaMalloc(&a, n * sizeof(double)));
+  CK(cudaMalloc(&b, n * sizeof(double)));
+  CK(cudaMemsetAsync(a, 0, n * sizeof(double), ctx->stream));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_copy(ctx->stream, ctx->device, a, b, n));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best) best = ms;
+    ctx->launches += 1;
+  }
+  cudaFree(a); cudaFree(b);
+  if (gbs) *gbs = 2.0 * n * sizeof(double) / (best * 1e-3) / 1e9;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// nexoclom_b200 -- initial packet state (K1): surface position, speed and
+// direction draws.  Reference: initial_state/source_distribution.py:12-283,
+// math/randomdeviates.py:8-83, particle_tracking/Output.py:136-147.
+// The reference draws from NumPy's PCG64 / global RandomState; here every packet
+// owns a Philox4x32-10 stream keyed by (seed, global packet id), so results do
+// not depend on launch geometry or on how packets are sharded over GPUs.
+#pragma once
+#include "nx_surface.cuh"
+
+namespace nx {
+
+enum SpatialType { SPATIAL_UNIFORM = 0, SPATIAL_MAP = 1 };
+enum SpeedType { SPEED_FLAT = 0, SPEED_GAUSSIAN = 1, SPEED_TABLE = 2 };
+enum AngularType { ANGULAR_RADIAL = 0, ANGULAR_ISOTROPIC = 1 };
+
+struct SourceParams {
+  int32_t spatial_type, speed_type, angular_type, is_planet;
+  double exobase;
+  double sinlat0, sinlat1;
+  double lon0, lon1;
+  double vprob, vsigma, delv;
+  double v_scale;
+  double sinalt0, sinalt1;
+  double az0, az1;
+  double endtime;
+  int32_t random_time;
+  int32_t map_nx, map_ny;
+  int32_t map_lat_is_sin;
+  double map_fmax;
+};
+
+// 2-D source map on a uniform (x, y) grid, row-major [nx][ny]
+// (random_deviates_2d re-grids onto linspace(min, max, n), randomdeviates.py:58-59)
+struct SourceMap {
+  const double* f;
+  double x_lo, x_hi, y_lo, y_hi;
+};
+
+NX_HD double bilinear(const SourceMap& m, int nx, int ny, double x, double y) {
+  const double dx = (m.x_hi - m.x_lo) / (nx - 1), dy = (m.y_hi - m.y_lo) / (ny - 1);
+  int i = (int)((x - m.x_lo) / dx), j = (int)((y - m.y_lo) / dy);
+  i = i < 0 ? 0 : (i > nx - 2 ? nx - 2 : i);
+  j = j < 0 ? 0 : (j > ny - 2 ? ny - 2 : j);
+  const double tx = (x - (m.x_lo + i * dx)) / dx, ty = (y - (m.y_lo + j * dy)) / dy;
+  const double* r0 = m.f + (size_t)i * ny + j;
+  const double* r1 = r0 + ny;
+  return r0[0] * (1 - tx) * (1 - ty) + r0[1] * (1 - tx) * ty + r1[0] * tx * (1 - ty) + r1[1] * tx * ty;
+}
+
+// Fills x0[NCOL_X0] = time,x,y,z,vx,vy,vz,frac,v,longitude,latitude,local_time,
+// altitude,azimuth for packet `id`.
+NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const InterpTable& speed,
+                       uint64_t seed, uint64_t id, double* x0) {
+  double u_time, u_sinlat, u_lon, u_speed, u_alt, u_az, g0, g1;
+  uniform_pair(seed, id, STREAM_INIT, 0, u_time, u_sinlat);
+  uniform_pair(seed, id, STREAM_INIT, 1, u_lon, u_speed);
+  uniform_pair(seed, id, STREAM_INIT, 2, u_alt, u_az);
+
+  // time until the image is taken (Output.py:136-139)
+  const double time = sp.random_time ? mul_rn(u_time, sp.endtime) : sp.endtime;
+
+  // ---- position (source_distribution.py:47-62, 96-121) ----
+  double lon, lat;
+  if (sp.spatial_type == SPATIAL_UNIFORM) {
+    const double sinlat = add_rn(sp.sinlat0, mul_rn(sub_rn(sp.sinlat1, sp.sinlat0), u_sinlat));
+    lat = asin(sinlat);
+    lon = fmod(add_rn(sp.lon0, mul_rn(sub_rn(sp.lon1, sp.lon0), u_lon)), NX_TWO_PI);
+  } else {
+    // acceptance / rejection on the map (randomdeviates.py:61-72)
+    uint32_t draw = 4;
+    for (;;) {
+      double ux, uy, uf, unused;
+      uniform_pair(seed, id, STREAM_INIT, draw, ux, uy);
+      uniform_pair(seed, id, STREAM_INIT, draw + 1, uf, unused);
+      draw += 2;
+      const double x = add_rn(mul_rn(ux, sub_rn(map.x_hi, map.x_lo)), map.x_lo);
+      const double y = add_rn(mul_rn(uy, sub_rn(map.y_hi, map.y_lo)), map.y_lo);
+      if (mul_rn(uf, sp.map_fmax) < bilinear(map, sp.map_nx, sp.map_ny, x, y) || draw > 4000) {
+        lon = x;
+        lat = sp.map_lat_is_sin ? asin(y) : y;
+        break;
+      }
+    }
+  }
+  const double cl = cos(lat);
+  const double sx = sp.is_planet ? sp.exobase : -sp.exobase;      // xyz_from_lonlat :18-28
+  const double px = mul_rn(mul_rn(sx, sin(lon)), cl);
+  const double py = mul_rn(mul_rn(-sp.exobase, cos(lon)), cl);
+  const double pz = mul_rn(sp.exobase, sin(lat));
+  const double local_time = fmod(add_rn(div_rn(mul_rn(lon, 12.0), NX_PI), 12.0), 24.0);
+
+  // ---- speed (source_distribution.py:137-189) ----
+  double v;
+  if (sp.speed_type == SPEED_FLAT) {
+    v = sub_rn(add_rn(mul_rn(mul_rn(u_speed, 2.0), sp.delv), sp.vprob), sp.delv);
+  } else if (sp.speed_type == SPEED_GAUSSIAN) {
+    if (sp.vsigma == 0.0) {
+      v = sp.vprob;
+    } else {
+      uniform_pair(seed, id, STREAM_INIT, 3, g0, g1);
+      // Box-Muller on (1-g0) in (0,1]
+      const double z = sqrt(-2.0 * log(1.0 - g0)) * cos(NX_TWO_PI * g1);
+      v = add_rn(mul_rn(z, sp.vsigma), sp.vprob);
+    }
+  } else {
+    v = interp(speed, u_speed);           // inverse CDF (randomdeviates.py:29-33)
+  }
+  v = mul_rn(v, sp.v_scale);
+
+  // ---- direction (source_distribution.py:192-252) ----
+  double alt, az;
+  if (sp.angular_type == ANGULAR_RADIAL) {
+    alt = NX_PI / 2.; az = 0.0;
+  } else {
+    const double sinalt = add_rn(mul_rn(u_alt, sub_rn(sp.sinalt1, sp.sinalt0)), sp.sinalt0);
+    alt = asin(sinalt);
+    az = add_rn(sp.az0, mul_rn(sub_rn(sp.az1, sp.az0), u_az));
+  }
+  double d[3];
+  local_direction(px, py, pz, alt, az, d);
+
+  x0[0] = time; x0[1] = px; x0[2] = py; x0[3] = pz;
+  x0[4] = mul_rn(d[0], v); x0[5] = mul_rn(d[1], v); x0[6] = mul_rn(d[2], v);
+  x0[7] = 1.0; x0[8] = v; x0[9] = lon; x0[10] = lat; x0[11] = local_time;
+  x0[12] = alt; x0[13] = az;
+}
+
+}  // namespace nx

@@ -1,0 +1,534 @@
+// nexoclom_b200 -- sm_100a kernels K1..K5.
+//
+//  K1 k_init_state            HBM-write bound   (14 + 9 f64 columns per packet)
+//  K2 k_integrate_adaptive    FP64-pipe bound   persistent lanes, per-lane refill
+//  K3 k_integrate_constant    FP64-pipe bound   + fused per-step image atomics
+//  K4 k_image_accumulate      HBM-read bound    40 B/packet + L2 atomics
+//  K5 k_los_accumulate        FP64-pipe bound   LOS-per-thread x packet tiles in smem
+//
+// Packet state lives in HBM as structure-of-arrays (one f64 column per field, all
+// columns of one slab, column stride = capacity rounded to 32) so that a warp's
+// loads/stores of one field are one or two fully-used 128-byte lines.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nx_image.cuh"
+#include "nx_init.cuh"
+#include "nx_kernels.h"
+#include "nx_physics.cuh"
+#include "nx_surface.cuh"
+
+namespace nx {
+
+#define FULL_MASK 0xffffffffu
+
+// ---------------------------------------------------------------------------
+// shared-memory staging of an np.interp table (x, f, slope, bucket index)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ size_t stage_table(const InterpTable& g, InterpTable& s,
+                                              unsigned char* base) {
+  s = g;
+  if (g.n == 0) return 0;
+  double* sx = reinterpret_cast<double*>(base);
+  double* sf = sx + g.n;
+  double* ss = sf + g.n;
+  unsigned short* sb = reinterpret_cast<unsigned short*>(ss + g.n);
+  for (int i = threadIdx.x; i < g.n; i += blockDim.x) {
+    sx[i] = g.x[i]; sf[i] = g.f[i]; ss[i] = g.slope[i];
+  }
+  for (int i = threadIdx.x; i < g.nbucket; i += blockDim.x) sb[i] = g.bucket[i];
+  s.x = sx; s.f = sf; s.slope = ss; s.bucket = sb;
+  size_t bytes = (size_t)g.n * 24 + (size_t)g.nbucket * 2;
+  return (bytes + 15) & ~(size_t)15;
+}
+
+size_t table_smem_bytes(const InterpTable& g) {
+  if (g.n == 0) return 0;
+  size_t bytes = (size_t)g.n * 24 + (size_t)g.nbucket * 2;
+  return (bytes + 15) & ~(size_t)15;
+}
+
+// ---------------------------------------------------------------------------
+// K1: initial state
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_init_state(StateCols P, X0Cols X, long long n, SourceParams sp, SourceMap map,
+             InterpTable speed, uint64_t seed, uint64_t first_id) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double x0[14];
+  init_packet(sp, map, speed, seed, first_id + (uint64_t)i, x0);
+#pragma unroll
+  for (int k = 0; k < 14; ++k) X.c[k][i] = x0[k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) P.c[k][i] = x0[k];
+  P.c[8][i] = 1000.0;            // initial step size (Output.py:246)
+}
+
+__global__ void k_fill(double* p, long long n, double v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// K2: adaptive driver.  Persistent lanes: every lane owns one packet at a time
+// and runs whole attempted steps; a lane whose packet finished stores it and
+// claims the next unprocessed packet from a global counter (warp-aggregated
+// atomicAdd), so warps stay full although step counts per packet differ by
+// orders of magnitude (p50 ~ 40, max ~ 4000).
+// ---------------------------------------------------------------------------
+template <bool STRICT>
+__global__ void __launch_bounds__(NX_INT_THREADS)
+k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
+                     unsigned long long* __restrict__ queue,
+                     unsigned long long* __restrict__ totals,
+                     unsigned* __restrict__ att_out, unsigned* __restrict__ acc_out,
+                     int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  InterpTable T;
+  stage_table(Tg, T, smem_raw);
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  bool have = false, drained = false;
+  long long idx = 0;
+  double s[8], step = 0.0;
+  unsigned att = 0, acc = 0;
+  unsigned long long tot_att = 0, tot_acc = 0;
+  int st = 0;
+
+  for (;;) {
+    const unsigned need = __ballot_sync(FULL_MASK, !have);
+    if (need && !drained) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(need));
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (!have) {
+        const long long i = (long long)base + __popc(need & ((1u << lane) - 1u));
+        if (i < n) {
+          idx = i;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s[k] = P.c[k][i];
+          step = P.c[8][i];
+          att = 0; acc = 0;
+          have = (s[0] > p.resolution) && (s[7] > 0.0);
+          if (!have) { att_out[i] = 0; acc_out[i] = 0; }
+        }
+      }
+      drained = ((long long)base + __popc(need) >= n);
+    }
+    if (!__any_sync(FULL_MASK, have)) {
+      if (drained) break;
+      continue;
+    }
+    if (have) {
+      const int fl = adaptive_attempt<STRICT>(p, T, s, step);
+      ++att;
+      if (fl & ATT_ACCEPTED) ++acc;
+      st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
+      if (!(fl & ATT_LIVE)) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) P.c[k][idx] = s[k];
+        P.c[8][idx] = step;
+        att_out[idx] = att; acc_out[idx] = acc;
+        tot_att += att; tot_acc += acc;
+        have = false;
+      }
+    }
+  }
+  // block-level totals
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot_att += __shfl_xor_sync(FULL_MASK, tot_att, o);
+    tot_acc += __shfl_xor_sync(FULL_MASK, tot_acc, o);
+    st |= __shfl_xor_sync(FULL_MASK, st, o);
+  }
+  if (lane == 0) {
+    if (tot_att) atomicAdd(&totals[0], tot_att);
+    if (tot_acc) atomicAdd(&totals[1], tot_acc);
+    if (st) atomicOr(status, st);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: constant-step driver (+ bounce) with optional fused image accumulation
+// and optional dense trajectory sink.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& G,
+                                          double step_x, double step_z, const double* s,
+                                          double* image, unsigned long long* counts) {
+  if (ip.skip_dead && !(s[7] > 0.0)) return;
+  double w;
+  const int pix = image_packet(ip, G, step_x, step_z, s[1], s[2], s[3], s[5], s[7], w);
+  if (pix >= 0) {
+    if (w != 0.0) atomicAdd(&image[pix], w);
+    atomicAdd(&counts[pix], 1ull);
+  }
+}
+
+template <bool STRICT>
+__global__ void __launch_bounds__(NX_INT_THREADS)
+k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Spline2D S,
+                     uint64_t seed, uint64_t first_id, int nsteps,
+                     ImageParams ip, GTables G, double* image, unsigned long long* counts,
+                     double* traj,
+                     unsigned long long* __restrict__ queue,
+                     unsigned long long* __restrict__ totals, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  InterpTable T;
+  stage_table(Tg, T, smem_raw);
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31u;
+  const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
+
+  bool have = false, drained = false;
+  long long idx = 0;
+  double s[8];
+  double curtime = 0.0;
+  int ct = 0;
+  unsigned long long tot = 0;
+  int st = 0;
+
+  for (;;) {
+    const unsigned need = __ballot_sync(FULL_MASK, !have);
+    if (need && !drained) {
+      const int leader = __ffs(need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(need));
+      base = __shfl_sync(FULL_MASK, base, leader);
+      if (!have) {
+        const long long i = (long long)base + __popc(need & ((1u << lane) - 1u));
+        if (i < n) {
+          idx = i;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s[k] = P.c[k][i];
+          curtime = p.endtime; ct = 1;
+          have = s[7] > 0.0;
+          if (traj) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) traj[((size_t)i * 8 + k) * nsteps] = s[k];
+          }
+          if (image) image_add(ip, G, step_x, step_z, s, image, counts);
+          if (!(curtime > 0.0) || ct >= nsteps) have = false;
+        }
+      }
+      drained = ((long long)base + __popc(need) >= n);
+    }
+    if (!__any_sync(FULL_MASK, have)) {
+      if (drained) break;
+      continue;
+    }
+    if (have) {
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
+      if (bad) st |= 32;
+      bool live = constant_step<STRICT>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+      ++tot;
+      if (traj) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) traj[((size_t)idx * 8 + k) * nsteps + ct] = s[k];
+      }
+      if (image) image_add(ip, G, step_x, step_z, s, image, counts);
+      ++ct;
+      curtime -= p.step_size;
+      if (!live || !(curtime > 0.0) || ct >= nsteps) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) P.c[k][idx] = s[k];
+        have = false;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot += __shfl_xor_sync(FULL_MASK, tot, o);
+    st |= __shfl_xor_sync(FULL_MASK, st, o);
+  }
+  if (lane == 0) {
+    if (tot) atomicAdd(&totals[0], tot);
+    if (st) atomicOr(status, st);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: image accumulation.  Streams x,y,z,vy,frac (40 B/packet, 16-byte vector
+// loads, two packets per thread per iteration) and scatters with f64 / u64
+// atomics into the L2-resident image (800x800: 5 MB + 5 MB).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
+                   double* __restrict__ image, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GTables G;
+  G.n = Gg.n;
+  size_t off = 0;
+  for (int t = 0; t < Gg.n; ++t) off += stage_table(Gg.t[t], G.t[t], smem_raw + off);
+  __syncthreads();
+  const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
+  const long long npair = n >> 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double2* __restrict__ X2 = reinterpret_cast<const double2*>(P.c[1]);
+  const double2* __restrict__ Y2 = reinterpret_cast<const double2*>(P.c[2]);
+  const double2* __restrict__ Z2 = reinterpret_cast<const double2*>(P.c[3]);
+  const double2* __restrict__ V2 = reinterpret_cast<const double2*>(P.c[5]);
+  const double2* __restrict__ F2 = reinterpret_cast<const double2*>(P.c[7]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
+    const double2 x = __ldcs(X2 + i), y = __ldcs(Y2 + i), z = __ldcs(Z2 + i);
+    const double2 v = __ldcs(V2 + i), f = __ldcs(F2 + i);
+    double w;
+    if (!(ip.skip_dead && !(f.x > 0.0))) {
+      const int pix = image_packet(ip, G, step_x, step_z, x.x, y.x, z.x, v.x, f.x, w);
+      if (pix >= 0) { if (w != 0.0) atomicAdd(&image[pix], w); atomicAdd(&counts[pix], 1ull); }
+    }
+    if (!(ip.skip_dead && !(f.y > 0.0))) {
+      const int pix = image_packet(ip, G, step_x, step_z, x.y, y.y, z.y, v.y, f.y, w);
+      if (pix >= 0) { if (w != 0.0) atomicAdd(&image[pix], w); atomicAdd(&counts[pix], 1ull); }
+    }
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long i = n - 1;
+    const double f = P.c[7][i];
+    if (!(ip.skip_dead && !(f > 0.0))) {
+      double w;
+      const int pix = image_packet(ip, G, step_x, step_z, P.c[1][i], P.c[2][i], P.c[3][i],
+                                   P.c[5][i], f, w);
+      if (pix >= 0) { if (w != 0.0) atomicAdd(&image[pix], w); atomicAdd(&counts[pix], 1ull); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5: lines of sight.  One LOS per thread (ray constants in registers), packet
+// positions staged through shared memory in tiles; every thread of the block
+// reads the same packet (smem broadcast) and runs the conservative cone reject;
+// the rare survivors take the exact (reference-order) path.
+// ---------------------------------------------------------------------------
+#define NX_LOS_TILE 1024
+
+__global__ void __launch_bounds__(NX_LOS_THREADS)
+k_los_accumulate(StateCols P, long long n, long long nlos, const double* __restrict__ los,
+                 const double* __restrict__ dist_plan, const int* __restrict__ nball,
+                 const double* __restrict__ ladder, const double* __restrict__ wid2,
+                 LosParams lp, LosConsts lc, GTables Gg,
+                 double* __restrict__ radiance, unsigned long long* __restrict__ npack,
+                 unsigned char* __restrict__ included, long long chunk) {
+  __shared__ double spx[NX_LOS_TILE], spy[NX_LOS_TILE], spz[NX_LOS_TILE];
+  const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  LosRay L;
+  const bool valid = l < nlos;
+  const long long ll = valid ? l : 0;
+  L.xs = los[ll]; L.ys = los[nlos + ll]; L.zs = los[2 * nlos + ll];
+  L.bx = los[3 * nlos + ll]; L.by = los[4 * nlos + ll]; L.bz = los[5 * nlos + ll];
+  L.dist_plan = valid ? dist_plan[ll] : -1.0;     // invalid rays reject everything
+  L.nball = nball[ll];
+
+  const long long p0 = (long long)blockIdx.y * chunk;
+  const long long p1 = (p0 + chunk < n) ? p0 + chunk : n;
+  double rad = 0.0;
+  unsigned long long cnt = 0;
+  for (long long base = p0; base < p1; base += NX_LOS_TILE) {
+    const int m = (int)((p1 - base < NX_LOS_TILE) ? (p1 - base) : NX_LOS_TILE);
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+      double x = P.c[1][base + j], y = P.c[2][base + j], z = P.c[3][base + j];
+      if (lp.round_f32) { x = round_f32(x); y = round_f32(y); z = round_f32(z); }
+      if (lp.skip_dead && !(P.c[7][base + j] > 0.0)) x = y = z = 1e300;   // never hit
+      spx[j] = x; spy[j] = y; spz[j] = z;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) {
+      const double px = spx[j], py = spy[j], pz = spz[j];
+      // conservative reject, FMA-contracted (exact path below re-evaluates)
+      const double rx = px - L.xs, ry = py - L.ys, rz = pz - L.zs;
+      const double lr = fma(rz, L.bz, fma(ry, L.by, rx * L.bx));
+      const double d2 = fma(rz, rz, fma(ry, ry, rx * rx));
+      if (lr > 0.0 && lr * lr >= d2 * lc.cos_loose2) {
+        double losrad, dist;
+        if (los_hit(L, lp.dphi, lc.cos_margin2, ladder, wid2, lc.inv_log_ratio, lc.log_t0,
+                    lc.kwin, px, py, pz, losrad, dist)) {
+          ++cnt;
+          double vy = P.c[5][base + j], fr = P.c[7][base + j];
+          if (lp.round_f32) { vy = round_f32(vy); fr = round_f32(fr); }
+          rad += los_weight(L, lp, Gg, lc.sin_dphi, fr, vy, losrad, dist);
+          included[base + j] = 1;
+        }
+      }
+    }
+  }
+  if (valid && cnt) {
+    atomicAdd(&radiance[l], rad);
+    atomicAdd(&npack[l], cnt);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// measurement helpers
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fp64_peak(double* out, int iters, double a, double b) {
+  // 8 independent DFMA chains per thread: enough ILP to saturate the FP64 pipe
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void __launch_bounds__(256)
+k_copy(const double2* __restrict__ src, double2* __restrict__ dst, long long n2) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
+    dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------------------
+// launch wrappers (called from nx_api.cu)
+// ---------------------------------------------------------------------------
+static int sm_count(int device) {
+  int v = 148;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+  return v;
+}
+
+cudaError_t launch_init_state(cudaStream_t st, StateCols P, X0Cols X, long long n,
+                              const SourceParams& sp, const SourceMap& map,
+                              const InterpTable& speed, uint64_t seed, uint64_t first_id) {
+  const int threads = 256;
+  const long long blocks = (n + threads - 1) / threads;
+  k_init_state<<<(unsigned)blocks, threads, 0, st>>>(P, X, n, sp, map, speed, seed, first_id);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v) {
+  k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  return cudaGetLastError();
+}
+
+template <typename K>
+static cudaError_t persistent_grid(K kernel, int device, size_t smem, int* blocks) {
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NX_INT_THREADS, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  *blocks = per_sm * sm_count(device);
+  return cudaSuccess;
+}
+
+cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
+                                      const RunParams& p, const InterpTable& T,
+                                      unsigned long long* queue, unsigned long long* totals,
+                                      unsigned* att, unsigned* acc, int* status) {
+  const size_t smem = table_smem_bytes(T);
+  int blocks = 0;
+  cudaError_t e;
+  if (p.strict_math) {
+    e = persistent_grid(k_integrate_adaptive<true>, device, smem, &blocks);
+    if (e != cudaSuccess) return e;
+    long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
+    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+    k_integrate_adaptive<true><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, queue, totals,
+                                                                     att, acc, status);
+  } else {
+    e = persistent_grid(k_integrate_adaptive<false>, device, smem, &blocks);
+    if (e != cudaSuccess) return e;
+    long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
+    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+    k_integrate_adaptive<false><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, queue, totals,
+                                                                      att, acc, status);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,
+                                      const RunParams& p, const InterpTable& T,
+                                      const Spline2D& S, uint64_t seed, uint64_t first_id,
+                                      int nsteps, const ImageParams& ip, const GTables& G,
+                                      double* image, unsigned long long* counts, double* traj,
+                                      unsigned long long* queue, unsigned long long* totals,
+                                      int* status) {
+  const size_t smem = table_smem_bytes(T);
+  int blocks = 0;
+  cudaError_t e;
+  long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
+  if (p.strict_math) {
+    e = persistent_grid(k_integrate_constant<true>, device, smem, &blocks);
+    if (e != cudaSuccess) return e;
+    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+    k_integrate_constant<true><<<blocks, NX_INT_THREADS, smem, st>>>(
+        P, n, p, T, S, seed, first_id, nsteps, ip, G, image, counts, traj, queue, totals, status);
+  } else {
+    e = persistent_grid(k_integrate_constant<false>, device, smem, &blocks);
+    if (e != cudaSuccess) return e;
+    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+    k_integrate_constant<false><<<blocks, NX_INT_THREADS, smem, st>>>(
+        P, n, p, T, S, seed, first_id, nsteps, ip, G, image, counts, traj, queue, totals, status);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, long long n,
+                                    const ImageParams& ip, const GTables& G, double* image,
+                                    unsigned long long* counts) {
+  size_t smem = 0;
+  for (int t = 0; t < G.n; ++t) smem += table_smem_bytes(G.t[t]);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_image_accumulate,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_image_accumulate, 256, smem);
+  if (per_sm < 1) per_sm = 1;
+  long long blocks = (long long)per_sm * sm_count(device);
+  const long long need = ((n >> 1) + 255) / 256;
+  if (need < blocks) blocks = need > 0 ? need : 1;
+  k_image_accumulate<<<(unsigned)blocks, 256, smem, st>>>(P, n, ip, G, image, counts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_los_accumulate(cudaStream_t st, int device, StateCols P, long long n,
+                                  long long nlos, const double* los, const double* dist_plan,
+                                  const int* nball, const double* ladder, const double* wid2,
+                                  const LosParams& lp, const LosConsts& lc, const GTables& G,
+                                  double* radiance, unsigned long long* npack,
+                                  unsigned char* included) {
+  const long long bx = (nlos + NX_LOS_THREADS - 1) / NX_LOS_THREADS;
+  // enough packet chunks to fill the machine a few times over
+  long long target = 4LL * sm_count(device) * 4;
+  long long by = (target + bx - 1) / bx;
+  if (by < 1) by = 1;
+  long long chunk = (n + by - 1) / by;
+  chunk = ((chunk + NX_LOS_TILE - 1) / NX_LOS_TILE) * NX_LOS_TILE;
+  by = (n + chunk - 1) / chunk;
+  if (by > 65535) { by = 65535; chunk = (n + by - 1) / by; chunk = ((chunk + NX_LOS_TILE - 1) / NX_LOS_TILE) * NX_LOS_TILE; by = (n + chunk - 1) / chunk; }
+  dim3 grid((unsigned)bx, (unsigned)by);
+  k_los_accumulate<<<grid, NX_LOS_THREADS, 0, st>>>(P, n, nlos, los, dist_plan, nball, ladder,
+                                                     wid2, lp, lc, G, radiance, npack, included,
+                                                     chunk);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(cudaStream_t st, int device, double* out, int iters, int* blocks,
+                             int* threads) {
+  *threads = 256;
+  *blocks = sm_count(device) * 8;
+  k_fp64_peak<<<*blocks, *threads, 0, st>>>(out, iters, 0.999999, 1e-7);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_copy(cudaStream_t st, int device, const double* src, double* dst,
+                        long long n) {
+  k_copy<<<sm_count(device) * 8, 256, 0, st>>>(reinterpret_cast<const double2*>(src),
+                                               reinterpret_cast<double2*>(dst), n / 2);
+  return cudaGetLastError();
+}
+
+}  // namespace nx

@@ -1,0 +1,60 @@
+// Internal interface between the kernels (nx_kernels.cu) and the C ABI (nx_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nx_image.cuh"
+#include "nx_init.cuh"
+#include "nx_physics.cuh"
+#include "nx_surface.cuh"
+
+#define NX_INT_THREADS 128
+#define NX_LOS_THREADS 128
+
+namespace nx {
+
+struct StateCols { double* c[9]; };    // time,x,y,z,vx,vy,vz,frac,step_size
+struct X0Cols { double* c[14]; };
+
+struct LosConsts {
+  double sin_dphi;
+  double cos_margin2;     // (cos(dphi) (1 - 1e-9))^2   conservative reject, exact-order path
+  double cos_loose2;      // (cos(dphi) (1 - 1e-6))^2   conservative reject, FMA path
+  double inv_log_ratio;   // 1 / log(1 + sin dphi)
+  double log_t0;          // log(sin dphi)
+  int kwin;
+  int nladder;
+};
+
+size_t table_smem_bytes(const InterpTable& g);
+
+cudaError_t launch_init_state(cudaStream_t st, StateCols P, X0Cols X, long long n,
+                              const SourceParams& sp, const SourceMap& map,
+                              const InterpTable& speed, uint64_t seed, uint64_t first_id);
+cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v);
+cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
+                                      const RunParams& p, const InterpTable& T,
+                                      unsigned long long* queue, unsigned long long* totals,
+                                      unsigned* att, unsigned* acc, int* status);
+cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,
+                                      const RunParams& p, const InterpTable& T,
+                                      const Spline2D& S, uint64_t seed, uint64_t first_id,
+                                      int nsteps, const ImageParams& ip, const GTables& G,
+                                      double* image, unsigned long long* counts, double* traj,
+                                      unsigned long long* queue, unsigned long long* totals,
+                                      int* status);
+cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, long long n,
+                                    const ImageParams& ip, const GTables& G, double* image,
+                                    unsigned long long* counts);
+cudaError_t launch_los_accumulate(cudaStream_t st, int device, StateCols P, long long n,
+                                  long long nlos, const double* los, const double* dist_plan,
+                                  const int* nball, const double* ladder, const double* wid2,
+                                  const LosParams& lp, const LosConsts& lc, const GTables& G,
+                                  double* radiance, unsigned long long* npack,
+                                  unsigned char* included);
+cudaError_t launch_fp64_peak(cudaStream_t st, int device, double* out, int iters, int* blocks,
+                             int* threads);
+cudaError_t launch_copy(cudaStream_t st, int device, const double* src, double* dst,
+                        long long n);
+
+}  // namespace nx

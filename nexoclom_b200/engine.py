@@ -1,0 +1,250 @@
+"""Thin object wrapper over the C ABI (one ``Engine`` == one ``nx_ctx`` == one GPU).
+
+All arrays crossing this layer are plain NumPy float64 / int64 host buffers
+(or raw device pointers for the ``*_dev`` calls); there is no CPU fallback --
+construction raises if the library or a CUDA device is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (RunParams, SourceParams, ImageParams, LosParams, as_f64, dptr,
+                   c_double_p)
+
+STATE_COLS = ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac')
+X0_COLS = ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac', 'v', 'longitude', 'latitude',
+           'local_time', 'altitude', 'azimuth')
+
+
+class NexoclomCudaError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.nx_ctx_create(int(device), C.byref(self.ctx))
+        if rc != 0 or not self.ctx:
+            raise NexoclomCudaError(
+                f'nx_ctx_create(device={device}) failed with code {rc}: nexoclom_b200 needs a '
+                'CUDA device (sm_100a); there is no CPU fallback')
+        self.device = int(device)
+        self.n = 0
+        self.params = None
+
+    # -- plumbing -------------------------------------------------------------
+    def close(self):
+        if getattr(self, 'ctx', None):
+            self.lib.nx_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            msg = self.lib.nx_last_error(self.ctx)
+            raise NexoclomCudaError(f'{what} failed ({rc}): {msg.decode() if msg else ""}')
+        if rc > 0:
+            # device-side numerical invariants == the reference's bare asserts
+            msgs = []
+            if rc & 4:
+                msgs.append('\n\tInfinite values of emax')                  # Output.py:284
+            if rc & 8:
+                msgs.append('Found new values of frac that are negative')   # Output.py:287
+            if rc & 16:
+                msgs.append('\n\tInfinite values of step_size')             # Output.py:338
+            if rc & 32:
+                msgs.append('non-finite packet state')                      # Output.py:389
+            raise AssertionError('; '.join(msgs) or f'invariant bits {rc}')
+        return rc
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.nx_ctx_set_stream(self.ctx, C.c_void_p(int(cuda_stream_ptr))),
+                    'nx_ctx_set_stream')
+
+    def sync(self):
+        self._check(self.lib.nx_ctx_sync(self.ctx), 'nx_ctx_sync')
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        self._check(self.lib.nx_last_kernel_ms(self.ctx, C.byref(ms)), 'nx_last_kernel_ms')
+        return float(ms.value)
+
+    def kernel_launches(self):
+        v = C.c_ulonglong()
+        self.lib.nx_kernel_launches(self.ctx, C.byref(v))
+        return int(v.value)
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(self.lib.nx_measure_fp64_peak(self.ctx, C.byref(v)), 'nx_measure_fp64_peak')
+        return float(v.value)
+
+    def measure_copy_bw(self, nbytes=1 << 30):
+        v = C.c_double()
+        self._check(self.lib.nx_measure_copy_bw(self.ctx, int(nbytes), C.byref(v)),
+                    'nx_measure_copy_bw')
+        return float(v.value)
+
+    # -- tables ---------------------------------------------------------------
+    def upload_tables(self, params, radpres_v=None, radpres_a=None, spline_tck=None):
+        """params: RunParams; radpres_* in R_p/s, R_p/s^2; spline_tck = (tx, ty, c)."""
+        self.params = params
+        if radpres_v is not None:
+            rv, ra = as_f64(radpres_v), as_f64(radpres_a)
+            nrp = len(rv)
+            prv, pra = dptr(rv), dptr(ra)
+        else:
+            nrp, prv, pra = 0, None, None
+        if spline_tck is not None:
+            tx, ty, c = (as_f64(a) for a in spline_tck)
+            args = (dptr(tx), len(tx), dptr(ty), len(ty), dptr(c))
+        else:
+            args = (None, 0, None, 0, None)
+        self._check(self.lib.nx_tables_upload(self.ctx, C.byref(params), prv, pra, nrp, *args),
+                    'nx_tables_upload')
+
+    def upload_gtables(self, tables):
+        """tables: list of (velocity [R_p/s], g [1/s]) arrays, one per emission line."""
+        sizes = (C.c_int * len(tables))(*[len(v) for v, _ in tables])
+        v = as_f64(np.concatenate([t[0] for t in tables])) if tables else np.zeros(1)
+        g = as_f64(np.concatenate([t[1] for t in tables])) if tables else np.zeros(1)
+        self._check(self.lib.nx_gtables_upload(self.ctx, len(tables), sizes, dptr(v), dptr(g)),
+                    'nx_gtables_upload')
+
+    def upload_sourcemap(self, fmap, xaxis, yaxis):
+        f = as_f64(fmap)
+        xa, ya = as_f64(xaxis), as_f64(yaxis)
+        self._check(self.lib.nx_sourcemap_upload(self.ctx, dptr(f), f.shape[0], f.shape[1],
+                                                 dptr(xa), dptr(ya)), 'nx_sourcemap_upload')
+
+    def upload_speedtable(self, cdf, v):
+        c, vv = as_f64(cdf), as_f64(v)
+        self._check(self.lib.nx_speedtable_upload(self.ctx, dptr(c), dptr(vv), len(c)),
+                    'nx_speedtable_upload')
+
+    # -- packets --------------------------------------------------------------
+    def import_state(self, cols):
+        """cols: sequence of 8 arrays (time,x,y,z,vx,vy,vz,frac) or an (N,8) array."""
+        if isinstance(cols, np.ndarray) and cols.ndim == 2:
+            cols = [cols[:, k] for k in range(8)]
+        arrs = [as_f64(c) for c in cols]
+        n = len(arrs[0])
+        ptrs = (c_double_p * 8)(*[dptr(a) for a in arrs])
+        self._check(self.lib.nx_import_state(self.ctx, n, ptrs), 'nx_import_state')
+        self.n = n
+
+    def export_state(self):
+        out = np.empty((8, self.n))
+        ptrs = (c_double_p * 8)(*[dptr(out[k]) for k in range(8)])
+        self._check(self.lib.nx_export_state(self.ctx, self.n, ptrs), 'nx_export_state')
+        return out
+
+    def export_x0(self):
+        out = np.empty((14, self.n))
+        ptrs = (c_double_p * 14)(*[dptr(out[k]) for k in range(14)])
+        self._check(self.lib.nx_export_x0(self.ctx, self.n, ptrs), 'nx_export_x0')
+        return out
+
+    def export_stats(self):
+        a = np.empty(self.n, dtype=np.uint32)
+        b = np.empty(self.n, dtype=np.uint32)
+        self._check(self.lib.nx_export_stats(self.ctx, self.n,
+                                             a.ctypes.data_as(_lib.c_u32_p),
+                                             b.ctypes.data_as(_lib.c_u32_p)), 'nx_export_stats')
+        return a, b
+
+    def export_step(self):
+        s = np.empty(self.n)
+        self._check(self.lib.nx_export_step(self.ctx, self.n, dptr(s)), 'nx_export_step')
+        return s
+
+    def state_device_ptr(self, column):
+        p = C.c_void_p()
+        self._check(self.lib.nx_state_device_ptr(self.ctx, int(column), C.byref(p)),
+                    'nx_state_device_ptr')
+        return p.value
+
+    def init_state(self, source_params, seed, first_id, n):
+        self._check(self.lib.nx_init_state(self.ctx, C.byref(source_params), int(seed),
+                                           int(first_id), int(n)), 'nx_init_state')
+        self.n = int(n)
+
+    # -- hot kernels ----------------------------------------------------------
+    def integrate_adaptive(self, n=None):
+        att, acc = C.c_ulonglong(), C.c_ulonglong()
+        n = self.n if n is None else n
+        self._check(self.lib.nx_integrate_adaptive(self.ctx, n, C.byref(att), C.byref(acc)),
+                    'nx_integrate_adaptive')
+        return int(att.value), int(acc.value)
+
+    def integrate_constant(self, seed=0, first_id=0, image_params=None, image_dev=None,
+                           counts_dev=None, trajectory=False, n=None):
+        n = self.n if n is None else n
+        p = self.params
+        nsteps = int(np.ceil(p.endtime / p.step_size + 1))
+        traj = np.zeros((n, 8, nsteps)) if trajectory else None
+        steps = C.c_ulonglong()
+        self._check(self.lib.nx_integrate_constant(
+            self.ctx, n, int(seed), int(first_id),
+            C.byref(image_params) if image_params is not None else None,
+            C.c_void_p(image_dev) if image_dev else None,
+            C.c_void_p(counts_dev) if counts_dev else None,
+            dptr(traj) if traj is not None else None, C.byref(steps)), 'nx_integrate_constant')
+        return traj, nsteps, int(steps.value)
+
+    def image_accumulate(self, image_params, n=None):
+        n = self.n if n is None else n
+        img = np.zeros((image_params.nx, image_params.nz))
+        cnt = np.zeros((image_params.nx, image_params.nz), dtype=np.int64)
+        self._check(self.lib.nx_image_accumulate(self.ctx, n, C.byref(image_params), dptr(img),
+                                                 cnt.ctypes.data_as(_lib.c_i64_p)),
+                    'nx_image_accumulate')
+        return img, cnt
+
+    def image_accumulate_dev(self, image_params, image_dev, counts_dev, n=None):
+        n = self.n if n is None else n
+        self._check(self.lib.nx_image_accumulate_dev(self.ctx, n, C.byref(image_params),
+                                                     C.c_void_p(image_dev),
+                                                     C.c_void_p(counts_dev)),
+                    'nx_image_accumulate_dev')
+
+    def los_accumulate(self, los, dist_from_plan, los_params, n=None):
+        """los: (6, nlos) array x,y,z,xbore,ybore,zbore."""
+        n = self.n if n is None else n
+        los = as_f64(los)
+        nlos = los.shape[1]
+        dist = as_f64(dist_from_plan)
+        rad = np.zeros(nlos)
+        npk = np.zeros(nlos, dtype=np.int64)
+        inc = np.zeros(max(n, 1), dtype=np.uint8)
+        self._check(self.lib.nx_los_accumulate(self.ctx, n, nlos, dptr(los), dptr(dist),
+                                               C.byref(los_params), dptr(rad),
+                                               npk.ctypes.data_as(_lib.c_i64_p),
+                                               inc.ctypes.data_as(_lib.c_u8_p)),
+                    'nx_los_accumulate')
+        return rad, npk, inc[:n].astype(bool)
+
+    def los_accumulate_dev(self, nlos, los_dev, dist_dev, los_params, rad_dev, npk_dev, inc_dev,
+                           n=None):
+        n = self.n if n is None else n
+        self._check(self.lib.nx_los_accumulate_dev(
+            self.ctx, n, int(nlos), C.c_void_p(los_dev), C.c_void_p(dist_dev),
+            C.byref(los_params), C.c_void_p(rad_dev), C.c_void_p(npk_dev),
+            C.c_void_p(inc_dev)), 'nx_los_accumulate_dev')
+
+
+_engines = {}
+
+
+def get_engine(device=0):
+    """Process-wide engine per device (the reference is single-threaded too)."""
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

@@ -1,0 +1,89 @@
+// TEST-ONLY: compiles the kernels' shared per-packet physics (nx_physics.cuh)
+// with g++ so that logic can be debugged against the oracle on machines without
+// a GPU.  Never loaded by nexoclom_b200 (the product fails loudly without CUDA).
+#include "../../nexoclom_b200/csrc/nx_physics.cuh"
+#include "../../nexoclom_b200/csrc/nx_tables.h"
+#include "../../nexoclom_b200/csrc/nx_surface.cuh"
+
+using namespace nx;
+
+static InterpTable view(const HostInterp& h) {
+  InterpTable t;
+  t.x = h.x.data(); t.f = h.f.data(); t.slope = h.slope.data(); t.bucket = h.bucket.data();
+  t.n = (int)h.x.size(); t.nbucket = h.nbucket; t.blo = h.blo; t.binvw = h.binvw;
+  return t;
+}
+
+extern "C" int hc_dp_step(long n, const double* X, const double* h, double* out, double* delta,
+                          const RunParams* p, const double* rpv, const double* rpa, int nrp,
+                          int strict) {
+  HostInterp hi; InterpTable T{};
+  if (nrp > 0) { hi = make_interp(rpv, rpa, nrp); T = view(hi); }
+  for (long i = 0; i < n; ++i) {
+    double d[7];
+    if (strict) dp_step<true, true>(*p, T, X + 8 * i, h[i], out + 8 * i, d);
+    else dp_step<false, true>(*p, T, X + 8 * i, h[i], out + 8 * i, d);
+    delta[8 * i] = 0.0;
+    for (int k = 0; k < 7; ++k) delta[8 * i + 1 + k] = d[k];
+  }
+  return 0;
+}
+
+extern "C" int hc_integrate_adaptive(long n, double* X /* n x 8 row-major */, double* step,
+                                     unsigned* att, unsigned* acc, const RunParams* p,
+                                     const double* rpv, const double* rpa, int nrp, int strict) {
+  HostInterp hi; InterpTable T{};
+  if (nrp > 0) { hi = make_interp(rpv, rpa, nrp); T = view(hi); }
+  int status = 0;
+  for (long i = 0; i < n; ++i) {
+    double* s = X + 8 * i;
+    att[i] = acc[i] = 0;
+    bool live = (s[0] > p->resolution) && (s[7] > 0.0);
+    while (live) {
+      int fl = strict ? adaptive_attempt<true>(*p, T, s, step[i])
+                      : adaptive_attempt<false>(*p, T, s, step[i]);
+      att[i]++;
+      if (fl & ATT_ACCEPTED) acc[i]++;
+      status |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
+      live = fl & ATT_LIVE;
+    }
+  }
+  return status;
+}
+
+extern "C" int hc_integrate_constant(long n, double* X /* n x 8 */, double* traj /* n x 8 x nsteps or null */,
+                                     int nsteps, unsigned long long seed, unsigned long long first_id,
+                                     const RunParams* p, const double* rpv, const double* rpa, int nrp,
+                                     const double* tx, int ntx, const double* ty, int nty,
+                                     const double* c, int strict) {
+  HostInterp hi; InterpTable T{};
+  if (nrp > 0) { hi = make_interp(rpv, rpa, nrp); T = view(hi); }
+  Spline2D S{tx, ty, c, ntx, nty};
+  for (long i = 0; i < n; ++i) {
+    double* s = X + 8 * i;
+    if (traj) for (int k = 0; k < 8; ++k) traj[(i * 8 + k) * (long)nsteps + 0] = s[k];
+    bool live = s[7] > 0.0;
+    double curtime = p->endtime;
+    int ct = 1;
+    while (curtime > 0 && ct < nsteps) {
+      if (live) {
+        live = strict ? constant_step<true>(*p, T, S, s, seed, first_id + i, (uint32_t)ct)
+                      : constant_step<false>(*p, T, S, s, seed, first_id + i, (uint32_t)ct);
+        if (traj) for (int k = 0; k < 8; ++k) traj[(i * 8 + k) * (long)nsteps + ct] = s[k];
+      }
+      ++ct; curtime -= p->step_size;
+    }
+  }
+  return 0;
+}
+
+extern "C" void hc_uniform_pairs(long n, unsigned long long seed, unsigned long long first_id,
+                                 unsigned stream, unsigned draw, double* u0, double* u1) {
+  for (long i = 0; i < n; ++i) uniform_pair(seed, first_id + i, stream, draw, u0[i], u1[i]);
+}
+
+extern "C" void hc_spline_ev(long n, const double* x, const double* y, double* out,
+                             const double* tx, int ntx, const double* ty, int nty, const double* c) {
+  Spline2D S{tx, ty, c, ntx, nty};
+  for (long i = 0; i < n; ++i) out[i] = spline2d_ev(S, x[i], y[i]);
+}

@@ -1,0 +1,57 @@
+"""Shared helpers for the tests: workload loading, oracle constants from a
+RunSetup, comparison metrics."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+WORKLOADS = os.path.join(REPO, 'nexoclom_b200', 'workloads')
+GOLDEN = os.path.join(REPO, 'tests', 'golden')
+
+
+def workload(name):
+    from nexoclom_b200.Input import Input
+    return Input(os.path.join(WORKLOADS, name))
+
+
+def oracle_constants(setup):
+    """oracle.tracking.RunConstants carrying the same numbers as setup.params."""
+    from oracle.tracking import RunConstants
+    p = setup.params
+    sint = setup.inputs.surfaceinteraction
+    return RunConstants(
+        GM=p.GM, vrplanet=p.vrplanet, gravity=bool(p.gravity), radpres=bool(p.radpres),
+        radpres_v=setup.radpres_v, radpres_a=setup.radpres_a,
+        lifetime=(1.0 / p.loss_rate if p.loss_mode == 1 else 0.0),
+        photo=(p.loss_rate if p.loss_mode == 2 else None),
+        resolution=p.resolution if p.resolution > 0 else 1e-4, outeredge=p.outeredge,
+        step_size=p.step_size, endtime=p.endtime, sticktype=sint.sticktype,
+        stickcoef=getattr(sint, 'stickcoef', 1.0),
+        accomfactor=sint.accomfactor, A=tuple(p.stick_A),
+        taa=float(np.asarray(setup.inputs.geometry.taa)),
+        planet_radius_km=p.planet_radius_km,
+        v_interp=(setup.surfaceint.v_interp if setup.surfaceint is not None and
+                  setup.surfaceint.tck is not None else None))
+
+
+def vec_rel(a, b):
+    """|a-b| / |b| per row for (N,3) arrays."""
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)
+
+
+def state_parity(X_gpu, X_ref):
+    """Relative differences (position vector, velocity vector, frac) over packets
+    alive in both; X_* are (N,8).  Returns dict of maxima and mismatch counts."""
+    alive_g, alive_r = X_gpu[:, 7] > 0, X_ref[:, 7] > 0
+    both = alive_g & alive_r
+    out = dict(alive_mismatch=int((alive_g != alive_r).sum()), n_both=int(both.sum()))
+    if both.any():
+        out['pos'] = float(vec_rel(X_gpu[both, 1:4], X_ref[both, 1:4]).max())
+        out['vel'] = float(vec_rel(X_gpu[both, 4:7], X_ref[both, 4:7]).max())
+        out['frac'] = float((np.abs(X_gpu[both, 7] - X_ref[both, 7]) / X_ref[both, 7]).max())
+        out['time'] = float(np.abs(X_gpu[both, 0] - X_ref[both, 0]).max())
+    return out

@@ -95,29 +95,17 @@ def install():
                                  surface_temperature=surface_temperature, Output=Output)
 
 
-class TaaQuantity(float):
-    """``geometry.taa`` stand-in: ``np.cos(taa)`` must yield something with
-    ``.value`` (reference ``surface_temperature.py:9-10``)."""
+class TaaQuantity(__import__('numpy').ndarray):
+    """``geometry.taa`` stand-in: ``np.cos(taa)`` and the arithmetic after it must
+    yield something with ``.value`` (reference ``surface_temperature.py:9-10``)."""
 
-    def cos(self):
-        return _Val(__import__('math').cos(float(self)))
+    def __new__(cls, v):
+        import numpy as np
+        return np.asarray(float(v), dtype=np.float64).view(cls)
 
-
-class _Val(float):
     @property
     def value(self):
         return float(self)
-
-    def _wrap(self, r):
-        return _Val(r)
-
-    def __sub__(self, o): return _Val(float(self) - o)
-    def __rsub__(self, o): return _Val(o - float(self))
-    def __add__(self, o): return _Val(float(self) + o)
-    __radd__ = __add__
-    def __mul__(self, o): return _Val(float(self) * o)
-    __rmul__ = __mul__
-    def __truediv__(self, o): return _Val(float(self) / o)
 
 
 class Lifetime(float):
