@@ -1,0 +1,228 @@
+"""``LOSResult``: model radiance along spacecraft lines of sight.
+
+Drop-in for the reference ``data_simulation/LOSResult.py:75-308`` and
+``data_simulation/compute_iteration.py:90-240``.  The per-spectrum Python loop
+(KD-tree ball query, cone test, planet truncation, weighting, foot-point shadow
+test; compute_iteration.py:151-222) is one CUDA kernel (K5,
+``nx_los_accumulate``) that evaluates every (line of sight, packet) pair with
+the same membership rule.  The SQL model cache is replaced by an in-memory one.
+
+``scdata`` is duck-typed exactly as in the reference: ``.data`` DataFrame with
+``x, y, z, xbore, ybore, zbore, radiance, sigma, alttan``; ``.species``;
+``.query``; ``.set_frame('Model')``; ``len()``; ``.subslong``.
+"""
+import numpy as np
+import pandas as pd
+
+from .engine import get_engine
+from .ModelResult import ModelResult
+from .Output import Output
+from .runsetup import RunSetup
+from ._lib import LosParams
+from .units import Quantity, value_of
+
+
+class IterationResult:
+    """Per-outputfile LOS result (reference compute_iteration.py:15-35)."""
+
+    def __init__(self, iteration, losresult):
+        self.radiance = iteration['radiance']
+        self.npackets = iteration['npackets']
+        self.totalsource = iteration['totalsource']
+        self.outputfile = iteration['outputfile']
+        self.out_idnum = iteration['out_idnum']
+        self.included = iteration['included']
+        self.modelfile = None
+        self.model_idnum = None
+        self.used_packets = iteration.get('used', None)
+        self.used_packets0 = iteration.get('used0', None)
+        self.quantity = losresult.quantity
+        self.query = losresult.query
+        self.dphi = losresult.dphi
+        self.mechanism = losresult.mechanism
+        self.wavelength = losresult.wavelength
+        self.fitted = losresult.fitted
+
+
+def dist_from_planet_cut(data):
+    """LOS truncation distance: |x_sc| if the boresight hits the planet, else
+    1e30 (reference compute_iteration.py:105-115)."""
+    dist_from_plan = np.sqrt(data.x**2 + data.y**2 + data.z**2)
+    ang = np.arccos((-data.x * data.xbore - data.y * data.ybore -
+                     data.z * data.zbore) / dist_from_plan)
+    asize_plan = np.arcsin(1. / dist_from_plan)
+    dist_from_plan = dist_from_plan.copy()
+    dist_from_plan.loc[ang > asize_plan] = 1e30
+    return dist_from_plan
+
+
+def compute_iteration(self, outputfile, scdata, delay=False):
+    """One output file against all spectra (reference compute_iteration.py:90-240)."""
+    data = scdata.data
+    dist_from_plan = dist_from_planet_cut(data)
+
+    output = Output.restore(outputfile)
+    X0_index = output.X0.index
+    packets = output.X
+    if 'Index' not in packets.columns:
+        packets['Index'] = list(packets.index)
+    totalsource = output.totalsource
+    idnum = output.idnum
+
+    eng = get_engine(self._device)
+    setup = RunSetup(self.inputs)
+    self._upload_weighting_tables(eng, setup)
+    eng.import_state([packets[c].values for c in
+                      ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac')])
+    lp = LosParams()
+    lp.dphi = self.dphi
+    lp.outeredge = float(self.inputs.options.outeredge)
+    lp.vrplanet = setup.vrplanet
+    lp.rp_cm = setup.radius_km * 1e5
+    if self.quantity != 'radiance':
+        assert False, 'Other quantities not set up.'          # compute_iteration.py:213
+    lp.quantity = 1
+    los = np.stack([data[c].values.astype(float) for c in
+                    ('x', 'y', 'z', 'xbore', 'ybore', 'zbore')])
+    print(f'{data.shape[0]} spectra taken.')
+    rad_, npack_, inc_ = eng.los_accumulate(los, dist_from_plan.values, lp)
+    self.kernel_ms = eng.last_kernel_ms()
+
+    rad = pd.Series(rad_, index=data.index)
+    npack = pd.Series(npack_, index=data.index, dtype=int)
+    included = pd.Series(False, index=X0_index, dtype=bool)
+    included[packets['Index'].values[inc_]] = True
+    assert np.all(np.isfinite(rad_))
+
+    iteration_ = {'radiance': rad, 'npackets': npack, 'totalsource': totalsource,
+                  'outputfile': outputfile, 'out_idnum': idnum, 'query': scdata.query,
+                  'used': None, 'used0': None, 'included': included}
+    return IterationResult(iteration_, self)
+
+
+class LOSResult(ModelResult):
+    def __init__(self, scdata, inputs, params=None, dphi=Quantity(1., 'deg'), device=0,
+                 **kwargs):
+        if params is None:
+            params = {'quantity': 'radiance'}
+        scdata.set_frame('Model')
+        super().__init__(inputs, params)
+        self.species = scdata.species
+        self.query = scdata.query
+        self.type = 'LineOfSight'
+        self.dphi = (float(dphi.to('rad').value) if isinstance(dphi, Quantity)
+                     else float(np.radians(dphi)))
+        self._oedge = np.min([self.inputs.options.outeredge * 2, 100])
+        self.fitted = self.inputs.options.fitted
+        nspec = len(scdata)
+        self.radiance = pd.Series(np.zeros(nspec), index=scdata.data.index)
+        self.radiance_unit = 'kR'
+        self.sourcemap = None
+        self.modelfiles = None
+        self.goodness_of_fit = None
+        self.mask = None
+        self.masking = kwargs.get('masking', None)
+        self.fit_method = kwargs.get('fit_method', None)
+        self.label = kwargs.get('label', 'LOSResult')
+        self._device = device
+        self._iterations = {}
+
+    def __repr__(self):
+        return self.__str__()
+
+    def __str__(self):
+        return f'''Model Label = {self.label}
+quantity = {self.quantity}
+npackets = {self.npackets}
+totalsource = {self.totalsource}
+atoms per packet = {self.atoms_per_packet}
+sourcerate = {self.sourcerate}
+dphi = {self.dphi}
+fit_method = {self.fit_method}
+fitted = {self.fitted}'''
+
+    def make_mask(self, data):
+        """reference LOSResult.py:171-200."""
+        mask = np.array([True for _ in data.radiance])
+        sigmalimit = None
+        if self.masking is not None:
+            for masktype in self.masking.split(';'):
+                masktype = masktype.strip().lower()
+                if masktype.startswith('middle'):
+                    perinterval = float(masktype[6:])
+                    lo = np.percentile(data.radiance, (100 - perinterval) / 2)
+                    hi = np.percentile(data.radiance, 100 - (100 - perinterval) / 2)
+                    mask = mask & (data.radiance >= lo) & (data.radiance <= hi)
+                elif masktype.startswith('minalt'):
+                    mask = mask & (data.alttan >= float(masktype[6:]))
+                elif masktype.startswith('minsnr'):
+                    snr = data.radiance / data.sigma
+                    mask = mask & (snr > float(masktype[6:]))
+                elif masktype.startswith('siglimit'):
+                    sigmalimit = float(masktype[8:])
+                else:
+                    raise ValueError('nexoclom.math.fit_model',
+                                     f'masking = {masktype} not defined.')
+        return np.asarray(mask), sigmalimit
+
+    def simulate_data_from_inputs(self, scdata, distribute=None):
+        """reference LOSResult.py:202-276."""
+        if ((self.inputs.spatialdist.type == 'surface map') and
+                (self.inputs.spatialdist.coordinate_system == 'planet-fixed')):
+            self.inputs.spatialdist.subsolarlon = Quantity(scdata.subslong.median(), 'rad')
+
+        (self.outid, self.outputfiles, self.npackets, self.totalsource) = self.inputs.search()
+        print(f'LOSResult: {len(self.outid)} output files found.')
+        if self.npackets == 0:
+            raise RuntimeError('No packets found for these Inputs.')
+        if distribute in (True, 'delay', 'delayed'):
+            assert False, "Don't do this"                       # LOSResult.py:230
+
+        data = scdata.data
+        iteration_results = []
+        for outputfile in self.outputfiles:
+            if outputfile not in self._iterations:
+                self._iterations[outputfile] = compute_iteration(self, outputfile, scdata)
+            it = self._iterations[outputfile]
+            assert len(it.radiance) == len(data)
+            iteration_results.append(it)
+
+        self.modelfiles = {}
+        self.npackets_los = pd.Series(np.zeros(len(data), dtype=int), index=data.index)
+        for it in iteration_results:
+            self.radiance += it.radiance
+            self.npackets_los += it.npackets
+            self.modelfiles[it.outputfile] = it.modelfile
+
+        model_rate = self.totalsource / float(value_of(self.inputs.options.endtime))
+        self.atoms_per_packet = 1e23 / model_rate
+        self.radiance *= self.atoms_per_packet / 1e3  # kR
+        self.determine_source_rate(scdata, use_weight=False)
+        self.outputfiles = list(self.modelfiles.keys())
+        print(self.totalsource, self.atoms_per_packet)
+
+    def determine_source_rate(self, scdata, use_weight=True):
+        """Linear least-squares scale factor model -> data (reference
+        LOSResult.py:278-308; astropy's LinearLSQFitter on a Multiply model is the
+        closed form sum(w m d) / sum(w m m))."""
+        mask, sigmalimit = self.make_mask(scdata.data)
+        d = scdata.data.radiance.values
+        m = self.radiance.values
+
+        def fit(msk):
+            w = (1. / scdata.data.sigma.values[msk]**2 if use_weight
+                 else np.ones_like(scdata.data.sigma.values[msk]))
+            return np.sum(w * m[msk] * d[msk]) / np.sum(w * m[msk] * m[msk])
+
+        if not np.all(m == 0):
+            factor = fit(mask)
+            if sigmalimit is not None:
+                diff = np.abs((d - factor * m) / scdata.data.sigma.values)
+                mask = mask & (diff < sigmalimit)
+                factor = fit(mask)
+            self.radiance *= factor
+            self.sourcerate = Quantity(factor, '')      # x 10**23 atoms/s
+        else:
+            self.sourcerate = Quantity(0., '')
+        self.goodness_of_fit = None
+        self.mask = mask

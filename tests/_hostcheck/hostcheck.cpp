@@ -87,3 +87,47 @@ extern "C" void hc_spline_ev(long n, const double* x, const double* y, double* o
   Spline2D S{tx, ty, c, ntx, nty};
   for (long i = 0; i < n; ++i) out[i] = spline2d_ev(S, x[i], y[i]);
 }
+
+#include "../../nexoclom_b200/csrc/nx_init.cuh"
+#include "../../nexoclom_b200/csrc/nx_image.cuh"
+
+extern "C" void hc_init_state(long n, const SourceParams* sp, unsigned long long seed,
+                              unsigned long long first_id, const double* fmap,
+                              const double* axes /* x_lo,x_hi,y_lo,y_hi */,
+                              const double* cdf, const double* vtab, int ntab,
+                              double* out /* n x 14 */) {
+  HostInterp hs; InterpTable speed{};
+  if (ntab > 0) { hs = make_interp(cdf, vtab, ntab); speed = view(hs); }
+  SourceMap map{};
+  if (fmap) { map.f = fmap; map.x_lo = axes[0]; map.x_hi = axes[1]; map.y_lo = axes[2]; map.y_hi = axes[3]; }
+  for (long i = 0; i < n; ++i) init_packet(*sp, map, speed, seed, first_id + i, out + 14 * i);
+}
+
+static GTables make_gtables(std::vector<HostInterp>& store, int nt, const int* sizes,
+                            const double* v, const double* g) {
+  GTables G{};
+  G.n = nt;
+  size_t off = 0;
+  store.resize(nt);
+  for (int t = 0; t < nt; ++t) {
+    store[t] = make_interp(v + off, g + off, sizes[t]);
+    G.t[t] = view(store[t]);
+    off += sizes[t];
+  }
+  return G;
+}
+
+extern "C" void hc_image(long n, const double* X /* n x 8 */, const ImageParams* ip, int nt,
+                         const int* sizes, const double* v, const double* g,
+                         double* image, long long* counts) {
+  std::vector<HostInterp> store;
+  GTables G = make_gtables(store, nt, sizes, v, g);
+  const double sx = (ip->x1 - ip->x0) / ip->nx, sz = (ip->z1 - ip->z0) / ip->nz;
+  for (long i = 0; i < n; ++i) {
+    const double* s = X + 8 * i;
+    if (ip->skip_dead && !(s[7] > 0.0)) continue;
+    double w;
+    int pix = image_packet(*ip, G, sx, sz, s[1], s[2], s[3], s[5], s[7], w);
+    if (pix >= 0) { image[pix] += w; counts[pix] += 1; }
+  }
+}

@@ -1,0 +1,295 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle and the
+golden vectors of the reference.  Gates (BASELINE.json north_star): packet state
+1e-8 relative (compared before the f32 down-cast), images / LOS radiance 1e-6
+relative, pixel indices and per-LOS hit counts bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, workload, oracle_constants, state_parity
+from nexoclom_b200._lib import ImageParams, LosParams
+from nexoclom_b200.ModelImage import image_rotation
+from nexoclom_b200.runsetup import RunSetup
+from nexoclom_b200.units import Quantity
+from oracle import tracking, initial_state, imaging
+
+pytestmark = pytest.mark.gpu
+STATE_TOL = 1e-8
+IMAGE_TOL = 1e-6
+
+
+def _image_params(setup, quantity, view=(0.0, np.pi / 2), dims=(800, 800), round_f32=0):
+    M = image_rotation(*view)
+    ip = ImageParams()
+    for k in range(9):
+        ip.M[k] = float(M.flat[k])
+    ip.x0, ip.x1, ip.z0, ip.z1 = -4, 4, -4, 4
+    ip.nx, ip.nz = dims
+    rcm = setup.radius_km * 1e5
+    ip.apix = (8 / dims[0] * rcm) * (8 / dims[1] * rcm)
+    ip.vrplanet = setup.vrplanet
+    ip.quantity = quantity
+    ip.round_f32 = round_f32
+    ip.skip_dead = 0
+    return ip
+
+
+@pytest.mark.parametrize('wl', ['Na.maxwellian.radpres.input', 'Ca.isotropic.flat.input'])
+@pytest.mark.parametrize('strict', [False, True])
+def test_adaptive_driver_vs_oracle(engine, wl, strict):
+    setup = RunSetup(workload(wl), strict_math=strict)
+    setup.upload(engine)
+    n = 3000
+    X0 = initial_state.draw_x0(setup, n, 21)[:, :8]
+    engine.import_state(X0)
+    att, acc = engine.integrate_adaptive()
+    Xg = engine.export_state().T
+    a_g, c_g = engine.export_stats()
+    Xo, a_o, c_o = tracking.integrate_adaptive(X0, oracle_constants(setup))
+    par = state_parity(Xg, Xo)
+    assert par['alive_mismatch'] == 0, par
+    assert max(par['pos'], par['vel'], par['frac']) < STATE_TOL, par
+    assert att == int(a_o.sum()) and acc == int(c_o.sum())      # same step sequences
+    assert np.array_equal(a_g, a_o) and np.array_equal(c_g, c_o)
+    dead = Xo[:, 7] == 0
+    assert np.all(Xg[dead, 0] == 0)                              # dead => time = 0 (Q8)
+
+
+def test_adaptive_import_mode_vs_reference_golden(engine):
+    """Reference-generated initial states -> final state of the reference's own
+    driver (tests/golden/adaptive_driver.npz)."""
+    g = np.load(os.path.join(GOLDEN, 'adaptive_driver.npz'))
+    for tag, wl in (('na', 'Na.maxwellian.radpres.input'), ('ca', 'Ca.isotropic.flat.input')):
+        setup = RunSetup(workload(wl))
+        setup.upload(engine)
+        engine.import_state(g[f'{tag}_x0'])
+        engine.integrate_adaptive()
+        par = state_parity(engine.export_state().T, g[f'{tag}_final'])
+        assert par['alive_mismatch'] == 0, par
+        assert max(par['pos'], par['vel'], par['frac']) < STATE_TOL, par
+        step = engine.export_step()
+        assert np.max(np.abs(step - g[f'{tag}_step']) / g[f'{tag}_step']) < STATE_TOL
+
+
+def test_energy_conservation_gravity_only(engine):
+    """The reference's only hot-path test (test_gravity.py:46-55): specific
+    energy v^2/2 + GM/r is constant along each trajectory -- at full chunk size."""
+    inputs = workload('Gravity.input')
+    inputs.options.step_size = 0.
+    inputs.options.resolution = 1e-4
+    inputs.options.lifetime = Quantity(1e30, 's')        # no loss: isolate the orbit
+    setup = RunSetup(inputs)
+    setup.upload(engine)
+    n = 1_000_000
+    engine.init_state(setup.source_params(engine), 3, 0, n)
+    x0 = engine.export_x0()
+    engine.integrate_adaptive()
+    x = engine.export_state()
+    alive = x[7] > 0
+    assert alive.sum() > 1000
+
+    def energy(a):
+        return 0.5 * (a[4]**2 + a[5]**2 + a[6]**2) + setup.GM / np.sqrt(a[1]**2 + a[2]**2 + a[3]**2)
+    e0, e1 = energy(x0[:8])[alive], energy(x)[alive]
+    assert np.max(np.abs(e1 - e0) / np.abs(e0)) < 1e-6
+    assert np.all(x[0][alive] <= 1e-4)                   # everybody reached the image time
+
+
+@pytest.mark.parametrize('wl', ['Na.maxwellian.radpres.input', 'Ca.isotropic.flat.input',
+                                'Na.bounce.stick05.input'])
+def test_init_state_vs_oracle(engine, wl):
+    setup = RunSetup(workload(wl))
+    setup.upload(engine)
+    n = 20000
+    engine.init_state(setup.source_params(engine), 42, 1000, n)
+    got = engine.export_x0().T
+    ref = initial_state.draw_x0(setup, n, 42, first_id=1000)
+    assert np.max(np.abs(got - ref)) < 1e-12
+    assert np.array_equal(engine.export_state().T, got[:, :8])
+    assert np.all(engine.export_step() == 1000.)
+
+
+def test_init_state_sharding_invariance(engine):
+    """Global-id Philox counters: two shards == one run (GPU-count invariance)."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    sp = setup.source_params(engine)
+    engine.init_state(sp, 9, 0, 4096)
+    whole = engine.export_x0()
+    engine.init_state(sp, 9, 0, 2048)
+    a = engine.export_x0()
+    engine.init_state(sp, 9, 2048, 2048)
+    b = engine.export_x0()
+    assert np.array_equal(whole, np.concatenate([a, b], axis=1))
+
+
+@pytest.mark.parametrize('quantity', [0, 1])
+@pytest.mark.parametrize('view', [(0.0, np.pi / 2), (0.7, 0.3)])
+def test_image_vs_oracle(engine, quantity, view):
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    gt = setup.gtables([5891, 5897])
+    engine.upload_gtables(gt)
+    rng = np.random.default_rng(5)
+    n = 300001
+    X = np.zeros((n, 8))
+    X[:, 1:4] = rng.normal(size=(n, 3)) * 1.7
+    X[:, 5] = rng.normal(size=n) * 2 / setup.radius_km
+    X[:, 7] = rng.random(n)
+    X[:64, 1] = 4.0
+    X[64:128, 3] = -4.0
+    X = X.astype(np.float32).astype(np.float64)        # what Output.restore delivers (Q14)
+    engine.import_state(X)
+    ip = _image_params(setup, quantity, view, dims=(800, 640))
+    img, cnt = engine.image_accumulate(ip)
+    oi, oc, _, _ = imaging.create_image(X[:, 1], X[:, 2], X[:, 3], X[:, 5], X[:, 7],
+                                        vrplanet=setup.vrplanet, M=imaging.image_rotation(*view),
+                                        dims=[800, 640], xrange=(-4, 4), zrange=(-4, 4),
+                                        apix=ip.apix, quantity='radiance' if quantity else 'column',
+                                        gtables=gt)
+    assert np.array_equal(cnt, oc.astype(np.int64))     # bit-exact pixel indexing
+    assert cnt.sum() > 0.9 * n * 0.9
+    nz = oi > 0
+    assert np.max(np.abs(img[nz] - oi[nz]) / oi[nz]) < IMAGE_TOL
+    assert np.all(img[~nz] == 0)
+
+
+@pytest.mark.parametrize('tag, wl', [('tdep', 'Na.bounce.input'),
+                                     ('c05', 'Na.bounce.stick05.input'),
+                                     ('grav', 'Gravity.input')])
+def test_constant_driver_vs_oracle(engine, tag, wl):
+    inputs = workload(wl)
+    inputs.options.endtime = Quantity(1500., 's')
+    setup = RunSetup(inputs)
+    setup.upload(engine)
+    n, seed, first = 2000, 99, 7
+    X0 = initial_state.draw_x0(setup, n, 9)[:, :8]
+    ref, nsteps, natt = tracking.integrate_constant(
+        X0, oracle_constants(setup), uniforms=initial_state.bounce_uniforms(seed, first))
+    engine.import_state(X0)
+    traj, ns, steps = engine.integrate_constant(seed=seed, first_id=first, trajectory=True)
+    assert ns == nsteps and traj.shape == ref.shape
+    assert np.array_equal(traj[:, 7, :] > 0, ref[:, 7, :] > 0)
+    scale = np.maximum(np.abs(ref), 1e-3)
+    assert np.max(np.abs(traj - ref) / scale) < STATE_TOL
+    assert steps == int(natt.sum())
+
+
+def test_constant_driver_vs_reference_golden(engine):
+    """Gravity-only constant-step run of the reference driver itself."""
+    g = np.load(os.path.join(GOLDEN, 'constant_driver.npz'))
+    setup = RunSetup(workload('Gravity.input'))
+    setup.upload(engine)
+    engine.import_state(g['grav_x0'])
+    traj, ns, _ = engine.integrate_constant(trajectory=True)
+    ref = g['grav_traj']
+    assert traj.shape == ref.shape
+    assert np.array_equal(traj[:, 7, :] > 0, ref[:, 7, :] > 0)
+    assert np.max(np.abs(traj - ref) / np.maximum(np.abs(ref), 1e-3)) < STATE_TOL
+
+
+def test_fused_image_equals_separate(engine):
+    """K3 with fused per-step accumulation == K4 over the dense trajectory."""
+    import torch
+    inputs = workload('Na.bounce.stick05.input')
+    inputs.options.endtime = Quantity(600., 's')
+    setup = RunSetup(inputs)
+    setup.upload(engine)
+    gt = setup.gtables([5891, 5897])
+    engine.upload_gtables(gt)
+    n = 5000
+    X0 = initial_state.draw_x0(setup, n, 3)[:, :8]
+    ip = _image_params(setup, 1, dims=(200, 200))
+    ip.skip_dead = 1
+    img = torch.zeros((200, 200), dtype=torch.float64, device='cuda')
+    cnt = torch.zeros((200, 200), dtype=torch.int64, device='cuda')
+    engine.import_state(X0)
+    traj, ns, _ = engine.integrate_constant(seed=1, image_params=ip, image_dev=img.data_ptr(),
+                                            counts_dev=cnt.data_ptr(), trajectory=True)
+    torch.cuda.synchronize()
+    rows = traj.transpose(0, 2, 1).reshape(-1, 8)
+    rows = rows[rows[:, 7] > 0]
+    oi, oc, _, _ = imaging.create_image(rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 5], rows[:, 7],
+                                        vrplanet=setup.vrplanet, M=imaging.image_rotation(0, np.pi / 2),
+                                        dims=[200, 200], xrange=(-4, 4), zrange=(-4, 4),
+                                        apix=ip.apix, quantity='radiance', gtables=gt)
+    assert np.array_equal(cnt.cpu().numpy(), oc.astype(np.int64))
+    nz = oi > 0
+    assert np.max(np.abs(img.cpu().numpy()[nz] - oi[nz]) / oi[nz]) < IMAGE_TOL
+
+
+def _synthetic_los(nlos, seed=1):
+    """MESSENGER-UVVS-like sweep: spacecraft on a polar ellipse 1.1-6 R_p,
+    boresights sweeping limb tangent altitudes 0-3 R_p."""
+    rng = np.random.default_rng(seed)
+    th = rng.random(nlos) * 2 * np.pi
+    r = 1.1 + 4.9 * rng.random(nlos)
+    x_sc = np.stack([0.3 * r * np.cos(th), r * np.cos(th) * 0.2 - 0.5, r * np.sin(th)], axis=1)
+    x_sc *= (np.maximum(np.linalg.norm(x_sc, axis=1), 1.1) / np.linalg.norm(x_sc, axis=1))[:, None]
+    target = rng.normal(size=(nlos, 3))
+    target *= ((1 + 3 * rng.random(nlos)) / np.linalg.norm(target, axis=1))[:, None]
+    bore = target - x_sc
+    bore /= np.linalg.norm(bore, axis=1)[:, None]
+    return np.concatenate([x_sc, bore], axis=1)
+
+
+def test_los_vs_oracle(engine):
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    gt = setup.gtables([5891, 5897])
+    engine.upload_gtables(gt)
+    rng = np.random.default_rng(11)
+    n = 200000
+    X = np.zeros((n, 8))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    X[:, 1:4] = d * (1 + 9 * rng.random(n)**2)[:, None]
+    X[:, 5] = rng.normal(size=n) * 2 / setup.radius_km
+    X[:, 7] = rng.random(n)
+    X = X.astype(np.float32).astype(np.float64)
+    los = _synthetic_los(300)
+    dphi = np.radians(1.0)
+    rad_o, np_o, inc_o, dist = imaging.los_iteration(
+        X[:, 1], X[:, 2], X[:, 3], X[:, 5], X[:, 7], los, vrplanet=setup.vrplanet, dphi=dphi,
+        outeredge=25., rp_cm=setup.radius_km * 1e5, gtables=gt)
+    engine.import_state(X)
+    lp = LosParams()
+    lp.dphi, lp.outeredge, lp.vrplanet, lp.rp_cm = dphi, 25., setup.vrplanet, setup.radius_km * 1e5
+    lp.quantity = 1
+    rad_g, np_g, inc_g = engine.los_accumulate(los.T.copy(), dist, lp)
+    assert np_o.sum() > 1000
+    assert np.array_equal(np_g, np_o)                   # bit-exact hit counts
+    assert np.array_equal(inc_g, inc_o)
+    nz = rad_o > 0
+    assert np.max(np.abs(rad_g[nz] - rad_o[nz]) / rad_o[nz]) < IMAGE_TOL
+    assert np.all(rad_g[~nz] == 0)
+
+
+def test_public_api_end_to_end(engine):
+    """Input -> Output (device-drawn packets) -> ModelImage through the
+    reference-facing classes; the image equals the oracle's create_image on the
+    Output's own (f32-saved) packets."""
+    from nexoclom_b200 import Output, ModelImage
+    inputs = workload('Ca.isotropic.flat.input')
+    inputs.delete_files()
+    out = Output(inputs, 20000, seed=5)
+    assert out.X0.shape == (20000, 14) and str(out.X0['x'].dtype) == 'float32'
+    assert (out.X.frac > 0).all() and out.totalsource == 20000.
+    ids, files, npack, tot = inputs.search()
+    assert npack == 20000 and files == [out.filename]
+    im = ModelImage(inputs, {'quantity': 'radiance', 'dims': '300,300'})
+    restored = Output.restore(out.filename)
+    P = restored.X
+    setup = RunSetup(inputs)
+    gt = setup.gtables([4227])
+    oi, oc, _, _ = imaging.create_image(
+        P.x.values, P.y.values, P.z.values, P.vy.values, P.frac.values, vrplanet=setup.vrplanet,
+        M=imaging.image_rotation(0, np.pi / 2), dims=[300, 300], xrange=(-4, 4), zrange=(-4, 4),
+        apix=float(im.Apix), quantity='radiance', gtables=gt)
+    assert np.array_equal(im.packet_image, oc)
+    oi *= im.atoms_per_packet
+    nz = oi > 0
+    assert nz.sum() > 100
+    assert np.max(np.abs(im.image[nz] - oi[nz]) / oi[nz]) < IMAGE_TOL
+    assert im.atoms_per_packet == 1e23 / (20000 / 10800.)
