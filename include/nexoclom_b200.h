@@ -115,6 +115,8 @@ int nx_ctx_destroy(nx_ctx* ctx);
 /* adopt a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) */
 int nx_ctx_set_stream(nx_ctx* ctx, void* cuda_stream);
 int nx_ctx_sync(nx_ctx* ctx);
+/* tuning switches: "order_packets" (1 = longest-first scheduling of K2, default 1) */
+int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value);
 const char* nx_last_error(nx_ctx* ctx);
 int nx_status(nx_ctx* ctx, int* invariant_bits);
 

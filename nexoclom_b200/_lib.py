@@ -93,6 +93,7 @@ def load():
         'nx_ctx_destroy': [vp],
         'nx_ctx_set_stream': [vp, vp],
         'nx_ctx_sync': [vp],
+        'nx_ctx_set_option': [vp, C.c_char_p, C.c_int],
         'nx_last_error': [vp],
         'nx_status': [vp, C.POINTER(C.c_int)],
         'nx_tables_upload': [vp, C.POINTER(RunParams), c_double_p, c_double_p, C.c_int,

@@ -50,6 +50,10 @@ struct nx_ctx {
   double* state = nullptr;     // 9 columns
   double* x0 = nullptr;        // 14 columns
   unsigned *att = nullptr, *acc = nullptr;
+  unsigned* perm = nullptr;          // longest-first processing order
+  unsigned char* cost = nullptr;     // cost bucket per packet
+  unsigned* hist = nullptr;          // 32 histogram + 32 cursors
+  int order_packets = 1;
   unsigned long long* scalars = nullptr;   // [0] queue, [1] total attempted, [2] total accepted
   int* status = nullptr;
   int status_host = 0;
@@ -145,6 +149,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   cudaFree(ctx->spl_tx); cudaFree(ctx->spl_ty); cudaFree(ctx->spl_c);
   cudaFree(ctx->srcmap);
   cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
+  cudaFree(ctx->perm); cudaFree(ctx->cost); cudaFree(ctx->hist);
   cudaFree(ctx->scalars); cudaFree(ctx->status);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -165,6 +170,12 @@ int nx_ctx_sync(nx_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
+  if (name && std::strcmp(name, "order_packets") == 0) { ctx->order_packets = value; return 0; }
+  ctx->err = std::string("unknown option ") + (name ? name : "(null)");
+  return -1;
 }
 
 const char* nx_last_error(nx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -228,11 +239,17 @@ int nx_packets_resize(nx_ctx* ctx, long long n) {
   if (n <= ctx->cap) return 0;
   const long long cap = ((n + 31) / 32) * 32;
   cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
+  cudaFree(ctx->perm); cudaFree(ctx->cost);
   ctx->state = ctx->x0 = nullptr; ctx->att = ctx->acc = nullptr; ctx->cap = 0;
+  ctx->perm = nullptr; ctx->cost = nullptr;
+  if (n >= (1LL << 32)) { ctx->err = "more than 2^32 packets per GPU"; return -1; }
   CK(cudaMalloc(&ctx->state, (size_t)9 * cap * sizeof(double)));
   CK(cudaMalloc(&ctx->x0, (size_t)14 * cap * sizeof(double)));
   CK(cudaMalloc(&ctx->att, (size_t)cap * sizeof(unsigned)));
   CK(cudaMalloc(&ctx->acc, (size_t)cap * sizeof(unsigned)));
+  CK(cudaMalloc(&ctx->perm, (size_t)cap * sizeof(unsigned)));
+  CK(cudaMalloc(&ctx->cost, (size_t)cap));
+  if (!ctx->hist) CK(cudaMalloc(&ctx->hist, 64 * sizeof(unsigned)));
   CK(cudaMemsetAsync(ctx->att, 0, (size_t)cap * sizeof(unsigned), ctx->stream));
   CK(cudaMemsetAsync(ctx->acc, 0, (size_t)cap * sizeof(unsigned), ctx->stream));
   ctx->cap = cap;
@@ -354,10 +371,14 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
   int r;
   if (n > 0) {
     if ((r = begin_timed(ctx))) return r;
+    const bool order = ctx->order_packets && n >= 4096;
+    if (order)
+      CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params, ctx->cost,
+                           ctx->hist, ctx->perm));
     CK(launch_integrate_adaptive(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
-                                 ctx->radpres.view, ctx->scalars, ctx->scalars + 1, ctx->att,
-                                 ctx->acc, ctx->status));
-    if ((r = end_timed(ctx, 1))) return r;
+                                 ctx->radpres.view, order ? ctx->perm : nullptr, ctx->scalars,
+                                 ctx->scalars + 1, ctx->att, ctx->acc, ctx->status));
+    if ((r = end_timed(ctx, order ? 4 : 1))) return r;
   }
   unsigned long long h[3] = {0, 0, 0};
   CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,239 @@
+// nexoclom_b200 -- throughput-oriented adaptive step (STRICT = false product path).
+//
+// Same algorithm and the same accept / reject DECISIONS as adaptive_attempt<true>
+// (reference Output.py:249-353 + rk5.py + state.py), re-associated for the FP64
+// pipe of sm_100a:
+//   * stage sums are FMA chains started from the base state (no separate adds),
+//     tableau constants come from the constant bank (no immediate moves);
+//   * gravity uses one MUFU.RSQ64H seed + one third-order correction;
+//   * frac is advanced as f*exp(dlogf) (== exp(log f + dlogf) in exact arithmetic),
+//     so no log/exp pair per step and no per-stage log-frac bookkeeping;
+//   * the radiation-pressure table interval is cached across RHS evaluations;
+//   * accept test is "every delta_j < scale_j" (exactly equivalent to
+//     max_j fl(delta_j/scale_j) < 1 for correctly rounded division); the
+//     quotient itself is only formed on the reject path, with Newton reciprocals;
+//   * forces / loss mode are template parameters (no per-stage uniform branches).
+// Differences from the NumPy operation order are a few ulp per step; parity
+// against the oracle stays ~1e-14 (gate 1e-8), see tests/test_hostcheck.py.
+#pragma once
+#include "nx_physics.cuh"
+
+namespace nx {
+
+// Dormand-Prince coefficients, flattened: A rows 1..6 (21 entries), BD (6 entries).
+#define NX_DP_A_LIST                                                                        \
+  0.2,                                                                                      \
+  3. / 40., 9. / 40.,                                                                       \
+  44. / 45., -56. / 15., 32. / 9.,                                                          \
+  19372. / 6561., -25360. / 2187., 64448. / 6561., -212. / 729.,                            \
+  9017. / 3168., -355. / 33., 46732. / 5247., 49. / 176., -5103. / 18656.,                  \
+  35. / 384., 0., 500. / 1113., 125. / 192., -2187. / 6784., 11. / 84.
+#define NX_DP_BD_LIST                                                                       \
+  35. / 384. - 5179. / 57600., 0., 500. / 1113. - 7571. / 16695., 125. / 192. - 393. / 640., \
+  -2187. / 6784. - -92097. / 339200., 11. / 84. - 187. / 2100.
+
+#if defined(__CUDACC__)
+__constant__ double c_dp_a[21] = {NX_DP_A_LIST};
+__constant__ double c_dp_bd[6] = {NX_DP_BD_LIST};
+#endif
+static const double h_dp_a[21] = {NX_DP_A_LIST};
+static const double h_dp_bd[6] = {NX_DP_BD_LIST};
+
+NX_HD double dp_a(int n, int i) {          // a[n][i], 1 <= n <= 6, i < n
+  const int k = n * (n - 1) / 2 + i;
+#if defined(__CUDA_ARCH__)
+  return c_dp_a[k];
+#else
+  return h_dp_a[k];
+#endif
+}
+NX_HD double dp_bd(int i) {
+#if defined(__CUDA_ARCH__)
+  return c_dp_bd[i];
+#else
+  return h_dp_bd[i];
+#endif
+}
+
+// 1/sqrt(a): hardware seed + one third-order (Halley) step  -> ~0.2 ulp
+NX_HD double rsqrt_h(double a) {
+#if defined(__CUDA_ARCH__)
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double t = a * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = fma(0.375, e, 0.5) * e;
+  return fma(y, q, y);
+#else
+  return 1.0 / sqrt(a);
+#endif
+}
+
+// 1/a to ~2^-40: hardware seed + one Newton step (only feeds the step-size
+// update on the reject path, never a decision)
+NX_HD double rcp_n(double a) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  const double e = fma(-a, r, 1.0);
+  return fma(r, e, r);
+#else
+  return 1.0 / a;
+#endif
+}
+
+// exp(d) for the small log-frac increments of one step
+NX_HD double exp_step(double d) {
+  if (fabs(d) < 0.03125) {
+    double p = 1.0 / 5040.0;
+    p = fma(p, d, 1.0 / 720.0);
+    p = fma(p, d, 1.0 / 120.0);
+    p = fma(p, d, 1.0 / 24.0);
+    p = fma(p, d, 1.0 / 6.0);
+    p = fma(p, d, 0.5);
+    p = fma(p, d, 1.0);
+    return fma(p, d, 1.0);
+  }
+  return exp(d);
+}
+
+// One attempted adaptive step, fast arithmetic.  Same contract as
+// adaptive_attempt<>(): s[0..7] = time,x,y,z,vx,vy,vz,frac; returns AttemptFlags.
+template <int GR, int RP, int LOSS>
+NX_HD int adaptive_attempt_fast(const RunParams& p, const InterpTable& T, double* s,
+                                double& step, InterpCache& cache) {
+  const double res = p.resolution;
+  const double resv = 0.1 * res;
+  const double h = fmin(s[0], step);
+
+  double kv[6][3], ka[6][3];
+  unsigned litmask = 0;
+  double px = s[1], py = s[2], pz = s[3], vx = s[4], vy = s[5], vz = s[6];
+#pragma unroll
+  for (int n = 0; n < 6; ++n) {
+    kv[n][0] = vx; kv[n][1] = vy; kv[n][2] = vz;
+    const double s2 = fma(pz, pz, px * px);
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    if (GR) {
+      const double r2 = fma(py, py, s2);
+      const double ri = rsqrt_h(r2);
+      const double g = (p.GM * ri) * (ri * ri);
+      ax = g * px; ay = g * py; az = g * pz;
+    }
+    bool lit = true;
+    if (RP || LOSS == LOSS_PHOTO) lit = (s2 > NX_ONE_PLUS_ULP) || (py < 0.0);
+    if (RP) {
+      const double ar = interp_cached(T, vy + p.vrplanet, cache);
+      ay += lit ? ar : 0.0;
+    }
+    if (LOSS == LOSS_PHOTO) litmask |= (lit ? 1u : 0u) << n;
+    ka[n][0] = ax; ka[n][1] = ay; ka[n][2] = az;
+
+    double ap0 = s[1], ap1 = s[2], ap2 = s[3], av0 = s[4], av1 = s[5], av2 = s[6];
+#pragma unroll
+    for (int i = 0; i <= n; ++i) {
+      if (n == 5 && i == 1) continue;                 // b[1] = 0
+      const double ha = h * dp_a(n + 1, i);
+      ap0 = fma(ha, kv[i][0], ap0); ap1 = fma(ha, kv[i][1], ap1); ap2 = fma(ha, kv[i][2], ap2);
+      av0 = fma(ha, ka[i][0], av0); av1 = fma(ha, ka[i][1], av1); av2 = fma(ha, ka[i][2], av2);
+    }
+    px = ap0; py = ap1; pz = ap2; vx = av0; vy = av1; vz = av2;
+  }
+
+  // fractional content: dlogf = -h sum b_i rate_i ; error term h sum bd_i rate_i
+  double sb = 0.0, sbd = 0.0;
+  if (LOSS == LOSS_LIFETIME) {
+    sb = p.loss_rate * ((((dp_a(6, 0) + dp_a(6, 2)) + dp_a(6, 3)) + dp_a(6, 4)) + dp_a(6, 5));
+    sbd = p.loss_rate * ((((dp_bd(0) + dp_bd(2)) + dp_bd(3)) + dp_bd(4)) + dp_bd(5));
+  } else if (LOSS == LOSS_PHOTO) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      if (i == 1) continue;
+      const double r = (litmask >> i) & 1u ? p.loss_rate : 0.0;
+      sb = fma(dp_a(6, i), r, sb);
+      sbd = fma(dp_bd(i), r, sbd);
+    }
+  }
+  const double fn = (LOSS == LOSS_NONE) ? s[7] : s[7] * exp_step(-(h * sb));
+  const double delta_f = fabs(h * sbd);
+
+  // error vector |h sum_{i<6} bd_i k_i|  (stage 7 not included: quirk Q1)
+  double d[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double ep = dp_bd(0) * kv[0][k], ev = dp_bd(0) * ka[0][k];
+#pragma unroll
+    for (int i = 2; i < 6; ++i) { ep = fma(dp_bd(i), kv[i][k], ep); ev = fma(dp_bd(i), ka[i][k], ev); }
+    d[k] = fabs(h * ep); d[3 + k] = fabs(h * ev);
+  }
+  const double nx[6] = {px, py, pz, vx, vy, vz};
+  const double sf = fma(fabs(fn), res, res);
+  bool ok = delta_f < sf;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    ok = ok && (d[k] < fma(fabs(nx[k]), res, res));
+    ok = ok && (d[3 + k] < fma(fabs(nx[3 + k]), resv, resv));
+  }
+  // "no error" (Q4): every ratio < 1e-7 -- screened by one component, rare
+  bool tiny = false;
+  if (d[3] < 1e-7 * fma(fabs(nx[3]), resv, resv)) {
+    tiny = delta_f < 1e-7 * sf;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      tiny = tiny && (d[k] < 1e-7 * fma(fabs(nx[k]), res, res));
+      tiny = tiny && (d[3 + k] < 1e-7 * fma(fabs(nx[3 + k]), resv, resv));
+    }
+  }
+
+  int flags = 0;
+  if (ok && !tiny) {
+    const double r2 = fma(pz, pz, fma(py, py, px * px));
+    double f = fn;
+    if (fn < 0.0) flags |= ATT_NEG_FRAC;
+    if (r2 < 1.0) f = 0.0;                 // impact, stickcoef == 1 (Q6)
+    if (r2 > p.outeredge) f = 0.0;         // escape: r^2 vs outeredge (Q7)
+    if (f < 1e-10) f = 0.0;                // vanish (Q8)
+    s[0] = (f == 0.0) ? 0.0 : s[0] - h;
+    s[1] = px; s[2] = py; s[3] = pz; s[4] = vx; s[5] = vy; s[6] = vz;
+    s[7] = f;
+    flags |= ATT_ACCEPTED;
+  } else {
+    double errmax = delta_f * rcp_n(sf);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      errmax = fmax(errmax, d[k] * rcp_n(fma(fabs(nx[k]), res, res)));
+      errmax = fmax(errmax, d[3 + k] * rcp_n(fma(fabs(nx[3 + k]), resv, resv)));
+    }
+    // NaN deltas fall through every comparison above; fmax drops NaN, so test the inputs
+    bool bad = !(delta_f <= 1.7976931348623157e308);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bad = bad || !(d[k] <= 1.7976931348623157e308);
+    if (bad) flags |= ATT_BAD_ERRMAX;
+    double htried = h;
+    if (tiny) { errmax = 1.0; htried = h * 10.0; }
+    else if ((fn - s[7] > sf) && (errmax > 1.0)) errmax = 1.1;      // quirk Q9
+    const double grow = rsqrt_h(errmax * rsqrt_h(errmax));           // errmax^-0.25
+    const double cand = (0.95 * htried) * grow;
+    if (!(fabs(cand) <= 1.7976931348623157e308)) flags |= ATT_BAD_STEP;
+    step = fmax(cand, 0.1 * htried);
+  }
+  if (s[0] > res && s[7] > 0.0) flags |= ATT_LIVE;
+  return flags;
+}
+
+// runtime dispatch over the compile-time force / loss combinations
+NX_HD int adaptive_attempt_fast_rt(const RunParams& p, const InterpTable& T, double* s,
+                                   double& step, InterpCache& c) {
+  const int key = (p.gravity ? 4 : 0) | (p.radpres ? 2 : 0);
+#define NX_CASE(G, R)                                                                    \
+  if (key == ((G) * 4 + (R) * 2)) {                                                      \
+    if (p.loss_mode == LOSS_PHOTO) return adaptive_attempt_fast<G, R, LOSS_PHOTO>(p, T, s, step, c);       \
+    if (p.loss_mode == LOSS_LIFETIME) return adaptive_attempt_fast<G, R, LOSS_LIFETIME>(p, T, s, step, c); \
+    return adaptive_attempt_fast<G, R, LOSS_NONE>(p, T, s, step, c);                     \
+  }
+  NX_CASE(1, 1) NX_CASE(1, 0) NX_CASE(0, 1) NX_CASE(0, 0)
+#undef NX_CASE
+  return 0;
+}
+
+}  // namespace nx

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "nx_fast.cuh"
 #include "nx_image.cuh"
 #include "nx_init.cuh"
 #include "nx_kernels.h"
@@ -27,8 +28,8 @@ namespace nx {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ size_t stage_table(const InterpTable& g, InterpTable& s,
                                               unsigned char* base) {
-  s = g;
-  if (g.n == 0) return 0;
+  // pointers are ALWAYS derived from the shared-memory base so that the compiler
+  // can prove the address space (LDS instead of generic LD)
   double* sx = reinterpret_cast<double*>(base);
   double* sf = sx + g.n;
   double* ss = sf + g.n;
@@ -36,9 +37,11 @@ __device__ __forceinline__ size_t stage_table(const InterpTable& g, InterpTable&
   for (int i = threadIdx.x; i < g.n; i += blockDim.x) {
     sx[i] = g.x[i]; sf[i] = g.f[i]; ss[i] = g.slope[i];
   }
-  for (int i = threadIdx.x; i < g.nbucket; i += blockDim.x) sb[i] = g.bucket[i];
+  const int nb = g.n ? g.nbucket : 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sb[i] = g.bucket[i];
   s.x = sx; s.f = sf; s.slope = ss; s.bucket = sb;
-  size_t bytes = (size_t)g.n * 24 + (size_t)g.nbucket * 2;
+  s.n = g.n; s.nbucket = g.nbucket; s.blo = g.blo; s.binvw = g.binvw;
+  size_t bytes = (size_t)g.n * 24 + (size_t)nb * 2;
   return (bytes + 15) & ~(size_t)15;
 }
 
@@ -77,9 +80,13 @@ __global__ void k_fill(double* p, long long n, double v) {
 // atomicAdd), so warps stay full although step counts per packet differ by
 // orders of magnitude (p50 ~ 40, max ~ 4000).
 // ---------------------------------------------------------------------------
-template <bool STRICT>
-__global__ void __launch_bounds__(NX_INT_THREADS)
+// MODE: -1 = strict (NumPy operation order, runtime force flags);
+//       otherwise fast arithmetic with compile-time forces:
+//       MODE = GR*8 + RP*4 + LOSS.
+template <int MODE>
+__global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
 k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
+                     const unsigned* __restrict__ perm,
                      unsigned long long* __restrict__ queue,
                      unsigned long long* __restrict__ totals,
                      unsigned* __restrict__ att_out, unsigned* __restrict__ acc_out,
@@ -93,6 +100,8 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
   bool have = false, drained = false;
   long long idx = 0;
   double s[8], step = 0.0;
+  InterpCache cache;
+  interp_cache_reset(cache);
   unsigned att = 0, acc = 0;
   unsigned long long tot_att = 0, tot_acc = 0;
   int st = 0;
@@ -105,13 +114,15 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
       if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(need));
       base = __shfl_sync(FULL_MASK, base, leader);
       if (!have) {
-        const long long i = (long long)base + __popc(need & ((1u << lane) - 1u));
-        if (i < n) {
+        const long long q = (long long)base + __popc(need & ((1u << lane) - 1u));
+        if (q < n) {
+          const long long i = perm ? (long long)perm[q] : q;
           idx = i;
 #pragma unroll
           for (int k = 0; k < 8; ++k) s[k] = P.c[k][i];
           step = P.c[8][i];
           att = 0; acc = 0;
+          if (MODE >= 0) interp_cache_reset(cache);
           have = (s[0] > p.resolution) && (s[7] > 0.0);
           if (!have) { att_out[i] = 0; acc_out[i] = 0; }
         }
@@ -123,7 +134,9 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
       continue;
     }
     if (have) {
-      const int fl = adaptive_attempt<STRICT>(p, T, s, step);
+      int fl;
+      if (MODE < 0) fl = adaptive_attempt<true>(p, T, s, step);
+      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, T, s, step, cache);
       ++att;
       if (fl & ATT_ACCEPTED) ++acc;
       st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
@@ -148,6 +161,99 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
     if (tot_att) atomicAdd(&totals[0], tot_att);
     if (tot_acc) atomicAdd(&totals[1], tot_acc);
     if (st) atomicOr(status, st);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Longest-first scheduling.  Attempted steps per packet span 1 .. ~10^4, and one
+// packet's steps are strictly sequential, so a long packet claimed late leaves
+// the whole GPU waiting for one lane.  k_cost_* predict the step count from the
+// Kepler flight time and the position-error step bound h ~ 40 res (1+r)/v, bin
+// it in half-octaves and counting-sort packet indices, longest first.  The
+// prediction only orders the queue; it never touches the physics.
+// ---------------------------------------------------------------------------
+#define NX_NBUCKET 32
+
+__device__ __forceinline__ int cost_bucket(const RunParams& p, double t, double x, double y,
+                                           double z, double vx, double vy, double vz, double f) {
+  if (!(t > p.resolution) || !(f > 0.0)) return 0;
+  const double mu = fabs(p.GM);
+  const double r2 = x * x + y * y + z * z, r = sqrt(r2);
+  const double v2 = vx * vx + vy * vy + vz * vz;
+  const double rv = x * vx + y * vy + z * vz;
+  double tfl = t;
+  const double en = 0.5 * v2 - mu / r;
+  if (p.gravity && en < 0.0 && mu > 0.0) {
+    const double a = -mu / (2.0 * en);
+    const double l2 = fmax(r2 * v2 - rv * rv, 0.0);
+    const double e = sqrt(fmax(1.0 + 2.0 * en * l2 / (mu * mu), 0.0));
+    if (a * (1.0 - e) < 1.0 && e > 1e-12) {
+      // bound orbit that dips below the surface: time from here to r = 1 inbound
+      const double c1 = fmin(fmax((1.0 - 1.0 / a) / e, -1.0), 1.0);
+      const double c0 = fmin(fmax((1.0 - r / a) / e, -1.0), 1.0);
+      const double E1 = acos(c1);
+      double E0 = acos(c0);
+      if (rv < 0.0) E0 = 2.0 * NX_PI - E0;
+      const double Ei = 2.0 * NX_PI - E1;
+      const double dM = (Ei - e * sin(Ei)) - (E0 - e * sin(E0));
+      const double tk = dM * sqrt(a * a * a / mu);
+      if (tk > 0.0 && tk < tfl) tfl = tk;
+    }
+  }
+  const double est = tfl * sqrt(v2) / (40.0 * p.resolution * (1.0 + r)) + 4.0;
+  int b = (int)(2.0 * log2(est));
+  return b < 0 ? 0 : (b > NX_NBUCKET - 1 ? NX_NBUCKET - 1 : b);
+}
+
+__global__ void __launch_bounds__(256)
+k_cost_histogram(StateCols P, long long n, RunParams p, unsigned char* __restrict__ bucket,
+                 unsigned* __restrict__ hist) {
+  __shared__ unsigned sh[NX_NBUCKET];
+  if (threadIdx.x < NX_NBUCKET) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int b = cost_bucket(p, P.c[0][i], P.c[1][i], P.c[2][i], P.c[3][i], P.c[4][i],
+                              P.c[5][i], P.c[6][i], P.c[7][i]);
+    bucket[i] = (unsigned char)b;
+    atomicAdd(&sh[b], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < NX_NBUCKET && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// cursor[b] = number of packets in buckets > b  (descending order of cost)
+__global__ void k_cost_offsets(const unsigned* __restrict__ hist, unsigned* __restrict__ cursor) {
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int b = NX_NBUCKET - 1; b >= 0; --b) { cursor[b] = run; run += hist[b]; }
+  }
+}
+
+#define NX_SCATTER_ITEMS 8
+__global__ void __launch_bounds__(256)
+k_cost_scatter(long long n, const unsigned char* __restrict__ bucket,
+               unsigned* __restrict__ cursor, unsigned* __restrict__ perm) {
+  __shared__ unsigned cnt[NX_NBUCKET], base[NX_NBUCKET];
+  if (threadIdx.x < NX_NBUCKET) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long first = (long long)blockIdx.x * (256 * NX_SCATTER_ITEMS);
+  int b[NX_SCATTER_ITEMS];
+  unsigned r[NX_SCATTER_ITEMS];
+#pragma unroll
+  for (int k = 0; k < NX_SCATTER_ITEMS; ++k) {
+    const long long i = first + (long long)k * 256 + threadIdx.x;
+    b[k] = (i < n) ? bucket[i] : -1;
+    r[k] = (b[k] >= 0) ? atomicAdd(&cnt[b[k]], 1u) : 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x < NX_NBUCKET)
+    base[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]) : 0u;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NX_SCATTER_ITEMS; ++k) {
+    const long long i = first + (long long)k * 256 + threadIdx.x;
+    if (b[k] >= 0) perm[base[b[k]] + r[k]] = (unsigned)i;
   }
 }
 
@@ -422,29 +528,63 @@ static cudaError_t persistent_grid(K kernel, int device, size_t smem, int* block
   return cudaSuccess;
 }
 
-cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
-                                      const RunParams& p, const InterpTable& T,
-                                      unsigned long long* queue, unsigned long long* totals,
-                                      unsigned* att, unsigned* acc, int* status) {
+template <int MODE>
+static cudaError_t launch_adaptive_mode(cudaStream_t st, int device, StateCols P, long long n,
+                                        const RunParams& p, const InterpTable& T,
+                                        const unsigned* perm, unsigned long long* queue,
+                                        unsigned long long* totals, unsigned* att, unsigned* acc,
+                                        int* status) {
   const size_t smem = table_smem_bytes(T);
   int blocks = 0;
-  cudaError_t e;
-  if (p.strict_math) {
-    e = persistent_grid(k_integrate_adaptive<true>, device, smem, &blocks);
-    if (e != cudaSuccess) return e;
-    long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
-    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-    k_integrate_adaptive<true><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, queue, totals,
-                                                                     att, acc, status);
-  } else {
-    e = persistent_grid(k_integrate_adaptive<false>, device, smem, &blocks);
-    if (e != cudaSuccess) return e;
-    long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
-    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-    k_integrate_adaptive<false><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, queue, totals,
-                                                                      att, acc, status);
-  }
+  cudaError_t e = persistent_grid(k_integrate_adaptive<MODE>, device, smem, &blocks);
+  if (e != cudaSuccess) return e;
+  const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
+  if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+  k_integrate_adaptive<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, perm, queue,
+                                                                   totals, att, acc, status);
   return cudaGetLastError();
+}
+
+cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long long n,
+                              const RunParams& p, unsigned char* bucket, unsigned* hist_cursor,
+                              unsigned* perm) {
+  // hist_cursor: [0..31] histogram, [32..63] cursors
+  cudaError_t e = cudaMemsetAsync(hist_cursor, 0, 2 * NX_NBUCKET * sizeof(unsigned), st);
+  if (e != cudaSuccess) return e;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count(device) * 8;
+  if (blocks > cap) blocks = cap;
+  k_cost_histogram<<<(unsigned)blocks, 256, 0, st>>>(P, n, p, bucket, hist_cursor);
+  k_cost_offsets<<<1, 32, 0, st>>>(hist_cursor, hist_cursor + NX_NBUCKET);
+  const long long sb = (n + 256 * NX_SCATTER_ITEMS - 1) / (256 * NX_SCATTER_ITEMS);
+  k_cost_scatter<<<(unsigned)sb, 256, 0, st>>>(n, bucket, hist_cursor + NX_NBUCKET, perm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
+                                      const RunParams& p, const InterpTable& T,
+                                      const unsigned* perm,
+                                      unsigned long long* queue, unsigned long long* totals,
+                                      unsigned* att, unsigned* acc, int* status) {
+#define NX_ARGS st, device, P, n, p, T, perm, queue, totals, att, acc, status
+  if (p.strict_math) return launch_adaptive_mode<-1>(NX_ARGS);
+  const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
+  switch (mode) {
+    case 0: return launch_adaptive_mode<0>(NX_ARGS);
+    case 1: return launch_adaptive_mode<1>(NX_ARGS);
+    case 2: return launch_adaptive_mode<2>(NX_ARGS);
+    case 4: return launch_adaptive_mode<4>(NX_ARGS);
+    case 5: return launch_adaptive_mode<5>(NX_ARGS);
+    case 6: return launch_adaptive_mode<6>(NX_ARGS);
+    case 8: return launch_adaptive_mode<8>(NX_ARGS);
+    case 9: return launch_adaptive_mode<9>(NX_ARGS);
+    case 10: return launch_adaptive_mode<10>(NX_ARGS);
+    case 12: return launch_adaptive_mode<12>(NX_ARGS);
+    case 13: return launch_adaptive_mode<13>(NX_ARGS);
+    case 14: return launch_adaptive_mode<14>(NX_ARGS);
+    default: return cudaErrorInvalidValue;
+  }
+#undef NX_ARGS
 }
 
 cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,

@@ -9,6 +9,7 @@
 #include "nx_surface.cuh"
 
 #define NX_INT_THREADS 128
+#define NX_INT_MINBLOCKS 3
 #define NX_LOS_THREADS 128
 
 namespace nx {
@@ -32,8 +33,12 @@ cudaError_t launch_init_state(cudaStream_t st, StateCols P, X0Cols X, long long 
                               const SourceParams& sp, const SourceMap& map,
                               const InterpTable& speed, uint64_t seed, uint64_t first_id);
 cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v);
+cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long long n,
+                              const RunParams& p, unsigned char* bucket, unsigned* hist_cursor,
+                              unsigned* perm);
 cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
                                       const RunParams& p, const InterpTable& T,
+                                      const unsigned* perm,
                                       unsigned long long* queue, unsigned long long* totals,
                                       unsigned* att, unsigned* acc, int* status);
 cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,

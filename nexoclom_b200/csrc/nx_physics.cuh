@@ -117,20 +117,59 @@ NX_HD double cube_cr(double r) {
 // np.interp (numpy/core/src/multiarray/compiled_base.c: arr_interp) semantics:
 // clamped ends, exact-node shortcut, slope*(x-xj)+fj without FMA.
 // ---------------------------------------------------------------------------
+// index j with x[j] <= v < x[j+1] for x[0] <= v <= x[n-1] (j = n-1 iff v == x[n-1]):
+// the bucket index bounds the search to [bucket[b], bucket[b+1]], a short
+// bisection finishes it (what numpy's binary_search_with_guess returns).
+NX_HD int interp_locate(const InterpTable& T, double v) {
+  const int n = T.n;
+  int b = (int)((v - T.blo) * T.binvw);
+  b = b < 0 ? 0 : (b >= T.nbucket ? T.nbucket - 1 : b);
+  int lo = T.bucket[b];
+  int hi = (b + 1 < T.nbucket) ? (int)T.bucket[b + 1] + 1 : n - 1;
+  if (lo > 0) --lo;                       // slack for the rounding of b
+  if (hi > n - 1) hi = n - 1;
+  while (lo > 0 && T.x[lo] > v) --lo;
+  while (hi < n - 1 && T.x[hi] <= v) ++hi;
+  // invariant: x[lo] <= v, and (v < x[hi] or hi == n-1)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (T.x[mid] <= v) lo = mid; else hi = mid;
+  }
+  if (hi == n - 1 && T.x[hi] <= v) lo = hi;
+  return lo;
+}
+
 NX_HD double interp(const InterpTable& T, double x) {
   const int n = T.n;
   if (x != x) return x;
   if (x > T.x[n - 1]) return T.f[n - 1];
   if (x < T.x[0]) return T.f[0];
-  int b = (int)((x - T.blo) * T.binvw);
-  b = b < 0 ? 0 : (b >= T.nbucket ? T.nbucket - 1 : b);
-  int j = T.bucket[b];
-  while (j + 1 < n && T.x[j + 1] <= x) ++j;
-  while (j > 0 && T.x[j] > x) --j;
+  const int j = interp_locate(T, x);
   if (j == n - 1) return T.f[j];
   const double xj = T.x[j];
   if (xj == x) return T.f[j];
   return add_rn(mul_rn(T.slope[j], sub_rn(x, xj)), T.f[j]);
+}
+
+// Interval cache for the fast path: consecutive RHS evaluations of one packet
+// almost always fall into the same table interval.
+struct InterpCache {
+  double lo, hi, f, slope;       // value = fma(slope, x - lo, f) for lo <= x < hi
+};
+NX_HD void interp_cache_reset(InterpCache& c) { c.lo = 1.0; c.hi = 0.0; c.f = 0.0; c.slope = 0.0; }
+
+NX_HD double interp_cached(const InterpTable& T, double x, InterpCache& c) {
+  if (!(x >= c.lo && x < c.hi)) {
+    if (x != x) return x;
+    const int n = T.n;
+    if (x >= T.x[n - 1]) { c.lo = T.x[n - 1]; c.hi = 1.7976931348623157e308; c.f = T.f[n - 1]; c.slope = 0.0; }
+    else if (x < T.x[0]) { c.lo = -1e300; c.hi = T.x[0]; c.f = T.f[0]; c.slope = 0.0; }
+    else {
+      const int j = interp_locate(T, x);
+      c.lo = T.x[j]; c.hi = T.x[j + 1]; c.f = T.f[j]; c.slope = T.slope[j];
+    }
+  }
+  return fma(c.slope, x - c.lo, c.f);
 }
 
 // ---------------------------------------------------------------------------

@@ -68,6 +68,10 @@ class Engine:
         self._check(self.lib.nx_ctx_set_stream(self.ctx, C.c_void_p(int(cuda_stream_ptr))),
                     'nx_ctx_set_stream')
 
+    def set_option(self, name, value):
+        self._check(self.lib.nx_ctx_set_option(self.ctx, name.encode(), int(value)),
+                    'nx_ctx_set_option')
+
     def sync(self):
         self._check(self.lib.nx_ctx_sync(self.ctx), 'nx_ctx_sync')
 

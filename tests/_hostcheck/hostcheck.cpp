@@ -2,6 +2,7 @@
 // with g++ so that logic can be debugged against the oracle on machines without
 // a GPU.  Never loaded by nexoclom_b200 (the product fails loudly without CUDA).
 #include "../../nexoclom_b200/csrc/nx_physics.cuh"
+#include "../../nexoclom_b200/csrc/nx_fast.cuh"
 #include "../../nexoclom_b200/csrc/nx_tables.h"
 #include "../../nexoclom_b200/csrc/nx_surface.cuh"
 
@@ -39,9 +40,14 @@ extern "C" int hc_integrate_adaptive(long n, double* X /* n x 8 row-major */, do
     double* s = X + 8 * i;
     att[i] = acc[i] = 0;
     bool live = (s[0] > p->resolution) && (s[7] > 0.0);
+    InterpCache cache;
+    interp_cache_reset(cache);
     while (live) {
-      int fl = strict ? adaptive_attempt<true>(*p, T, s, step[i])
-                      : adaptive_attempt<false>(*p, T, s, step[i]);
+      // strict = 1: NumPy operation order; 0: the product's fast path; 2: FMA-contracted
+      // variant of the strict template (kept for A/B comparisons)
+      int fl = strict == 1 ? adaptive_attempt<true>(*p, T, s, step[i])
+               : strict == 2 ? adaptive_attempt<false>(*p, T, s, step[i])
+                             : adaptive_attempt_fast_rt(*p, T, s, step[i], cache);
       att[i]++;
       if (fl & ATT_ACCEPTED) acc[i]++;
       status |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
