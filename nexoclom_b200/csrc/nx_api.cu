@@ -24,6 +24,9 @@ struct DevInterp {
   double *x = nullptr, *f = nullptr, *slope = nullptr;
   unsigned short* bucket = nullptr;
   InterpTable view{};
+  double* rec = nullptr;                 // record form for the fast path
+  unsigned short* fbucket = nullptr;
+  FastTable fast{};
 };
 
 struct nx_ctx {
@@ -70,6 +73,7 @@ struct nx_ctx {
 
 static void free_interp(DevInterp& d) {
   cudaFree(d.x); cudaFree(d.f); cudaFree(d.slope); cudaFree(d.bucket);
+  cudaFree(d.rec); cudaFree(d.fbucket);
   d = DevInterp{};
 }
 
@@ -86,7 +90,15 @@ static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const doubl
   CK(cudaMemcpyAsync(d.slope, h.slope.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d.bucket, h.bucket.data(), h.nbucket * sizeof(unsigned short),
                      cudaMemcpyHostToDevice, ctx->stream));
+  HostFastTable hf = make_fast_table(x, f, n);
+  CK(cudaMalloc(&d.rec, hf.rec.size() * sizeof(double)));
+  CK(cudaMalloc(&d.fbucket, hf.bucket.size() * sizeof(unsigned short)));
+  CK(cudaMemcpyAsync(d.rec, hf.rec.data(), hf.rec.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d.fbucket, hf.bucket.data(), hf.bucket.size() * sizeof(unsigned short),
+                     cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  d.fast.rec = reinterpret_cast<const InterpRec*>(d.rec); d.fast.bucket = d.fbucket;
+  d.fast.nrec = hf.nrec; d.fast.nbucket = hf.nbucket; d.fast.blo = hf.blo; d.fast.binvw = hf.binvw;
   d.view.x = d.x; d.view.f = d.f; d.view.slope = d.slope; d.view.bucket = d.bucket;
   d.view.n = n; d.view.nbucket = h.nbucket; d.view.blo = h.blo; d.view.binvw = h.binvw;
   return 0;
@@ -376,7 +388,8 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
       CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params, ctx->cost,
                            ctx->hist, ctx->perm));
     CK(launch_integrate_adaptive(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
-                                 ctx->radpres.view, order ? ctx->perm : nullptr, ctx->scalars,
+                                 ctx->radpres.view, ctx->radpres.fast, order ? ctx->perm : nullptr,
+                                 ctx->scalars,
                                  ctx->scalars + 1, ctx->att, ctx->acc, ctx->status));
     if ((r = end_timed(ctx, order ? 4 : 1))) return r;
   }

@@ -8,7 +8,8 @@
 //   * gravity uses one MUFU.RSQ64H seed + one third-order correction;
 //   * frac is advanced as f*exp(dlogf) (== exp(log f + dlogf) in exact arithmetic),
 //     so no log/exp pair per step and no per-stage log-frac bookkeeping;
-//   * the radiation-pressure table interval is cached across RHS evaluations;
+//   * the radiation-pressure table is looked up through a bucket index + 32-byte
+//     interval records (one LDS.U16 + two LDS.128, no search loop in the common case);
 //   * accept test is "every delta_j < scale_j" (exactly equivalent to
 //     max_j fl(delta_j/scale_j) < 1 for correctly rounded division); the
 //     quotient itself is only formed on the reject path, with Newton reciprocals;
@@ -100,8 +101,8 @@ NX_HD double exp_step(double d) {
 // One attempted adaptive step, fast arithmetic.  Same contract as
 // adaptive_attempt<>(): s[0..7] = time,x,y,z,vx,vy,vz,frac; returns AttemptFlags.
 template <int GR, int RP, int LOSS>
-NX_HD int adaptive_attempt_fast(const RunParams& p, const InterpTable& T, double* s,
-                                double& step, InterpCache& cache) {
+NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* s,
+                                double& step) {
   const double res = p.resolution;
   const double resv = 0.1 * res;
   const double h = fmin(s[0], step);
@@ -123,7 +124,7 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const InterpTable& T, double
     bool lit = true;
     if (RP || LOSS == LOSS_PHOTO) lit = (s2 > NX_ONE_PLUS_ULP) || (py < 0.0);
     if (RP) {
-      const double ar = interp_cached(T, vy + p.vrplanet, cache);
+      const double ar = interp_fast(T, vy + p.vrplanet);
       ay += lit ? ar : 0.0;
     }
     if (LOSS == LOSS_PHOTO) litmask |= (lit ? 1u : 0u) << n;
@@ -222,14 +223,14 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const InterpTable& T, double
 }
 
 // runtime dispatch over the compile-time force / loss combinations
-NX_HD int adaptive_attempt_fast_rt(const RunParams& p, const InterpTable& T, double* s,
-                                   double& step, InterpCache& c) {
+NX_HD int adaptive_attempt_fast_rt(const RunParams& p, const FastTable& T, double* s,
+                                   double& step) {
   const int key = (p.gravity ? 4 : 0) | (p.radpres ? 2 : 0);
 #define NX_CASE(G, R)                                                                    \
   if (key == ((G) * 4 + (R) * 2)) {                                                      \
-    if (p.loss_mode == LOSS_PHOTO) return adaptive_attempt_fast<G, R, LOSS_PHOTO>(p, T, s, step, c);       \
-    if (p.loss_mode == LOSS_LIFETIME) return adaptive_attempt_fast<G, R, LOSS_LIFETIME>(p, T, s, step, c); \
-    return adaptive_attempt_fast<G, R, LOSS_NONE>(p, T, s, step, c);                     \
+    if (p.loss_mode == LOSS_PHOTO) return adaptive_attempt_fast<G, R, LOSS_PHOTO>(p, T, s, step);       \
+    if (p.loss_mode == LOSS_LIFETIME) return adaptive_attempt_fast<G, R, LOSS_LIFETIME>(p, T, s, step); \
+    return adaptive_attempt_fast<G, R, LOSS_NONE>(p, T, s, step);                     \
   }
   NX_CASE(1, 1) NX_CASE(1, 0) NX_CASE(0, 1) NX_CASE(0, 0)
 #undef NX_CASE

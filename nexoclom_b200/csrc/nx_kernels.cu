@@ -45,6 +45,25 @@ __device__ __forceinline__ size_t stage_table(const InterpTable& g, InterpTable&
   return (bytes + 15) & ~(size_t)15;
 }
 
+__device__ __forceinline__ void stage_fast_table(const FastTable& g, FastTable& s,
+                                                 unsigned char* base) {
+  double4* sr = reinterpret_cast<double4*>(base);
+  const double4* gr = reinterpret_cast<const double4*>(g.rec);
+  for (int i = threadIdx.x; i < g.nrec; i += blockDim.x) sr[i] = gr[i];   // 32 B per record
+  unsigned short* sb = reinterpret_cast<unsigned short*>(sr + g.nrec);
+  const int nb = g.nrec ? g.nbucket : 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sb[i] = g.bucket[i];
+  s.rec = reinterpret_cast<const InterpRec*>(sr);
+  s.bucket = sb;
+  s.nrec = g.nrec; s.nbucket = g.nbucket; s.blo = g.blo; s.binvw = g.binvw;
+}
+
+size_t fast_table_smem_bytes(const FastTable& g) {
+  if (g.nrec == 0) return 0;
+  size_t bytes = (size_t)g.nrec * 32 + (size_t)g.nbucket * 2;
+  return (bytes + 15) & ~(size_t)15;
+}
+
 size_t table_smem_bytes(const InterpTable& g) {
   if (g.n == 0) return 0;
   size_t bytes = (size_t)g.n * 24 + (size_t)g.nbucket * 2;
@@ -85,7 +104,7 @@ __global__ void k_fill(double* p, long long n, double v) {
 //       MODE = GR*8 + RP*4 + LOSS.
 template <int MODE>
 __global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
-k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
+k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, FastTable Fg,
                      const unsigned* __restrict__ perm,
                      unsigned long long* __restrict__ queue,
                      unsigned long long* __restrict__ totals,
@@ -93,15 +112,15 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
                      int* __restrict__ status) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   InterpTable T;
-  stage_table(Tg, T, smem_raw);
+  FastTable F;
+  if (MODE < 0) stage_table(Tg, T, smem_raw);
+  else stage_fast_table(Fg, F, smem_raw);
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
   bool have = false, drained = false;
   long long idx = 0;
   double s[8], step = 0.0;
-  InterpCache cache;
-  interp_cache_reset(cache);
   unsigned att = 0, acc = 0;
   unsigned long long tot_att = 0, tot_acc = 0;
   int st = 0;
@@ -122,7 +141,6 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
           for (int k = 0; k < 8; ++k) s[k] = P.c[k][i];
           step = P.c[8][i];
           att = 0; acc = 0;
-          if (MODE >= 0) interp_cache_reset(cache);
           have = (s[0] > p.resolution) && (s[7] > 0.0);
           if (!have) { att_out[i] = 0; acc_out[i] = 0; }
         }
@@ -136,7 +154,7 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg,
     if (have) {
       int fl;
       if (MODE < 0) fl = adaptive_attempt<true>(p, T, s, step);
-      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, T, s, step, cache);
+      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s, step);
       ++att;
       if (fl & ATT_ACCEPTED) ++acc;
       st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
@@ -531,16 +549,17 @@ static cudaError_t persistent_grid(K kernel, int device, size_t smem, int* block
 template <int MODE>
 static cudaError_t launch_adaptive_mode(cudaStream_t st, int device, StateCols P, long long n,
                                         const RunParams& p, const InterpTable& T,
+                                        const FastTable& F,
                                         const unsigned* perm, unsigned long long* queue,
                                         unsigned long long* totals, unsigned* att, unsigned* acc,
                                         int* status) {
-  const size_t smem = table_smem_bytes(T);
+  const size_t smem = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
   int blocks = 0;
   cudaError_t e = persistent_grid(k_integrate_adaptive<MODE>, device, smem, &blocks);
   if (e != cudaSuccess) return e;
   const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
   if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-  k_integrate_adaptive<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, perm, queue,
+  k_integrate_adaptive<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, F, perm, queue,
                                                                    totals, att, acc, status);
   return cudaGetLastError();
 }
@@ -563,10 +582,10 @@ cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long lon
 
 cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
                                       const RunParams& p, const InterpTable& T,
-                                      const unsigned* perm,
+                                      const FastTable& F, const unsigned* perm,
                                       unsigned long long* queue, unsigned long long* totals,
                                       unsigned* att, unsigned* acc, int* status) {
-#define NX_ARGS st, device, P, n, p, T, perm, queue, totals, att, acc, status
+#define NX_ARGS st, device, P, n, p, T, F, perm, queue, totals, att, acc, status
   if (p.strict_math) return launch_adaptive_mode<-1>(NX_ARGS);
   const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
   switch (mode) {

@@ -38,7 +38,7 @@ cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long lon
                               unsigned* perm);
 cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
                                       const RunParams& p, const InterpTable& T,
-                                      const unsigned* perm,
+                                      const FastTable& F, const unsigned* perm,
                                       unsigned long long* queue, unsigned long long* totals,
                                       unsigned* att, unsigned* acc, int* status);
 cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,

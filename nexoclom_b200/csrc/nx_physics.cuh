@@ -151,25 +151,25 @@ NX_HD double interp(const InterpTable& T, double x) {
   return add_rn(mul_rn(T.slope[j], sub_rn(x, xj)), T.f[j]);
 }
 
-// Interval cache for the fast path: consecutive RHS evaluations of one packet
-// almost always fall into the same table interval.
-struct InterpCache {
-  double lo, hi, f, slope;       // value = fma(slope, x - lo, f) for lo <= x < hi
+// Record-form table of the fast path (see nx_tables.h: make_fast_table).
+struct InterpRec { double lo, hi, f, slope; };
+struct FastTable {
+  const InterpRec* rec;
+  const unsigned short* bucket;
+  int nrec, nbucket;
+  double blo, binvw;
 };
-NX_HD void interp_cache_reset(InterpCache& c) { c.lo = 1.0; c.hi = 0.0; c.f = 0.0; c.slope = 0.0; }
 
-NX_HD double interp_cached(const InterpTable& T, double x, InterpCache& c) {
-  if (!(x >= c.lo && x < c.hi)) {
-    if (x != x) return x;
-    const int n = T.n;
-    if (x >= T.x[n - 1]) { c.lo = T.x[n - 1]; c.hi = 1.7976931348623157e308; c.f = T.f[n - 1]; c.slope = 0.0; }
-    else if (x < T.x[0]) { c.lo = -1e300; c.hi = T.x[0]; c.f = T.f[0]; c.slope = 0.0; }
-    else {
-      const int j = interp_locate(T, x);
-      c.lo = T.x[j]; c.hi = T.x[j + 1]; c.f = T.f[j]; c.slope = T.slope[j];
-    }
-  }
-  return fma(c.slope, x - c.lo, c.f);
+// np.interp through the record table: bucket -> record, then (rarely) walk to the
+// neighbouring record; clamp records make the ends branch-free.
+NX_HD double interp_fast(const FastTable& T, double v) {
+  int b = (v == v) ? (int)((v - T.blo) * T.binvw) : 0;
+  b = b < 0 ? 0 : (b >= T.nbucket ? T.nbucket - 1 : b);
+  int idx = T.bucket[b];
+  InterpRec r = T.rec[idx];
+  while (v >= r.hi && idx < T.nrec - 1) r = T.rec[++idx];
+  while (v < r.lo && idx > 0) r = T.rec[--idx];
+  return fma(r.slope, v - r.lo, r.f);
 }
 
 // ---------------------------------------------------------------------------

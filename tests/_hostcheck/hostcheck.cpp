@@ -34,20 +34,24 @@ extern "C" int hc_integrate_adaptive(long n, double* X /* n x 8 row-major */, do
                                      unsigned* att, unsigned* acc, const RunParams* p,
                                      const double* rpv, const double* rpa, int nrp, int strict) {
   HostInterp hi; InterpTable T{};
-  if (nrp > 0) { hi = make_interp(rpv, rpa, nrp); T = view(hi); }
+  HostFastTable hf; FastTable F{};
+  if (nrp > 0) {
+    hi = make_interp(rpv, rpa, nrp); T = view(hi);
+    hf = make_fast_table(rpv, rpa, nrp);
+    F.rec = reinterpret_cast<const InterpRec*>(hf.rec.data()); F.bucket = hf.bucket.data();
+    F.nrec = hf.nrec; F.nbucket = hf.nbucket; F.blo = hf.blo; F.binvw = hf.binvw;
+  }
   int status = 0;
   for (long i = 0; i < n; ++i) {
     double* s = X + 8 * i;
     att[i] = acc[i] = 0;
     bool live = (s[0] > p->resolution) && (s[7] > 0.0);
-    InterpCache cache;
-    interp_cache_reset(cache);
     while (live) {
       // strict = 1: NumPy operation order; 0: the product's fast path; 2: FMA-contracted
       // variant of the strict template (kept for A/B comparisons)
       int fl = strict == 1 ? adaptive_attempt<true>(*p, T, s, step[i])
                : strict == 2 ? adaptive_attempt<false>(*p, T, s, step[i])
-                             : adaptive_attempt_fast_rt(*p, T, s, step[i], cache);
+                             : adaptive_attempt_fast_rt(*p, F, s, step[i]);
       att[i]++;
       if (fl & ATT_ACCEPTED) acc[i]++;
       status |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
