@@ -3,8 +3,10 @@
 // Same algorithm and the same accept / reject DECISIONS as adaptive_attempt<true>
 // (reference Output.py:249-353 + rk5.py + state.py), re-associated for the FP64
 // pipe of sm_100a:
-//   * stage sums are FMA chains started from the base state (no separate adds),
-//     tableau constants come from the constant bank (no immediate moves);
+//   * stage sums are FMA chains started from the base state, written on the scaled
+//     accelerations K_j = h a_j only (Nystrom form: stage velocities are never
+//     stored -> 30 fewer registers -> one more resident block per SM); tableau
+//     constants come from the constant bank;
 //   * gravity uses one MUFU.RSQ64H seed + one third-order correction;
 //   * frac is advanced as f*exp(dlogf) (== exp(log f + dlogf) in exact arithmetic),
 //     so no log/exp pair per step and no per-stage log-frac bookkeeping;
@@ -21,40 +23,81 @@
 
 namespace nx {
 
-// Dormand-Prince coefficients, flattened: A rows 1..6 (21 entries), BD (6 entries).
-#define NX_DP_A_LIST                                                                        \
-  0.2,                                                                                      \
-  3. / 40., 9. / 40.,                                                                       \
-  44. / 45., -56. / 15., 32. / 9.,                                                          \
-  19372. / 6561., -25360. / 2187., 64448. / 6561., -212. / 729.,                            \
-  9017. / 3168., -355. / 33., 46732. / 5247., 49. / 176., -5103. / 18656.,                  \
-  35. / 384., 0., 500. / 1113., 125. / 192., -2187. / 6784., 11. / 84.
-#define NX_DP_BD_LIST                                                                       \
-  35. / 384. - 5179. / 57600., 0., 500. / 1113. - 7571. / 16695., 125. / 192. - 393. / 640., \
-  -2187. / 6784. - -92097. / 339200., 11. / 84. - 187. / 2100.
+// Dormand-Prince coefficients (reference rk5.py:5-18) and the derived "Nystrom"
+// constants that let the position stages be written on the accelerations alone
+// (so the six stage velocities never have to be stored):
+//   v_m = v0 + sum_{j<m} a_mj K_j,                 K_j = h a_j
+//   p_m = p0 + c_m (h v0) + sum_{j<m-1} (h A2_mj) K_j,  A2_mj = sum_{i=j+1}^{m-1} a_mi a_ij
+//   h sum_{i<6} bd_i kv_i = BDS (h v0) + sum_{j<5} (h BD2_j) K_j
+constexpr double dpc_a(int n, int i) {
+  switch (n * 8 + i) {
+    case 1 * 8 + 0: return 0.2;
+    case 2 * 8 + 0: return 3. / 40.;  case 2 * 8 + 1: return 9. / 40.;
+    case 3 * 8 + 0: return 44. / 45.; case 3 * 8 + 1: return -56. / 15.; case 3 * 8 + 2: return 32. / 9.;
+    case 4 * 8 + 0: return 19372. / 6561.; case 4 * 8 + 1: return -25360. / 2187.;
+    case 4 * 8 + 2: return 64448. / 6561.; case 4 * 8 + 3: return -212. / 729.;
+    case 5 * 8 + 0: return 9017. / 3168.; case 5 * 8 + 1: return -355. / 33.;
+    case 5 * 8 + 2: return 46732. / 5247.; case 5 * 8 + 3: return 49. / 176.;
+    case 5 * 8 + 4: return -5103. / 18656.;
+    case 6 * 8 + 0: return 35. / 384.; case 6 * 8 + 1: return 0.;
+    case 6 * 8 + 2: return 500. / 1113.; case 6 * 8 + 3: return 125. / 192.;
+    case 6 * 8 + 4: return -2187. / 6784.; case 6 * 8 + 5: return 11. / 84.;
+    default: return 0.;
+  }
+}
+constexpr double dpc_bd(int i) {
+  switch (i) {
+    case 0: return 35. / 384. - 5179. / 57600.;
+    case 2: return 500. / 1113. - 7571. / 16695.;
+    case 3: return 125. / 192. - 393. / 640.;
+    case 4: return -2187. / 6784. - -92097. / 339200.;
+    case 5: return 11. / 84. - 187. / 2100.;
+    default: return 0.;
+  }
+}
+constexpr double dpc_c(int m) { double s = 0; for (int i = 0; i < m; ++i) s += dpc_a(m, i); return s; }
+constexpr double dpc_a2(int m, int j) {
+  double s = 0;
+  for (int i = j + 1; i < m; ++i) s += dpc_a(m, i) * dpc_a(i, j);
+  return s;
+}
+constexpr double dpc_bds() { double s = 0; for (int i = 0; i < 6; ++i) s += dpc_bd(i); return s; }
+constexpr double dpc_bd2(int j) {
+  double s = 0;
+  for (int i = j + 1; i < 6; ++i) s += dpc_bd(i) * dpc_a(i, j);
+  return s;
+}
+constexpr double dpc_bsum() { double s = 0; for (int i = 0; i < 6; ++i) s += dpc_a(6, i); return s; }
+
+#define NX_ROW(f, m) f(m, 0), f(m, 1), f(m, 2), f(m, 3), f(m, 4), f(m, 5), 0., 0.
+#define NX_TAB(f) {NX_ROW(f, 0), NX_ROW(f, 1), NX_ROW(f, 2), NX_ROW(f, 3), NX_ROW(f, 4), \
+                   NX_ROW(f, 5), NX_ROW(f, 6)}
+#define NX_VEC6(f) {f(0), f(1), f(2), f(3), f(4), f(5), 0., 0.}
+#define NX_VEC7(f) {f(0), f(1), f(2), f(3), f(4), f(5), f(6), 0.}
 
 #if defined(__CUDACC__)
-__constant__ double c_dp_a[21] = {NX_DP_A_LIST};
-__constant__ double c_dp_bd[6] = {NX_DP_BD_LIST};
+__constant__ double c_dp_a[56] = NX_TAB(dpc_a);
+__constant__ double c_dp_a2[56] = NX_TAB(dpc_a2);
+__constant__ double c_dp_c[8] = NX_VEC7(dpc_c);
+__constant__ double c_dp_bd[8] = NX_VEC6(dpc_bd);
+__constant__ double c_dp_bd2[8] = NX_VEC6(dpc_bd2);
 #endif
-static const double h_dp_a[21] = {NX_DP_A_LIST};
-static const double h_dp_bd[6] = {NX_DP_BD_LIST};
+static const double h_dp_a[56] = NX_TAB(dpc_a);
+static const double h_dp_a2[56] = NX_TAB(dpc_a2);
+static const double h_dp_c[8] = NX_VEC7(dpc_c);
+static const double h_dp_bd[8] = NX_VEC6(dpc_bd);
+static const double h_dp_bd2[8] = NX_VEC6(dpc_bd2);
 
-NX_HD double dp_a(int n, int i) {          // a[n][i], 1 <= n <= 6, i < n
-  const int k = n * (n - 1) / 2 + i;
 #if defined(__CUDA_ARCH__)
-  return c_dp_a[k];
+#define NX_CONST(name, k) c_##name[k]
 #else
-  return h_dp_a[k];
+#define NX_CONST(name, k) h_##name[k]
 #endif
-}
-NX_HD double dp_bd(int i) {
-#if defined(__CUDA_ARCH__)
-  return c_dp_bd[i];
-#else
-  return h_dp_bd[i];
-#endif
-}
+NX_HD double dp_a(int m, int j) { return NX_CONST(dp_a, m * 8 + j); }
+NX_HD double dp_a2(int m, int j) { return NX_CONST(dp_a2, m * 8 + j); }
+NX_HD double dp_c(int m) { return NX_CONST(dp_c, m); }
+NX_HD double dp_bd(int i) { return NX_CONST(dp_bd, i); }
+NX_HD double dp_bd2(int j) { return NX_CONST(dp_bd2, j); }
 
 // 1/sqrt(a): hardware seed + one third-order (Halley) step  -> ~0.2 ulp
 NX_HD double rsqrt_h(double a) {
@@ -107,12 +150,12 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
   const double resv = 0.1 * res;
   const double h = fmin(s[0], step);
 
-  double kv[6][3], ka[6][3];
+  double K[6][3];                      // K_j = h * accel_j  (the only per-stage storage)
+  const double hv0 = h * s[4], hv1 = h * s[5], hv2 = h * s[6];
   unsigned litmask = 0;
   double px = s[1], py = s[2], pz = s[3], vx = s[4], vy = s[5], vz = s[6];
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
-    kv[n][0] = vx; kv[n][1] = vy; kv[n][2] = vz;
     const double s2 = fma(pz, pz, px * px);
     double ax = 0.0, ay = 0.0, az = 0.0;
     if (GR) {
@@ -128,15 +171,22 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
       ay += lit ? ar : 0.0;
     }
     if (LOSS == LOSS_PHOTO) litmask |= (lit ? 1u : 0u) << n;
-    ka[n][0] = ax; ka[n][1] = ay; ka[n][2] = az;
+    K[n][0] = h * ax; K[n][1] = h * ay; K[n][2] = h * az;
 
-    double ap0 = s[1], ap1 = s[2], ap2 = s[3], av0 = s[4], av1 = s[5], av2 = s[6];
+    const int m = n + 1;
+    const double cm = dp_c(m);
+    double ap0 = fma(cm, hv0, s[1]), ap1 = fma(cm, hv1, s[2]), ap2 = fma(cm, hv2, s[3]);
+    double av0 = s[4], av1 = s[5], av2 = s[6];
 #pragma unroll
-    for (int i = 0; i <= n; ++i) {
-      if (n == 5 && i == 1) continue;                 // b[1] = 0
-      const double ha = h * dp_a(n + 1, i);
-      ap0 = fma(ha, kv[i][0], ap0); ap1 = fma(ha, kv[i][1], ap1); ap2 = fma(ha, kv[i][2], ap2);
-      av0 = fma(ha, ka[i][0], av0); av1 = fma(ha, ka[i][1], av1); av2 = fma(ha, ka[i][2], av2);
+    for (int j = 0; j <= n; ++j) {
+      if (!(m == 6 && j == 1)) {                       // b[1] = 0
+        const double a = dp_a(m, j);
+        av0 = fma(a, K[j][0], av0); av1 = fma(a, K[j][1], av1); av2 = fma(a, K[j][2], av2);
+      }
+      if (j < n) {
+        const double ha2 = h * dp_a2(m, j);
+        ap0 = fma(ha2, K[j][0], ap0); ap1 = fma(ha2, K[j][1], ap1); ap2 = fma(ha2, K[j][2], ap2);
+      }
     }
     px = ap0; py = ap1; pz = ap2; vx = av0; vy = av1; vz = av2;
   }
@@ -144,8 +194,8 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
   // fractional content: dlogf = -h sum b_i rate_i ; error term h sum bd_i rate_i
   double sb = 0.0, sbd = 0.0;
   if (LOSS == LOSS_LIFETIME) {
-    sb = p.loss_rate * ((((dp_a(6, 0) + dp_a(6, 2)) + dp_a(6, 3)) + dp_a(6, 4)) + dp_a(6, 5));
-    sbd = p.loss_rate * ((((dp_bd(0) + dp_bd(2)) + dp_bd(3)) + dp_bd(4)) + dp_bd(5));
+    sb = p.loss_rate * dpc_bsum();
+    sbd = p.loss_rate * dpc_bds();
   } else if (LOSS == LOSS_PHOTO) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -160,12 +210,22 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
 
   // error vector |h sum_{i<6} bd_i k_i|  (stage 7 not included: quirk Q1)
   double d[6];
+  {
+    const double bds = dpc_bds();
+    double ep0 = bds * hv0, ep1 = bds * hv1, ep2 = bds * hv2;
+    double ev0 = dp_bd(0) * K[0][0], ev1 = dp_bd(0) * K[0][1], ev2 = dp_bd(0) * K[0][2];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    double ep = dp_bd(0) * kv[0][k], ev = dp_bd(0) * ka[0][k];
+    for (int j = 0; j < 5; ++j) {
+      const double hb = h * dp_bd2(j);
+      ep0 = fma(hb, K[j][0], ep0); ep1 = fma(hb, K[j][1], ep1); ep2 = fma(hb, K[j][2], ep2);
+    }
 #pragma unroll
-    for (int i = 2; i < 6; ++i) { ep = fma(dp_bd(i), kv[i][k], ep); ev = fma(dp_bd(i), ka[i][k], ev); }
-    d[k] = fabs(h * ep); d[3 + k] = fabs(h * ev);
+    for (int i = 2; i < 6; ++i) {
+      const double b = dp_bd(i);
+      ev0 = fma(b, K[i][0], ev0); ev1 = fma(b, K[i][1], ev1); ev2 = fma(b, K[i][2], ev2);
+    }
+    d[0] = fabs(ep0); d[1] = fabs(ep1); d[2] = fabs(ep2);
+    d[3] = fabs(ev0); d[4] = fabs(ev1); d[5] = fabs(ev2);
   }
   const double nx[6] = {px, py, pz, vx, vy, vz};
   const double sf = fma(fabs(fn), res, res);

@@ -9,7 +9,7 @@
 #include "nx_surface.cuh"
 
 #define NX_INT_THREADS 128
-#define NX_INT_MINBLOCKS 3
+#define NX_INT_MINBLOCKS 4
 #define NX_LOS_THREADS 128
 
 namespace nx {

@@ -167,8 +167,10 @@ NX_HD double interp_fast(const FastTable& T, double v) {
   b = b < 0 ? 0 : (b >= T.nbucket ? T.nbucket - 1 : b);
   int idx = T.bucket[b];
   InterpRec r = T.rec[idx];
-  while (v >= r.hi && idx < T.nrec - 1) r = T.rec[++idx];
-  while (v < r.lo && idx > 0) r = T.rec[--idx];
+  if (!(v >= r.lo && v < r.hi)) {              // crowded bucket / clamp: rare walk
+    while (v >= r.hi && idx < T.nrec - 1) r = T.rec[++idx];
+    while (v < r.lo && idx > 0) r = T.rec[--idx];
+  }
   return fma(r.slope, v - r.lo, r.f);
 }
 
