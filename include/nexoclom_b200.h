@@ -57,6 +57,7 @@ typedef struct nx_run_params {
   double stick_A[3];       /* SurfaceInteraction.A (temperature dependent)         */
   double surf_t1;          /* 600+125(cos taa-1)/2 (surface_temperature.py:9)      */
   double planet_radius_km;
+  double radpres_amax;     /* max |radiation accel| of the table (scheduling heuristic only) */
   int32_t gravity, radpres;
   int32_t loss_mode;       /* 0 none, 1 constant lifetime, 2 photo x sunlit        */
   int32_t sticktype;       /* 0 constant, 1 temperature dependent                  */

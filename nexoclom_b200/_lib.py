@@ -25,6 +25,7 @@ class RunParams(C.Structure):
         ('outeredge', C.c_double), ('resolution', C.c_double), ('step_size', C.c_double),
         ('endtime', C.c_double), ('stickcoef', C.c_double), ('accomfactor', C.c_double),
         ('stick_A', C.c_double * 3), ('surf_t1', C.c_double), ('planet_radius_km', C.c_double),
+        ('radpres_amax', C.c_double),
         ('gravity', C.c_int32), ('radpres', C.c_int32), ('loss_mode', C.c_int32),
         ('sticktype', C.c_int32), ('strict_math', C.c_int32), ('reserved', C.c_int32),
     ]

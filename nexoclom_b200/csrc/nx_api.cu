@@ -90,7 +90,7 @@ static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const doubl
   CK(cudaMemcpyAsync(d.slope, h.slope.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d.bucket, h.bucket.data(), h.nbucket * sizeof(unsigned short),
                      cudaMemcpyHostToDevice, ctx->stream));
-  HostFastTable hf = make_fast_table(x, f, n);
+  HostFastTable hf = make_fast_table(x, f, n, 32768);
   CK(cudaMalloc(&d.rec, hf.rec.size() * sizeof(double)));
   CK(cudaMalloc(&d.fbucket, hf.bucket.size() * sizeof(unsigned short)));
   CK(cudaMemcpyAsync(d.rec, hf.rec.data(), hf.rec.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -98,7 +98,7 @@ static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const doubl
                      cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   d.fast.rec = reinterpret_cast<const InterpRec*>(d.rec); d.fast.bucket = d.fbucket;
-  d.fast.nrec = hf.nrec; d.fast.nbucket = hf.nbucket; d.fast.blo = hf.blo; d.fast.binvw = hf.binvw;
+  d.fast.nrec = hf.nrec; d.fast.nbucket = hf.nbucket; d.fast.blo = hf.blo; d.fast.binvw = hf.binvw; d.fast.boff = -hf.blo * hf.binvw;
   d.view.x = d.x; d.view.f = d.f; d.view.slope = d.slope; d.view.bucket = d.bucket;
   d.view.n = n; d.view.nbucket = h.nbucket; d.view.blo = h.blo; d.view.binvw = h.binvw;
   return 0;
@@ -385,8 +385,8 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
     if ((r = begin_timed(ctx))) return r;
     const bool order = ctx->order_packets && n >= 4096;
     if (order)
-      CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params, ctx->cost,
-                           ctx->hist, ctx->perm));
+      CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
+                           ctx->order_packets, ctx->cost, ctx->hist, ctx->perm));
     CK(launch_integrate_adaptive(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
                                  ctx->radpres.view, ctx->radpres.fast, order ? ctx->perm : nullptr,
                                  ctx->scalars,

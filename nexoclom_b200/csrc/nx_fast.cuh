@@ -19,6 +19,8 @@
 // Differences from the NumPy operation order are a few ulp per step; parity
 // against the oracle stays ~1e-14 (gate 1e-8), see tests/test_hostcheck.py.
 #pragma once
+#include <string.h>
+
 #include "nx_physics.cuh"
 
 namespace nx {
@@ -99,6 +101,19 @@ NX_HD double dp_c(int m) { return NX_CONST(dp_c, m); }
 NX_HD double dp_bd(int i) { return NX_CONST(dp_bd, i); }
 NX_HD double dp_bd2(int j) { return NX_CONST(dp_bd2, j); }
 
+// Comparisons of NON-NEGATIVE doubles through their bit patterns: integer compares
+// run on the ALU pipe and leave the (half-rate) FP64 pipe to the arithmetic.
+NX_HD long long dbits(double a) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(a);
+#else
+  long long r; memcpy(&r, &a, 8); return r;
+#endif
+}
+NX_HD bool lt_nonneg(double a, double b) { return dbits(a) < dbits(b); }   // a, b >= 0 (NaN > all)
+NX_HD bool is_negative(double a) { return dbits(a) < 0 && a != 0.0; }
+NX_HD double max_nonneg(double a, double b) { return lt_nonneg(a, b) ? b : a; }
+
 // 1/sqrt(a): hardware seed + one third-order (Halley) step  -> ~0.2 ulp
 NX_HD double rsqrt_h(double a) {
 #if defined(__CUDA_ARCH__)
@@ -152,26 +167,29 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
 
   double K[6][3];                      // K_j = h * accel_j  (the only per-stage storage)
   const double hv0 = h * s[4], hv1 = h * s[5], hv2 = h * s[6];
+  const double hGM = h * p.GM;
   unsigned litmask = 0;
   double px = s[1], py = s[2], pz = s[3], vx = s[4], vy = s[5], vz = s[6];
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
     const double s2 = fma(pz, pz, px * px);
-    double ax = 0.0, ay = 0.0, az = 0.0;
+    // K_n = h * accel: h is folded into GM, the radiation term is scaled once
+    double kx = 0.0, ky = 0.0, kz = 0.0;
     if (GR) {
       const double r2 = fma(py, py, s2);
       const double ri = rsqrt_h(r2);
-      const double g = (p.GM * ri) * (ri * ri);
-      ax = g * px; ay = g * py; az = g * pz;
+      const double g = (hGM * ri) * (ri * ri);
+      kx = g * px; ky = g * py; kz = g * pz;
     }
     bool lit = true;
-    if (RP || LOSS == LOSS_PHOTO) lit = (s2 > NX_ONE_PLUS_ULP) || (py < 0.0);
+    if (RP || LOSS == LOSS_PHOTO)
+      lit = (dbits(s2) > dbits(NX_ONE_PLUS_ULP)) || (dbits(py) < 0);   // s2 >= 0
     if (RP) {
       const double ar = interp_fast(T, vy + p.vrplanet);
-      ay += lit ? ar : 0.0;
+      ky = fma(lit ? h : 0.0, ar, ky);
     }
     if (LOSS == LOSS_PHOTO) litmask |= (lit ? 1u : 0u) << n;
-    K[n][0] = h * ax; K[n][1] = h * ay; K[n][2] = h * az;
+    K[n][0] = kx; K[n][1] = ky; K[n][2] = kz;
 
     const int m = n + 1;
     const double cm = dp_c(m);
@@ -228,26 +246,36 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
     d[3] = fabs(ev0); d[4] = fabs(ev1); d[5] = fabs(ev2);
   }
   const double nx[6] = {px, py, pz, vx, vy, vz};
+  // accept  <=>  every delta_j < scale_j  (== max_j fl(delta_j/scale_j) < 1).  The
+  // quotient itself (Newton reciprocal, ~2^-40) only sizes the next step after a
+  // reject and screens the "no error" case (Q4); it is formed for every lane so
+  // that the warp does not split into an accept and a reject instruction stream.
   const double sf = fma(fabs(fn), res, res);
-  bool ok = delta_f < sf;
+  bool ok = lt_nonneg(delta_f, sf);
+  double errmax = delta_f * rcp_n(sf);
+  double dsum = delta_f;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    ok = ok && (d[k] < fma(fabs(nx[k]), res, res));
-    ok = ok && (d[3 + k] < fma(fabs(nx[3 + k]), resv, resv));
+    const double sp = fma(fabs(nx[k]), res, res);
+    const double sv = fma(fabs(nx[3 + k]), resv, resv);
+    ok = ok && lt_nonneg(d[k], sp) && lt_nonneg(d[3 + k], sv);
+    errmax = max_nonneg(errmax, max_nonneg(d[k] * rcp_n(sp), d[3 + k] * rcp_n(sv)));
+    dsum += d[k] + d[3 + k];
   }
-  // "no error" (Q4): every ratio < 1e-7 -- screened by one component, rare
-  bool tiny = false;
-  if (d[3] < 1e-7 * fma(fabs(nx[3]), resv, resv)) {
-    tiny = delta_f < 1e-7 * sf;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      tiny = tiny && (d[k] < 1e-7 * fma(fabs(nx[k]), res, res));
-      tiny = tiny && (d[3 + k] < 1e-7 * fma(fabs(nx[3 + k]), resv, resv));
-    }
-  }
+  const bool tiny = errmax < 1e-7;                                   // quirk Q4
+  const bool accept = ok && !tiny;
+
+  // step-size update of a rejected attempt (reference Output.py:333-342)
+  const double htried = tiny ? h * 10.0 : h;
+  double e = errmax;
+  if ((fn - s[7] > sf) && (errmax > 1.0)) e = 1.1;                  // quirk Q9
+  if (tiny) e = 1.0;
+  const double grow = rsqrt_h(e * rsqrt_h(e));                       // e^-0.25
+  const double cand = (0.95 * htried) * grow;
 
   int flags = 0;
-  if (ok && !tiny) {
+  if (!(dsum <= 1.7976931348623157e308)) flags |= ATT_BAD_ERRMAX;    // NaN / inf deltas
+  if (accept) {
     const double r2 = fma(pz, pz, fma(py, py, px * px));
     double f = fn;
     if (fn < 0.0) flags |= ATT_NEG_FRAC;
@@ -259,22 +287,6 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
     s[7] = f;
     flags |= ATT_ACCEPTED;
   } else {
-    double errmax = delta_f * rcp_n(sf);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      errmax = fmax(errmax, d[k] * rcp_n(fma(fabs(nx[k]), res, res)));
-      errmax = fmax(errmax, d[3 + k] * rcp_n(fma(fabs(nx[3 + k]), resv, resv)));
-    }
-    // NaN deltas fall through every comparison above; fmax drops NaN, so test the inputs
-    bool bad = !(delta_f <= 1.7976931348623157e308);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) bad = bad || !(d[k] <= 1.7976931348623157e308);
-    if (bad) flags |= ATT_BAD_ERRMAX;
-    double htried = h;
-    if (tiny) { errmax = 1.0; htried = h * 10.0; }
-    else if ((fn - s[7] > sf) && (errmax > 1.0)) errmax = 1.1;      // quirk Q9
-    const double grow = rsqrt_h(errmax * rsqrt_h(errmax));           // errmax^-0.25
-    const double cand = (0.95 * htried) * grow;
     if (!(fabs(cand) <= 1.7976931348623157e308)) flags |= ATT_BAD_STEP;
     step = fmax(cand, 0.1 * htried);
   }

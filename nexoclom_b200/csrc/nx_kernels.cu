@@ -45,23 +45,20 @@ __device__ __forceinline__ size_t stage_table(const InterpTable& g, InterpTable&
   return (bytes + 15) & ~(size_t)15;
 }
 
+// fast path: interval records in shared memory, the (large) bucket index stays in
+// global memory and is served by L1
 __device__ __forceinline__ void stage_fast_table(const FastTable& g, FastTable& s,
                                                  unsigned char* base) {
   double4* sr = reinterpret_cast<double4*>(base);
   const double4* gr = reinterpret_cast<const double4*>(g.rec);
   for (int i = threadIdx.x; i < g.nrec; i += blockDim.x) sr[i] = gr[i];   // 32 B per record
-  unsigned short* sb = reinterpret_cast<unsigned short*>(sr + g.nrec);
-  const int nb = g.nrec ? g.nbucket : 0;
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) sb[i] = g.bucket[i];
   s.rec = reinterpret_cast<const InterpRec*>(sr);
-  s.bucket = sb;
-  s.nrec = g.nrec; s.nbucket = g.nbucket; s.blo = g.blo; s.binvw = g.binvw;
+  s.bucket = g.bucket;
+  s.nrec = g.nrec; s.nbucket = g.nbucket; s.blo = g.blo; s.binvw = g.binvw; s.boff = g.boff;
 }
 
 size_t fast_table_smem_bytes(const FastTable& g) {
-  if (g.nrec == 0) return 0;
-  size_t bytes = (size_t)g.nrec * 32 + (size_t)g.nbucket * 2;
-  return (bytes + 15) & ~(size_t)15;
+  return (size_t)g.nrec * 32;
 }
 
 size_t table_smem_bytes(const InterpTable& g) {
@@ -99,6 +96,90 @@ __global__ void k_fill(double* p, long long n, double v) {
 // atomicAdd), so warps stay full although step counts per packet differ by
 // orders of magnitude (p50 ~ 40, max ~ 4000).
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// Per-warp packet feeder: the work queue is consumed in batches of 32 packets
+// that are copied global -> shared memory with cp.async (LDGSTS) one batch AHEAD
+// of their use, so a lane that finishes its packet picks the next one out of
+// shared memory instead of stalling the whole warp on a chain of dependent
+// global loads (queue index -> permutation -> 9 state columns).
+// Layout per warp: 2 buffers x (9 columns x 32 doubles + 32 indices).
+// ---------------------------------------------------------------------------
+#define NX_FEED_COLS 9
+#define NX_FEED_BYTES_PER_WARP (2 * (NX_FEED_COLS * 32 * 8 + 32 * 4))
+#define NX_INVALID 0xffffffffu
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct PacketFeeder {
+  double* vals;              // this warp's staging area: [2][9][32]
+  unsigned* ids;             // [2][32]
+  const StateCols* P;
+  const unsigned* perm;
+  unsigned long long* queue;
+  long long n;
+  unsigned lane;
+  unsigned pnext;            // queue entry this lane will prefetch next (NX_INVALID: none)
+  int buf, pos, cnt;         // buffer being consumed, read position, packets in it
+  int cnt_pending;           // packets of the batch in flight into buffer buf^1
+  bool queue_done;
+
+  __device__ __forceinline__ void claim_indices() {
+    // claim the next 32 queue entries; the permutation load is NOT waited for here
+    unsigned long long base = 0;
+    if (!queue_done) {
+      if (lane == 0) base = atomicAdd(queue, 32ull);
+      base = __shfl_sync(FULL_MASK, base, 0);
+      if ((long long)base + 32 >= n) queue_done = true;
+      const long long q = (long long)base + lane;
+      pnext = (q < n) ? (perm ? __ldg(perm + q) : (unsigned)q) : NX_INVALID;
+    } else {
+      pnext = NX_INVALID;
+    }
+  }
+  __device__ __forceinline__ void issue_prefetch() {
+    const unsigned my = pnext;
+    const unsigned valid = __ballot_sync(FULL_MASK, my != NX_INVALID);
+    cnt_pending = __popc(valid);
+    if (cnt_pending) {
+      const int b = buf ^ 1;
+      if (my != NX_INVALID) {
+        double* dst = vals + (size_t)b * NX_FEED_COLS * 32 + lane;
+#pragma unroll
+        for (int k = 0; k < NX_FEED_COLS; ++k) cp_async8(dst + k * 32, P->c[k] + my);
+        ids[b * 32 + lane] = my;
+      }
+      cp_async_commit();
+    }
+    claim_indices();
+  }
+  __device__ __forceinline__ void init(unsigned char* smem, const StateCols* P_,
+                                       const unsigned* perm_, unsigned long long* queue_,
+                                       long long n_) {
+    const unsigned warp = threadIdx.x >> 5;
+    lane = threadIdx.x & 31u;
+    vals = reinterpret_cast<double*>(smem + (size_t)warp * NX_FEED_BYTES_PER_WARP);
+    ids = reinterpret_cast<unsigned*>(vals + 2 * NX_FEED_COLS * 32);
+    P = P_; perm = perm_; queue = queue_; n = n_;
+    buf = 0; pos = 0; cnt = 0; cnt_pending = 0; queue_done = false; pnext = NX_INVALID;
+    claim_indices();
+    issue_prefetch();
+  }
+  // make the pending batch current; returns false when nothing is left
+  __device__ __forceinline__ bool advance() {
+    if (cnt_pending == 0) return false;
+    cp_async_wait_all();
+    __syncwarp();
+    buf ^= 1; pos = 0; cnt = cnt_pending;
+    issue_prefetch();
+    return true;
+  }
+};
+
 // MODE: -1 = strict (NumPy operation order, runtime force flags);
 //       otherwise fast arithmetic with compile-time forces:
 //       MODE = GR*8 + RP*4 + LOSS.
@@ -109,43 +190,43 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
                      unsigned long long* __restrict__ queue,
                      unsigned long long* __restrict__ totals,
                      unsigned* __restrict__ att_out, unsigned* __restrict__ acc_out,
-                     int* __restrict__ status) {
+                     int* __restrict__ status, unsigned table_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   InterpTable T;
   FastTable F;
   if (MODE < 0) stage_table(Tg, T, smem_raw);
   else stage_fast_table(Fg, F, smem_raw);
+  PacketFeeder feed;
+  feed.init(smem_raw + table_bytes, &P, perm, queue, n);
   __syncthreads();
 
   const unsigned lane = threadIdx.x & 31u;
   bool have = false, drained = false;
-  long long idx = 0;
+  unsigned idx = 0;
   double s[8], step = 0.0;
   unsigned att = 0, acc = 0;
   unsigned long long tot_att = 0, tot_acc = 0;
   int st = 0;
 
   for (;;) {
-    const unsigned need = __ballot_sync(FULL_MASK, !have);
-    if (need && !drained) {
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(need));
-      base = __shfl_sync(FULL_MASK, base, leader);
-      if (!have) {
-        const long long q = (long long)base + __popc(need & ((1u << lane) - 1u));
-        if (q < n) {
-          const long long i = perm ? (long long)perm[q] : q;
-          idx = i;
+    unsigned need = __ballot_sync(FULL_MASK, !have);
+    while (need && !drained) {
+      if (feed.pos == feed.cnt && !feed.advance()) { drained = true; break; }
+      const int take = min(__popc(need), feed.cnt - feed.pos);
+      const int rank = __popc(need & ((1u << lane) - 1u));
+      if (!have && rank < take) {
+        const int slot = feed.pos + rank;
+        const double* v = feed.vals + (size_t)feed.buf * NX_FEED_COLS * 32 + slot;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s[k] = P.c[k][i];
-          step = P.c[8][i];
-          att = 0; acc = 0;
-          have = (s[0] > p.resolution) && (s[7] > 0.0);
-          if (!have) { att_out[i] = 0; acc_out[i] = 0; }
-        }
+        for (int k = 0; k < 8; ++k) s[k] = v[k * 32];
+        step = v[8 * 32];
+        idx = feed.ids[feed.buf * 32 + slot];
+        att = 0; acc = 0;
+        have = (s[0] > p.resolution) && (s[7] > 0.0);
+        if (!have) { att_out[idx] = 0; acc_out[idx] = 0; }
       }
-      drained = ((long long)base + __popc(need) >= n);
+      feed.pos += take;
+      need = __ballot_sync(FULL_MASK, !have);
     }
     if (!__any_sync(FULL_MASK, have)) {
       if (drained) break;
@@ -160,8 +241,8 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
       st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
       if (!(fl & ATT_LIVE)) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) P.c[k][idx] = s[k];
-        P.c[8][idx] = step;
+        for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
+        __stcs(P.c[8] + idx, step);
         att_out[idx] = att; acc_out[idx] = acc;
         tot_att += att; tot_acc += acc;
         have = false;
@@ -192,7 +273,7 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
 // ---------------------------------------------------------------------------
 #define NX_NBUCKET 32
 
-__device__ __forceinline__ int cost_bucket(const RunParams& p, double t, double x, double y,
+__device__ __forceinline__ int cost_bucket(const RunParams& p, int model, double t, double x, double y,
                                            double z, double vx, double vy, double vz, double f) {
   if (!(t > p.resolution) || !(f > 0.0)) return 0;
   const double mu = fabs(p.GM);
@@ -215,7 +296,11 @@ __device__ __forceinline__ int cost_bucket(const RunParams& p, double t, double 
       const double Ei = 2.0 * NX_PI - E1;
       const double dM = (Ei - e * sin(Ei)) - (E0 - e * sin(E0));
       const double tk = dM * sqrt(a * a * a / mu);
-      if (tk > 0.0 && tk < tfl) tfl = tk;
+      // radiation pressure can turn a ballistic hop into a long excursion (Na at
+      // Mercury: up to half the surface gravity): if it can change the speed by
+      // more than ~15% during the hop, budget the full remaining time
+      const bool perturbed = (model == 2) && p.radpres && (p.radpres_amax * tk > 0.15 * sqrt(v2));
+      if (tk > 0.0 && tk < tfl && !perturbed) tfl = tk;
     }
   }
   const double est = tfl * sqrt(v2) / (40.0 * p.resolution * (1.0 + r)) + 4.0;
@@ -224,14 +309,14 @@ __device__ __forceinline__ int cost_bucket(const RunParams& p, double t, double 
 }
 
 __global__ void __launch_bounds__(256)
-k_cost_histogram(StateCols P, long long n, RunParams p, unsigned char* __restrict__ bucket,
-                 unsigned* __restrict__ hist) {
+k_cost_histogram(StateCols P, long long n, RunParams p, int model,
+                 unsigned char* __restrict__ bucket, unsigned* __restrict__ hist) {
   __shared__ unsigned sh[NX_NBUCKET];
   if (threadIdx.x < NX_NBUCKET) sh[threadIdx.x] = 0;
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int b = cost_bucket(p, P.c[0][i], P.c[1][i], P.c[2][i], P.c[3][i], P.c[4][i],
+    const int b = cost_bucket(p, model, P.c[0][i], P.c[1][i], P.c[2][i], P.c[3][i], P.c[4][i],
                               P.c[5][i], P.c[6][i], P.c[7][i]);
     bucket[i] = (unsigned char)b;
     atomicAdd(&sh[b], 1u);
@@ -553,27 +638,29 @@ static cudaError_t launch_adaptive_mode(cudaStream_t st, int device, StateCols P
                                         const unsigned* perm, unsigned long long* queue,
                                         unsigned long long* totals, unsigned* att, unsigned* acc,
                                         int* status) {
-  const size_t smem = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
+  const size_t tbytes = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
+  const size_t smem = tbytes + (size_t)(NX_INT_THREADS / 32) * NX_FEED_BYTES_PER_WARP;
   int blocks = 0;
   cudaError_t e = persistent_grid(k_integrate_adaptive<MODE>, device, smem, &blocks);
   if (e != cudaSuccess) return e;
   const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
   if (need < blocks) blocks = (int)(need > 0 ? need : 1);
   k_integrate_adaptive<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, F, perm, queue,
-                                                                   totals, att, acc, status);
+                                                                   totals, att, acc, status,
+                                                                   (unsigned)tbytes);
   return cudaGetLastError();
 }
 
 cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long long n,
-                              const RunParams& p, unsigned char* bucket, unsigned* hist_cursor,
-                              unsigned* perm) {
+                              const RunParams& p, int model, unsigned char* bucket,
+                              unsigned* hist_cursor, unsigned* perm) {
   // hist_cursor: [0..31] histogram, [32..63] cursors
   cudaError_t e = cudaMemsetAsync(hist_cursor, 0, 2 * NX_NBUCKET * sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)sm_count(device) * 8;
   if (blocks > cap) blocks = cap;
-  k_cost_histogram<<<(unsigned)blocks, 256, 0, st>>>(P, n, p, bucket, hist_cursor);
+  k_cost_histogram<<<(unsigned)blocks, 256, 0, st>>>(P, n, p, model, bucket, hist_cursor);
   k_cost_offsets<<<1, 32, 0, st>>>(hist_cursor, hist_cursor + NX_NBUCKET);
   const long long sb = (n + 256 * NX_SCATTER_ITEMS - 1) / (256 * NX_SCATTER_ITEMS);
   k_cost_scatter<<<(unsigned)sb, 256, 0, st>>>(n, bucket, hist_cursor + NX_NBUCKET, perm);

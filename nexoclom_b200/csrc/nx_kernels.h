@@ -34,8 +34,8 @@ cudaError_t launch_init_state(cudaStream_t st, StateCols P, X0Cols X, long long 
                               const InterpTable& speed, uint64_t seed, uint64_t first_id);
 cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v);
 cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long long n,
-                              const RunParams& p, unsigned char* bucket, unsigned* hist_cursor,
-                              unsigned* perm);
+                              const RunParams& p, int model, unsigned char* bucket,
+                              unsigned* hist_cursor, unsigned* perm);
 cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
                                       const RunParams& p, const InterpTable& T,
                                       const FastTable& F, const unsigned* perm,

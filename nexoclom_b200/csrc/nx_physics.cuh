@@ -42,6 +42,7 @@ struct RunParams {
   double stick_A[3];      // T-dependent sticking  A0*exp(A1*T)+A2
   double surf_t1;         // 600 + 125 (cos(taa) - 1)/2  (surface_temperature.py:9)
   double planet_radius_km;
+  double radpres_amax;    // max |a_rad| [R_p/s^2]; only orders the K2 work queue
   int32_t gravity;
   int32_t radpres;
   int32_t loss_mode;      // LossMode
@@ -157,17 +158,23 @@ struct FastTable {
   const InterpRec* rec;
   const unsigned short* bucket;
   int nrec, nbucket;
-  double blo, binvw;
+  double blo, binvw, boff;
 };
 
 // np.interp through the record table: bucket -> record, then (rarely) walk to the
 // neighbouring record; clamp records make the ends branch-free.
 NX_HD double interp_fast(const FastTable& T, double v) {
-  int b = (v == v) ? (int)((v - T.blo) * T.binvw) : 0;
+#if defined(__CUDA_ARCH__)
+  int b = __double2int_rz(fma(v, T.binvw, T.boff));    // boff = -blo*binvw; NaN -> 0
+  b = max(0, min(b, T.nbucket - 1));
+  int idx = __ldg(T.bucket + b);                       // 64 KB index, L1-resident
+#else
+  int b = (v == v) ? (int)fmax(fmin((v - T.blo) * T.binvw, 2e9), -2e9) : 0;
   b = b < 0 ? 0 : (b >= T.nbucket ? T.nbucket - 1 : b);
   int idx = T.bucket[b];
+#endif
   InterpRec r = T.rec[idx];
-  if (!(v >= r.lo && v < r.hi)) {              // crowded bucket / clamp: rare walk
+  if (!(v >= r.lo && v < r.hi)) {              // bucket holding a node / clamp: rare walk
     while (v >= r.hi && idx < T.nrec - 1) r = T.rec[++idx];
     while (v < r.lo && idx > 0) r = T.rec[--idx];
   }

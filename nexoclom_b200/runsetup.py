@@ -75,6 +75,8 @@ class RunSetup:
         taa = float(value_of(inputs.geometry.taa))
         p.surf_t1 = 600. + 125 * (np.cos(taa) - 1) / 2.
         p.planet_radius_km = self.radius_km
+        p.radpres_amax = (float(np.max(np.abs(self.radpres_a)))
+                          if self.radpres_a is not None else 0.0)
         p.strict_math = int(bool(strict_math))
         self.params = p
 

@@ -37,9 +37,9 @@ extern "C" int hc_integrate_adaptive(long n, double* X /* n x 8 row-major */, do
   HostFastTable hf; FastTable F{};
   if (nrp > 0) {
     hi = make_interp(rpv, rpa, nrp); T = view(hi);
-    hf = make_fast_table(rpv, rpa, nrp);
+    hf = make_fast_table(rpv, rpa, nrp, 32768);
     F.rec = reinterpret_cast<const InterpRec*>(hf.rec.data()); F.bucket = hf.bucket.data();
-    F.nrec = hf.nrec; F.nbucket = hf.nbucket; F.blo = hf.blo; F.binvw = hf.binvw;
+    F.nrec = hf.nrec; F.nbucket = hf.nbucket; F.blo = hf.blo; F.binvw = hf.binvw; F.boff = -hf.blo * hf.binvw;
   }
   int status = 0;
   for (long i = 0; i < n; ++i) {
