@@ -57,6 +57,8 @@ struct nx_ctx {
   unsigned char* cost = nullptr;     // cost bucket per packet
   unsigned* hist = nullptr;          // 32 histogram + 32 cursors
   int order_packets = 1;
+  int los_mode = 0;                  // 0 auto, 1 brute force, 2 cell grid
+  LosGridWork losw;
   unsigned long long* scalars = nullptr;   // [0] queue, [1] total attempted, [2] total accepted
   int* status = nullptr;
   int status_host = 0;
@@ -101,6 +103,37 @@ static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const doubl
   d.fast.nrec = hf.nrec; d.fast.nbucket = hf.nbucket; d.fast.blo = hf.blo; d.fast.binvw = hf.binvw; d.fast.boff = -hf.blo * hf.binvw;
   d.view.x = d.x; d.view.f = d.f; d.view.slope = d.slope; d.view.bucket = d.bucket;
   d.view.n = n; d.view.nbucket = h.nbucket; d.view.blo = h.blo; d.view.binvw = h.binvw;
+  return 0;
+}
+
+static void free_los_work(LosGridWork& w) {
+  cudaFree(w.sorted.x); cudaFree(w.sorted.y); cudaFree(w.sorted.z); cudaFree(w.sorted.vy);
+  cudaFree(w.sorted.frac); cudaFree(w.sorted.idx); cudaFree(w.cell_id); cudaFree(w.count);
+  cudaFree(w.start); cudaFree(w.block_sum); cudaFree(w.total); cudaFree(w.extent_bits);
+  const int G = w.G;
+  w = LosGridWork{};
+  w.G = G;
+}
+
+static int alloc_los_work(nx_ctx* ctx, long long n) {
+  LosGridWork& w = ctx->losw;
+  if (w.cap >= n && w.sorted.x) return 0;
+  free_los_work(w);
+  const size_t ncell = (size_t)w.G * w.G * w.G;
+  const size_t nn = (size_t)n;
+  CK(cudaMalloc(&w.sorted.x, nn * sizeof(double)));
+  CK(cudaMalloc(&w.sorted.y, nn * sizeof(double)));
+  CK(cudaMalloc(&w.sorted.z, nn * sizeof(double)));
+  CK(cudaMalloc(&w.sorted.vy, nn * sizeof(double)));
+  CK(cudaMalloc(&w.sorted.frac, nn * sizeof(double)));
+  CK(cudaMalloc(&w.sorted.idx, nn * sizeof(unsigned)));
+  CK(cudaMalloc(&w.cell_id, nn * sizeof(unsigned)));
+  CK(cudaMalloc(&w.count, ncell * sizeof(unsigned)));
+  CK(cudaMalloc(&w.start, (ncell + 1) * sizeof(unsigned)));
+  CK(cudaMalloc(&w.block_sum, ((ncell + 4095) / 4096 + 1) * sizeof(unsigned)));
+  CK(cudaMalloc(&w.total, sizeof(unsigned)));
+  CK(cudaMalloc(&w.extent_bits, sizeof(unsigned long long)));
+  w.cap = n;
   return 0;
 }
 
@@ -162,6 +195,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   cudaFree(ctx->srcmap);
   cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
   cudaFree(ctx->perm); cudaFree(ctx->cost); cudaFree(ctx->hist);
+  free_los_work(ctx->losw);
   cudaFree(ctx->scalars); cudaFree(ctx->status);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -186,6 +220,8 @@ int nx_ctx_sync(nx_ctx* ctx) {
 
 int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   if (name && std::strcmp(name, "order_packets") == 0) { ctx->order_packets = value; return 0; }
+  if (name && std::strcmp(name, "los_mode") == 0) { ctx->los_mode = value; return 0; }
+  if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G = value; ctx->losw.cap = 0; return 0; }
   ctx->err = std::string("unknown option ") + (name ? name : "(null)");
   return -1;
 }
@@ -553,14 +589,29 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
   CK(cudaMemcpyAsync(d_nball, nball.data(), nlos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_ladder, ladder.data(), ladder.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_wid2, wid2.data(), wid2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  int r = begin_timed(ctx);
+  // candidate generation: brute force for small problems, cell grid otherwise
+  const bool use_grid = ctx->los_mode == 2 ||
+                        (ctx->los_mode == 0 && (double)n * (double)nlos > 2e9 && n < (1LL << 32));
+  int nlaunch = 1;
+  int r = 0;
+  if (use_grid) r = alloc_los_work(ctx, n);
+  if (r == 0) r = begin_timed(ctx);
   if (r == 0) {
-    cudaError_t e = launch_los_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, nlos,
-                                          los_dev, dist_dev, d_nball, d_ladder, d_wid2, lp, lc,
-                                          ctx->gtables, rad_dev, np_dev, inc_dev);
+    cudaError_t e;
+    if (use_grid) {
+      e = launch_los_grid_build(ctx->stream, ctx->device, state_cols(ctx), n, lp, ctx->losw);
+      if (e == cudaSuccess)
+        e = launch_los_grid(ctx->stream, ctx->losw, nlos, los_dev, dist_dev, d_nball, d_ladder,
+                            d_wid2, lp, lc, ctx->gtables, rad_dev, np_dev, inc_dev);
+      nlaunch = 8;
+    } else {
+      e = launch_los_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, nlos, los_dev,
+                                dist_dev, d_nball, d_ladder, d_wid2, lp, lc, ctx->gtables,
+                                rad_dev, np_dev, inc_dev);
+    }
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
   }
-  if (r == 0) r = end_timed(ctx, 1);
+  if (r == 0) r = end_timed(ctx, nlaunch);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (r == 0 && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
   cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2);

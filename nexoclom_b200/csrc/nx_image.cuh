@@ -51,7 +51,9 @@ NX_HD int hist_bin(double v, int n, double lo, double hi, double step) {
 // (ModelResult.py:152-157: gg = 0 + g_1 + g_2 ...).
 NX_HD double gvalue_sum(const GTables& G, double rv) {
   double gg = 0.0;
-  for (int i = 0; i < G.n; ++i) gg = add_rn(gg, interp(G.t[i], rv));
+#pragma unroll
+  for (int i = 0; i < NX_MAX_GTABLES; ++i)
+    if (i < G.n) gg = add_rn(gg, interp(G.t[i], rv));
   return gg;
 }
 

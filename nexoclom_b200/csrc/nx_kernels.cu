@@ -465,6 +465,22 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Spli
 // loads, two packets per thread per iteration) and scatters with f64 / u64
 // atomics into the L2-resident image (800x800: 5 MB + 5 MB).
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void image_one(const ImageParams& ip, const GTables& G, double step_x,
+                                          double step_z, double x, double y, double z, double v,
+                                          double f, double* image, unsigned long long* counts) {
+  if (ip.skip_dead && !(f > 0.0)) return;
+  double w;
+  const int pix = image_packet(ip, G, step_x, step_z, x, y, z, v, f, w);
+  if (pix >= 0) {
+    if (w != 0.0) atomicAdd(&image[pix], w);
+    atomicAdd(&counts[pix], 1ull);
+  }
+}
+
+// Four packets per thread per iteration: the frac column is read first (two
+// 16-byte loads); the other four columns (8 more 16-byte loads, all issued before
+// any use) are only fetched for pairs that contain a live packet when skip_dead
+// is set (compress=True semantics: frac == 0 rows do not exist for the reference).
 __global__ void __launch_bounds__(256)
 k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
                    double* __restrict__ image, unsigned long long* __restrict__ counts) {
@@ -472,39 +488,40 @@ k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
   GTables G;
   G.n = Gg.n;
   size_t off = 0;
-  for (int t = 0; t < Gg.n; ++t) off += stage_table(Gg.t[t], G.t[t], smem_raw + off);
+#pragma unroll
+  for (int t = 0; t < NX_MAX_GTABLES; ++t)
+    if (t < Gg.n) off += stage_table(Gg.t[t], G.t[t], smem_raw + off);
   __syncthreads();
   const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
-  const long long npair = n >> 1;
+  const long long nquad = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const double2* __restrict__ X2 = reinterpret_cast<const double2*>(P.c[1]);
   const double2* __restrict__ Y2 = reinterpret_cast<const double2*>(P.c[2]);
   const double2* __restrict__ Z2 = reinterpret_cast<const double2*>(P.c[3]);
   const double2* __restrict__ V2 = reinterpret_cast<const double2*>(P.c[5]);
   const double2* __restrict__ F2 = reinterpret_cast<const double2*>(P.c[7]);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
-    const double2 x = __ldcs(X2 + i), y = __ldcs(Y2 + i), z = __ldcs(Z2 + i);
-    const double2 v = __ldcs(V2 + i), f = __ldcs(F2 + i);
-    double w;
-    if (!(ip.skip_dead && !(f.x > 0.0))) {
-      const int pix = image_packet(ip, G, step_x, step_z, x.x, y.x, z.x, v.x, f.x, w);
-      if (pix >= 0) { if (w != 0.0) atomicAdd(&image[pix], w); atomicAdd(&counts[pix], 1ull); }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquad; i += stride) {
+    const long long a = 2 * i, b = 2 * i + 1;
+    const double2 fa = __ldcs(F2 + a), fb = __ldcs(F2 + b);
+    const bool la = !ip.skip_dead || fa.x > 0.0 || fa.y > 0.0;
+    const bool lb = !ip.skip_dead || fb.x > 0.0 || fb.y > 0.0;
+    double2 xa, ya, za, va, xb, yb, zb, vb;
+    if (la) { xa = __ldcs(X2 + a); ya = __ldcs(Y2 + a); za = __ldcs(Z2 + a); va = __ldcs(V2 + a); }
+    if (lb) { xb = __ldcs(X2 + b); yb = __ldcs(Y2 + b); zb = __ldcs(Z2 + b); vb = __ldcs(V2 + b); }
+    if (la) {
+      image_one(ip, G, step_x, step_z, xa.x, ya.x, za.x, va.x, fa.x, image, counts);
+      image_one(ip, G, step_x, step_z, xa.y, ya.y, za.y, va.y, fa.y, image, counts);
     }
-    if (!(ip.skip_dead && !(f.y > 0.0))) {
-      const int pix = image_packet(ip, G, step_x, step_z, x.y, y.y, z.y, v.y, f.y, w);
-      if (pix >= 0) { if (w != 0.0) atomicAdd(&image[pix], w); atomicAdd(&counts[pix], 1ull); }
-    }
-  }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const long long i = n - 1;
-    const double f = P.c[7][i];
-    if (!(ip.skip_dead && !(f > 0.0))) {
-      double w;
-      const int pix = image_packet(ip, G, step_x, step_z, P.c[1][i], P.c[2][i], P.c[3][i],
-                                   P.c[5][i], f, w);
-      if (pix >= 0) { if (w != 0.0) atomicAdd(&image[pix], w); atomicAdd(&counts[pix], 1ull); }
+    if (lb) {
+      image_one(ip, G, step_x, step_z, xb.x, yb.x, zb.x, vb.x, fb.x, image, counts);
+      image_one(ip, G, step_x, step_z, xb.y, yb.y, zb.y, vb.y, fb.y, image, counts);
     }
   }
+  // tail (n not a multiple of 4)
+  const long long i = (nquad << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    image_one(ip, G, step_x, step_z, P.c[1][i], P.c[2][i], P.c[3][i], P.c[5][i], P.c[7][i],
+              image, counts);
 }
 
 // ---------------------------------------------------------------------------
@@ -734,7 +751,7 @@ cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, lo
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_image_accumulate, 256, smem);
   if (per_sm < 1) per_sm = 1;
   long long blocks = (long long)per_sm * sm_count(device);
-  const long long need = ((n >> 1) + 255) / 256;
+  const long long need = ((n >> 2) + 255) / 256;
   if (need < blocks) blocks = need > 0 ? need : 1;
   k_image_accumulate<<<(unsigned)blocks, 256, smem, st>>>(P, n, ip, G, image, counts);
   return cudaGetLastError();

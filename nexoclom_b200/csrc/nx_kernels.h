@@ -27,6 +27,26 @@ struct LosConsts {
   int nladder;
 };
 
+// ---- K5 spatial culling (nx_los_grid.cu) ----
+struct LosGrid { int G; double half, cell, inv_cell; };
+struct LosSorted { double *x, *y, *z, *vy, *frac; unsigned* idx; };
+struct LosGridWork {
+  int G = 128;
+  LosGrid grid{};
+  LosSorted sorted{};
+  unsigned *cell_id = nullptr, *count = nullptr, *start = nullptr, *block_sum = nullptr,
+           *total = nullptr;
+  unsigned long long* extent_bits = nullptr;
+  long long cap = 0;
+};
+cudaError_t launch_los_grid_build(cudaStream_t st, int device, StateCols P, long long n,
+                                  const LosParams& lp, LosGridWork& w);
+cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlos,
+                            const double* los, const double* dist_plan, const int* nball,
+                            const double* ladder, const double* wid2, const LosParams& lp,
+                            const LosConsts& lc, const GTables& G, double* radiance,
+                            unsigned long long* npack, unsigned char* included);
+
 size_t table_smem_bytes(const InterpTable& g);
 
 cudaError_t launch_init_state(cudaStream_t st, StateCols P, X0Cols X, long long n,

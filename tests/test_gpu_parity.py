@@ -234,7 +234,8 @@ def _synthetic_los(nlos, seed=1):
     return np.concatenate([x_sc, bore], axis=1)
 
 
-def test_los_vs_oracle(engine):
+@pytest.mark.parametrize('los_mode', [1, 2])
+def test_los_vs_oracle(engine, los_mode):
     setup = RunSetup(workload('Na.maxwellian.radpres.input'))
     setup.upload(engine)
     gt = setup.gtables([5891, 5897])
@@ -257,7 +258,11 @@ def test_los_vs_oracle(engine):
     lp = LosParams()
     lp.dphi, lp.outeredge, lp.vrplanet, lp.rp_cm = dphi, 25., setup.vrplanet, setup.radius_km * 1e5
     lp.quantity = 1
-    rad_g, np_g, inc_g = engine.los_accumulate(los.T.copy(), dist, lp)
+    engine.set_option('los_mode', los_mode)        # 1 brute force, 2 cell-grid culling
+    try:
+        rad_g, np_g, inc_g = engine.los_accumulate(los.T.copy(), dist, lp)
+    finally:
+        engine.set_option('los_mode', 0)
     assert np_o.sum() > 1000
     assert np.array_equal(np_g, np_o)                   # bit-exact hit counts
     assert np.array_equal(inc_g, inc_o)
