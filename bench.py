@@ -313,6 +313,50 @@ def run_gpu(args):
         e2e_ms, e2e_steps = float(tm[0]), float(ts[1])
     e2e_value = e2e_steps / (e2e_ms * 1e-3)
 
+    # ---- line-of-sight sweep over the resident final state (not part of `value`) ----
+    los_info = None
+    if not args.no_los:
+        from nexoclom_b200._lib import LosParams
+        nlos = args.los
+        g = torch.Generator(device='cpu').manual_seed(1)
+        th = torch.rand(nlos, generator=g, dtype=torch.float64) * 2 * np.pi
+        rr = 1.1 + 4.9 * torch.rand(nlos, generator=g, dtype=torch.float64)
+        x_sc = torch.stack([0.3 * rr * torch.cos(th), 0.2 * rr * torch.cos(th) - 0.5,
+                            rr * torch.sin(th)], dim=0)
+        x_sc *= torch.clamp(x_sc.norm(dim=0), min=1.1) / x_sc.norm(dim=0)
+        tgt = torch.randn(3, nlos, generator=g, dtype=torch.float64)
+        tgt *= (1 + 3 * torch.rand(nlos, generator=g, dtype=torch.float64)) / tgt.norm(dim=0)
+        bore = tgt - x_sc
+        bore /= bore.norm(dim=0)
+        dist = x_sc.norm(dim=0)
+        ang = torch.arccos(-(x_sc * bore).sum(dim=0) / dist)
+        dist = torch.where(ang > torch.arcsin(1. / dist), torch.full_like(dist, 1e30), dist)
+        los_dev = torch.cat([x_sc, bore], dim=0).contiguous().cuda()
+        dist_dev = dist.contiguous().cuda()
+        rad_dev = torch.zeros(nlos, dtype=torch.float64, device='cuda')
+        npk_dev = torch.zeros(nlos, dtype=torch.int64, device='cuda')
+        inc_dev = torch.zeros(n, dtype=torch.uint8, device='cuda')
+        lp = LosParams()
+        lp.dphi, lp.outeredge = float(np.radians(1.0)), 25.0
+        lp.vrplanet, lp.rp_cm = setup.vrplanet, setup.radius_km * 1e5
+        lp.quantity, lp.round_f32, lp.skip_dead = 1, 1, 0
+        los_ms = []
+        for it in range(3):
+            rad_dev.zero_(); npk_dev.zero_(); inc_dev.zero_()
+            eng.los_accumulate_dev(nlos, los_dev.data_ptr(), dist_dev.data_ptr(), lp,
+                                   rad_dev.data_ptr(), npk_dev.data_ptr(), inc_dev.data_ptr(), n)
+            if world > 1:
+                dist_mod = dist  # noqa: F841
+                torch.distributed.all_reduce(rad_dev)
+                torch.distributed.all_reduce(npk_dev)
+            torch.cuda.synchronize()
+            los_ms.append(eng.last_kernel_ms())
+        los_info = {'lines_of_sight': nlos, 'packets_per_gpu': n, 'dphi_deg': 1.0,
+                    'ms': float(min(los_ms)), 'ms_per_1e8_packets': float(min(los_ms)) * 1e8 / n,
+                    'hits': int(npk_dev.sum().item()),
+                    'note': 'K5 cell-grid path over all resident packets (skip_dead=0), '
+                            'grid build included'}
+
     if rank == 0:
         fp64_peak = eng.measure_fp64_peak()
         peaks, peak_kind = measured_peaks()
@@ -343,6 +387,7 @@ def run_gpu(args):
                 'image_ms_per_1e8_packets': k4 * 1e8 / n,
                 'image_hbm_gbs': 40.0 * n / (k4 * 1e-3) / 1e9,
                 'image_hbm_frac_of_' + peak_kind: 40.0 * n / (k4 * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                'los_sweep': los_info,
             },
             'roofline': {
                 'bound': 'fp64', 'kernel': 'k_integrate_adaptive', 'achieved': achieved,
@@ -384,6 +429,8 @@ def main():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-los', action='store_true')
+    ap.add_argument('--los', type=int, default=100_000, help='lines of sight of the K5 sweep')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

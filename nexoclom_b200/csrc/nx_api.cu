@@ -470,7 +470,8 @@ int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t firs
   if (n > 0) {
     if ((r = begin_timed(ctx))) return r;
     CK(launch_integrate_constant(ctx->stream, ctx->device, state_cols(ctx), n, p,
-                                 ctx->radpres.view, ctx->spline, seed, first_id, nsteps, ip,
+                                 ctx->radpres.view, ctx->radpres.fast, ctx->spline, seed,
+                                 first_id, nsteps, ip,
                                  ctx->gtables, (double*)image_dev,
                                  (unsigned long long*)counts_dev, traj, ctx->scalars,
                                  ctx->scalars + 1, ctx->status));

@@ -156,15 +156,13 @@ NX_HD double exp_step(double d) {
   return exp(d);
 }
 
-// One attempted adaptive step, fast arithmetic.  Same contract as
-// adaptive_attempt<>(): s[0..7] = time,x,y,z,vx,vy,vz,frac; returns AttemptFlags.
-template <int GR, int RP, int LOSS>
-NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* s,
-                                double& step) {
-  const double res = p.resolution;
-  const double resv = 0.1 * res;
-  const double h = fmin(s[0], step);
-
+// The six Dormand-Prince stages in Nystrom form.  Inputs s[0..7], step h.
+// Outputs: nx[6] = new position / velocity, fn = new frac; if ERR also the error
+// vector d[6] = |h sum_{i<6} bd_i k_i| (stage 7 not included: quirk Q1) and
+// delta_f for the log-frac component.
+template <int GR, int RP, int LOSS, bool ERR>
+NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, double h,
+                       double* nx, double& fn, double* d, double& delta_f) {
   double K[6][3];                      // K_j = h * accel_j  (the only per-stage storage)
   const double hv0 = h * s[4], hv1 = h * s[5], hv2 = h * s[6];
   const double hGM = h * p.GM;
@@ -208,6 +206,7 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
     }
     px = ap0; py = ap1; pz = ap2; vx = av0; vy = av1; vz = av2;
   }
+  nx[0] = px; nx[1] = py; nx[2] = pz; nx[3] = vx; nx[4] = vy; nx[5] = vz;
 
   // fractional content: dlogf = -h sum b_i rate_i ; error term h sum bd_i rate_i
   double sb = 0.0, sbd = 0.0;
@@ -220,15 +219,12 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
       if (i == 1) continue;
       const double r = (litmask >> i) & 1u ? p.loss_rate : 0.0;
       sb = fma(dp_a(6, i), r, sb);
-      sbd = fma(dp_bd(i), r, sbd);
+      if (ERR) sbd = fma(dp_bd(i), r, sbd);
     }
   }
-  const double fn = (LOSS == LOSS_NONE) ? s[7] : s[7] * exp_step(-(h * sb));
-  const double delta_f = fabs(h * sbd);
-
-  // error vector |h sum_{i<6} bd_i k_i|  (stage 7 not included: quirk Q1)
-  double d[6];
-  {
+  fn = (LOSS == LOSS_NONE) ? s[7] : s[7] * exp_step(-(h * sb));
+  if (ERR) {
+    delta_f = fabs(h * sbd);
     const double bds = dpc_bds();
     double ep0 = bds * hv0, ep1 = bds * hv1, ep2 = bds * hv2;
     double ev0 = dp_bd(0) * K[0][0], ev1 = dp_bd(0) * K[0][1], ev2 = dp_bd(0) * K[0][2];
@@ -245,7 +241,19 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
     d[0] = fabs(ep0); d[1] = fabs(ep1); d[2] = fabs(ep2);
     d[3] = fabs(ev0); d[4] = fabs(ev1); d[5] = fabs(ev2);
   }
-  const double nx[6] = {px, py, pz, vx, vy, vz};
+}
+
+// One attempted adaptive step, fast arithmetic.  Same contract as
+// adaptive_attempt<>(): s[0..7] = time,x,y,z,vx,vy,vz,frac; returns AttemptFlags.
+template <int GR, int RP, int LOSS>
+NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* s,
+                                double& step) {
+  const double res = p.resolution;
+  const double resv = 0.1 * res;
+  const double h = fmin(s[0], step);
+  double nx[6], d[6], fn, delta_f;
+  fast_stages<GR, RP, LOSS, true>(p, T, s, h, nx, fn, d, delta_f);
+  const double px = nx[0], py = nx[1], pz = nx[2], vx = nx[3], vy = nx[4], vz = nx[5];
   // accept  <=>  every delta_j < scale_j  (== max_j fl(delta_j/scale_j) < 1).  The
   // quotient itself (Newton reciprocal, ~2^-40) only sizes the next step after a
   // reject and screens the "no error" case (Q4); it is formed for every lane so

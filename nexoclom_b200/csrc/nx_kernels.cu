@@ -376,23 +376,29 @@ __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& 
   }
 }
 
-template <bool STRICT>
-__global__ void __launch_bounds__(NX_INT_THREADS)
-k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Spline2D S,
-                     uint64_t seed, uint64_t first_id, int nsteps,
+// MODE as in k_integrate_adaptive: -1 strict, else fast with MODE = GR*8 + RP*4 + LOSS.
+template <int MODE>
+__global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
+k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, FastTable Fg,
+                     Spline2D S, uint64_t seed, uint64_t first_id, int nsteps,
                      ImageParams ip, GTables G, double* image, unsigned long long* counts,
                      double* traj,
                      unsigned long long* __restrict__ queue,
-                     unsigned long long* __restrict__ totals, int* __restrict__ status) {
+                     unsigned long long* __restrict__ totals, int* __restrict__ status,
+                     unsigned table_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   InterpTable T;
-  stage_table(Tg, T, smem_raw);
+  FastTable F;
+  if (MODE < 0) stage_table(Tg, T, smem_raw);
+  else stage_fast_table(Fg, F, smem_raw);
+  PacketFeeder feed;
+  feed.init(smem_raw + table_bytes, &P, nullptr, queue, n);
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u;
   const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
 
   bool have = false, drained = false;
-  long long idx = 0;
+  unsigned idx = 0;
   double s[8];
   double curtime = 0.0;
   int ct = 0;
@@ -400,29 +406,28 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Spli
   int st = 0;
 
   for (;;) {
-    const unsigned need = __ballot_sync(FULL_MASK, !have);
-    if (need && !drained) {
-      const int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(need));
-      base = __shfl_sync(FULL_MASK, base, leader);
-      if (!have) {
-        const long long i = (long long)base + __popc(need & ((1u << lane) - 1u));
-        if (i < n) {
-          idx = i;
+    unsigned need = __ballot_sync(FULL_MASK, !have);
+    while (need && !drained) {
+      if (feed.pos == feed.cnt && !feed.advance()) { drained = true; break; }
+      const int take = min(__popc(need), feed.cnt - feed.pos);
+      const int rank = __popc(need & ((1u << lane) - 1u));
+      if (!have && rank < take) {
+        const int slot = feed.pos + rank;
+        const double* v = feed.vals + (size_t)feed.buf * NX_FEED_COLS * 32 + slot;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s[k] = P.c[k][i];
-          curtime = p.endtime; ct = 1;
-          have = s[7] > 0.0;
-          if (traj) {
+        for (int k = 0; k < 8; ++k) s[k] = v[k * 32];
+        idx = feed.ids[feed.buf * 32 + slot];
+        curtime = p.endtime; ct = 1;
+        have = s[7] > 0.0;
+        if (traj) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) traj[((size_t)i * 8 + k) * nsteps] = s[k];
-          }
-          if (image) image_add(ip, G, step_x, step_z, s, image, counts);
-          if (!(curtime > 0.0) || ct >= nsteps) have = false;
+          for (int k = 0; k < 8; ++k) traj[((size_t)idx * 8 + k) * nsteps] = s[k];
         }
+        if (image) image_add(ip, G, step_x, step_z, s, image, counts);
+        if (!(curtime > 0.0) || ct >= nsteps) have = false;
       }
-      drained = ((long long)base + __popc(need) >= n);
+      feed.pos += take;
+      need = __ballot_sync(FULL_MASK, !have);
     }
     if (!__any_sync(FULL_MASK, have)) {
       if (drained) break;
@@ -433,7 +438,12 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Spli
 #pragma unroll
       for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
       if (bad) st |= 32;
-      bool live = constant_step<STRICT>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+      bool live;
+      if (MODE < 0)
+        live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+      else
+        live = constant_step_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(
+            p, F, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
       ++tot;
       if (traj) {
 #pragma unroll
@@ -444,7 +454,7 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Spli
       curtime -= p.step_size;
       if (!live || !(curtime > 0.0) || ct >= nsteps) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) P.c[k][idx] = s[k];
+        for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
         have = false;
       }
     }
@@ -710,31 +720,56 @@ cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, 
 #undef NX_ARGS
 }
 
+template <int MODE>
+static cudaError_t launch_constant_mode(cudaStream_t st, int device, StateCols P, long long n,
+                                        const RunParams& p, const InterpTable& T,
+                                        const FastTable& F, const Spline2D& S, uint64_t seed,
+                                        uint64_t first_id, int nsteps, const ImageParams& ip,
+                                        const GTables& G, double* image,
+                                        unsigned long long* counts, double* traj,
+                                        unsigned long long* queue, unsigned long long* totals,
+                                        int* status) {
+  const size_t tbytes = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
+  const size_t smem = tbytes + (size_t)(NX_INT_THREADS / 32) * NX_FEED_BYTES_PER_WARP;
+  int blocks = 0;
+  cudaError_t e = persistent_grid(k_integrate_constant<MODE>, device, smem, &blocks);
+  if (e != cudaSuccess) return e;
+  const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
+  if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+  k_integrate_constant<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(
+      P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, queue, totals, status,
+      (unsigned)tbytes);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,
                                       const RunParams& p, const InterpTable& T,
-                                      const Spline2D& S, uint64_t seed, uint64_t first_id,
-                                      int nsteps, const ImageParams& ip, const GTables& G,
-                                      double* image, unsigned long long* counts, double* traj,
+                                      const FastTable& F, const Spline2D& S, uint64_t seed,
+                                      uint64_t first_id, int nsteps, const ImageParams& ip,
+                                      const GTables& G, double* image,
+                                      unsigned long long* counts, double* traj,
                                       unsigned long long* queue, unsigned long long* totals,
                                       int* status) {
-  const size_t smem = table_smem_bytes(T);
-  int blocks = 0;
-  cudaError_t e;
-  long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
-  if (p.strict_math) {
-    e = persistent_grid(k_integrate_constant<true>, device, smem, &blocks);
-    if (e != cudaSuccess) return e;
-    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-    k_integrate_constant<true><<<blocks, NX_INT_THREADS, smem, st>>>(
-        P, n, p, T, S, seed, first_id, nsteps, ip, G, image, counts, traj, queue, totals, status);
-  } else {
-    e = persistent_grid(k_integrate_constant<false>, device, smem, &blocks);
-    if (e != cudaSuccess) return e;
-    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-    k_integrate_constant<false><<<blocks, NX_INT_THREADS, smem, st>>>(
-        P, n, p, T, S, seed, first_id, nsteps, ip, G, image, counts, traj, queue, totals, status);
+#define NX_ARGS st, device, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, \
+                queue, totals, status
+  if (p.strict_math) return launch_constant_mode<-1>(NX_ARGS);
+  const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
+  switch (mode) {
+    case 0: return launch_constant_mode<0>(NX_ARGS);
+    case 1: return launch_constant_mode<1>(NX_ARGS);
+    case 2: return launch_constant_mode<2>(NX_ARGS);
+    case 4: return launch_constant_mode<4>(NX_ARGS);
+    case 5: return launch_constant_mode<5>(NX_ARGS);
+    case 6: return launch_constant_mode<6>(NX_ARGS);
+    case 8: return launch_constant_mode<8>(NX_ARGS);
+    case 9: return launch_constant_mode<9>(NX_ARGS);
+    case 10: return launch_constant_mode<10>(NX_ARGS);
+    case 12: return launch_constant_mode<12>(NX_ARGS);
+    case 13: return launch_constant_mode<13>(NX_ARGS);
+    case 14: return launch_constant_mode<14>(NX_ARGS);
+    default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
+#undef NX_ARGS
 }
 
 cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, long long n,

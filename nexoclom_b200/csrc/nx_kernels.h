@@ -63,6 +63,7 @@ cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, 
                                       unsigned* att, unsigned* acc, int* status);
 cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,
                                       const RunParams& p, const InterpTable& T,
+                                      const FastTable& F,
                                       const Spline2D& S, uint64_t seed, uint64_t first_id,
                                       int nsteps, const ImageParams& ip, const GTables& G,
                                       double* image, unsigned long long* counts, double* traj,

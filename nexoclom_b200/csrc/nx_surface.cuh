@@ -3,6 +3,7 @@
 // NX_HD like nx_physics.cuh: inlined into kernels, and compiled by g++ for
 // tests/_hostcheck.
 #pragma once
+#include "nx_fast.cuh"
 #include "nx_physics.cuh"
 
 namespace nx {
@@ -63,12 +64,22 @@ NX_HD double surface_temperature(double t1, double lon, double lat) {
 // (what scipy RectBivariateSpline.ev runs; reference SurfaceInteraction.py:56-58)
 // ---------------------------------------------------------------------------
 NX_HD int spl_interval(const double* t, int nt, double& arg) {
+  // FITPACK fpbisp: l = k1; while (arg >= t(l+1) && l != nk1) l++  (1-based).
+  // The interior knots of an interpolating spline on a linspace grid are uniform,
+  // so l is first guessed by division and then corrected with the same
+  // comparisons -- identical result, no 200-iteration scan.
   const int k1 = 4, nk1 = nt - k1;          // 1-based: tb=t(k1), te=t(nk1+1)
   const double tb = t[k1 - 1], te = t[nk1];
   if (arg < tb) arg = tb;
   if (arg > te) arg = te;
-  int l = k1;                                // 1-based interval index
-  while (!(arg < t[l]) && l != nk1) ++l;     // t(l+1) is t[l] 0-based
+  int l = k1;
+  if (nk1 > k1) {
+    const double dtk = (te - tb) / (double)(nk1 - k1 + 1);   // mean knot spacing
+    int g = k1 + (int)((arg - tb) / dtk);
+    l = g < k1 ? k1 : (g > nk1 ? nk1 : g);
+    while (l > k1 && arg < t[l - 1]) --l;        // need t(l) <= arg
+    while (l != nk1 && !(arg < t[l])) ++l;       // and arg < t(l+1) unless l == nk1
+  }
   return l;
 }
 
@@ -194,11 +205,71 @@ NX_HD void bounce(const RunParams& p, const Spline2D& S, double* s, double r_hit
 // keeps its final position with frac = 0, time = 0 for THIS step; all later
 // rows of the reference's dense tensor are zero.
 // ---------------------------------------------------------------------------
-template <bool STRICT>
-NX_HD bool constant_step(const RunParams& p, const InterpTable& T, const Spline2D& S,
-                         double* s, uint64_t seed, uint64_t id, uint32_t stepidx) {
-  double nx[8];
-  dp_step<STRICT, false>(p, T, s, p.step_size, nx, nullptr);
+// Fast-arithmetic bounce: same physics as bounce(), with the trigonometry of the
+// reference folded analytically for a point on the unit sphere:
+//   sin(asin(u)) = u, cos(asin(u)) = sqrt(1-u^2);
+//   cos(lon) cos(lat) = -y  (x = sin lon cos lat, y = -cos lon cos lat, z = sin lat),
+//   dayside (lon <= pi/2 or lon >= 3pi/2)  <=>  y <= 0,
+// so no asin / atan2 / fmod is needed for the surface temperature.
+NX_HD void bounce_fast(const RunParams& p, const Spline2D& S, double* s, double r_hit,
+                       double u_alt, double u_az, double u_prob) {
+  double x = s[1], y = s[2], z = s[3];
+  const double vx = s[4], vy = s[5], vz = s[6];
+  const double a = fma(vz, vz, fma(vy, vy, vx * vx));
+  const double b = 2.0 * fma(z, vz, fma(y, vy, x * vx));
+  const double c = fma(z, z, fma(y, y, x * x)) - 1.0;
+  const double disc = sqrt(fma(b, b, -4.0 * a * c));
+  const double inv2a = 1.0 / (2.0 * a);
+  const double t = fmin((-b - disc) * inv2a, (-b + disc) * inv2a);
+  x = fma(vx, t, x); y = fma(vy, t, y); z = fma(vz, t, z);
+
+  double v_old2 = a + (2.0 * p.GM) * (1.0 / r_hit - 1.0);
+  if (v_old2 < 0.0) v_old2 = 0.0;
+
+  // cosine-law direction in the local frame (rad, east, north)
+  const double v_rad = u_alt, ca = sqrt(fmax(1.0 - u_alt * u_alt, 0.0));
+  double sa, cz;
+#if defined(__CUDA_ARCH__)
+  sincospi(2.0 * u_az, &sa, &cz);
+#else
+  sa = sin(NX_TWO_PI * u_az); cz = cos(NX_TWO_PI * u_az);
+#endif
+  const double v_tan0 = ca * cz, v_tan1 = ca * sa;
+  const double rxy2 = fma(y, y, x * x);
+  const double rinv = rsqrt_h(rxy2 + z * z), einv = rsqrt_h(rxy2);
+  const double nn = rsqrt_h(fma(rxy2, rxy2, (z * z) * rxy2));
+  const double nx_ = -z * x * nn, ny_ = -z * y * nn, nz_ = rxy2 * nn;
+  const double ex = y * einv, ey = -x * einv;
+  const double dx = fma(v_rad, x * rinv, fma(v_tan1, ex, v_tan0 * nx_));
+  const double dy = fma(v_rad, y * rinv, fma(v_tan1, ey, v_tan0 * ny_));
+  const double dz = fma(v_rad, z * rinv, v_tan0 * nz_);
+
+  const bool need_t = (p.accomfactor != 0.0) || (p.sticktype == STICK_TEMPERATURE);
+  double tsurf = 100.0;
+  if (need_t && y <= 0.0) tsurf = fma(p.surf_t1, sqrt(sqrt(fabs(y))), 100.0);
+  double v_new;
+  if (p.accomfactor == 0.0) {
+    v_new = sqrt(v_old2);
+  } else {
+    const double v_emit = spline2d_ev(S, tsurf, u_prob) / p.planet_radius_km;
+    const double af = p.accomfactor;
+    v_new = sqrt(fma(v_emit * v_emit, af, v_old2 * (1.0 - af)));
+  }
+  s[1] = x; s[2] = y; s[3] = z;
+  s[4] = dx * v_new; s[5] = dy * v_new; s[6] = dz * v_new;
+  if (p.sticktype == STICK_TEMPERATURE) {
+    double coef = fma(p.stick_A[0], exp(p.stick_A[1] * tsurf), p.stick_A[2]);
+    coef = fmin(fmax(coef, 0.0), 1.0);
+    s[7] *= (1.0 - coef);
+  } else if (p.stickcoef > 0.0) {
+    s[7] *= (1.0 - p.stickcoef);
+  }
+}
+
+// post-step handling shared by the strict and the fast constant step
+template <bool FAST>
+NX_HD bool constant_step_finish(const RunParams& p, const Spline2D& S, double* nx, double* s,
+                                uint64_t seed, uint64_t id, uint32_t stepidx) {
   const double r = sqrt(add_rn(add_rn(mul_rn(nx[1], nx[1]), mul_rn(nx[2], nx[2])), mul_rn(nx[3], nx[3])));
   if (sub_rn(r, 1.0) < 0.0) {
     if (p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0) {
@@ -207,7 +278,8 @@ NX_HD bool constant_step(const RunParams& p, const InterpTable& T, const Spline2
       double u_alt, u_az, u_prob, unused;
       uniform_pair(seed, id, STREAM_BOUNCE, 2u * stepidx, u_alt, u_az);
       uniform_pair(seed, id, STREAM_BOUNCE, 2u * stepidx + 1u, u_prob, unused);
-      bounce(p, S, nx, r, u_alt, u_az, u_prob);
+      if (FAST) bounce_fast(p, S, nx, r, u_alt, u_az, u_prob);
+      else bounce(p, S, nx, r, u_alt, u_az, u_prob);
     }
   }
   if (r > p.outeredge) nx[7] = 0.0;
@@ -216,6 +288,38 @@ NX_HD bool constant_step(const RunParams& p, const InterpTable& T, const Spline2
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = nx[k];
   return nx[7] > 0.0;
+}
+
+template <bool STRICT>
+NX_HD bool constant_step(const RunParams& p, const InterpTable& T, const Spline2D& S,
+                         double* s, uint64_t seed, uint64_t id, uint32_t stepidx) {
+  double nx[8];
+  dp_step<STRICT, false>(p, T, s, p.step_size, nx, nullptr);
+  return constant_step_finish<false>(p, S, nx, s, seed, id, stepidx);
+}
+
+// fast arithmetic (Nystrom stages of nx_fast.cuh), same decisions
+template <int GR, int RP, int LOSS>
+NX_HD bool constant_step_fast(const RunParams& p, const FastTable& T, const Spline2D& S,
+                              double* s, uint64_t seed, uint64_t id, uint32_t stepidx) {
+  double q[6], d[6], fn, df;
+  fast_stages<GR, RP, LOSS, false>(p, T, s, p.step_size, q, fn, d, df);
+  double nx[8] = {s[0] - p.step_size, q[0], q[1], q[2], q[3], q[4], q[5], fn};
+  return constant_step_finish<true>(p, S, nx, s, seed, id, stepidx);
+}
+
+NX_HD bool constant_step_fast_rt(const RunParams& p, const FastTable& T, const Spline2D& S,
+                                 double* s, uint64_t seed, uint64_t id, uint32_t stepidx) {
+  const int key = (p.gravity ? 4 : 0) | (p.radpres ? 2 : 0);
+#define NX_CASE(G, R)                                                                          \
+  if (key == ((G) * 4 + (R) * 2)) {                                                            \
+    if (p.loss_mode == LOSS_PHOTO) return constant_step_fast<G, R, LOSS_PHOTO>(p, T, S, s, seed, id, stepidx);       \
+    if (p.loss_mode == LOSS_LIFETIME) return constant_step_fast<G, R, LOSS_LIFETIME>(p, T, S, s, seed, id, stepidx); \
+    return constant_step_fast<G, R, LOSS_NONE>(p, T, S, s, seed, id, stepidx);                 \
+  }
+  NX_CASE(1, 1) NX_CASE(1, 0) NX_CASE(0, 1) NX_CASE(0, 0)
+#undef NX_CASE
+  return false;
 }
 
 }  // namespace nx

@@ -67,7 +67,13 @@ extern "C" int hc_integrate_constant(long n, double* X /* n x 8 */, double* traj
                                      const double* tx, int ntx, const double* ty, int nty,
                                      const double* c, int strict) {
   HostInterp hi; InterpTable T{};
-  if (nrp > 0) { hi = make_interp(rpv, rpa, nrp); T = view(hi); }
+  HostFastTable hf; FastTable F{};
+  if (nrp > 0) {
+    hi = make_interp(rpv, rpa, nrp); T = view(hi);
+    hf = make_fast_table(rpv, rpa, nrp, 32768);
+    F.rec = reinterpret_cast<const InterpRec*>(hf.rec.data()); F.bucket = hf.bucket.data();
+    F.nrec = hf.nrec; F.nbucket = hf.nbucket; F.blo = hf.blo; F.binvw = hf.binvw; F.boff = -hf.blo * hf.binvw;
+  }
   Spline2D S{tx, ty, c, ntx, nty};
   for (long i = 0; i < n; ++i) {
     double* s = X + 8 * i;
@@ -78,7 +84,7 @@ extern "C" int hc_integrate_constant(long n, double* X /* n x 8 */, double* traj
     while (curtime > 0 && ct < nsteps) {
       if (live) {
         live = strict ? constant_step<true>(*p, T, S, s, seed, first_id + i, (uint32_t)ct)
-                      : constant_step<false>(*p, T, S, s, seed, first_id + i, (uint32_t)ct);
+                      : constant_step_fast_rt(*p, F, S, s, seed, first_id + i, (uint32_t)ct);
         if (traj) for (int k = 0; k < 8; ++k) traj[(i * 8 + k) * (long)nsteps + ct] = s[k];
       }
       ++ct; curtime -= p->step_size;
