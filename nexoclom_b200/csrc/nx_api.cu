@@ -276,6 +276,7 @@ int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* 
     int r = upload_interp(ctx, ctx->gtab[t], v + off, g + off, sizes[t]);
     if (r) return r;
     ctx->gtables.t[t] = ctx->gtab[t].view;
+    ctx->gtables.f[t] = ctx->gtab[t].fast;
     off += sizes[t];
   }
   ctx->gtables.n = ntables;

@@ -27,6 +27,7 @@ struct LosParams {
 
 struct GTables {
   InterpTable t[NX_MAX_GTABLES];
+  FastTable f[NX_MAX_GTABLES];      // record form of the same tables (kernels)
   int n;
 };
 
@@ -56,9 +57,19 @@ NX_HD double gvalue_sum(const GTables& G, double rv) {
     if (i < G.n) gg = add_rn(gg, interp(G.t[i], rv));
   return gg;
 }
+// same sum through the record tables (value differs from np.interp by <= 1 ulp:
+// fma(slope, x - lo, f) instead of slope*(x - lo) + f)
+NX_HD double gvalue_sum_fast(const GTables& G, double rv) {
+  double gg = 0.0;
+#pragma unroll
+  for (int i = 0; i < NX_MAX_GTABLES; ++i)
+    if (i < G.n) gg += interp_fast(G.f[i], rv);
+  return gg;
+}
 
 // One packet's contribution to the image.  Returns the flat pixel index
 // ix*nz + iz (or -1) and the weight.
+template <bool FASTG = false>
 NX_HD int image_packet(const ImageParams& ip, const GTables& G, double step_x, double step_z,
                        double x, double y, double z, double vy, double frac, double& weight) {
   if (ip.round_f32) { x = round_f32(x); y = round_f32(y); z = round_f32(z);
@@ -74,7 +85,7 @@ NX_HD int image_packet(const ImageParams& ip, const GTables& G, double step_x, d
   if (ip.quantity == 1) {
     const bool lit = out_of_shadow(x, y, z);                    // ModelImage.py:257-258
     const double rv = add_rn(vy, ip.vrplanet);                  // ModelImage.py:242
-    const double gg = gvalue_sum(G, rv);
+    const double gg = FASTG ? gvalue_sum_fast(G, rv) : gvalue_sum(G, rv);
     f = div_rn(mul_rn(mul_rn(f, lit ? 1.0 : 0.0), gg), 1e6);    // ModelResult.py:161
   }
   weight = div_rn(f, ip.apix);                                  // ModelImage.py:262

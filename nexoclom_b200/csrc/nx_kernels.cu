@@ -369,7 +369,7 @@ __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& 
                                           double* image, unsigned long long* counts) {
   if (ip.skip_dead && !(s[7] > 0.0)) return;
   double w;
-  const int pix = image_packet(ip, G, step_x, step_z, s[1], s[2], s[3], s[5], s[7], w);
+  const int pix = image_packet<true>(ip, G, step_x, step_z, s[1], s[2], s[3], s[5], s[7], w);
   if (pix >= 0) {
     if (w != 0.0) atomicAdd(&image[pix], w);
     atomicAdd(&counts[pix], 1ull);
@@ -480,17 +480,16 @@ __device__ __forceinline__ void image_one(const ImageParams& ip, const GTables& 
                                           double f, double* image, unsigned long long* counts) {
   if (ip.skip_dead && !(f > 0.0)) return;
   double w;
-  const int pix = image_packet(ip, G, step_x, step_z, x, y, z, v, f, w);
+  const int pix = image_packet<true>(ip, G, step_x, step_z, x, y, z, v, f, w);
   if (pix >= 0) {
     if (w != 0.0) atomicAdd(&image[pix], w);
     atomicAdd(&counts[pix], 1ull);
   }
 }
 
-// Four packets per thread per iteration: the frac column is read first (two
-// 16-byte loads); the other four columns (8 more 16-byte loads, all issued before
-// any use) are only fetched for pairs that contain a live packet when skip_dead
-// is set (compress=True semantics: frac == 0 rows do not exist for the reference).
+// Two packets per thread and iteration, two iterations in flight (ten 16-byte
+// loads issued before the first use); g-value tables as interval records in
+// shared memory (bucket index in L1).
 __global__ void __launch_bounds__(256)
 k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
                    double* __restrict__ image, unsigned long long* __restrict__ counts) {
@@ -500,38 +499,39 @@ k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
   size_t off = 0;
 #pragma unroll
   for (int t = 0; t < NX_MAX_GTABLES; ++t)
-    if (t < Gg.n) off += stage_table(Gg.t[t], G.t[t], smem_raw + off);
+    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off); off += (size_t)Gg.f[t].nrec * 32; }
   __syncthreads();
   const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
-  const long long nquad = n >> 2;
+  const long long npair = n >> 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const double2* __restrict__ X2 = reinterpret_cast<const double2*>(P.c[1]);
   const double2* __restrict__ Y2 = reinterpret_cast<const double2*>(P.c[2]);
   const double2* __restrict__ Z2 = reinterpret_cast<const double2*>(P.c[3]);
   const double2* __restrict__ V2 = reinterpret_cast<const double2*>(P.c[5]);
   const double2* __restrict__ F2 = reinterpret_cast<const double2*>(P.c[7]);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquad; i += stride) {
-    const long long a = 2 * i, b = 2 * i + 1;
-    const double2 fa = __ldcs(F2 + a), fb = __ldcs(F2 + b);
-    const bool la = !ip.skip_dead || fa.x > 0.0 || fa.y > 0.0;
-    const bool lb = !ip.skip_dead || fb.x > 0.0 || fb.y > 0.0;
-    double2 xa, ya, za, va, xb, yb, zb, vb;
-    if (la) { xa = __ldcs(X2 + a); ya = __ldcs(Y2 + a); za = __ldcs(Z2 + a); va = __ldcs(V2 + a); }
-    if (lb) { xb = __ldcs(X2 + b); yb = __ldcs(Y2 + b); zb = __ldcs(Z2 + b); vb = __ldcs(V2 + b); }
-    if (la) {
-      image_one(ip, G, step_x, step_z, xa.x, ya.x, za.x, va.x, fa.x, image, counts);
-      image_one(ip, G, step_x, step_z, xa.y, ya.y, za.y, va.y, fa.y, image, counts);
-    }
-    if (lb) {
-      image_one(ip, G, step_x, step_z, xb.x, yb.x, zb.x, vb.x, fb.x, image, counts);
-      image_one(ip, G, step_x, step_z, xb.y, yb.y, zb.y, vb.y, fb.y, image, counts);
-    }
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < npair; i += 2 * stride) {
+    const long long j = i + stride;
+    const double2 xa = __ldcs(X2 + i), ya = __ldcs(Y2 + i), za = __ldcs(Z2 + i),
+                  va = __ldcs(V2 + i), fa = __ldcs(F2 + i);
+    const double2 xb = __ldcs(X2 + j), yb = __ldcs(Y2 + j), zb = __ldcs(Z2 + j),
+                  vb = __ldcs(V2 + j), fb = __ldcs(F2 + j);
+    image_one(ip, G, step_x, step_z, xa.x, ya.x, za.x, va.x, fa.x, image, counts);
+    image_one(ip, G, step_x, step_z, xa.y, ya.y, za.y, va.y, fa.y, image, counts);
+    image_one(ip, G, step_x, step_z, xb.x, yb.x, zb.x, vb.x, fb.x, image, counts);
+    image_one(ip, G, step_x, step_z, xb.y, yb.y, zb.y, vb.y, fb.y, image, counts);
   }
-  // tail (n not a multiple of 4)
-  const long long i = (nquad << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n)
-    image_one(ip, G, step_x, step_z, P.c[1][i], P.c[2][i], P.c[3][i], P.c[5][i], P.c[7][i],
+  if (i < npair) {
+    const double2 xa = __ldcs(X2 + i), ya = __ldcs(Y2 + i), za = __ldcs(Z2 + i),
+                  va = __ldcs(V2 + i), fa = __ldcs(F2 + i);
+    image_one(ip, G, step_x, step_z, xa.x, ya.x, za.x, va.x, fa.x, image, counts);
+    image_one(ip, G, step_x, step_z, xa.y, ya.y, za.y, va.y, fa.y, image, counts);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long q = n - 1;
+    image_one(ip, G, step_x, step_z, P.c[1][q], P.c[2][q], P.c[3][q], P.c[5][q], P.c[7][q],
               image, counts);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -776,7 +776,7 @@ cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, lo
                                     const ImageParams& ip, const GTables& G, double* image,
                                     unsigned long long* counts) {
   size_t smem = 0;
-  for (int t = 0; t < G.n; ++t) smem += table_smem_bytes(G.t[t]);
+  for (int t = 0; t < G.n; ++t) smem += fast_table_smem_bytes(G.f[t]);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_image_accumulate,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -786,7 +786,7 @@ cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, lo
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_image_accumulate, 256, smem);
   if (per_sm < 1) per_sm = 1;
   long long blocks = (long long)per_sm * sm_count(device);
-  const long long need = ((n >> 2) + 255) / 256;
+  const long long need = ((n >> 1) + 255) / 256;
   if (need < blocks) blocks = need > 0 ? need : 1;
   k_image_accumulate<<<(unsigned)blocks, 256, smem, st>>>(P, n, ip, G, image, counts);
   return cudaGetLastError();

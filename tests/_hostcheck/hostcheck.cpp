@@ -128,6 +128,7 @@ static GTables make_gtables(std::vector<HostInterp>& store, int nt, const int* s
   for (int t = 0; t < nt; ++t) {
     store[t] = make_interp(v + off, g + off, sizes[t]);
     G.t[t] = view(store[t]);
+    G.f[t] = FastTable{};
     off += sizes[t];
   }
   return G;

@@ -155,13 +155,14 @@ def test_image_vs_oracle(engine, quantity, view):
     assert np.all(img[~nz] == 0)
 
 
+@pytest.mark.parametrize('strict', [False, True])
 @pytest.mark.parametrize('tag, wl', [('tdep', 'Na.bounce.input'),
                                      ('c05', 'Na.bounce.stick05.input'),
                                      ('grav', 'Gravity.input')])
-def test_constant_driver_vs_oracle(engine, tag, wl):
+def test_constant_driver_vs_oracle(engine, tag, wl, strict):
     inputs = workload(wl)
     inputs.options.endtime = Quantity(1500., 's')
-    setup = RunSetup(inputs)
+    setup = RunSetup(inputs, strict_math=strict)
     setup.upload(engine)
     n, seed, first = 2000, 99, 7
     X0 = initial_state.draw_x0(setup, n, 9)[:, :8]
@@ -298,3 +299,33 @@ def test_public_api_end_to_end(engine):
     assert nz.sum() > 100
     assert np.max(np.abs(im.image[nz] - oi[nz]) / oi[nz]) < IMAGE_TOL
     assert im.atoms_per_packet == 1e23 / (20000 / 10800.)
+
+
+def test_packet_order_does_not_change_results(engine):
+    """Longest-first scheduling only permutes the work queue."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    X0 = initial_state.draw_x0(setup, 20000, 4)[:, :8]
+    out = []
+    for order in (0, 1, 2):
+        engine.set_option('order_packets', order)
+        engine.import_state(X0)
+        att, acc = engine.integrate_adaptive()
+        out.append((engine.export_state(), att, acc))
+    engine.set_option('order_packets', 1)
+    for o in out[1:]:
+        assert np.array_equal(o[0], out[0][0]) and o[1:] == out[0][1:]
+    with pytest.raises(Exception):
+        engine.set_option('no_such_option', 1)
+
+
+def test_adaptive_rejects_bounce_inputs(engine):
+    """Q6: the adaptive driver only supports stickcoef == 1 (reference Output.py:309-315)."""
+    inputs = workload('Na.bounce.stick05.input')
+    inputs.options.step_size = 0.
+    inputs.options.resolution = 1e-4
+    setup = RunSetup(inputs)
+    setup.upload(engine)
+    engine.import_state(initial_state.draw_x0(setup, 256, 1)[:, :8])
+    with pytest.raises(Exception, match='Not set up'):
+        engine.integrate_adaptive()
