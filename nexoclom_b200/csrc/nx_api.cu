@@ -3,6 +3,7 @@
 // launches and CUDA-event timing.  No torch types, no global mutable state.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -285,8 +286,8 @@ int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* 
 
 int nx_packets_resize(nx_ctx* ctx, long long n) {
   CK(cudaSetDevice(ctx->device));
-  if (n <= ctx->cap) return 0;
-  const long long cap = ((n + 31) / 32) * 32;
+  if (n <= ctx->cap && ctx->state) return 0;
+  const long long cap = ((std::max(n, 1LL) + 31) / 32) * 32;
   cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
   cudaFree(ctx->perm); cudaFree(ctx->cost);
   ctx->state = ctx->x0 = nullptr; ctx->att = ctx->acc = nullptr; ctx->cap = 0;
@@ -312,8 +313,10 @@ int nx_import_state(nx_ctx* ctx, long long n, const double* const* cols) {
   for (int k = 0; k < 8; ++k)
     CK(cudaMemcpyAsync(P.c[k], cols[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
                        ctx->stream));
-  CK(launch_fill(ctx->stream, P.c[8], n, 1000.0));       // Output.py:246
-  ctx->launches += 1;
+  if (n > 0) {
+    CK(launch_fill(ctx->stream, P.c[8], n, 1000.0));     // Output.py:246
+    ctx->launches += 1;
+  }
   return 0;
 }
 
