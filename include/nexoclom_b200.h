@@ -178,6 +178,15 @@ int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_de
                           void* dist_dev, const nx_los_params* lp,
                           void* radiance_dev, void* npackets_dev, void* included_dev);
 
+/* `used` packet sets (compute_iteration.py:143-144, 210-211; consumed by
+ * LOSResultFitted): packets with weight > 0 per line of sight, as CSR.  Call once
+ * with used_indices == NULL to get used_count[nlos]; build used_offsets[nlos+1]
+ * (exclusive prefix sum) and call again to fill used_indices[used_offsets[nlos]]
+ * (original packet indices, unordered within a line of sight).                   */
+int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                const double* dist_from_plan, const nx_los_params* lp,
+                const long long* used_offsets, long long* used_count, uint32_t* used_indices);
+
 /* ---- measurement --------------------------------------------------------------- */
 int nx_last_kernel_ms(nx_ctx* ctx, float* ms);          /* CUDA-event time of last K* */
 int nx_kernel_launches(nx_ctx* ctx, unsigned long long* count);

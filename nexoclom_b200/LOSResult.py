@@ -42,6 +42,21 @@ class IterationResult:
         self.mechanism = losresult.mechanism
         self.wavelength = losresult.wavelength
         self.fitted = losresult.fitted
+        self.used_csr = None
+        self.spectrum_index = None
+
+    def used_sets(self):
+        """(used, used0) as pandas Series of sets, exactly what the reference stores
+        (row labels of the output's X and values of its 'Index' column)."""
+        if self.used_csr is None:
+            return None, None
+        off, idx0, labels = self.used_csr
+        n = len(off) - 1
+        used = pd.Series([set(labels[off[i]:off[i + 1]].tolist()) for i in range(n)],
+                         index=self.spectrum_index)
+        used0 = pd.Series([set(idx0[off[i]:off[i + 1]].tolist()) for i in range(n)],
+                          index=self.spectrum_index)
+        return used, used0
 
 
 def dist_from_planet_cut(data):
@@ -94,10 +109,20 @@ def compute_iteration(self, outputfile, scdata, delay=False):
     included[packets['Index'].values[inc_]] = True
     assert np.all(np.isfinite(rad_))
 
+    # `used` / `used0` (compute_iteration.py:143-144, 210-211): packets with weight > 0
+    # per spectrum, delivered by the kernel as CSR and kept in that form (the sets
+    # the reference stores are built on demand by IterationResult.used_sets()).
+    used_csr = None
+    if getattr(self, 'keep_used', True):
+        off, idx = eng.los_used(los, dist_from_plan.values, lp)
+        used_csr = (off, packets['Index'].values[idx], packets.index.values[idx])
     iteration_ = {'radiance': rad, 'npackets': npack, 'totalsource': totalsource,
                   'outputfile': outputfile, 'out_idnum': idnum, 'query': scdata.query,
                   'used': None, 'used0': None, 'included': included}
-    return IterationResult(iteration_, self)
+    result = IterationResult(iteration_, self)
+    result.used_csr = used_csr
+    result.spectrum_index = data.index
+    return result
 
 
 class LOSResult(ModelResult):

@@ -117,6 +117,8 @@ def load():
         'nx_los_accumulate': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams),
                               c_double_p, c_i64_p, c_u8_p],
         'nx_los_accumulate_dev': [vp, i64, i64, vp, vp, C.POINTER(LosParams), vp, vp, vp],
+        'nx_los_used': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams), c_i64_p,
+                        c_i64_p, c_u32_p],
         'nx_state_device_ptr': [vp, C.c_int, C.POINTER(vp)],
         'nx_last_kernel_ms': [vp, C.POINTER(C.c_float)],
         'nx_kernel_launches': [vp, C.POINTER(u64)],

@@ -677,6 +677,69 @@ int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* lo
   return r;
 }
 
+int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                const double* dist_from_plan, const nx_los_params* lp_, const long long* used_offsets,
+                long long* used_count, uint32_t* used_indices) {
+  CK(cudaSetDevice(ctx->device));
+  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  LosParams lp;
+  std::memcpy(&lp, lp_, sizeof(lp));
+  if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }
+  if (ctx->gtables.n == 0) { ctx->err = "no g-value tables uploaded"; return -1; }
+  if (nlos <= 0) return 0;
+  if (n <= 0) { for (long long i = 0; i < nlos; ++i) used_count[i] = 0; return 0; }
+  if (n >= (1LL << 32)) { ctx->err = "more than 2^32 packets per GPU"; return -1; }
+  std::vector<int> nball;
+  std::vector<double> ladder, wid2;
+  LosConsts lc;
+  los_prepare(los, nlos, lp, nball, ladder, wid2, lc);
+  const long long total = used_indices ? used_offsets[nlos] : 0;
+  double *d_los = nullptr, *d_dist = nullptr, *d_ladder = nullptr, *d_wid2 = nullptr;
+  int* d_nball = nullptr;
+  unsigned long long *d_nused = nullptr, *d_cursor = nullptr;
+  long long* d_off = nullptr;
+  unsigned* d_idx = nullptr;
+  CK(cudaMalloc(&d_los, 6 * (size_t)nlos * sizeof(double)));
+  CK(cudaMalloc(&d_dist, (size_t)nlos * sizeof(double)));
+  CK(cudaMalloc(&d_nball, (size_t)nlos * sizeof(int)));
+  CK(cudaMalloc(&d_ladder, ladder.size() * sizeof(double)));
+  CK(cudaMalloc(&d_wid2, wid2.size() * sizeof(double)));
+  CK(cudaMalloc(&d_nused, (size_t)nlos * sizeof(unsigned long long)));
+  CK(cudaMemcpyAsync(d_los, los, 6 * (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_dist, dist_from_plan, (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_nball, nball.data(), (size_t)nlos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_ladder, ladder.data(), ladder.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_wid2, wid2.data(), wid2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (used_indices) {
+    CK(cudaMalloc(&d_cursor, (size_t)nlos * sizeof(unsigned long long)));
+    CK(cudaMalloc(&d_off, (size_t)(nlos + 1) * sizeof(long long)));
+    CK(cudaMalloc(&d_idx, (size_t)(total > 0 ? total : 1) * sizeof(unsigned)));
+    CK(cudaMemsetAsync(d_cursor, 0, (size_t)nlos * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemcpyAsync(d_off, used_offsets, (size_t)(nlos + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int r = alloc_los_work(ctx, n);
+  if (r == 0) r = begin_timed(ctx);
+  if (r == 0) {
+    cudaError_t e = launch_los_grid_build(ctx->stream, ctx->device, state_cols(ctx), n, lp, ctx->losw);
+    if (e == cudaSuccess)
+      e = launch_los_grid(ctx->stream, ctx->losw, nlos, d_los, d_dist, d_nball, d_ladder, d_wid2, lp,
+                          lc, ctx->gtables, nullptr, nullptr, nullptr, d_nused, d_off, d_cursor, d_idx);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  }
+  if (r == 0) r = end_timed(ctx, 8);
+  if (r == 0) {
+    static_assert(sizeof(long long) == sizeof(unsigned long long), "");
+    cudaMemcpyAsync(used_count, d_nused, (size_t)nlos * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (used_indices && total > 0)
+      cudaMemcpyAsync(used_indices, d_idx, (size_t)total * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  }
+  cudaFree(d_los); cudaFree(d_dist); cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2);
+  cudaFree(d_nused); cudaFree(d_cursor); cudaFree(d_off); cudaFree(d_idx);
+  return r;
+}
+
 int nx_last_kernel_ms(nx_ctx* ctx, float* ms) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventSynchronize(ctx->ev1));

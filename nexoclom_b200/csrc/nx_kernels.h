@@ -45,7 +45,9 @@ cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlo
                             const double* los, const double* dist_plan, const int* nball,
                             const double* ladder, const double* wid2, const LosParams& lp,
                             const LosConsts& lc, const GTables& G, double* radiance,
-                            unsigned long long* npack, unsigned char* included);
+                            unsigned long long* npack, unsigned char* included,
+                            unsigned long long* nused = nullptr, const long long* used_off = nullptr,
+                            unsigned long long* used_cursor = nullptr, unsigned* used_idx = nullptr);
 
 size_t table_smem_bytes(const InterpTable& g);
 

@@ -178,7 +178,9 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
            const int* __restrict__ nball, const double* __restrict__ ladder,
            const double* __restrict__ wid2, LosParams lp, LosConsts lc, GTables G,
            double* __restrict__ radiance, unsigned long long* __restrict__ npack,
-           unsigned char* __restrict__ included) {
+           unsigned char* __restrict__ included,
+           unsigned long long* __restrict__ nused, const long long* __restrict__ used_off,
+           unsigned long long* __restrict__ used_cursor, unsigned* __restrict__ used_idx) {
   const long long l = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (l >= nlos) return;
   const unsigned lane = threadIdx.x & 31u;
@@ -200,7 +202,7 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
   const int nseg = (int)ceil(t_end / dt);
 
   double rad = 0.0;
-  unsigned long long cnt = 0;
+  unsigned long long cnt = 0, used = 0;
   for (int m = 0; m < nseg; ++m) {
     const double t0 = m * dt, t1 = (m + 1) * dt;     // t1 of segment m == t0 of segment m+1
     const double rho = t1 * tan_phi + 1e-9 * (1.0 + t1);
@@ -232,8 +234,13 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
           if (los_hit(L, lp.dphi, lc.cos_margin2, ladder, wid2, lc.inv_log_ratio, lc.log_t0,
                       lc.kwin, px, py, pz, losrad, dist)) {
             ++cnt;
-            rad += los_weight(L, lp, G, lc.sin_dphi, S.frac[q], S.vy[q], losrad, dist);
-            included[S.idx[q]] = 1;
+            const double w = los_weight(L, lp, G, lc.sin_dphi, S.frac[q], S.vy[q], losrad, dist);
+            rad += w;
+            if (included) included[S.idx[q]] = 1;
+            if (w > 0.0) {                    // `used` packets (compute_iteration.py:210-211)
+              ++used;
+              if (used_idx) used_idx[used_off[l] + atomicAdd(&used_cursor[l], 1ull)] = S.idx[q];
+            }
           }
         }
       }
@@ -243,8 +250,13 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
   for (int o = 16; o > 0; o >>= 1) {
     rad += __shfl_xor_sync(FULL_MASK, rad, o);
     cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
+    used += __shfl_xor_sync(FULL_MASK, used, o);
   }
-  if (lane == 0) { radiance[l] += rad; npack[l] += cnt; }
+  if (lane == 0) {
+    if (radiance) radiance[l] += rad;
+    if (npack) npack[l] += cnt;
+    if (nused) nused[l] = used;
+  }
 }
 
 // ---- host-side launch sequence ------------------------------------------------------
@@ -282,12 +294,14 @@ cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlo
                             const double* los, const double* dist_plan, const int* nball,
                             const double* ladder, const double* wid2, const LosParams& lp,
                             const LosConsts& lc, const GTables& G, double* radiance,
-                            unsigned long long* npack, unsigned char* included) {
+                            unsigned long long* npack, unsigned char* included,
+                            unsigned long long* nused, const long long* used_off,
+                            unsigned long long* used_cursor, unsigned* used_idx) {
   const long long threads = nlos * 32;
   const long long blocks = (threads + 127) / 128;
   k_los_grid<<<(unsigned)blocks, 128, 0, st>>>(w.sorted, w.grid, w.start, nlos, los, dist_plan,
                                                nball, ladder, wid2, lp, lc, G, radiance, npack,
-                                               included);
+                                               included, nused, used_off, used_cursor, used_idx);
   return cudaGetLastError();
 }
 

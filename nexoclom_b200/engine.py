@@ -235,6 +235,28 @@ class Engine:
                     'nx_los_accumulate')
         return rad, npk, inc[:n].astype(bool)
 
+    def los_used(self, los, dist_from_plan, los_params, n=None):
+        """CSR of the `used` packets (weight > 0) per line of sight:
+        (offsets[nlos+1], packet indices)."""
+        n = self.n if n is None else n
+        los = as_f64(los)
+        nlos = los.shape[1]
+        dist = as_f64(dist_from_plan)
+        cnt = np.zeros(nlos, dtype=np.int64)
+        self._check(self.lib.nx_los_used(self.ctx, n, nlos, dptr(los), dptr(dist),
+                                         C.byref(los_params), None,
+                                         cnt.ctypes.data_as(_lib.c_i64_p), None), 'nx_los_used')
+        off = np.zeros(nlos + 1, dtype=np.int64)
+        np.cumsum(cnt, out=off[1:])
+        idx = np.zeros(max(int(off[-1]), 1), dtype=np.uint32)
+        if off[-1] > 0:
+            self._check(self.lib.nx_los_used(self.ctx, n, nlos, dptr(los), dptr(dist),
+                                             C.byref(los_params),
+                                             off.ctypes.data_as(_lib.c_i64_p),
+                                             cnt.ctypes.data_as(_lib.c_i64_p),
+                                             idx.ctypes.data_as(_lib.c_u32_p)), 'nx_los_used')
+        return off, idx[:int(off[-1])]
+
     def los_accumulate_dev(self, nlos, los_dev, dist_dev, los_params, rad_dev, npk_dev, inc_dev,
                            n=None):
         n = self.n if n is None else n

@@ -74,11 +74,14 @@ def create_image(x, y, z, vy, frac, *, vrplanet, M, dims, xrange, zrange, apix, 
     return image, packim, xe, ze
 
 
-def los_iteration(x, y, z, vy, frac, los, *, vrplanet, dphi, outeredge, rp_cm, gtables):
+def los_iteration(x, y, z, vy, frac, los, *, vrplanet, dphi, outeredge, rp_cm, gtables,
+                  used=None):
     """reference compute_iteration.py:98-222 for quantity == 'radiance'.
 
     los: (nlos, 6) rows x,y,z,xbore,ybore,zbore.  Returns radiance (nlos,),
-    npackets (nlos,) int64, included (N,) bool, dist_from_plan (nlos,)."""
+    npackets (nlos,) int64, included (N,) bool, dist_from_plan (nlos,).  If ``used`` is a
+    list it receives, per line of sight, the set of packet indices with weight > 0
+    (reference compute_iteration.py:210-211)."""
     from sklearn.neighbors import KDTree
     los = np.asarray(los, dtype=np.float64)
     sx, sy, sz, bx, by, bz = (los[:, k] for k in range(6))
@@ -130,4 +133,8 @@ def los_iteration(x, y, z, vy, frac, los, *, vrplanet, dphi, outeredge, rp_cm, g
             wtemp = wtemp * ((rhohit > 1) | (hit[:, 1] < 0))
             rad[i] = wtemp.sum()
             npack[i] = np.sum(inview)
+            if used is not None:
+                used.append(set(int(k) for k in sel[wtemp > 0]))
+        elif used is not None:
+            used.append(set())
     return rad, npack, included, dist_from_plan

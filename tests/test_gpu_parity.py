@@ -252,9 +252,10 @@ def test_los_vs_oracle(engine, los_mode):
     X = X.astype(np.float32).astype(np.float64)
     los = _synthetic_los(300)
     dphi = np.radians(1.0)
+    used_o = []
     rad_o, np_o, inc_o, dist = imaging.los_iteration(
         X[:, 1], X[:, 2], X[:, 3], X[:, 5], X[:, 7], los, vrplanet=setup.vrplanet, dphi=dphi,
-        outeredge=25., rp_cm=setup.radius_km * 1e5, gtables=gt)
+        outeredge=25., rp_cm=setup.radius_km * 1e5, gtables=gt, used=used_o)
     engine.import_state(X)
     lp = LosParams()
     lp.dphi, lp.outeredge, lp.vrplanet, lp.rp_cm = dphi, 25., setup.vrplanet, setup.radius_km * 1e5
@@ -270,6 +271,12 @@ def test_los_vs_oracle(engine, los_mode):
     nz = rad_o > 0
     assert np.max(np.abs(rad_g[nz] - rad_o[nz]) / rad_o[nz]) < IMAGE_TOL
     assert np.all(rad_g[~nz] == 0)
+    if los_mode == 2:
+        # `used` packet sets as CSR
+        off, idx = engine.los_used(los.T.copy(), dist, lp)
+        assert off[-1] == sum(len(u) for u in used_o) > 0
+        for i, u in enumerate(used_o):
+            assert set(int(k) for k in idx[off[i]:off[i + 1]]) == u
 
 
 def test_public_api_end_to_end(engine):
@@ -366,16 +373,21 @@ def test_ragged_sizes(engine, n):
     lp = LosParams()
     lp.dphi, lp.outeredge, lp.vrplanet, lp.rp_cm = np.radians(2.0), 15., setup.vrplanet, setup.radius_km * 1e5
     lp.quantity = 1
+    if n:
+        ro, no_, io, dist = imaging.los_iteration(Xg[:, 1], Xg[:, 2], Xg[:, 3], Xg[:, 5], Xg[:, 7], los,
+                                                  vrplanet=setup.vrplanet, dphi=lp.dphi, outeredge=15.,
+                                                  rp_cm=lp.rp_cm, gtables=gt)
+    else:
+        dist = np.full(3, 1e30)
     for mode in (1, 2):
         engine.set_option('los_mode', mode)
         try:
-            rad, npk, inc = engine.los_accumulate(los.T.copy(), np.full(3, 1e30), lp)
+            rad, npk, inc = engine.los_accumulate(los.T.copy(), dist, lp)
         finally:
             engine.set_option('los_mode', 0)
+        assert rad.shape == (3,) and npk.shape == (3,) and inc.shape == (n,)
         if n:
-            ro, no_, io, _ = imaging.los_iteration(Xg[:, 1], Xg[:, 2], Xg[:, 3], Xg[:, 5], Xg[:, 7], los,
-                                                   vrplanet=setup.vrplanet, dphi=lp.dphi, outeredge=15.,
-                                                   rp_cm=lp.rp_cm, gtables=gt)
-            # dist_from_plan forced to 1e30 above: recompute the oracle's planet cut off
-            assert np.array_equal(inc, io) or True
-        assert rad.shape == (3,) and npk.shape == (3,)
+            assert np.array_equal(npk, no_) and np.array_equal(inc, io)
+            assert np.allclose(rad, ro, rtol=IMAGE_TOL, atol=0)
+        else:
+            assert npk.sum() == 0 and rad.sum() == 0
