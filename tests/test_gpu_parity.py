@@ -391,3 +391,55 @@ def test_ragged_sizes(engine, n):
             assert np.allclose(rad, ro, rtol=IMAGE_TOL, atol=0)
         else:
             assert npk.sum() == 0 and rad.sum() == 0
+
+
+class _FakeSCData:
+    """Duck type of MESSENGERuvvs' data object as LOSResult uses it (reference
+    LOSResult.py:82-94, 211; compute_iteration.py:104-109)."""
+
+    def __init__(self, los, radiance):
+        import pandas as pd
+        self.data = pd.DataFrame(los, columns=['x', 'y', 'z', 'xbore', 'ybore', 'zbore'])
+        self.data['radiance'] = radiance
+        self.data['sigma'] = 0.1 * radiance + 1e-3
+        self.data['alttan'] = 1.0
+        self.species = 'Ca'
+        self.query = 'synthetic'
+        self.subslong = self.data.x * 0
+        self.frame = None
+
+    def set_frame(self, frame):
+        self.frame = frame
+
+    def __len__(self):
+        return len(self.data)
+
+
+def test_losresult_public_api(engine):
+    from nexoclom_b200 import Output, LOSResult
+    inputs = workload('Ca.isotropic.flat.input')
+    inputs.delete_files()
+    out = Output(inputs, 30000, seed=11)
+    los = _synthetic_los(200, seed=3)
+    truth = np.linspace(1.0, 3.0, 200)
+    sc = _FakeSCData(los, truth)
+    res = LOSResult(sc, inputs, dphi=Quantity(2.0, 'deg'))
+    assert sc.frame == 'Model'
+    res.simulate_data_from_inputs(sc)
+    P = Output.restore(out.filename).X
+    setup = RunSetup(inputs)
+    gt = setup.gtables([4227])
+    rad_o, np_o, inc_o, _ = imaging.los_iteration(
+        P.x.values, P.y.values, P.z.values, P.vy.values, P.frac.values, los,
+        vrplanet=setup.vrplanet, dphi=np.radians(2.0), outeredge=15.,
+        rp_cm=setup.radius_km * 1e5, gtables=gt)
+    assert np.array_equal(res.npackets_los.values, np_o) and np_o.sum() > 100
+    kR = rad_o * res.atoms_per_packet / 1e3
+    m = kR
+    factor = np.sum(m * truth) / np.sum(m * m)          # determine_source_rate, unweighted
+    nz = kR > 0
+    assert np.max(np.abs(res.radiance.values[nz] - (kR * factor)[nz]) / (kR * factor)[nz]) < IMAGE_TOL
+    assert float(res.sourcerate) == pytest.approx(factor, rel=1e-9)
+    it = res._iterations[out.filename]
+    used, used0 = it.used_sets()
+    assert sum(len(u) for u in used) > 0 and (used.apply(len) <= np_o).all()
