@@ -154,6 +154,13 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n,
                           unsigned long long* attempted_steps,
                           unsigned long long* accepted_steps);
 
+/* End-to-end variant: imports `cols` (host, ideally pinned) and integrates in
+ * `nchunks` pipelined ranges so that the H2D copy overlaps the integration.
+ * Equivalent to nx_import_state + nx_integrate_adaptive.                          */
+int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* cols, int nchunks,
+                               unsigned long long* attempted_steps,
+                               unsigned long long* accepted_steps);
+
 /* ---- K3: constant-step driver with bounce (Output.py:368-455, bouncepackets.py)
  * Optional fused per-step image accumulation (image_dev / counts_dev device
  * pointers, may be NULL) and optional dense trajectory sink traj_host

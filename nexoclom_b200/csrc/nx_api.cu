@@ -59,6 +59,10 @@ struct nx_ctx {
   unsigned* hist = nullptr;          // 32 histogram + 32 cursors
   int order_packets = 1;
   int los_mode = 0;                  // 0 auto, 1 brute force, 2 cell grid
+  cudaStream_t pipe[16] = {};                  // H2D / compute pipeline of the host-buffer path
+  cudaEvent_t pipe_ev[17] = {};
+  unsigned long long* pipe_scalars = nullptr;  // 4 u64 per chunk
+  unsigned* pipe_hist = nullptr;               // 64 u32 per chunk
   LosGridWork losw;
   unsigned long long* scalars = nullptr;   // [0] queue, [1] total attempted, [2] total accepted
   int* status = nullptr;
@@ -197,6 +201,9 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
   cudaFree(ctx->perm); cudaFree(ctx->cost); cudaFree(ctx->hist);
   free_los_work(ctx->losw);
+  for (auto& s : ctx->pipe) if (s) cudaStreamDestroy(s);
+  for (auto& e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
+  cudaFree(ctx->pipe_scalars); cudaFree(ctx->pipe_hist);
   cudaFree(ctx->scalars); cudaFree(ctx->status);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -439,6 +446,73 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
   if (r < 0) return r;
   if (attempted) *attempted = h[1];
   if (accepted) *accepted = h[2];
+  return r;
+}
+
+// Host-buffer variant of K2 for the end-to-end path: the packets are cut into
+// `nchunks` ranges, each on its own stream: the pinned H2D copies queue up on the
+// copy engine while the ranges already on the device integrate; the kernels of
+// different ranges are co-resident, so one range's long packets overlap the next
+// range's bulk (each range is scheduled longest-first on its own).
+#define NX_MAX_CHUNKS 16
+int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* cols, int nchunks,
+                               unsigned long long* attempted, unsigned long long* accepted) {
+  int r = nx_packets_resize(ctx, n);
+  if (r) return r;
+  if (!ctx->have_params) { ctx->err = "nx_tables_upload not called"; return -1; }
+  if (!(ctx->params.sticktype == STICK_CONSTANT && ctx->params.stickcoef == 1.0)) {
+    ctx->err = "Not set up";
+    return -1;
+  }
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > NX_MAX_CHUNKS) nchunks = NX_MAX_CHUNKS;
+  if (n < (long long)nchunks * 65536) nchunks = (int)std::max(1LL, n / 65536);
+  if (!ctx->pipe[0]) {
+    for (auto& s : ctx->pipe) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : ctx->pipe_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaMalloc(&ctx->pipe_scalars, NX_MAX_CHUNKS * 4 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->pipe_hist, NX_MAX_CHUNKS * 64 * sizeof(unsigned)));
+  }
+  CK(cudaMemsetAsync(ctx->pipe_scalars, 0, NX_MAX_CHUNKS * 4 * sizeof(unsigned long long), ctx->stream));
+  if ((r = begin_timed(ctx))) return r;
+  CK(cudaEventRecord(ctx->pipe_ev[16], ctx->stream));
+  for (int s = 0; s < nchunks; ++s) CK(cudaStreamWaitEvent(ctx->pipe[s], ctx->pipe_ev[16], 0));
+  StateCols P = state_cols(ctx);
+  int nlaunch = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    const long long first = n * c / nchunks, count = n * (c + 1) / nchunks - first;
+    if (count <= 0) continue;
+    cudaStream_t st = ctx->pipe[c];
+    StateCols Pc;
+    for (int k = 0; k < 9; ++k) Pc.c[k] = P.c[k] + first;
+    for (int k = 0; k < 8; ++k)
+      CK(cudaMemcpyAsync(Pc.c[k], cols[k] + first, (size_t)count * sizeof(double),
+                         cudaMemcpyHostToDevice, st));
+    CK(launch_fill(st, Pc.c[8], count, 1000.0));
+    const bool order = ctx->order_packets && count >= 4096;
+    if (order)
+      CK(launch_cost_order(st, ctx->device, Pc, count, ctx->params, ctx->order_packets,
+                           ctx->cost + first, ctx->pipe_hist + 64 * c, ctx->perm + first));
+    unsigned long long* sc = ctx->pipe_scalars + 4 * c;
+    CK(launch_integrate_adaptive(st, ctx->device, Pc, count, ctx->params, ctx->radpres.view,
+                                 ctx->radpres.fast, order ? ctx->perm + first : nullptr, sc, sc + 1,
+                                 ctx->att + first, ctx->acc + first, ctx->status));
+    nlaunch += order ? 5 : 2;
+  }
+  for (int s = 0; s < nchunks; ++s) {
+    CK(cudaEventRecord(ctx->pipe_ev[s], ctx->pipe[s]));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[s], 0));
+  }
+  if ((r = end_timed(ctx, nlaunch))) return r;
+  std::vector<unsigned long long> h((size_t)nchunks * 4, 0);
+  CK(cudaMemcpyAsync(h.data(), ctx->pipe_scalars, h.size() * sizeof(unsigned long long),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  r = check_status(ctx);
+  if (r < 0) return r;
+  unsigned long long a = 0, b = 0;
+  for (int c = 0; c < nchunks; ++c) { a += h[4 * c + 1]; b += h[4 * c + 2]; }
+  if (attempted) *attempted = a;
+  if (accepted) *accepted = b;
   return r;
 }
 

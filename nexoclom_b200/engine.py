@@ -188,6 +188,21 @@ class Engine:
                     'nx_integrate_adaptive')
         return int(att.value), int(acc.value)
 
+    def integrate_adaptive_host(self, cols, nchunks=8):
+        """import_state + integrate_adaptive with the H2D copy pipelined against
+        the integration (host columns should be pinned for real overlap)."""
+        if isinstance(cols, np.ndarray) and cols.ndim == 2:
+            cols = [cols[:, k] for k in range(8)]
+        arrs = [as_f64(c) for c in cols]
+        n = len(arrs[0])
+        ptrs = (c_double_p * 8)(*[dptr(a) for a in arrs])
+        att, acc = C.c_ulonglong(), C.c_ulonglong()
+        self._check(self.lib.nx_integrate_adaptive_host(self.ctx, n, ptrs, int(nchunks),
+                                                        C.byref(att), C.byref(acc)),
+                    'nx_integrate_adaptive_host')
+        self.n = n
+        return int(att.value), int(acc.value)
+
     def integrate_constant(self, seed=0, first_id=0, image_params=None, image_dev=None,
                            counts_dev=None, trajectory=False, n=None):
         n = self.n if n is None else n

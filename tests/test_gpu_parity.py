@@ -443,3 +443,20 @@ def test_losresult_public_api(engine):
     it = res._iterations[out.filename]
     used, used0 = it.used_sets()
     assert sum(len(u) for u in used) > 0 and (used.apply(len) <= np_o).all()
+
+
+def test_pipelined_host_path_equals_resident_path(engine):
+    """nx_integrate_adaptive_host (chunked H2D/compute pipeline) == import + integrate."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    X0 = initial_state.draw_x0(setup, 300_000, 6)[:, :8]
+    engine.import_state(X0)
+    att0, acc0 = engine.integrate_adaptive()
+    ref = engine.export_state()
+    a0, c0 = engine.export_stats()
+    for nchunks in (1, 3):
+        att, acc = engine.integrate_adaptive_host(X0, nchunks=nchunks)
+        assert (att, acc) == (att0, acc0)
+        assert np.array_equal(engine.export_state(), ref)
+        a1, c1 = engine.export_stats()
+        assert np.array_equal(a0, a1) and np.array_equal(c0, c1)
