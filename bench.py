@@ -328,11 +328,11 @@ def run_gpu(args):
         tgt *= (1 + 3 * torch.rand(nlos, generator=g, dtype=torch.float64)) / tgt.norm(dim=0)
         bore = tgt - x_sc
         bore /= bore.norm(dim=0)
-        dist = x_sc.norm(dim=0)
-        ang = torch.arccos(-(x_sc * bore).sum(dim=0) / dist)
-        dist = torch.where(ang > torch.arcsin(1. / dist), torch.full_like(dist, 1e30), dist)
+        dplan = x_sc.norm(dim=0)
+        ang = torch.arccos(-(x_sc * bore).sum(dim=0) / dplan)
+        dplan = torch.where(ang > torch.arcsin(1. / dplan), torch.full_like(dplan, 1e30), dplan)
         los_dev = torch.cat([x_sc, bore], dim=0).contiguous().cuda()
-        dist_dev = dist.contiguous().cuda()
+        dist_dev = dplan.contiguous().cuda()
         rad_dev = torch.zeros(nlos, dtype=torch.float64, device='cuda')
         npk_dev = torch.zeros(nlos, dtype=torch.int64, device='cuda')
         inc_dev = torch.zeros(n, dtype=torch.uint8, device='cuda')
@@ -346,9 +346,8 @@ def run_gpu(args):
             eng.los_accumulate_dev(nlos, los_dev.data_ptr(), dist_dev.data_ptr(), lp,
                                    rad_dev.data_ptr(), npk_dev.data_ptr(), inc_dev.data_ptr(), n)
             if world > 1:
-                dist_mod = dist  # noqa: F841
-                torch.distributed.all_reduce(rad_dev)
-                torch.distributed.all_reduce(npk_dev)
+                dist.all_reduce(rad_dev)
+                dist.all_reduce(npk_dev)
             torch.cuda.synchronize()
             los_ms.append(eng.last_kernel_ms())
         los_info = {'lines_of_sight': nlos, 'packets_per_gpu': n, 'dphi_deg': 1.0,
