@@ -460,3 +460,58 @@ def test_pipelined_host_path_equals_resident_path(engine):
         assert np.array_equal(engine.export_state(), ref)
         a1, c1 = engine.export_stats()
         assert np.array_equal(a0, a1) and np.array_equal(c0, c1)
+
+
+@pytest.mark.parametrize('sparams', [{'type': 'uniform'},
+                                     {'type': 'uniform', 'exobase': '1.0', 'longitude': '1, 2',
+                                      'latitude': '0, 1'},
+                                     {'type': 'uniform', 'exobase': '1.0', 'longitude': '5, 1',
+                                      'latitude': '-0.5, 0.25'},
+                                     {'type': 'uniform', 'exobase': '1.0', 'longitude': '0, 0',
+                                      'latitude': '0, 0'}])
+def test_initial_state_distributions_ks(engine, sparams):
+    """Statistical parity of the on-device sampler (the reference's own test of
+    this function is a KS test: tests/unit_tests/Initial_state/test_spatial_distribution.py:95-143):
+    longitude uniform on its (possibly wrapping) range, sin(latitude) uniform, sin(altitude)
+    uniform, azimuth uniform, Maxwellian flux speeds, times uniform on [0, endtime]."""
+    from scipy import stats
+    from nexoclom_b200.input_classes import SpatialDist
+    from nexoclom_b200.surfaceinteraction import thermal_speed_kms
+    inputs = workload('Na.maxwellian.radpres.input')
+    inputs.spatialdist = SpatialDist(sparams)
+    setup = RunSetup(inputs)
+    setup.upload(engine)
+    n = 100_000
+    engine.init_state(setup.source_params(engine), 2024, 0, n)
+    X0 = engine.export_x0()
+    t, x, y, z, vx, vy, vz, f, v, lon, lat, loct, alt, az = X0
+    lon0, lon1 = (float(a) for a in inputs.spatialdist.longitude)
+    lat0, lat1 = (float(a) for a in inputs.spatialdist.latitude)
+    pmin = 1e-4
+    if lon0 == lon1:
+        assert np.all(lon == lon0) and np.all(lat == lat0)
+    else:
+        span = lon1 - lon0 if lon1 > lon0 else lon1 + 2 * np.pi - lon0
+        u = ((lon - lon0) % (2 * np.pi)) / span
+        assert u.max() <= 1 + 1e-12
+        assert stats.kstest(u, 'uniform').pvalue > pmin
+        s0, s1 = np.sin(lat0), np.sin(lat1)
+        assert stats.kstest((np.sin(lat) - s0) / (s1 - s0), 'uniform').pvalue > pmin
+    assert stats.kstest(np.sin(alt), 'uniform').pvalue > pmin
+    assert stats.kstest(az / (2 * np.pi), 'uniform').pvalue > pmin
+    assert stats.kstest(t / 50000., 'uniform').pvalue > pmin
+    assert np.all(f == 1.0)
+    assert np.allclose(np.sqrt(x**2 + y**2 + z**2), 1.0, rtol=1e-14)
+    assert np.allclose(np.sqrt(vx**2 + vy**2 + vz**2), v, rtol=1e-13)
+    assert np.allclose(loct, (lon * 12 / np.pi + 12) % 24, rtol=1e-14)
+    # Maxwellian flux distribution f(v) ~ v^3 exp(-v^2/vth^2) on [0.1, 5 vth] km/s
+    vth = thermal_speed_kms(1200., 'Na')
+    grid = np.linspace(0.1, 5 * vth, 20001)
+    pdf = grid**3 * np.exp(-grid**2 / vth**2)
+    cdf = np.cumsum(pdf)
+    cdf = (cdf - cdf[0]) / (cdf[-1] - cdf[0])
+    vk = v * setup.radius_km
+    assert stats.kstest(vk, lambda q: np.interp(q, grid, cdf)).pvalue > pmin
+    # geometry: packets leave the surface outward, |v_radial| = v sin(alt)
+    vr = (x * vx + y * vy + z * vz)
+    assert np.allclose(vr, v * np.sin(alt), rtol=1e-9, atol=1e-18)
