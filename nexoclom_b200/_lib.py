@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnexo_b200.so')
+LIB_PATH = os.environ.get('NEXOCLOM_B200_LIB', os.path.join(_HERE, 'libnexo_b200.so'))
 
 c_double_p = C.POINTER(C.c_double)
 c_i64_p = C.POINTER(C.c_longlong)
