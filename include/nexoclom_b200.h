@@ -68,7 +68,7 @@ typedef struct nx_run_params {
 /* Initial-state distributions (source_distribution.py:37-283). */
 enum { NX_SPATIAL_UNIFORM = 0, NX_SPATIAL_MAP = 1 };
 enum { NX_SPEED_FLAT = 0, NX_SPEED_GAUSSIAN = 1, NX_SPEED_TABLE = 2 };
-enum { NX_ANGULAR_RADIAL = 0, NX_ANGULAR_ISOTROPIC = 1 };
+enum { NX_ANGULAR_RADIAL = 0, NX_ANGULAR_ISOTROPIC = 1, NX_ANGULAR_2D = 2 };
 typedef struct nx_source_params {
   int32_t spatial_type, speed_type, angular_type, is_planet;
   double exobase;
@@ -76,7 +76,7 @@ typedef struct nx_source_params {
   double lon0, lon1;         /* uniform: longitude range (lon1 > lon0, may be > 2pi) */
   double vprob, vsigma, delv;/* km/s                                                */
   double v_scale;            /* km/s -> R_p/s  (1/R_km)                             */
-  double sinalt0, sinalt1;   /* isotropic: sin(altitude) range                      */
+  double sinalt0, sinalt1;   /* isotropic: sin(altitude) range; 2d: cos(altitude)   */
   double az0, az1;           /* isotropic: azimuth range                            */
   double endtime;
   int32_t random_time;       /* 1: time = U*endtime (adaptive); 0: time = endtime   */

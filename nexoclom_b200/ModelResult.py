@@ -75,7 +75,12 @@ class ModelResult:
             return 0
         if self.quantity in ('radiance', 'difrad'):
             if self.g is not None:
-                raise NotImplementedError('constant user-supplied g')
-            engine.upload_gtables(setup.gtables(self.wavelength))
+                # user-supplied constant g-value (ModelResult.py:158-159): a two-point
+                # table whose clamped ends make np.interp return g everywhere
+                import numpy as np
+                g = float(np.asarray(self.g))
+                engine.upload_gtables([(np.array([-1.0, 1.0]), np.array([g, g]))])
+            else:
+                engine.upload_gtables(setup.gtables(self.wavelength))
             return 1
         raise InputError('ModelResults.packet_weighting', f'{self.quantity} is invalid.')

@@ -11,7 +11,7 @@ namespace nx {
 
 enum SpatialType { SPATIAL_UNIFORM = 0, SPATIAL_MAP = 1 };
 enum SpeedType { SPEED_FLAT = 0, SPEED_GAUSSIAN = 1, SPEED_TABLE = 2 };
-enum AngularType { ANGULAR_RADIAL = 0, ANGULAR_ISOTROPIC = 1 };
+enum AngularType { ANGULAR_RADIAL = 0, ANGULAR_ISOTROPIC = 1, ANGULAR_2D = 2 };
 
 struct SourceParams {
   int32_t spatial_type, speed_type, angular_type, is_planet;
@@ -109,15 +109,29 @@ NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const Inter
 
   // ---- direction (source_distribution.py:192-252) ----
   double alt, az;
-  if (sp.angular_type == ANGULAR_RADIAL) {
-    alt = NX_PI / 2.; az = 0.0;
-  } else {
-    const double sinalt = add_rn(mul_rn(u_alt, sub_rn(sp.sinalt1, sp.sinalt0)), sp.sinalt0);
-    alt = asin(sinalt);
-    az = add_rn(sp.az0, mul_rn(sub_rn(sp.az1, sp.az0), u_az));
-  }
   double d[3];
-  local_direction(px, py, pz, alt, az, d);
+  if (sp.angular_type == ANGULAR_2D) {
+    // '2d' (source_distribution.py:213-222, 253-283): cos(alt) uniform, motion in the
+    // equatorial plane; sinalt0/1 carry cos(altitude) of the two limits
+    const double cosalt = add_rn(mul_rn(u_alt, sub_rn(sp.sinalt1, sp.sinalt0)), sp.sinalt0);
+    alt = acos(cosalt); az = 0.0;
+    const double v_rad = sin(alt), v_tan = cos(alt);
+    const double rn = sqrt(add_rn(mul_rn(px, px), mul_rn(py, py)));
+    const double rx = div_rn(px, rn), ry = div_rn(py, rn);
+    const double tx = div_rn(py, rn), ty = div_rn(-px, rn);
+    d[0] = add_rn(mul_rn(v_tan, tx), mul_rn(v_rad, rx));
+    d[1] = add_rn(mul_rn(v_tan, ty), mul_rn(v_rad, ry));
+    d[2] = 0.0;
+  } else {
+    if (sp.angular_type == ANGULAR_RADIAL) {
+      alt = NX_PI / 2.; az = 0.0;
+    } else {
+      const double sinalt = add_rn(mul_rn(u_alt, sub_rn(sp.sinalt1, sp.sinalt0)), sp.sinalt0);
+      alt = asin(sinalt);
+      az = add_rn(sp.az0, mul_rn(sub_rn(sp.az1, sp.az0), u_az));
+    }
+    local_direction(px, py, pz, alt, az, d);
+  }
 
   x0[0] = time; x0[1] = px; x0[2] = py; x0[3] = pz;
   x0[4] = mul_rn(d[0], v); x0[5] = mul_rn(d[1], v); x0[6] = mul_rn(d[2], v);

@@ -215,8 +215,10 @@ class RunSetup:
             az0, az1 = (float(value_of(v)) for v in ad.azimuth)
             m = (az0, az1) if az0 <= az1 else (az1, az0 + 2 * np.pi)
             sp.az0, sp.az1 = m
-        elif ad.type == '2d':
-            raise NotImplementedError("AngularDist.type = '2d' (no reference test uses it)")
+        elif ad.type == '2d':                                       # :213-222
+            sp.angular_type = 2
+            alt = [float(value_of(v)) for v in ad.altitude]
+            sp.sinalt0, sp.sinalt1 = np.cos(alt[0]), np.cos(alt[1])
         else:
             assert 0, 'Angular Distribution not defined.'
         return sp

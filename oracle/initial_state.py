@@ -145,17 +145,22 @@ def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None):
         v0 = np.interp(u['speed'], cdf, xv)
     v = v0 * sp.v_scale
 
-    if sp.angular_type == 0:
+    pos = X_.T.copy()
+    if sp.angular_type == 2:
+        # '2d' (source_distribution.py:213-222, 253-283)
+        cosalt = u['alt'] * (sp.sinalt1 - sp.sinalt0) + sp.sinalt0
+        alt = np.arccos(cosalt)
+        az = np.zeros(n)
+        v_rad, v_tan = np.sin(alt), np.cos(alt)
+        rad = pos[:, :2] / np.sqrt(pos[:, 0] * pos[:, 0] + pos[:, 1] * pos[:, 1])[:, None]
+        tan = np.stack([pos[:, 1], -pos[:, 0]], axis=1)
+        tan = tan / np.sqrt(tan[:, 0]**2 + tan[:, 1]**2)[:, None]
+        d2 = v_tan[:, None] * tan + v_rad[:, None] * rad
+        d = np.concatenate([d2, np.zeros((n, 1))], axis=1)
+    elif sp.angular_type == 0:
+        # alt = pi/2 exactly: sin/cos evaluated on alt itself as the reference does
         alt = np.zeros(n) + np.pi / 2.
         az = np.zeros(n)
-        sinalt = np.sin(alt)
-    else:
-        sinalt = u['alt'] * (sp.sinalt1 - sp.sinalt0) + sp.sinalt0
-        alt = np.arcsin(sinalt)
-        az = sp.az0 + (sp.az1 - sp.az0) * u['az']
-    pos = X_.T.copy()
-    if sp.angular_type == 0:
-        # alt = pi/2 exactly: sin/cos evaluated on alt itself as the reference does
         k = n
         v_rad = np.sin(alt)
         v_tan0 = np.cos(alt) * np.cos(az)
@@ -168,6 +173,9 @@ def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None):
         north = north / np.sqrt((north[:, 0]**2 + north[:, 1]**2) + north[:, 2]**2)[:, None]
         d = v_tan0[:, None] * north + v_tan1[:, None] * east + v_rad[:, None] * rad
     else:
+        sinalt = u['alt'] * (sp.sinalt1 - sp.sinalt0) + sp.sinalt0
+        alt = np.arcsin(sinalt)
+        az = sp.az0 + (sp.az1 - sp.az0) * u['az']
         d = local_frame_direction(pos, sinalt, az)
 
     out = np.empty((n, 14))

@@ -101,6 +101,23 @@ def test_init_state_matches_oracle(hc, wl):
     assert np.all(np.sum(out[:, 1:4] * out[:, 4:7], axis=1) >= -1e-18)
 
 
+def test_2d_angular_distribution(hc):
+    inputs = workload('Ca.isotropic.flat.input')
+    from nexoclom_b200.input_classes import AngularDist
+    inputs.angulardist = AngularDist({'type': '2d', 'altitude': '0.3, 2.5'})
+    setup = RunSetup(inputs)
+    sp = setup.source_params(None)
+    n = 4000
+    out = np.zeros((n, 14))
+    hc.hc_init_state(C.c_long(n), C.byref(sp), C.c_ulonglong(1), C.c_ulonglong(0), None, None,
+                     None, None, C.c_int(0), dptr(out))
+    ref = initial_state.draw_x0(setup, n, 1)
+    assert np.max(np.abs(out - ref)) < 1e-13
+    assert np.all(out[:, 6] == 0) and np.all(out[:, 13] == 0)          # vz = 0, azimuth = 0
+    assert out[:, 12].min() >= 0.3 - 1e-12 and out[:, 12].max() <= 2.5 + 1e-12
+    assert np.allclose(np.hypot(out[:, 4], out[:, 5]), out[:, 8], rtol=1e-13)
+
+
 def test_surface_spot_sampling(hc):
     """surface-spot rejection sampling (source_distribution.py:96-121): device
     logic == oracle transform fed with the same Philox triples."""
