@@ -376,6 +376,8 @@ __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& 
   }
 }
 
+#define NX_BOUNCE_BATCH 10
+#define NX_BOUNCE_MAXWAIT 6
 // MODE as in k_integrate_adaptive: -1 strict, else fast with MODE = GR*8 + RP*4 + LOSS.
 template <int MODE>
 __global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
@@ -397,11 +399,11 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
   const unsigned lane = threadIdx.x & 31u;
   const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
 
-  bool have = false, drained = false;
+  bool have = false, drained = false, pending = false;
   unsigned idx = 0;
-  double s[8];
+  double s[8], rhit = 0.0;
   double curtime = 0.0;
-  int ct = 0;
+  int ct = 0, wait_iters = 0;
   unsigned long long tot = 0;
   int st = 0;
 
@@ -433,18 +435,8 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
       if (drained) break;
       continue;
     }
-    if (have) {
-      bool bad = false;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
-      if (bad) st |= 32;
-      bool live;
-      if (MODE < 0)
-        live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
-      else
-        live = constant_step_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(
-            p, F, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
-      ++tot;
+    // finish one row of the reference's trajectory tensor: outputs, clocks, retire
+    auto finish_row = [&](bool live) {
       if (traj) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) traj[((size_t)idx * 8 + k) * nsteps + ct] = s[k];
@@ -456,6 +448,45 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
 #pragma unroll
         for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
         have = false;
+      }
+    };
+    if (MODE < 0) {
+      if (have) {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
+        if (bad) st |= 32;
+        const bool live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+        ++tot;
+        finish_row(live);
+      }
+    } else {
+      // Fast mode: the bounce is ~2x the cost of a step but only ~10% of the lanes
+      // need it in a given step, so lanes that hit the surface PARK (pending) and
+      // the warp runs the bounce code once enough of them have accumulated; results
+      // do not depend on the batching (Philox is keyed by packet id and step).
+      if (have && !pending) {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
+        if (bad) st |= 32;
+        const double r = constant_stages_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s);
+        ++tot;
+        bool hit = sub_rn(r, 1.0) < 0.0;
+        if (hit && p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0) { s[7] = 0.0; hit = false; }
+        if (hit) { pending = true; rhit = r; }
+        else finish_row(constant_post(p, s, r));
+      }
+      const int npend = __popc(__ballot_sync(FULL_MASK, pending));
+      const int nrun = __popc(__ballot_sync(FULL_MASK, have && !pending));
+      wait_iters = npend ? wait_iters + 1 : 0;
+      if (npend >= NX_BOUNCE_BATCH || (npend > 0 && (nrun == 0 || wait_iters >= NX_BOUNCE_MAXWAIT))) {
+        if (pending) {
+          constant_bounce_fast(p, S, s, rhit, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+          pending = false;
+          finish_row(constant_post(p, s, rhit));
+        }
+        wait_iters = 0;
       }
     }
   }

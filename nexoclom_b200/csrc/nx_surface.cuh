@@ -308,6 +308,34 @@ NX_HD bool constant_step_fast(const RunParams& p, const FastTable& T, const Spli
   return constant_step_finish<true>(p, S, nx, s, seed, id, stepidx);
 }
 
+// --- split form of the fast constant step, for kernels that batch the bounces ---
+// stage part: s <- post-step state (before any surface interaction); returns r.
+template <int GR, int RP, int LOSS>
+NX_HD double constant_stages_fast(const RunParams& p, const FastTable& T, double* s) {
+  double q[6], d[6], fn, df;
+  fast_stages<GR, RP, LOSS, false>(p, T, s, p.step_size, q, fn, d, df);
+  s[0] -= p.step_size;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s[1 + k] = q[k];
+  s[7] = fn;
+  return sqrt(add_rn(add_rn(mul_rn(q[0], q[0]), mul_rn(q[1], q[1])), mul_rn(q[2], q[2])));
+}
+// surface interaction of a packet whose post-step radius r is below the surface
+NX_HD void constant_bounce_fast(const RunParams& p, const Spline2D& S, double* s, double r,
+                                uint64_t seed, uint64_t id, uint32_t stepidx) {
+  double u_alt, u_az, u_prob, unused;
+  uniform_pair(seed, id, STREAM_BOUNCE, 2u * stepidx, u_alt, u_az);
+  uniform_pair(seed, id, STREAM_BOUNCE, 2u * stepidx + 1u, u_prob, unused);
+  bounce_fast(p, S, s, r, u_alt, u_az, u_prob);
+}
+// escape / vanish / done tests (Output.py:409-416); r is the pre-bounce radius
+NX_HD bool constant_post(const RunParams& p, double* s, double r) {
+  if (r > p.outeredge) s[7] = 0.0;
+  if (s[7] < 1e-10) s[7] = 0.0;
+  if (s[7] == 0.0) s[0] = 0.0;
+  return s[7] > 0.0;
+}
+
 NX_HD bool constant_step_fast_rt(const RunParams& p, const FastTable& T, const Spline2D& S,
                                  double* s, uint64_t seed, uint64_t id, uint32_t stepidx) {
   const int key = (p.gravity ? 4 : 0) | (p.radpres ? 2 : 0);
