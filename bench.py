@@ -133,7 +133,7 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
-    n = args.cpu_packets * procs
+    n = args.ref_packets * procs
     X0 = synth_x0_host(n)
     vals = []
     for it in range(args.warmup + args.steps):
@@ -142,7 +142,7 @@ def run_reference(args):
             vals.append((sps, steps, wall))
     sps = float(np.mean([v[0] for v in vals]))
     ms = float(np.mean([v[2] for v in vals])) * 1e3
-    sample = f'{n} packets of {WORKLOAD} per step ({procs} processes x {args.cpu_packets})'
+    sample = f'{n} packets of {WORKLOAD} per step ({procs} processes x {args.ref_packets})'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': sps, 'unit': 'packet-steps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
@@ -426,12 +426,16 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--packets', type=int, default=10_000_000, help='packets per GPU')
-    ap.add_argument('--cpu-packets', type=int, default=20000)
+    ap.add_argument('--cpu-packets', type=int, default=100000,
+                    help='packets of the bounded CPU sample (about 15 s on one core)')
+    ap.add_argument('--ref-packets', type=int, default=20000,
+                    help='packets per host process and step of the --impl reference arm')
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-los', action='store_true')
-    ap.add_argument('--e2e-chunks', type=int, default=2)
+    ap.add_argument('--e2e-chunks', type=int, default=16,
+                    help='segments of the streamed H2D copy of the end-to-end path')
     ap.add_argument('--los', type=int, default=100_000, help='lines of sight of the K5 sweep')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -67,7 +67,13 @@ class Output:
 
             if X0 is not None:
                 cols = self._coerce_x0(X0, npackets)
-                eng.import_state(cols)
+                self._host_cols = None
+                if self.inputs.options.step_size == 0:
+                    # adaptive run on imported packets: the copy is streamed behind the
+                    # integrator (nx_integrate_adaptive_host), see variable_step_size_driver
+                    self._host_cols = cols
+                else:
+                    eng.import_state(cols)
                 self.X0 = pd.DataFrame({c: cols[k] for k, c in enumerate(STATE_COLS)})
             else:
                 if self.inputs.spatialdist.type not in ('uniform', 'surface map',
@@ -118,7 +124,13 @@ class Output:
         """Adaptive driver on the GPU (K2).  Semantics of reference
         Output.py:221-366, including quirks Q1-Q9."""
         eng = self._engine
-        self.attempted_steps, self.accepted_steps = eng.integrate_adaptive(self.npackets)
+        host_cols = getattr(self, '_host_cols', None)
+        if host_cols is not None:
+            self.attempted_steps, self.accepted_steps = eng.integrate_adaptive_host(
+                host_cols, nchunks=16)
+            self._host_cols = None
+        else:
+            self.attempted_steps, self.accepted_steps = eng.integrate_adaptive(self.npackets)
         self.kernel_ms = eng.last_kernel_ms()
         x = eng.export_state()
         X = pd.DataFrame({c: x[k] for k, c in enumerate(STATE_COLS)})

@@ -57,7 +57,12 @@ struct nx_ctx {
   unsigned* perm = nullptr;          // longest-first processing order
   unsigned char* cost = nullptr;     // cost bucket per packet
   unsigned* hist = nullptr;          // 32 histogram + 32 cursors
-  int order_packets = 1;
+  int order_packets = 1;              // cost model: 0 none, 1 ballistic, 2 + radiation pressure
+  int schedule = 1;                   // K2 queue: 1 class-ordered streaming passes, 0 sort + permutation
+  unsigned long long* squeue = nullptr;   // NX_STREAM_CURSORS cursors, then the `arrived` word
+  unsigned* seq_host = nullptr;           // pinned 0..32: source of the `arrived` updates
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[2] = {};
   int los_mode = 0;                  // 0 auto, 1 brute force, 2 cell grid
   cudaStream_t pipe[16] = {};                  // H2D / compute pipeline of the host-buffer path
   cudaEvent_t pipe_ev[17] = {};
@@ -179,12 +184,18 @@ int nx_ctx_create(int device, nx_ctx** out) {
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaMalloc(&ctx->scalars, 8 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMalloc(&ctx->status, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&ctx->squeue, (NX_STREAM_CURSORS + 1) * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaHostAlloc(&ctx->seq_host, 33 * sizeof(unsigned), cudaHostAllocDefault) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->copy_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->copy_ev[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaMemset(ctx->status, 0, sizeof(int)) != cudaSuccess) {
     fprintf(stderr, "nexoclom_b200: context setup failed: %s\n",
             cudaGetErrorString(cudaGetLastError()));
     delete ctx;
     return -2;
   }
+  for (unsigned i = 0; i <= 32; ++i) ctx->seq_host[i] = i;
   *out = ctx;
   return 0;
 }
@@ -205,6 +216,9 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   for (auto& e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
   cudaFree(ctx->pipe_scalars); cudaFree(ctx->pipe_hist);
   cudaFree(ctx->scalars); cudaFree(ctx->status);
+  cudaFree(ctx->squeue); cudaFreeHost(ctx->seq_host);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -228,10 +242,19 @@ int nx_ctx_sync(nx_ctx* ctx) {
 
 int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   if (name && std::strcmp(name, "order_packets") == 0) { ctx->order_packets = value; return 0; }
+  if (name && std::strcmp(name, "schedule") == 0) { ctx->schedule = value; return 0; }
   if (name && std::strcmp(name, "los_mode") == 0) { ctx->los_mode = value; return 0; }
   if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G = value; ctx->losw.cap = 0; return 0; }
   ctx->err = std::string("unknown option ") + (name ? name : "(null)");
   return -1;
+}
+
+// developer hook: K2 instrumentation words (all zero unless built with NX_STREAM_DEBUG)
+int nx_debug_queue(nx_ctx* ctx, unsigned long long* out, int count) {
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(debug_read(out, count));
+  return 0;
 }
 
 const char* nx_last_error(nx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -429,16 +452,19 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
   CK(cudaMemsetAsync(ctx->scalars, 0, 8 * sizeof(unsigned long long), ctx->stream));
   int r;
   if (n > 0) {
+    CK(debug_begin(ctx->stream));
     if ((r = begin_timed(ctx))) return r;
-    const bool order = ctx->order_packets && n >= 4096;
-    if (order)
-      CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
-                           ctx->order_packets, ctx->cost, ctx->hist, ctx->perm));
-    CK(launch_integrate_adaptive(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
-                                 ctx->radpres.view, ctx->radpres.fast, order ? ctx->perm : nullptr,
-                                 ctx->scalars,
-                                 ctx->scalars + 1, ctx->att, ctx->acc, ctx->status));
-    if ((r = end_timed(ctx, order ? 4 : 1))) return r;
+    {
+      const bool order = ctx->order_packets && n >= 4096;
+      if (order)
+        CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
+                             ctx->order_packets, ctx->cost, ctx->hist, ctx->perm));
+      CK(launch_integrate_adaptive(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
+                                   ctx->radpres.view, ctx->radpres.fast,
+                                   order ? ctx->perm : nullptr, ctx->scalars, ctx->scalars + 1,
+                                   ctx->att, ctx->acc, ctx->status));
+      if ((r = end_timed(ctx, order ? 4 : 1))) return r;
+    }
   }
   unsigned long long h[3] = {0, 0, 0};
   CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -449,11 +475,11 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
   return r;
 }
 
-// Host-buffer variant of K2 for the end-to-end path: the packets are cut into
-// `nchunks` ranges, each on its own stream: the pinned H2D copies queue up on the
-// copy engine while the ranges already on the device integrate; the kernels of
-// different ranges are co-resident, so one range's long packets overlap the next
-// range's bulk (each range is scheduled longest-first on its own).
+// Host-buffer variant of K2 for the end-to-end path.  schedule 1 (default): ONE
+// persistent class-ordered kernel consumes the packets segment by segment while the
+// copy engine is still delivering the later segments (k_integrate_adaptive_stream).
+// schedule 0 (kept for A/B runs): `nchunks` ranges, each on its own stream with its
+// own sort + kernel; co-resident kernels overlap one range's tail with the next.
 #define NX_MAX_CHUNKS 16
 int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* cols, int nchunks,
                                unsigned long long* attempted, unsigned long long* accepted) {
@@ -465,6 +491,54 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
     return -1;
   }
   if (nchunks < 1) nchunks = 1;
+  if (ctx->schedule == 1) {
+    // ONE persistent kernel; the copy engine delivers the packets segment by segment
+    // behind it and raises `arrived` after each one (stream order on copy_stream).
+    if (n == 0) { if (attempted) *attempted = 0; if (accepted) *accepted = 0; return 0; }
+    if (nchunks > NX_STREAM_MAX_SEG) nchunks = NX_STREAM_MAX_SEG;
+    long long seg = (n + nchunks - 1) / nchunks;
+    seg = (seg + NX_STREAM_GROUP - 1) / NX_STREAM_GROUP * NX_STREAM_GROUP;
+    const int nseg = (int)((n + seg - 1) / seg);
+    unsigned* arrived = reinterpret_cast<unsigned*>(ctx->squeue + NX_STREAM_CURSORS);
+    StateCols P = state_cols(ctx);
+    CK(cudaMemsetAsync(ctx->scalars, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->squeue, 0, (NX_STREAM_CURSORS + 1) * sizeof(unsigned long long),
+                       ctx->stream));
+    CK(cudaMemsetAsync(ctx->att, 0, (size_t)n * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->acc, 0, (size_t)n * sizeof(unsigned), ctx->stream));
+    CK(debug_begin(ctx->stream));
+    if ((r = begin_timed(ctx))) return r;
+    CK(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));  // `arrived` is 0 before any copy
+    // the copies land in the X0 slab (the imported initial state, Output.py:180-182);
+    // the kernel writes the final state and the step size (Output.py:246: 1000 s) to the state slab
+    double* const in0 = ctx->x0;
+    const size_t in_stride = (size_t)ctx->cap;
+    CK(launch_integrate_adaptive_stream(ctx->stream, ctx->device, in0, in_stride, 1000.0, P, n,
+                                        ctx->params,
+                                        ctx->radpres.view, ctx->radpres.fast, seg, nseg,
+                                        ctx->order_packets, ctx->squeue, arrived,
+                                        ctx->scalars + 1, ctx->att, ctx->acc, ctx->status));
+    for (int c = 0; c < nseg; ++c) {
+      const long long first = (long long)c * seg, count = std::min(seg, n - first);
+      for (int k = 0; k < 8; ++k)
+        CK(cudaMemcpyAsync(in0 + (size_t)k * in_stride + first, cols[k] + first,
+                           (size_t)count * sizeof(double), cudaMemcpyHostToDevice,
+                           ctx->copy_stream));
+      CK(cudaMemcpyAsync(arrived, ctx->seq_host + c + 1, sizeof(unsigned),
+                         cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    CK(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
+    if ((r = end_timed(ctx, 2))) return r;
+    unsigned long long h[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    r = check_status(ctx);
+    if (r < 0) return r;
+    if (attempted) *attempted = h[1];
+    if (accepted) *accepted = h[2];
+    return r;
+  }
   if (nchunks > NX_MAX_CHUNKS) nchunks = NX_MAX_CHUNKS;
   if (n < (long long)nchunks * 65536) nchunks = (int)std::max(1LL, n / 65536);
   if (!ctx->pipe[0]) {

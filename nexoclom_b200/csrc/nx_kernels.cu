@@ -23,6 +23,30 @@ namespace nx {
 
 #define FULL_MASK 0xffffffffu
 
+#ifdef NX_STREAM_DEBUG
+// developer instrumentation of K2 (never compiled into the product library):
+// [0] start ns, [1..8] first time class c ran out, [16] last warp exit ns, [17] warp
+// iterations, [18] feeder scans, [32..] live lane-steps per 0.25 ms of run time
+__device__ unsigned long long g_dbg[512];
+__device__ __forceinline__ unsigned long long dbg_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define NX_DBG_ITER(havemask)                                                        \
+  do {                                                                               \
+    ++dbg_iters;                                                                     \
+    const unsigned hm_ = (havemask);   /* evaluated by ALL lanes (it is a ballot) */   \
+    if ((threadIdx.x & 31u) == 0) {                                                  \
+      unsigned long long b_ = (dbg_now() - g_dbg[0]) / 250000ull;                    \
+      if (b_ > 400) b_ = 400;                                                        \
+      atomicAdd(&g_dbg[32 + b_], (unsigned long long)__popc(hm_));                   \
+    }                                                                                \
+  } while (0)
+#else
+#define NX_DBG_ITER(havemask) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------
 // shared-memory staging of an np.interp table (x, f, slope, bucket index)
 // ---------------------------------------------------------------------------
@@ -207,6 +231,9 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
   unsigned att = 0, acc = 0;
   unsigned long long tot_att = 0, tot_acc = 0;
   int st = 0;
+#ifdef NX_STREAM_DEBUG
+  unsigned long long dbg_iters = 0;
+#endif
 
   for (;;) {
     unsigned need = __ballot_sync(FULL_MASK, !have);
@@ -232,6 +259,7 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
       if (drained) break;
       continue;
     }
+    NX_DBG_ITER(__ballot_sync(FULL_MASK, have));
     if (have) {
       int fl;
       if (MODE < 0) fl = adaptive_attempt<true>(p, T, s, step);
@@ -260,6 +288,10 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
     if (tot_att) atomicAdd(&totals[0], tot_att);
     if (tot_acc) atomicAdd(&totals[1], tot_acc);
     if (st) atomicOr(status, st);
+#ifdef NX_STREAM_DEBUG
+    atomicMax(&g_dbg[16], dbg_now());
+    atomicAdd(&g_dbg[17], dbg_iters);
+#endif
   }
 }
 
@@ -357,6 +389,341 @@ k_cost_scatter(long long n, const unsigned char* __restrict__ bucket,
   for (int k = 0; k < NX_SCATTER_ITEMS; ++k) {
     const long long i = first + (long long)k * 256 + threadIdx.x;
     if (b[k] >= 0) perm[base[b[k]] + r[k]] = (unsigned)i;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2, class-ordered streaming queue (the default schedule).
+//
+// The sort above costs three extra kernels, turns every column access of K2 into a
+// scattered 8-byte access, and cannot start before ALL packets are on the device.
+// Here the queue stays in natural (coalesced) order and is walked NX_NCLASS times:
+// pass c only hands out packets whose predicted cost class is c (longest class
+// first), so long packets still start first, but a batch is 32 CONSECUTIVE packets
+// (nine 256-byte rows, 16-byte cp.async.cg).  The packet range is cut into up to 32
+// segments; segment s may be used once *arrived > s, which lets ONE persistent
+// kernel integrate while the copy engine is still delivering later segments
+// (nx_integrate_adaptive_host): lanes prefer the longest class of any segment that
+// has arrived, so there is a single tail at the very end of the run instead of
+// one per chunk.  The class is recomputed from the packet's INITIAL state in every
+// pass (float arithmetic, deterministic): the kernel reads the initial state from
+// one slab (the context's X0 columns, where the host-buffer path lands its copies)
+// and writes the final state to the state slab, so the input is immutable while
+// the kernel runs and every packet is handed out exactly once, in the pass of its
+// class.
+// ---------------------------------------------------------------------------
+// measured on B200, 1e7 Na packets through the host path, 16 segments: 6 classes at
+// 1024 / 2.83^c: 26.9 ms; 8 classes at 2048 / 2^c: 27.6 ms; 4 classes at 512 / 4^c: 27.7 ms
+#ifndef NX_NCLASS
+#define NX_NCLASS 6
+#endif
+#ifndef NX_CLASS_TOP
+#define NX_CLASS_TOP 1024.0f         // class 0: predicted steps >= TOP; class c: >= TOP / RATIO^c
+#endif
+#ifndef NX_CLASS_RATIO
+#define NX_CLASS_RATIO 2.83f
+#endif
+#define NX_GROUP 128                 // packets claimed per atomic
+#define NX_SFEED_COLS 8              // time,x,y,z,vx,vy,vz,frac (the step size starts as a constant)
+#define NX_SFEED_BYTES_PER_WARP (2 * NX_SFEED_COLS * 32 * 8 + 32)
+#ifndef NX_SCAN_MAX
+#define NX_SCAN_MAX 3                // batches scanned per step while some lane is live
+#endif
+#define NX_STREAM_TIMEOUT_NS 4000000000ull
+
+__device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+#ifdef NX_FEED_NOINLINE
+#define NX_FEED_INLINE __noinline__
+#else
+#define NX_FEED_INLINE __forceinline__
+#endif
+// float restatement of cost_bucket() folded into NX_NCLASS classes (0 = longest)
+__device__ NX_FEED_INLINE int cost_class(const RunParams& p, int model, float res, float mu,
+                                          float amax, double td, double xd, double yd, double zd,
+                                          double vxd, double vyd, double vzd, double fd) {
+  if (!(td > p.resolution) || !(fd > 0.0)) return NX_NCLASS - 1;
+  const float t = (float)td, x = (float)xd, y = (float)yd, z = (float)zd;
+  const float vx = (float)vxd, vy = (float)vyd, vz = (float)vzd;
+  const float r2 = x * x + y * y + z * z, r = sqrtf(r2);
+  const float v2 = vx * vx + vy * vy + vz * vz, v = sqrtf(v2);
+  const float rv = x * vx + y * vy + z * vz;
+  float tfl = t;
+  const float en = 0.5f * v2 - mu / r;
+  if (p.gravity && en < 0.0f && mu > 0.0f) {
+    const float a = -mu / (2.0f * en);
+    const float l2 = fmaxf(r2 * v2 - rv * rv, 0.0f);
+    const float e = sqrtf(fmaxf(1.0f + 2.0f * en * l2 / (mu * mu), 0.0f));
+    if (a * (1.0f - e) < 1.0f && e > 1e-6f) {
+      const float c1 = fminf(fmaxf((1.0f - 1.0f / a) / e, -1.0f), 1.0f);
+      const float c0 = fminf(fmaxf((1.0f - r / a) / e, -1.0f), 1.0f);
+      const float E1 = acosf(c1);
+      float E0 = acosf(c0);
+      if (rv < 0.0f) E0 = 6.2831853f - E0;
+      const float Ei = 6.2831853f - E1;
+      const float dM = (Ei - e * sinf(Ei)) - (E0 - e * sinf(E0));
+      const float tk = dM * sqrtf(a * a * a / mu);
+      const bool perturbed = (model == 2) && p.radpres && (amax * tk > 0.15f * v);
+      if (tk > 0.0f && tk < tfl && !perturbed) tfl = tk;
+    }
+  }
+  const float est = tfl * v / (40.0f * res * (1.0f + r)) + 4.0f;
+  int cls = 0;
+  float thr = NX_CLASS_TOP;
+#pragma unroll
+  for (int c = 0; c < NX_NCLASS - 1; ++c) {
+    if (est < thr) cls = c + 1;
+    thr *= (1.0f / NX_CLASS_RATIO);
+  }
+  return cls;
+}
+
+struct StreamQueue {
+  long long seg;                     // packets per segment (multiple of NX_GROUP)
+  int nseg;                          // <= 32
+  int model;                         // cost model (ctx option order_packets)
+  unsigned long long* cursor;        // [NX_NCLASS][32], zeroed before the launch
+  const unsigned* arrived;           // segments [0, *arrived) are on the device; nullptr: all
+};
+
+struct StreamFeeder {
+  double* vals;                      // this warp's staging area: [2][9][32]
+  unsigned lane;
+  // everything below is warp-uniform
+  unsigned base_cur, base_pend;      // packet index of slot 0 of the current / pending batch
+  int cnt_pend;                      // packets in the pending batch (0: none in flight)
+  int cls_cur, cls_pend;
+  unsigned char* order;              // [32] slots of the current batch that belong to cls_cur
+  int pos, cnt;                      // hand-out position / number of entries in order[]
+  int buf;
+  unsigned grp_next, grp_end;        // claimed group still to be walked
+  int grp_cls;
+  unsigned exh[NX_NCLASS];           // bit s: cursor (class, segment s) is exhausted
+  unsigned all_mask;
+
+  __device__ __forceinline__ bool all_done() const {
+    unsigned m = all_mask;
+#pragma unroll
+    for (int c = 0; c < NX_NCLASS; ++c) m &= exh[c];
+    return m == all_mask;
+  }
+  __device__ NX_FEED_INLINE bool claim_group(const StreamQueue& Q, long long n) {
+    unsigned nready = (unsigned)Q.nseg;
+    if (Q.arrived) nready = ld_volatile_u32(Q.arrived);
+    const unsigned ready = nready >= 32u ? 0xffffffffu : ((1u << nready) - 1u);
+#pragma unroll
+    for (int c = 0; c < NX_NCLASS; ++c) {
+      unsigned avail = ready & ~exh[c];
+      while (avail) {
+        const int s = __ffs(avail) - 1;
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(Q.cursor + c * 32 + s, (unsigned long long)NX_GROUP);
+        g = __shfl_sync(FULL_MASK, g, 0);
+        const long long first = (long long)s * Q.seg;
+        const long long count = min(Q.seg, n - first);
+        if ((long long)g + NX_GROUP >= count) {
+          exh[c] |= 1u << s;
+#ifdef NX_STREAM_DEBUG
+          if (lane == 0 && s == Q.nseg - 1)
+            atomicCAS(&g_dbg[1 + c], 0ull, global_timer_ns());
+#endif
+        }
+        if ((long long)g < count) {
+          grp_next = (unsigned)(first + (long long)g);
+          grp_end = (unsigned)min(first + count, first + (long long)g + NX_GROUP);
+          grp_cls = c;
+          return true;
+        }
+        avail &= ~(1u << s);
+      }
+    }
+    return false;
+  }
+  // start the copy of the next batch into the idle buffer
+  __device__ __forceinline__ void issue_prefetch(const StreamQueue& Q, long long n,
+                                                 const double* col0, size_t stride) {
+    cnt_pend = 0;
+    if (grp_next >= grp_end) {
+      if (all_done() || !claim_group(Q, n)) return;
+    }
+    base_pend = grp_next;
+    cnt_pend = (int)min(32u, grp_end - grp_next);
+    cls_pend = grp_cls;
+    grp_next += 32u;
+    double* dst = vals + (size_t)(buf ^ 1) * NX_SFEED_COLS * 32;
+    // 8 rows of 256 bytes = 128 chunks of 16 bytes (rows are padded to 32 packets)
+#pragma unroll
+    for (int i = 0; i < NX_SFEED_COLS / 2; ++i) {
+      const unsigned j = lane + 32u * i;
+      const unsigned col = j >> 4, part = (j & 15u) * 2u;
+      cp_async16_cg(dst + col * 32u + part, col0 + (size_t)col * stride + base_pend + part);
+    }
+    cp_async_commit();
+  }
+  __device__ __forceinline__ void init(unsigned char* smem, const StreamQueue& Q, long long n,
+                                       const double* col0, size_t stride) {
+    lane = threadIdx.x & 31u;
+    vals = reinterpret_cast<double*>(smem + (size_t)(threadIdx.x >> 5) * NX_SFEED_BYTES_PER_WARP);
+    order = reinterpret_cast<unsigned char*>(vals + 2 * NX_SFEED_COLS * 32);
+    buf = 0; pos = 0; cnt = 0; cnt_pend = 0; base_cur = base_pend = 0; cls_cur = cls_pend = 0;
+    grp_next = grp_end = 0; grp_cls = 0;
+#pragma unroll
+    for (int c = 0; c < NX_NCLASS; ++c) exh[c] = 0;
+    all_mask = Q.nseg >= 32 ? 0xffffffffu : ((1u << Q.nseg) - 1u);
+    issue_prefetch(Q, n, col0, stride);
+  }
+  // make the pending batch current.  1: a batch is current (match may be empty),
+  // 0: nothing available right now (segments still in flight), -1: queue finished.
+  __device__ __forceinline__ int advance(const StreamQueue& Q, long long n, const double* col0,
+                                         size_t stride, const RunParams& p, float res, float mu,
+                                         float amax) {
+    if (cnt_pend == 0) {
+      issue_prefetch(Q, n, col0, stride);
+      if (cnt_pend == 0) return all_done() ? -1 : 0;
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    buf ^= 1;
+    base_cur = base_pend; cls_cur = cls_pend;
+    const int nb = cnt_pend;
+    const double* v = vals + (size_t)buf * NX_SFEED_COLS * 32 + lane;
+    int cls = -1;
+    if ((int)lane < nb)
+      cls = (NX_NCLASS == 1) ? 0
+                             : cost_class(p, Q.model, res, mu, amax, v[0], v[32], v[64], v[96],
+                                          v[128], v[160], v[192], v[224]);
+    const unsigned match = __ballot_sync(FULL_MASK, cls == cls_cur);
+    if (cls == cls_cur) order[__popc(match & ((1u << lane) - 1u))] = (unsigned char)lane;
+    pos = 0; cnt = __popc(match);
+    __syncwarp();
+    issue_prefetch(Q, n, col0, stride);
+    return 1;
+  }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
+k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, double step0,
+                            StateCols P, long long n, RunParams p, InterpTable Tg, FastTable Fg,
+                            StreamQueue Q, unsigned long long* __restrict__ totals,
+                            unsigned* __restrict__ att_out, unsigned* __restrict__ acc_out,
+                            int* __restrict__ status, unsigned table_bytes) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  InterpTable T;
+  FastTable F;
+  if (MODE < 0) stage_table(Tg, T, smem_raw);
+  else stage_fast_table(Fg, F, smem_raw);
+  const float res = (float)p.resolution, mu = (float)fabs(p.GM), amax = (float)p.radpres_amax;
+  StreamFeeder feed;
+  feed.init(smem_raw + table_bytes, Q, n, col0, stride);
+  __syncthreads();
+
+  const unsigned lane = threadIdx.x & 31u;
+  bool have = false, drained = false;
+  unsigned idx = 0;
+  double s[8], step = 0.0;
+  unsigned att = 0, acc = 0;
+  unsigned long long tot_att = 0, tot_acc = 0;
+  unsigned long long wait_since = 0;
+  int st = 0;
+#ifdef NX_STREAM_DEBUG
+  unsigned long long dbg_iters = 0, dbg_scans = 0;
+#endif
+
+  for (;;) {
+    unsigned need = __ballot_sync(FULL_MASK, !have);
+    bool starved = false;
+    int scans = 0;
+    while (need && !drained) {
+      if (feed.pos == feed.cnt) {
+        if (scans >= NX_SCAN_MAX && need != FULL_MASK) break;   // let the live lanes step
+        const int r = feed.advance(Q, n, col0, stride, p, res, mu, amax);
+        ++scans;
+#ifdef NX_STREAM_DEBUG
+        ++dbg_scans;
+#endif
+        if (r < 0) { drained = true; break; }
+        if (r == 0) { starved = true; break; }
+        continue;
+      }
+      const int take = min(__popc(need), feed.cnt - feed.pos);
+      const int rank = __popc(need & ((1u << lane) - 1u));
+      if (!have && rank < take) {
+        const int slot = feed.order[feed.pos + rank];
+        const double* v = feed.vals + (size_t)feed.buf * NX_SFEED_COLS * 32 + slot;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] = v[k * 32];
+        step = step0;
+        idx = feed.base_cur + (unsigned)slot;
+        att = 0; acc = 0;
+        have = (s[0] > p.resolution) && (s[7] > 0.0);
+        if (!have) {                      // nothing to integrate: pass it through (att/acc pre-zeroed)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
+          __stcs(P.c[8] + idx, step);
+        }
+      }
+      feed.pos += take;
+      need = __ballot_sync(FULL_MASK, !have);
+    }
+    if (!__any_sync(FULL_MASK, have)) {
+      if (drained) break;
+      if (starved) {
+        // every resident segment is used up and later ones are still on the wire
+        const unsigned long long now = global_timer_ns();
+        if (wait_since == 0) wait_since = now;
+        if (now - wait_since > NX_STREAM_TIMEOUT_NS) { st |= 64; break; }
+        __nanosleep(400);
+      }
+      continue;
+    }
+    wait_since = 0;
+    NX_DBG_ITER(__ballot_sync(FULL_MASK, have));
+    if (have) {
+      int fl;
+      if (MODE < 0) fl = adaptive_attempt<true>(p, T, s, step);
+      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s, step);
+      ++att;
+      if (fl & ATT_ACCEPTED) ++acc;
+      st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
+      if (!(fl & ATT_LIVE)) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
+        __stcs(P.c[8] + idx, step);
+        att_out[idx] = att; acc_out[idx] = acc;
+        tot_att += att; tot_acc += acc;
+        have = false;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tot_att += __shfl_xor_sync(FULL_MASK, tot_att, o);
+    tot_acc += __shfl_xor_sync(FULL_MASK, tot_acc, o);
+    st |= __shfl_xor_sync(FULL_MASK, st, o);
+  }
+  if (lane == 0) {
+    if (tot_att) atomicAdd(&totals[0], tot_att);
+    if (tot_acc) atomicAdd(&totals[1], tot_acc);
+    if (st) atomicOr(status, st);
+#ifdef NX_STREAM_DEBUG
+    atomicMax(&g_dbg[16], global_timer_ns());
+    atomicAdd(&g_dbg[17], dbg_iters);
+    atomicAdd(&g_dbg[18], dbg_scans);
+#endif
   }
 }
 
@@ -707,6 +1074,80 @@ static cudaError_t launch_adaptive_mode(cudaStream_t st, int device, StateCols P
                                                                    totals, att, acc, status,
                                                                    (unsigned)tbytes);
   return cudaGetLastError();
+}
+
+#ifdef NX_STREAM_DEBUG
+__global__ void k_dbg_begin() {
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) g_dbg[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) g_dbg[0] = dbg_now();
+}
+#endif
+cudaError_t debug_begin(cudaStream_t st) {
+#ifdef NX_STREAM_DEBUG
+  k_dbg_begin<<<1, 256, 0, st>>>();
+#endif
+  return cudaGetLastError();
+}
+cudaError_t debug_read(unsigned long long* out, int count) {
+#ifdef NX_STREAM_DEBUG
+  return cudaMemcpyFromSymbol(out, g_dbg, (size_t)(count > 512 ? 512 : count) * 8);
+#else
+  for (int i = 0; i < count; ++i) out[i] = 0;
+  return cudaSuccess;
+#endif
+}
+
+template <int MODE>
+static cudaError_t launch_adaptive_stream_mode(cudaStream_t st, int device, const double* in0,
+                                               size_t in_stride, double step0, StateCols P,
+                                               long long n, const RunParams& p,
+                                               const InterpTable& T, const FastTable& F,
+                                               const StreamQueue& Q, unsigned long long* totals,
+                                               unsigned* att, unsigned* acc, int* status) {
+  const size_t tbytes = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
+  const size_t smem = tbytes + (size_t)(NX_INT_THREADS / 32) * NX_SFEED_BYTES_PER_WARP;
+  int blocks = 0;
+  cudaError_t e = persistent_grid(k_integrate_adaptive_stream<MODE>, device, smem, &blocks);
+  if (e != cudaSuccess) return e;
+  const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
+  if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+  k_integrate_adaptive_stream<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(
+      in0, in_stride, step0, P, n, p, T, F, Q, totals, att, acc, status, (unsigned)tbytes);
+  return cudaGetLastError();
+}
+
+// cursor: NX_STREAM_CURSORS zeroed u64; arrived: nullptr or a device word that the
+// copy stream raises to the number of resident segments.
+cudaError_t launch_integrate_adaptive_stream(cudaStream_t st, int device, const double* in0,
+                                             size_t in_stride, double step0, StateCols P,
+                                             long long n, const RunParams& p,
+                                             const InterpTable& T, const FastTable& F,
+                                             long long seg, int nseg, int model,
+                                             unsigned long long* cursor, const unsigned* arrived,
+                                             unsigned long long* totals, unsigned* att,
+                                             unsigned* acc, int* status) {
+  StreamQueue Q;
+  Q.seg = seg; Q.nseg = nseg; Q.model = model; Q.cursor = cursor; Q.arrived = arrived;
+#define NX_ARGS st, device, in0, in_stride, step0, P, n, p, T, F, Q, totals, att, acc, status
+  if (p.strict_math) return launch_adaptive_stream_mode<-1>(NX_ARGS);
+  const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
+  switch (mode) {
+    case 0: return launch_adaptive_stream_mode<0>(NX_ARGS);
+    case 1: return launch_adaptive_stream_mode<1>(NX_ARGS);
+    case 2: return launch_adaptive_stream_mode<2>(NX_ARGS);
+    case 4: return launch_adaptive_stream_mode<4>(NX_ARGS);
+    case 5: return launch_adaptive_stream_mode<5>(NX_ARGS);
+    case 6: return launch_adaptive_stream_mode<6>(NX_ARGS);
+    case 8: return launch_adaptive_stream_mode<8>(NX_ARGS);
+    case 9: return launch_adaptive_stream_mode<9>(NX_ARGS);
+    case 10: return launch_adaptive_stream_mode<10>(NX_ARGS);
+    case 12: return launch_adaptive_stream_mode<12>(NX_ARGS);
+    case 13: return launch_adaptive_stream_mode<13>(NX_ARGS);
+    case 14: return launch_adaptive_stream_mode<14>(NX_ARGS);
+    default: return cudaErrorInvalidValue;
+  }
+#undef NX_ARGS
 }
 
 cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long long n,

@@ -454,12 +454,57 @@ def test_pipelined_host_path_equals_resident_path(engine):
     att0, acc0 = engine.integrate_adaptive()
     ref = engine.export_state()
     a0, c0 = engine.export_stats()
-    for nchunks in (1, 3):
+    step0 = engine.export_step()
+    for schedule in (1, 0):          # 1: one streaming class-ordered kernel; 0: per-chunk sort + kernel
+        engine.set_option('schedule', schedule)
+        for nchunks in (1, 3, 32):
+            att, acc = engine.integrate_adaptive_host(X0, nchunks=nchunks)
+            assert (att, acc) == (att0, acc0)
+            assert np.array_equal(engine.export_state(), ref)
+            a1, c1 = engine.export_stats()
+            assert np.array_equal(a0, a1) and np.array_equal(c0, c1)
+            assert np.array_equal(engine.export_step(), step0)
+    engine.set_option('schedule', 1)
+
+
+@pytest.mark.parametrize('n', [1, 127, 129, 4097, 50_001])
+def test_streamed_host_path_ragged_and_dead_packets(engine, n):
+    """Ragged segment sizes, packets that are dead or finished on arrival (they must
+    pass through untouched with zero step counts), more segments than groups."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    X0 = initial_state.draw_x0(setup, n, 9)[:, :8].copy()
+    X0[::7, 7] = 0.0                  # dead on arrival
+    X0[3::11, 0] = 0.0                # no time left
+    engine.import_state(X0)
+    att0, acc0 = engine.integrate_adaptive()
+    ref = engine.export_state()
+    a0, c0 = engine.export_stats()
+    engine.set_option('schedule', 1)
+    for nchunks in (1, 5, 32):
         att, acc = engine.integrate_adaptive_host(X0, nchunks=nchunks)
         assert (att, acc) == (att0, acc0)
-        assert np.array_equal(engine.export_state(), ref)
+        got = engine.export_state()
+        assert np.array_equal(got, ref)
         a1, c1 = engine.export_stats()
         assert np.array_equal(a0, a1) and np.array_equal(c0, c1)
+    assert np.array_equal(got[:, ::7].T, X0[::7])             # untouched
+    assert np.all(a1[::7] == 0)
+
+
+def test_streamed_host_path_repeatable(engine):
+    """The class-ordered schedule must hand out every packet exactly once: ten
+    back-to-back runs give bit-identical states and step totals."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    X0 = initial_state.draw_x0(setup, 400_000, 12)[:, :8]
+    ref, tot = None, None
+    for rep in range(10):
+        t = engine.integrate_adaptive_host(X0, nchunks=16)
+        x = engine.export_state()
+        if ref is None:
+            ref, tot = x, t
+        assert t == tot and np.array_equal(x, ref)
 
 
 @pytest.mark.parametrize('sparams', [{'type': 'uniform'},
