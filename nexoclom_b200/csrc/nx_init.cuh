@@ -47,41 +47,23 @@ NX_HD double bilinear(const SourceMap& m, int nx, int ny, double x, double y) {
   return r0[0] * (1 - tx) * (1 - ty) + r0[1] * (1 - tx) * ty + r1[0] * tx * (1 - ty) + r1[1] * tx * ty;
 }
 
-// Fills x0[NCOL_X0] = time,x,y,z,vx,vy,vz,frac,v,longitude,latitude,local_time,
-// altitude,azimuth for packet `id`.
-NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const InterpTable& speed,
-                       uint64_t seed, uint64_t id, double* x0) {
-  double u_time, u_sinlat, u_lon, u_speed, u_alt, u_az, g0, g1;
-  uniform_pair(seed, id, STREAM_INIT, 0, u_time, u_sinlat);
-  uniform_pair(seed, id, STREAM_INIT, 1, u_lon, u_speed);
-  uniform_pair(seed, id, STREAM_INIT, 2, u_alt, u_az);
+// uniform surface band (source_distribution.py:47-62)
+NX_HD void uniform_lonlat(const SourceParams& sp, double u_sinlat, double u_lon, double& lon,
+                          double& lat) {
+  const double sinlat = add_rn(sp.sinlat0, mul_rn(sub_rn(sp.sinlat1, sp.sinlat0), u_sinlat));
+  lat = asin(sinlat);
+  lon = fmod(add_rn(sp.lon0, mul_rn(sub_rn(sp.lon1, sp.lon0), u_lon)), NX_TWO_PI);
+}
 
+// Everything after the surface point and the deviates are known: a pure transform
+// (replayed against the reference's recorded draws in tests/test_hostcheck.py).
+// z_normal is only used by the gaussian speed distribution.
+NX_HD void init_packet_finish(const SourceParams& sp, const InterpTable& speed, double u_time,
+                              double lon, double lat, double u_speed, double z_normal,
+                              double u_alt, double u_az, double* x0) {
   // time until the image is taken (Output.py:136-139)
   const double time = sp.random_time ? mul_rn(u_time, sp.endtime) : sp.endtime;
 
-  // ---- position (source_distribution.py:47-62, 96-121) ----
-  double lon, lat;
-  if (sp.spatial_type == SPATIAL_UNIFORM) {
-    const double sinlat = add_rn(sp.sinlat0, mul_rn(sub_rn(sp.sinlat1, sp.sinlat0), u_sinlat));
-    lat = asin(sinlat);
-    lon = fmod(add_rn(sp.lon0, mul_rn(sub_rn(sp.lon1, sp.lon0), u_lon)), NX_TWO_PI);
-  } else {
-    // acceptance / rejection on the map (randomdeviates.py:61-72)
-    uint32_t draw = 4;
-    for (;;) {
-      double ux, uy, uf, unused;
-      uniform_pair(seed, id, STREAM_INIT, draw, ux, uy);
-      uniform_pair(seed, id, STREAM_INIT, draw + 1, uf, unused);
-      draw += 2;
-      const double x = add_rn(mul_rn(ux, sub_rn(map.x_hi, map.x_lo)), map.x_lo);
-      const double y = add_rn(mul_rn(uy, sub_rn(map.y_hi, map.y_lo)), map.y_lo);
-      if (mul_rn(uf, sp.map_fmax) < bilinear(map, sp.map_nx, sp.map_ny, x, y) || draw > 4000) {
-        lon = x;
-        lat = sp.map_lat_is_sin ? asin(y) : y;
-        break;
-      }
-    }
-  }
   const double cl = cos(lat);
   const double sx = sp.is_planet ? sp.exobase : -sp.exobase;      // xyz_from_lonlat :18-28
   const double px = mul_rn(mul_rn(sx, sin(lon)), cl);
@@ -94,14 +76,7 @@ NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const Inter
   if (sp.speed_type == SPEED_FLAT) {
     v = sub_rn(add_rn(mul_rn(mul_rn(u_speed, 2.0), sp.delv), sp.vprob), sp.delv);
   } else if (sp.speed_type == SPEED_GAUSSIAN) {
-    if (sp.vsigma == 0.0) {
-      v = sp.vprob;
-    } else {
-      uniform_pair(seed, id, STREAM_INIT, 3, g0, g1);
-      // Box-Muller on (1-g0) in (0,1]
-      const double z = sqrt(-2.0 * log(1.0 - g0)) * cos(NX_TWO_PI * g1);
-      v = add_rn(mul_rn(z, sp.vsigma), sp.vprob);
-    }
+    v = (sp.vsigma == 0.0) ? sp.vprob : add_rn(mul_rn(z_normal, sp.vsigma), sp.vprob);
   } else {
     v = interp(speed, u_speed);           // inverse CDF (randomdeviates.py:29-33)
   }
@@ -137,6 +112,45 @@ NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const Inter
   x0[4] = mul_rn(d[0], v); x0[5] = mul_rn(d[1], v); x0[6] = mul_rn(d[2], v);
   x0[7] = 1.0; x0[8] = v; x0[9] = lon; x0[10] = lat; x0[11] = local_time;
   x0[12] = alt; x0[13] = az;
+}
+
+// Fills x0[NCOL_X0] = time,x,y,z,vx,vy,vz,frac,v,longitude,latitude,local_time,
+// altitude,azimuth for packet `id`.
+NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const InterpTable& speed,
+                       uint64_t seed, uint64_t id, double* x0) {
+  double u_time, u_sinlat, u_lon, u_speed, u_alt, u_az;
+  uniform_pair(seed, id, STREAM_INIT, 0, u_time, u_sinlat);
+  uniform_pair(seed, id, STREAM_INIT, 1, u_lon, u_speed);
+  uniform_pair(seed, id, STREAM_INIT, 2, u_alt, u_az);
+
+  // ---- position (source_distribution.py:47-62, 96-121) ----
+  double lon, lat;
+  if (sp.spatial_type == SPATIAL_UNIFORM) {
+    uniform_lonlat(sp, u_sinlat, u_lon, lon, lat);
+  } else {
+    // acceptance / rejection on the map (randomdeviates.py:61-72)
+    uint32_t draw = 4;
+    for (;;) {
+      double ux, uy, uf, unused;
+      uniform_pair(seed, id, STREAM_INIT, draw, ux, uy);
+      uniform_pair(seed, id, STREAM_INIT, draw + 1, uf, unused);
+      draw += 2;
+      const double x = add_rn(mul_rn(ux, sub_rn(map.x_hi, map.x_lo)), map.x_lo);
+      const double y = add_rn(mul_rn(uy, sub_rn(map.y_hi, map.y_lo)), map.y_lo);
+      if (mul_rn(uf, sp.map_fmax) < bilinear(map, sp.map_nx, sp.map_ny, x, y) || draw > 4000) {
+        lon = x;
+        lat = sp.map_lat_is_sin ? asin(y) : y;
+        break;
+      }
+    }
+  }
+  double z = 0.0;
+  if (sp.speed_type == SPEED_GAUSSIAN && sp.vsigma != 0.0) {
+    double g0, g1;
+    uniform_pair(seed, id, STREAM_INIT, 3, g0, g1);
+    z = sqrt(-2.0 * log(1.0 - g0)) * cos(NX_TWO_PI * g1);     // Box-Muller on (1-g0) in (0,1]
+  }
+  init_packet_finish(sp, speed, u_time, lon, lat, u_speed, z, u_alt, u_az, x0);
 }
 
 }  // namespace nx

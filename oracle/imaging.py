@@ -9,10 +9,16 @@ NumPy restatement of
   reference nexoclom/math/histogram.py:28-39                        -> np.histogram2d (same call)
   reference nexoclom/data_simulation/compute_iteration.py:98-222    -> los_iteration()
 using the same third-party routines the reference calls (np.matmul,
-np.histogram2d, np.interp, sklearn KDTree.query_radius).  The reference holds no
-golden images / LOS vectors (tests/unit_tests/math/test_histogram.py and
-test_rotation_matrix.py are empty): parity of these two functions is pinned
-only through those shared library calls.
+np.histogram2d, np.interp, sklearn KDTree.query_radius).
+
+Pinned by: the reference holds no golden images / LOS vectors of its own
+(tests/unit_tests/math/test_histogram.py and test_rotation_matrix.py are empty), so
+tools/make_golden_products.py EXECUTES the unmodified reference
+ModelImage.create_image() and compute_iteration() (with their packet_weighting,
+interpu, Histogram2d, KD-tree ladder) on committed packet sets; create_image() and
+los_iteration() below reproduce those outputs (tests/golden/image.npz, los.npz) with
+bit-identical pixel / hit counts, included masks and used sets and radiance within
+1e-12 (tests/test_oracle_products_golden.py).
 """
 import numpy as np
 

@@ -13,6 +13,13 @@ as a pure TRANSFORM of uniform deviates, so it can be driven either by NumPy's
 generator (statistical checks, CPU baseline inputs) or by the same
 Philox4x32-10 counters the CUDA kernel uses (exact parity of K1).
 
+Pinned by: tests/golden/source_distribution.npz holds the outputs of the unmodified
+reference surface_distribution / speed_distribution / angular_distribution together
+with every random deviate they drew (tools/make_golden_products.py); transform()
+replayed on those deviates reproduces them to < 5e-15 for five source configurations
+(tests/test_oracle_products_golden.py), and so does the kernel's own transform
+(csrc/nx_init.cuh, host build).
+
 Philox4x32-10 is the published algorithm of Salmon et al., "Parallel random
 numbers: as easy as 1, 2, 3" (SC'11); counter = (id_lo, id_hi, draw, stream),
 key = (seed_lo, seed_hi).  Known-answer vectors from the Random123 distribution
@@ -95,7 +102,28 @@ def _bilinear(fmap, xa, ya, x, y):
     return interpolate.interpn((xa, ya), fmap, (x, y))
 
 
-def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None):
+def pooled_rejection(fmap, xa, ya, fmax, rounds, n):
+    """reference math/randomdeviates.py:61-72 literally: every round draws n candidate
+    (ux, uy, uf) triples, the accepted ones are POOLED in order and the first n kept.
+    (transform() below gives every packet its own candidate sequence instead -- the same
+    distribution, needed for a counter-based generator; this function exists so that the
+    acceptance rule and the map interpolation can be replayed against the reference's
+    recorded draws.)  rounds: iterable of (ux, uy, uf) uniform arrays."""
+    xa_ = np.linspace(xa.min(), xa.max(), fmap.shape[0])
+    ya_ = np.linspace(ya.min(), ya.max(), fmap.shape[1])
+    xs, ys = [], []
+    for ux, uy, uf in rounds:
+        x = ux * (xa.max() - xa.min()) + xa.min()
+        y = uy * (ya.max() - ya.min()) + ya.min()
+        ok = uf * fmax < _bilinear(fmap, xa_, ya_, x, y)
+        xs.extend(x[ok])
+        ys.extend(y[ok])
+        if len(xs) >= n:
+            break
+    return np.array(xs[:n]), np.array(ys[:n])
+
+
+def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None, lonlat=None):
     """Uniform deviates -> X0 (N,14).
 
     sp: the SourceParams numbers (nexoclom_b200._lib.SourceParams or any object
@@ -106,7 +134,9 @@ def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None):
     n = len(u['time'])
     time = u['time'] * sp.endtime if sp.random_time else np.zeros(n) + sp.endtime
 
-    if sp.spatial_type == 0:
+    if lonlat is not None:
+        lon, lat = lonlat              # positions sampled elsewhere (pooled_rejection)
+    elif sp.spatial_type == 0:
         sinlat = sp.sinlat0 + (sp.sinlat1 - sp.sinlat0) * u['sinlat']
         lat = np.arcsin(sinlat)
         lon = (sp.lon0 + (sp.lon1 - sp.lon0) * u['lon']) % (2 * np.pi)
@@ -138,7 +168,10 @@ def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None):
         if sp.vsigma == 0.:
             v0 = np.zeros(n) + sp.vprob
         else:
-            z = np.sqrt(-2.0 * np.log(1.0 - u['g0'])) * np.cos(2 * np.pi * u['g1'])
+            if 'normal' in u:          # standard normal deviates supplied directly
+                z = u['normal']
+            else:
+                z = np.sqrt(-2.0 * np.log(1.0 - u['g0'])) * np.cos(2 * np.pi * u['g1'])
             v0 = z * sp.vsigma + sp.vprob
     else:
         cdf, xv = speed_table

@@ -119,6 +119,26 @@ extern "C" void hc_init_state(long n, const SourceParams* sp, unsigned long long
   for (long i = 0; i < n; ++i) init_packet(*sp, map, speed, seed, first_id + i, out + 14 * i);
 }
 
+// the pure transform of K1 on caller-supplied deviates (lon_in/lat_in: surface points
+// sampled elsewhere, or null for the uniform band computed from u_sinlat/u_lon)
+extern "C" void hc_init_from_deviates(long n, const SourceParams* sp, const double* cdf,
+                                      const double* vtab, int ntab, const double* u_time,
+                                      const double* u_sinlat, const double* u_lon,
+                                      const double* lon_in, const double* lat_in,
+                                      const double* u_speed, const double* z_normal,
+                                      const double* u_alt, const double* u_az,
+                                      double* out /* n x 14 */) {
+  HostInterp hs; InterpTable speed{};
+  if (ntab > 0) { hs = make_interp(cdf, vtab, ntab); speed = view(hs); }
+  for (long i = 0; i < n; ++i) {
+    double lon, lat;
+    if (lon_in) { lon = lon_in[i]; lat = lat_in[i]; }
+    else uniform_lonlat(*sp, u_sinlat[i], u_lon[i], lon, lat);
+    init_packet_finish(*sp, speed, u_time[i], lon, lat, u_speed[i], z_normal[i], u_alt[i],
+                       u_az[i], out + 14 * i);
+  }
+}
+
 static GTables make_gtables(std::vector<HostInterp>& store, int nt, const int* sizes,
                             const double* v, const double* g) {
   GTables G{};

@@ -279,6 +279,64 @@ def test_los_vs_oracle(engine, los_mode):
             assert set(int(k) for k in idx[off[i]:off[i + 1]]) == u
 
 
+@pytest.mark.parametrize('tag', ['col_pole', 'rad_pole', 'rad_side'])
+def test_image_vs_reference_golden(engine, tag):
+    """K4 through the C ABI against images made by the reference's own
+    ModelImage.create_image() (tests/golden/image.npz, tools/make_golden_products.py)."""
+    g = np.load(os.path.join(GOLDEN, 'image.npz'))
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    engine.upload_gtables(setup.gtables([5891, 5897]))
+    engine.import_state(g['X'])
+    view, dims = tuple(g[f'{tag}_view']), tuple(int(d) for d in g[f'{tag}_dims'])
+    ip = _image_params(setup, 0 if tag.startswith('col') else 1, view, dims=dims)
+    ip.apix = float(g[f'{tag}_apix'])
+    img, cnt = engine.image_accumulate(ip)
+    assert np.array_equal(cnt, g[f'{tag}_packim'].astype(np.int64))    # bit-exact pixel indexing
+    ref = g[f'{tag}_image']
+    nz = ref > 0
+    assert nz.sum() > 1000
+    assert np.max(np.abs(img[nz] - ref[nz]) / ref[nz]) < IMAGE_TOL
+    assert np.all(img[~nz] == 0)
+
+
+@pytest.mark.parametrize('los_mode', [1, 2])
+@pytest.mark.parametrize('tag', ['d1', 'd3'])
+def test_los_vs_reference_golden(engine, tag, los_mode):
+    """K5 through the C ABI against the reference's own compute_iteration()
+    (tests/golden/los.npz): radiance, hit counts, included mask, used sets."""
+    from nexoclom_b200.LOSResult import dist_from_planet_cut
+    import pandas as pd
+    g = np.load(os.path.join(GOLDEN, 'los.npz'))
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    engine.upload_gtables(setup.gtables([5891, 5897]))
+    engine.import_state(g['X'])
+    los = g['los']
+    data = pd.DataFrame(los, columns=['x', 'y', 'z', 'xbore', 'ybore', 'zbore'])
+    dist = np.asarray(dist_from_planet_cut(data), dtype=np.float64)
+    lp = LosParams()
+    lp.dphi, lp.outeredge = float(g[f'{tag}_dphi']), float(g['outeredge'])
+    lp.vrplanet, lp.rp_cm = setup.vrplanet, setup.radius_km * 1e5
+    lp.quantity = 1
+    engine.set_option('los_mode', los_mode)
+    try:
+        rad, npk, inc = engine.los_accumulate(los.T.copy(), dist, lp)
+        off, idx = engine.los_used(los.T.copy(), dist, lp)
+    finally:
+        engine.set_option('los_mode', 0)
+    assert np.array_equal(npk, g[f'{tag}_npackets'])                  # bit-exact hit counts
+    assert np.array_equal(inc, g[f'{tag}_included'])
+    ref = g[f'{tag}_radiance']
+    nz = ref > 0
+    assert np.max(np.abs(rad[nz] - ref[nz]) / ref[nz]) < IMAGE_TOL
+    assert np.all(rad[~nz] == 0)
+    roff, ridx = g[f'{tag}_used_off'], g[f'{tag}_used_idx']
+    assert np.array_equal(off, roff)
+    for i in range(len(los)):
+        assert np.array_equal(np.sort(idx[off[i]:off[i + 1]]), ridx[roff[i]:roff[i + 1]])
+
+
 def test_public_api_end_to_end(engine):
     """Input -> Output (device-drawn packets) -> ModelImage through the
     reference-facing classes; the image equals the oracle's create_image on the

@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Golden vectors for the PRODUCTS of the hot path, made by EXECUTING the unmodified
+reference code (build container only; needs /root/reference):
+
+  tests/golden/source_distribution.npz   reference surface_distribution(),
+        speed_distribution(), angular_distribution() (source_distribution.py:37-283)
+        with every random draw they make RECORDED, so that the oracle's pure transform
+        (oracle/initial_state.transform) and the device transform (tests/_hostcheck,
+        K1) can be replayed on exactly the same deviates;
+  tests/golden/image.npz                 reference ModelImage.create_image()
+        (ModelImage.py:229-274) incl. ModelResult.packet_weighting(), interpu(),
+        Histogram2d();
+  tests/golden/los.npz                   reference compute_iteration()
+        (compute_iteration.py:90-240) incl. the KD-tree candidate ladder, cone test,
+        planet truncation, foot-point shadow test and the used / included sets.
+
+astropy / periodictable / sqlalchemy are absent here: tools/refunits.py supplies a
+functional miniature of astropy.units, the g-value tables come from this repo's host
+port (nexoclom_b200.atomicdata.gValue, itself pinned to the reference's own golden
+pickle to 0 ulp -- tests/test_host_tables.py), everything else on the path is the
+reference's own source, imported from where it lies.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, 'tests'))
+REF = os.environ.get('NEXOCLOM_REFERENCE', '/root/reference')
+GOLD = os.path.join(REPO, 'tests', 'golden')
+
+import refunits as u                                    # noqa: E402
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def install():
+    """Namespace stub for ``nexoclom`` (its __init__ needs PostgreSQL) + stand-ins for the
+    absent third-party packages; the reference sub-packages are imported for real."""
+    u.install()
+    _stub('astropy.convolution', Gaussian2DKernel=None, convolve=None)
+    _stub('astropy.time', Time=None)
+    _stub('astropy.modeling', models=None, fitting=None)
+    _stub('astropy.visualization', PercentileInterval=None)
+    sa = _stub('sqlalchemy')
+    sa.__path__ = []
+    _stub('sqlalchemy.dialects').__path__ = []
+    _stub('sqlalchemy.dialects.postgresql')
+    masses = {'Na': 22.98977, 'Ca': 40.078, 'Mg': 24.305, 'K': 39.0983, 'O': 15.9994}
+    els = [types.SimpleNamespace(symbol=k, mass=v) for k, v in masses.items()]
+    _stub('periodictable', elements=els, **{e.symbol: e for e in els})
+    u.u = u.Unit(1.66053906660e-27, (0, 0, 1, 0, 0), 'u')
+    bk = _stub('bokeh')
+    bk.__path__ = []
+    for sub in ('plotting', 'palettes', 'models', 'io', 'themes'):
+        _stub('bokeh.' + sub, Inferno256=None, HoverTool=None, ColumnDataSource=None,
+              ColorBar=None, LogColorMapper=None, LogTicker=None, LinearColorMapper=None,
+              curdoc=None, export_png=None, Theme=None)
+    pkg = _stub('nexoclom', engine=None, config=None)
+    pkg.__path__ = [os.path.join(REF, 'nexoclom')]
+    pkg.__file__ = os.path.join(REF, 'nexoclom', '__init__.py')
+    for sub in ('particle_tracking', 'initial_state', 'data_simulation', 'atomicdata',
+                'utilities', 'solarsystem'):
+        m = _stub(f'nexoclom.{sub}')
+        m.__path__ = [os.path.join(REF, 'nexoclom', sub)]
+    from nexoclom.utilities.exceptions import InputError
+    sys.modules['nexoclom.utilities'].InputError = InputError
+    # g-values: this repo's host port, wrapped in the reference's Quantity interface
+    from nexoclom_b200 import atomicdata as ad
+
+    def gValue(species, wavelength, aplanet):
+        g = ad.gValue(species, float(np.asarray(wavelength)), float(np.asarray(aplanet)))
+        return types.SimpleNamespace(velocity=u.Quantity(g.velocity, u.km / u.s),
+                                     g=u.Quantity(g.g, 1 / u.s))
+    sys.modules['nexoclom.atomicdata'].gValue = gValue
+    sys.modules['nexoclom.atomicdata'].RadPresConst = None
+    from nexoclom.atomicdata.atomicmass import atomicmass
+    sys.modules['nexoclom.atomicdata'].atomicmass = atomicmass
+    sys.modules['nexoclom.solarsystem'].planet_dist = None
+    sys.modules['nexoclom.solarsystem'].SSObject = None
+    _stub('nexoclom.initial_state.satellite_initial_positions', satellite_initial_positions=None)
+    _stub('nexoclom.initial_state.LossInfo', LossInfo=None)
+    _stub('nexoclom.initial_state.SourceMap', SourceMap=None)
+    _stub('nexoclom.particle_tracking.SurfaceInteraction', SurfaceInteraction=None)
+    _stub('nexoclom.initial_state.input_classes', InputError=InputError)
+    _stub('nexoclom.math.smooth', smooth=None, smooth2d=None)
+
+
+class RecordingRNG:
+    """numpy Generator that keeps every deviate it hands out, in call order."""
+
+    def __init__(self, seed):
+        self.g = np.random.default_rng(seed)
+        self.uniform, self.normal = [], []
+
+    def random(self, n):
+        r = self.g.random(n)
+        self.uniform.append(r)
+        return r
+
+    def standard_normal(self, n):
+        r = self.g.standard_normal(n)
+        self.normal.append(r)
+        return r
+
+
+def q(v, unit):
+    return u.Quantity(v, unit)
+
+
+# ---------------------------------------------------------------------------
+def golden_source_distribution():
+    import nexoclom.math.randomdeviates as rd
+    from nexoclom.initial_state import source_distribution as sd
+    ns = types.SimpleNamespace
+    rp_km = 2440.53
+    unit = u.def_unit('R_Mercury', q(rp_km, u.km))
+    # the cases are inputfiles (tests/golden/source_cases/*.input) parsed by this repo's
+    # Input class; the reference side receives the same numbers as astropy-style Quantities
+    from nexoclom_b200 import Input
+    from nexoclom_b200.units import Quantity as PQ
+    umap = {'rad': u.rad, 'km/s': u.km / u.s, 'K': u.K, 'eV': u.eV, '': u.dimensionless}
+
+    def conv(v):
+        if isinstance(v, PQ):
+            return q(float(v.value), umap[v.unit])
+        if isinstance(v, tuple):
+            return tuple(conv(x) for x in v)
+        return v
+
+    def group(obj):
+        return ns(**{k: conv(v) for k, v in vars(obj).items()})
+    cases = {}
+    cdir = os.path.join(GOLD, 'source_cases')
+    for fn in sorted(os.listdir(cdir)):
+        inp = Input(os.path.join(cdir, fn))
+        cases[fn[:-len('.input')]] = dict(spatial=group(inp.spatialdist),
+                                          speed=group(inp.speeddist),
+                                          angular=group(inp.angulardist),
+                                          species=inp.options.species,
+                                          endtime=float(inp.options.endtime.value))
+    out = {}
+    n = 4000
+    for tag, c in cases.items():
+        rng = RecordingRNG(77)
+        legacy = []                       # draws of the module-level numpy.random.rand (Q12)
+        glob = np.random.RandomState(1234)
+
+        def rand(k, _l=legacy, _g=glob):
+            r = _g.rand(k)
+            _l.append(r)
+            return r
+        rd.random = types.SimpleNamespace(rand=rand)
+        # Output.py:136-147: the time draw comes first; 'time' and 'frac' are the first two
+        # columns, which angular_distribution() relies on (it reads x,y,z by POSITION 2:5)
+        X0 = pd.DataFrame()
+        X0['time'] = rng.random(n) * c['endtime']
+        X0['frac'] = np.ones(n)
+        outputs = ns(npackets=n, randgen=rng, unit=unit, X0=X0,
+                     inputs=ns(spatialdist=c['spatial'], speeddist=c['speed'],
+                               angulardist=c['angular'],
+                               options=ns(species=c['species']),
+                               geometry=ns(planet=ns(type='Planet'))))
+        sd.surface_distribution(outputs)
+        sd.speed_distribution(outputs)
+        sd.angular_distribution(outputs)
+        cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'v', 'longitude', 'latitude', 'local_time',
+                'altitude', 'azimuth']
+        for cname in cols:
+            out[f'{tag}_{cname}'] = np.asarray(outputs.X0[cname].values, dtype=np.float64)
+        out[f'{tag}_uniform'] = (np.stack(rng.uniform) if rng.uniform else np.zeros((0, n)))
+        out[f'{tag}_normal'] = (np.stack(rng.normal) if rng.normal else np.zeros((0, n)))
+        out[f'{tag}_legacy'] = (np.stack(legacy) if legacy else np.zeros((0, n)))
+        print(tag, 'uniform draws', len(rng.uniform), 'normal', len(rng.normal),
+              'legacy rand', len(legacy))
+    np.savez_compressed(os.path.join(GOLD, 'source_distribution.npz'), **out)
+    print('source_distribution.npz')
+
+
+# ---------------------------------------------------------------------------
+def _final_packets(n, seed, f32):
+    """A plausible cloud of packets (no GPU here): oracle initial state pushed outward."""
+    from common import workload
+    from nexoclom_b200.runsetup import RunSetup
+    from oracle import initial_state
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    rng = np.random.default_rng(seed)
+    X = initial_state.draw_x0(setup, n, seed)[:, :8].copy()
+    X[:, 1:4] *= (1.0 + 5.0 * rng.random(n) ** 2)[:, None]
+    X[:, 4:7] *= rng.normal(1.0, 0.5, n)[:, None]
+    X[:, 7] = rng.random(n) * (rng.random(n) > 0.2)
+    if f32:
+        X = X.astype(np.float32).astype(np.float64)      # Output.save / restore (Q14)
+    return setup, X
+
+
+def golden_image():
+    from nexoclom.data_simulation.ModelImage import ModelImage
+    from nexoclom.data_simulation import ModelImage as mi_mod
+    ns = types.SimpleNamespace
+    setup, X = _final_packets(60000, 5, True)
+    rp_km = setup.radius_km
+    unit = u.def_unit('R_Mercury', q(rp_km, u.km))
+    out = {'X': X, 'vrplanet': setup.vrplanet, 'aplanet': setup.aplanet}
+    cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac']
+    for tag, quantity, view, dims in (('col_pole', 'column', (0.0, np.pi / 2), (200, 200)),
+                                      ('rad_pole', 'radiance', (0.0, np.pi / 2), (200, 200)),
+                                      ('rad_side', 'radiance', (0.7, 0.3), (160, 120))):
+        packets = pd.DataFrame(X, columns=cols)
+        fake_out = ns(X=packets, vrplanet=q(setup.vrplanet, unit / u.s), aplanet=setup.aplanet,
+                      filename='none')
+        mi_mod.Output = ns(restore=lambda fname, _o=fake_out: _o)
+        planet = ns(object='Mercury', radius=q(rp_km, u.km))
+        width = (q(8., unit), q(8., unit))
+        center = (q(0., unit), q(0., unit))
+        self = ns(inputs=ns(geometry=ns(planet=planet), options=ns(species='Na')),
+                  origin=planet, unit=unit, quantity=quantity, g=None,
+                  mechanism=['resonant scattering'] if quantity == 'radiance' else None,
+                  wavelength=(q(5891, u.AA), q(5897, u.AA)) if quantity == 'radiance' else None,
+                  subobslongitude=q(view[0], u.rad), subobslatitude=q(view[1], u.rad),
+                  dims=dims,
+                  xrange=[center[0] - width[0] / 2, center[0] + width[0] / 2],
+                  zrange=[center[1] - width[1] / 2, center[1] + width[1] / 2])
+        scale = (width[0] / dims[0], width[1] / dims[1])
+        self.Apix = (scale[0] * scale[1]).to(u.cm ** 2)              # ModelImage.py:76-77
+        self.image_rotation = types.MethodType(ModelImage.image_rotation, self)
+        from nexoclom.data_simulation.ModelResult import ModelResult
+        self.packet_weighting = types.MethodType(ModelResult.packet_weighting, self)
+        self.save = lambda *a, **k: None
+        image, packim = ModelImage.create_image(self, 'none')
+        out[f'{tag}_image'] = np.asarray(image.histogram, dtype=np.float64)
+        out[f'{tag}_packim'] = np.asarray(packim.histogram, dtype=np.float64)
+        out[f'{tag}_xaxis'] = np.asarray(image.x, dtype=np.float64)
+        out[f'{tag}_zaxis'] = np.asarray(image.y, dtype=np.float64)
+        out[f'{tag}_M'] = np.asarray(self.image_rotation(), dtype=np.float64)
+        out[f'{tag}_apix'] = float(np.asarray(self.Apix))
+        out[f'{tag}_view'] = np.asarray(view)
+        out[f'{tag}_dims'] = np.asarray(dims)
+        print(tag, 'sum', float(image.histogram.sum()), 'packets in frame',
+              int(packim.histogram.sum()))
+    np.savez_compressed(os.path.join(GOLD, 'image.npz'), **out)
+    print('image.npz')
+
+
+def golden_los():
+    from nexoclom.data_simulation import compute_iteration as ci
+    from nexoclom.data_simulation.ModelResult import ModelResult
+    ns = types.SimpleNamespace
+    setup, X = _final_packets(40000, 8, True)
+    rp_km = setup.radius_km
+    unit = u.def_unit('R_Mercury', q(rp_km, u.km))
+    cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac']
+    rng = np.random.default_rng(3)
+    nlos = 120
+    th = rng.random(nlos) * 2 * np.pi
+    rr = 1.15 + 3.0 * rng.random(nlos)
+    x_sc = np.stack([0.3 * rr * np.cos(th), 0.2 * rr * np.cos(th) - 0.6, rr * np.sin(th)], axis=1)
+    x_sc *= (np.maximum(np.linalg.norm(x_sc, axis=1), 1.1) / np.linalg.norm(x_sc, axis=1))[:, None]
+    tgt = rng.normal(size=(nlos, 3))
+    tgt *= ((0.5 + 3 * rng.random(nlos)) / np.linalg.norm(tgt, axis=1))[:, None]
+    tgt[::3] *= 0.2                                   # every third boresight hits the planet
+    bore = tgt - x_sc
+    bore /= np.linalg.norm(bore, axis=1)[:, None]
+    data = pd.DataFrame({'x': x_sc[:, 0], 'y': x_sc[:, 1], 'z': x_sc[:, 2],
+                         'xbore': bore[:, 0], 'ybore': bore[:, 1], 'zbore': bore[:, 2]})
+    out = {'X': X, 'vrplanet': setup.vrplanet, 'aplanet': setup.aplanet,
+           'los': np.concatenate([x_sc, bore], axis=1), 'outeredge': 25.0}
+    captured = {}
+
+    class Capture:
+        def __init__(self, iteration, losresult):
+            captured.update(iteration)
+
+        def save_iteration(self):
+            pass
+    ci.IterationResult = Capture
+    for tag, dphi_deg in (('d1', 1.0), ('d3', 3.0)):
+        packets = pd.DataFrame(X, columns=cols)
+        fake_out = ns(X=packets, X0=pd.DataFrame(index=packets.index),
+                      vrplanet=q(setup.vrplanet, unit / u.s), aplanet=setup.aplanet,
+                      totalsource=float(len(X)), idnum=1, unit=unit)
+        ci.Output = ns(restore=lambda fname, _o=fake_out: _o)
+        self = ns(inputs=ns(options=ns(outeredge=25.0, species='Na')), unit=unit,
+                  quantity='radiance', g=None, mechanism=['resonant scattering'],
+                  wavelength=(q(5891, u.AA), q(5897, u.AA)), dphi=np.radians(dphi_deg),
+                  query='golden', fitted=False)
+        self.packet_weighting = types.MethodType(ModelResult.packet_weighting, self)
+        scdata = ns(data=data.copy(), query='golden')
+        ci.compute_iteration(self, 'none', scdata)
+        out[f'{tag}_radiance'] = np.asarray(captured['radiance'].values, dtype=np.float64)
+        out[f'{tag}_npackets'] = np.asarray(captured['npackets'].values, dtype=np.int64)
+        out[f'{tag}_included'] = np.asarray(captured['included'].values, dtype=bool)
+        used = captured['used0']
+        off = np.zeros(nlos + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(s_) for s_ in used])
+        out[f'{tag}_used_off'] = off
+        out[f'{tag}_used_idx'] = np.concatenate(
+            [np.sort(np.fromiter(s_, dtype=np.int64, count=len(s_))) for s_ in used]
+            + [np.zeros(0, dtype=np.int64)])
+        out[f'{tag}_dphi'] = np.radians(dphi_deg)
+        print(tag, 'hits', int(out[f'{tag}_npackets'].sum()), 'lines with signal',
+              int((out[f'{tag}_radiance'] > 0).sum()), 'included', int(out[f'{tag}_included'].sum()))
+    np.savez_compressed(os.path.join(GOLD, 'los.npz'), **out)
+    print('los.npz')
+
+
+if __name__ == '__main__':
+    install()
+    which = sys.argv[1:] or ['source', 'image', 'los']
+    if 'source' in which:
+        golden_source_distribution()
+    if 'image' in which:
+        golden_image()
+    if 'los' in which:
+        golden_los()
