@@ -454,7 +454,23 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
   if (n > 0) {
     CK(debug_begin(ctx->stream));
     if ((r = begin_timed(ctx))) return r;
-    {
+    if (ctx->schedule == 2) {
+      // developer option (profiling the streaming kernel with kernel replay, which cannot
+      // run the concurrent copies): class-ordered passes over the X0 slab, nothing in flight
+      CK(cudaMemsetAsync(ctx->squeue, 0, (NX_STREAM_CURSORS + 1) * sizeof(unsigned long long),
+                         ctx->stream));
+      CK(cudaMemsetAsync(ctx->att, 0, (size_t)n * sizeof(unsigned), ctx->stream));
+      CK(cudaMemsetAsync(ctx->acc, 0, (size_t)n * sizeof(unsigned), ctx->stream));
+      long long seg = (n + 15) / 16;
+      seg = (seg + NX_STREAM_GROUP - 1) / NX_STREAM_GROUP * NX_STREAM_GROUP;
+      CK(launch_integrate_adaptive_stream(ctx->stream, ctx->device, ctx->x0, (size_t)ctx->cap,
+                                          1000.0, state_cols(ctx), n, ctx->params,
+                                          ctx->radpres.view, ctx->radpres.fast, seg,
+                                          (int)((n + seg - 1) / seg), ctx->order_packets,
+                                          ctx->squeue, nullptr, ctx->scalars + 1, ctx->att,
+                                          ctx->acc, ctx->status));
+      if ((r = end_timed(ctx, 1))) return r;
+    } else {
       const bool order = ctx->order_packets && n >= 4096;
       if (order)
         CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,

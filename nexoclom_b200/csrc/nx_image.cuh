@@ -48,6 +48,31 @@ NX_HD int hist_bin(double v, int n, double lo, double hi, double step) {
   return k;
 }
 
+// same bin from a reciprocal first guess (the two correction loops make the result
+// independent of the guess; they run 0 or 1 times)
+NX_HD int hist_bin_fast(double v, int n, double lo, double hi, double step, double inv_step) {
+  if (!(v >= lo && v <= hi)) return -1;
+  int k = (int)((v - lo) * inv_step);
+  k = k < 0 ? 0 : (k > n - 1 ? n - 1 : k);
+  while (k > 0 && hist_edge(k, n, lo, hi, step) > v) --k;
+  while (k < n - 1 && hist_edge(k + 1, n, lo, hi, step) <= v) ++k;
+  return k;
+}
+
+// per-launch constants of the image kernels
+struct ImageSteps {
+  double step_x, step_z;          // bin widths, as np.histogram2d's linspace gives them
+  double inv_step_x, inv_step_z;
+  double wscale;                  // 1/apix (column) or 1/(1e6 apix) (radiance)
+};
+NX_HD ImageSteps image_steps(const ImageParams& ip) {
+  ImageSteps t;
+  t.step_x = (ip.x1 - ip.x0) / ip.nx; t.step_z = (ip.z1 - ip.z0) / ip.nz;
+  t.inv_step_x = 1.0 / t.step_x; t.inv_step_z = 1.0 / t.step_z;
+  t.wscale = (ip.quantity == 1) ? 1.0 / (1e6 * ip.apix) : 1.0 / ip.apix;
+  return t;
+}
+
 // Sum of g-values over the emission lines at radial velocity rv [R_p/s]
 // (ModelResult.py:152-157: gg = 0 + g_1 + g_2 ...).
 NX_HD double gvalue_sum(const GTables& G, double rv) {
@@ -91,6 +116,30 @@ NX_HD int image_packet(const ImageParams& ip, const GTables& G, double step_x, d
   weight = div_rn(f, ip.apix);                                  // ModelImage.py:262
   const int ix = hist_bin(xo, ip.nx, ip.x0, ip.x1, step_x);
   const int iz = hist_bin(zo, ip.nz, ip.z0, ip.z1, step_z);
+  if (ix < 0 || iz < 0) return -1;
+  return ix * ip.nz + iz;
+}
+
+// Kernel form: identical pixel (bit-exact), weight through one reciprocal scale
+// instead of the two divisions (<= 2 ulp from the form above; the gate is 1e-6).
+NX_HD int image_packet_fast(const ImageParams& ip, const GTables& G, const ImageSteps& t,
+                            double x, double y, double z, double vy, double frac,
+                            double& weight) {
+  if (ip.round_f32) { x = round_f32(x); y = round_f32(y); z = round_f32(z);
+                      vy = round_f32(vy); frac = round_f32(frac); }
+  const double xo = fma(ip.M[2], z, fma(ip.M[1], y, ip.M[0] * x));
+  const double yo = fma(ip.M[5], z, fma(ip.M[4], y, ip.M[3] * x));
+  const double zo = fma(ip.M[8], z, fma(ip.M[7], y, ip.M[6] * x));
+  const double so = add_rn(mul_rn(xo, xo), mul_rn(zo, zo));
+  const bool inview = (so > NX_ONE_PLUS_ULP) || (yo < 0.0);
+  double f = inview ? frac : 0.0;
+  if (ip.quantity == 1) {
+    const bool lit = out_of_shadow(x, y, z);
+    f = lit ? f * gvalue_sum_fast(G, add_rn(vy, ip.vrplanet)) : 0.0;
+  }
+  weight = f * t.wscale;
+  const int ix = hist_bin_fast(xo, ip.nx, ip.x0, ip.x1, t.step_x, t.inv_step_x);
+  const int iz = hist_bin_fast(zo, ip.nz, ip.z0, ip.z1, t.step_z, t.inv_step_z);
   if (ix < 0 || iz < 0) return -1;
   return ix * ip.nz + iz;
 }

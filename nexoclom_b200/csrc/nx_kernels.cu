@@ -446,11 +446,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-#ifdef NX_FEED_NOINLINE
-#define NX_FEED_INLINE __noinline__
-#else
 #define NX_FEED_INLINE __forceinline__
-#endif
 // float restatement of cost_bucket() folded into NX_NCLASS classes (0 = longest)
 __device__ NX_FEED_INLINE int cost_class(const RunParams& p, int model, float res, float mu,
                                           float amax, double td, double xd, double yd, double zd,
@@ -499,120 +495,144 @@ struct StreamQueue {
   const unsigned* arrived;           // segments [0, *arrived) are on the device; nullptr: all
 };
 
-struct StreamFeeder {
-  double* vals;                      // this warp's staging area: [2][9][32]
-  unsigned lane;
-  // everything below is warp-uniform
+// Feeder state of one warp.  It lives in SHARED memory and is advanced by ONE
+// non-inlined function: the whole queue logic (claims, class test with its acosf /
+// sinf slow paths, prefetch) stays out of the integration loop, whose code then fits
+// the 32 KB instruction cache like the sorted kernel's does (ncu: the inlined
+// version spent 1.7 cycles per issue waiting for instructions).
+struct StreamShared {
   unsigned base_cur, base_pend;      // packet index of slot 0 of the current / pending batch
   int cnt_pend;                      // packets in the pending batch (0: none in flight)
-  int cls_cur, cls_pend;
-  unsigned char* order;              // [32] slots of the current batch that belong to cls_cur
-  int pos, cnt;                      // hand-out position / number of entries in order[]
-  int buf;
+  int cls_pend;
+  int buf;                           // staging buffer holding the current batch
   unsigned grp_next, grp_end;        // claimed group still to be walked
   int grp_cls;
   unsigned exh[NX_NCLASS];           // bit s: cursor (class, segment s) is exhausted
-  unsigned all_mask;
+  unsigned char order[32];           // slots of the current batch that belong to its class
+};
+#define NX_SFEED_STATE_BYTES 96      // >= sizeof(StreamShared), multiple of 16
+#undef NX_SFEED_BYTES_PER_WARP
+#define NX_SFEED_BYTES_PER_WARP (2 * NX_SFEED_COLS * 32 * 8 + NX_SFEED_STATE_BYTES)
 
-  __device__ __forceinline__ bool all_done() const {
-    unsigned m = all_mask;
+struct StreamArgs {                  // everything the feeder needs, passed by value
+  const double* col0;
+  size_t stride;
+  long long n, seg;
+  unsigned long long* cursor;
+  const unsigned* arrived;
+  double resolution;
+  float res, mu, amax;
+  int nseg, model, gravity, radpres;
+};
+
+// Make the next batch current.  Returns the number of packets of the batch that are
+// handed out in this pass (their slots are in S->order), -1 when the queue is
+// finished, -2 when nothing is available right now (segments still on the wire).
+__device__ __noinline__ int stream_advance(StreamShared* S, double* vals, StreamArgs A) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned all_mask = A.nseg >= 32 ? 0xffffffffu : ((1u << A.nseg) - 1u);
+  unsigned base_pend = S->base_pend, grp_next = S->grp_next, grp_end = S->grp_end;
+  int cnt_pend = S->cnt_pend, cls_pend = S->cls_pend, buf = S->buf, grp_cls = S->grp_cls;
+  unsigned exh[NX_NCLASS];
 #pragma unroll
-    for (int c = 0; c < NX_NCLASS; ++c) m &= exh[c];
-    return m == all_mask;
-  }
-  __device__ NX_FEED_INLINE bool claim_group(const StreamQueue& Q, long long n) {
-    unsigned nready = (unsigned)Q.nseg;
-    if (Q.arrived) nready = ld_volatile_u32(Q.arrived);
-    const unsigned ready = nready >= 32u ? 0xffffffffu : ((1u << nready) - 1u);
+  for (int c = 0; c < NX_NCLASS; ++c) exh[c] = S->exh[c];
+  __syncwarp();
+  int result = -3;
+  unsigned base_cur = 0;
+  // two rounds at most: (0) nothing in flight -> start a copy, (1) consume it and start the next
+  for (int round = 0; round < 2; ++round) {
+    if (cnt_pend != 0) {
+      cp_async_wait_all();
+      __syncwarp();
+      buf ^= 1;
+      base_cur = base_pend;
+      const double* v = vals + (size_t)buf * NX_SFEED_COLS * 32 + lane;
+      int cls = -1;
+      if ((int)lane < cnt_pend) {
+        if (NX_NCLASS == 1) cls = 0;
+        else {
+          RunParams pp;               // only the fields cost_class reads
+          pp.resolution = A.resolution; pp.gravity = A.gravity; pp.radpres = A.radpres;
+          cls = cost_class(pp, A.model, A.res, A.mu, A.amax, v[0], v[32], v[64], v[96], v[128],
+                           v[160], v[192], v[224]);
+        }
+      }
+      const unsigned match = __ballot_sync(FULL_MASK, cls == cls_pend);
+      if (cls == cls_pend) S->order[__popc(match & ((1u << lane) - 1u))] = (unsigned char)lane;
+      result = __popc(match);
+      cnt_pend = 0;
+    }
+    // start the copy of the next batch into the idle buffer
+    if (grp_next >= grp_end) {
+      unsigned done = all_mask;
 #pragma unroll
-    for (int c = 0; c < NX_NCLASS; ++c) {
-      unsigned avail = ready & ~exh[c];
-      while (avail) {
-        const int s = __ffs(avail) - 1;
-        unsigned long long g = 0;
-        if (lane == 0) g = atomicAdd(Q.cursor + c * 32 + s, (unsigned long long)NX_GROUP);
-        g = __shfl_sync(FULL_MASK, g, 0);
-        const long long first = (long long)s * Q.seg;
-        const long long count = min(Q.seg, n - first);
-        if ((long long)g + NX_GROUP >= count) {
-          exh[c] |= 1u << s;
+      for (int c = 0; c < NX_NCLASS; ++c) done &= exh[c];
+      bool claimed = false;
+      if (done != all_mask) {
+        unsigned nready = (unsigned)A.nseg;
+        if (A.arrived) nready = ld_volatile_u32(A.arrived);
+        const unsigned ready = nready >= 32u ? 0xffffffffu : ((1u << nready) - 1u);
+#pragma unroll
+        for (int c = 0; c < NX_NCLASS; ++c) {
+          unsigned avail = claimed ? 0u : (ready & ~exh[c]);
+          while (avail) {
+            const int sgm = __ffs(avail) - 1;
+            unsigned long long g = 0;
+            if (lane == 0) g = atomicAdd(A.cursor + c * 32 + sgm, (unsigned long long)NX_GROUP);
+            g = __shfl_sync(FULL_MASK, g, 0);
+            const long long first = (long long)sgm * A.seg;
+            const long long count = min(A.seg, A.n - first);
+            if ((long long)g + NX_GROUP >= count) {
+              exh[c] |= 1u << sgm;
 #ifdef NX_STREAM_DEBUG
-          if (lane == 0 && s == Q.nseg - 1)
-            atomicCAS(&g_dbg[1 + c], 0ull, global_timer_ns());
+              if (lane == 0 && sgm == A.nseg - 1) atomicCAS(&g_dbg[1 + c], 0ull, global_timer_ns());
 #endif
+            }
+            if ((long long)g < count) {
+              grp_next = (unsigned)(first + (long long)g);
+              grp_end = (unsigned)min(first + count, first + (long long)g + NX_GROUP);
+              grp_cls = c;
+              claimed = true;
+              break;
+            }
+            avail &= ~(1u << sgm);
+          }
         }
-        if ((long long)g < count) {
-          grp_next = (unsigned)(first + (long long)g);
-          grp_end = (unsigned)min(first + count, first + (long long)g + NX_GROUP);
-          grp_cls = c;
-          return true;
-        }
-        avail &= ~(1u << s);
+      }
+      if (!claimed && result == -3) {
+        unsigned done2 = all_mask;
+#pragma unroll
+        for (int c = 0; c < NX_NCLASS; ++c) done2 &= exh[c];
+        result = (done2 == all_mask) ? -1 : -2;
       }
     }
-    return false;
-  }
-  // start the copy of the next batch into the idle buffer
-  __device__ __forceinline__ void issue_prefetch(const StreamQueue& Q, long long n,
-                                                 const double* col0, size_t stride) {
-    cnt_pend = 0;
-    if (grp_next >= grp_end) {
-      if (all_done() || !claim_group(Q, n)) return;
-    }
-    base_pend = grp_next;
-    cnt_pend = (int)min(32u, grp_end - grp_next);
-    cls_pend = grp_cls;
-    grp_next += 32u;
-    double* dst = vals + (size_t)(buf ^ 1) * NX_SFEED_COLS * 32;
-    // 8 rows of 256 bytes = 128 chunks of 16 bytes (rows are padded to 32 packets)
+    if (grp_next < grp_end) {
+      base_pend = grp_next;
+      cnt_pend = (int)min(32u, grp_end - grp_next);
+      cls_pend = grp_cls;
+      grp_next += 32u;
+      double* dst = vals + (size_t)(buf ^ 1) * NX_SFEED_COLS * 32;
+      // 8 rows of 256 bytes = 128 chunks of 16 bytes (rows are padded to 32 packets)
 #pragma unroll
-    for (int i = 0; i < NX_SFEED_COLS / 2; ++i) {
-      const unsigned j = lane + 32u * i;
-      const unsigned col = j >> 4, part = (j & 15u) * 2u;
-      cp_async16_cg(dst + col * 32u + part, col0 + (size_t)col * stride + base_pend + part);
+      for (int i = 0; i < NX_SFEED_COLS / 2; ++i) {
+        const unsigned j = lane + 32u * i;
+        const unsigned col = j >> 4, part = (j & 15u) * 2u;
+        cp_async16_cg(dst + col * 32u + part, A.col0 + (size_t)col * A.stride + base_pend + part);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
+    if (result != -3) break;          // a batch became current, or nothing can be had
   }
-  __device__ __forceinline__ void init(unsigned char* smem, const StreamQueue& Q, long long n,
-                                       const double* col0, size_t stride) {
-    lane = threadIdx.x & 31u;
-    vals = reinterpret_cast<double*>(smem + (size_t)(threadIdx.x >> 5) * NX_SFEED_BYTES_PER_WARP);
-    order = reinterpret_cast<unsigned char*>(vals + 2 * NX_SFEED_COLS * 32);
-    buf = 0; pos = 0; cnt = 0; cnt_pend = 0; base_cur = base_pend = 0; cls_cur = cls_pend = 0;
-    grp_next = grp_end = 0; grp_cls = 0;
+  if (lane == 0) {
+    S->base_pend = base_pend; S->grp_next = grp_next; S->grp_end = grp_end;
+    S->cnt_pend = cnt_pend; S->cls_pend = cls_pend; S->buf = buf; S->grp_cls = grp_cls;
+    if (result >= 0) S->base_cur = base_cur;
 #pragma unroll
-    for (int c = 0; c < NX_NCLASS; ++c) exh[c] = 0;
-    all_mask = Q.nseg >= 32 ? 0xffffffffu : ((1u << Q.nseg) - 1u);
-    issue_prefetch(Q, n, col0, stride);
+    for (int c = 0; c < NX_NCLASS; ++c) S->exh[c] = exh[c];
   }
-  // make the pending batch current.  1: a batch is current (match may be empty),
-  // 0: nothing available right now (segments still in flight), -1: queue finished.
-  __device__ __forceinline__ int advance(const StreamQueue& Q, long long n, const double* col0,
-                                         size_t stride, const RunParams& p, float res, float mu,
-                                         float amax) {
-    if (cnt_pend == 0) {
-      issue_prefetch(Q, n, col0, stride);
-      if (cnt_pend == 0) return all_done() ? -1 : 0;
-    }
-    cp_async_wait_all();
-    __syncwarp();
-    buf ^= 1;
-    base_cur = base_pend; cls_cur = cls_pend;
-    const int nb = cnt_pend;
-    const double* v = vals + (size_t)buf * NX_SFEED_COLS * 32 + lane;
-    int cls = -1;
-    if ((int)lane < nb)
-      cls = (NX_NCLASS == 1) ? 0
-                             : cost_class(p, Q.model, res, mu, amax, v[0], v[32], v[64], v[96],
-                                          v[128], v[160], v[192], v[224]);
-    const unsigned match = __ballot_sync(FULL_MASK, cls == cls_cur);
-    if (cls == cls_cur) order[__popc(match & ((1u << lane) - 1u))] = (unsigned char)lane;
-    pos = 0; cnt = __popc(match);
-    __syncwarp();
-    issue_prefetch(Q, n, col0, stride);
-    return 1;
-  }
-};
+  __syncwarp();
+  return result;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
@@ -626,12 +646,18 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
   FastTable F;
   if (MODE < 0) stage_table(Tg, T, smem_raw);
   else stage_fast_table(Fg, F, smem_raw);
-  const float res = (float)p.resolution, mu = (float)fabs(p.GM), amax = (float)p.radpres_amax;
-  StreamFeeder feed;
-  feed.init(smem_raw + table_bytes, Q, n, col0, stride);
+  const unsigned lane = threadIdx.x & 31u;
+  double* const vals = reinterpret_cast<double*>(smem_raw + table_bytes +
+                                                 (size_t)(threadIdx.x >> 5) * NX_SFEED_BYTES_PER_WARP);
+  StreamShared* const S = reinterpret_cast<StreamShared*>(vals + 2 * NX_SFEED_COLS * 32);
+  if (lane < NX_SFEED_STATE_BYTES / 4) reinterpret_cast<unsigned*>(S)[lane] = 0u;
+  StreamArgs A;
+  A.col0 = col0; A.stride = stride; A.n = n; A.seg = Q.seg; A.cursor = Q.cursor;
+  A.arrived = Q.arrived; A.resolution = p.resolution; A.res = (float)p.resolution;
+  A.mu = (float)fabs(p.GM); A.amax = (float)p.radpres_amax; A.nseg = Q.nseg; A.model = Q.model;
+  A.gravity = p.gravity; A.radpres = p.radpres;
   __syncthreads();
 
-  const unsigned lane = threadIdx.x & 31u;
   bool have = false, drained = false;
   unsigned idx = 0;
   double s[8], step = 0.0;
@@ -639,6 +665,7 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
   unsigned long long tot_att = 0, tot_acc = 0;
   unsigned long long wait_since = 0;
   int st = 0;
+  int fpos = 0, fcnt = 0;            // hand-out position / size of the current batch
 #ifdef NX_STREAM_DEBUG
   unsigned long long dbg_iters = 0, dbg_scans = 0;
 #endif
@@ -648,26 +675,27 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
     bool starved = false;
     int scans = 0;
     while (need && !drained) {
-      if (feed.pos == feed.cnt) {
+      if (fpos == fcnt) {
         if (scans >= NX_SCAN_MAX && need != FULL_MASK) break;   // let the live lanes step
-        const int r = feed.advance(Q, n, col0, stride, p, res, mu, amax);
+        const int r = stream_advance(S, vals, A);
         ++scans;
 #ifdef NX_STREAM_DEBUG
         ++dbg_scans;
 #endif
-        if (r < 0) { drained = true; break; }
-        if (r == 0) { starved = true; break; }
+        if (r == -1) { drained = true; break; }
+        if (r == -2) { starved = true; break; }
+        fpos = 0; fcnt = r;
         continue;
       }
-      const int take = min(__popc(need), feed.cnt - feed.pos);
+      const int take = min(__popc(need), fcnt - fpos);
       const int rank = __popc(need & ((1u << lane) - 1u));
       if (!have && rank < take) {
-        const int slot = feed.order[feed.pos + rank];
-        const double* v = feed.vals + (size_t)feed.buf * NX_SFEED_COLS * 32 + slot;
+        const int slot = S->order[fpos + rank];
+        const double* v = vals + (size_t)S->buf * NX_SFEED_COLS * 32 + slot;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[k] = v[k * 32];
         step = step0;
-        idx = feed.base_cur + (unsigned)slot;
+        idx = S->base_cur + (unsigned)slot;
         att = 0; acc = 0;
         have = (s[0] > p.resolution) && (s[7] > 0.0);
         if (!have) {                      // nothing to integrate: pass it through (att/acc pre-zeroed)
@@ -676,7 +704,7 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
           __stcs(P.c[8] + idx, step);
         }
       }
-      feed.pos += take;
+      fpos += take;
       need = __ballot_sync(FULL_MASK, !have);
     }
     if (!__any_sync(FULL_MASK, have)) {
@@ -732,11 +760,11 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
 // and optional dense trajectory sink.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& G,
-                                          double step_x, double step_z, const double* s,
+                                          const ImageSteps& t, const double* s,
                                           double* image, unsigned long long* counts) {
   if (ip.skip_dead && !(s[7] > 0.0)) return;
   double w;
-  const int pix = image_packet<true>(ip, G, step_x, step_z, s[1], s[2], s[3], s[5], s[7], w);
+  const int pix = image_packet_fast(ip, G, t, s[1], s[2], s[3], s[5], s[7], w);
   if (pix >= 0) {
     if (w != 0.0) atomicAdd(&image[pix], w);
     atomicAdd(&counts[pix], 1ull);
@@ -764,7 +792,7 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
   feed.init(smem_raw + table_bytes, &P, nullptr, queue, n);
   __syncthreads();
   const unsigned lane = threadIdx.x & 31u;
-  const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
+  const ImageSteps isteps = image_steps(ip);
 
   bool have = false, drained = false, pending = false;
   unsigned idx = 0;
@@ -774,7 +802,13 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
   unsigned long long tot = 0;
   int st = 0;
 
+  // One row of the reference's trajectory tensor (Output.py:376-421) is EMITTED at a
+  // single place per loop iteration -- for a packet that was just loaded (row 0), that
+  // completed a step, or whose bounce was just resolved -- so the image / trajectory /
+  // retire code exists once in the kernel (instruction-cache footprint: with one copy
+  // per call site the fused kernel stalled 4.4 cycles per issue on instruction fetch).
   for (;;) {
+    bool emit = false, live = true;
     unsigned need = __ballot_sync(FULL_MASK, !have);
     while (need && !drained) {
       if (feed.pos == feed.cnt && !feed.advance()) { drained = true; break; }
@@ -786,14 +820,8 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[k] = v[k * 32];
         idx = feed.ids[feed.buf * 32 + slot];
-        curtime = p.endtime; ct = 1;
-        have = s[7] > 0.0;
-        if (traj) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) traj[((size_t)idx * 8 + k) * nsteps] = s[k];
-        }
-        if (image) image_add(ip, G, step_x, step_z, s, image, counts);
-        if (!(curtime > 0.0) || ct >= nsteps) have = false;
+        curtime = p.endtime; ct = 0;       // row 0 (Output.py:379-386)
+        have = true; emit = true; live = s[7] > 0.0;
       }
       feed.pos += take;
       need = __ballot_sync(FULL_MASK, !have);
@@ -802,48 +830,28 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
       if (drained) break;
       continue;
     }
-    // finish one row of the reference's trajectory tensor: outputs, clocks, retire
-    auto finish_row = [&](bool live) {
-      if (traj) {
+    if (have && !pending && !emit) {
+      bool bad = false;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) traj[((size_t)idx * 8 + k) * nsteps + ct] = s[k];
+      for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
+      if (bad) st |= 32;
+      ++tot;
+      if (MODE < 0) {
+        live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+        emit = true;
+      } else {
+        const double r = constant_stages_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s);
+        bool hit = sub_rn(r, 1.0) < 0.0;
+        if (hit && p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0) { s[7] = 0.0; hit = false; }
+        if (hit) { pending = true; rhit = r; }
+        else { live = constant_post(p, s, r); emit = true; }
       }
-      if (image) image_add(ip, G, step_x, step_z, s, image, counts);
-      ++ct;
-      curtime -= p.step_size;
-      if (!live || !(curtime > 0.0) || ct >= nsteps) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
-        have = false;
-      }
-    };
-    if (MODE < 0) {
-      if (have) {
-        bool bad = false;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
-        if (bad) st |= 32;
-        const bool live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
-        ++tot;
-        finish_row(live);
-      }
-    } else {
+    }
+    if (MODE >= 0) {
       // Fast mode: the bounce is ~2x the cost of a step but only ~10% of the lanes
       // need it in a given step, so lanes that hit the surface PARK (pending) and
       // the warp runs the bounce code once enough of them have accumulated; results
       // do not depend on the batching (Philox is keyed by packet id and step).
-      if (have && !pending) {
-        bool bad = false;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
-        if (bad) st |= 32;
-        const double r = constant_stages_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s);
-        ++tot;
-        bool hit = sub_rn(r, 1.0) < 0.0;
-        if (hit && p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0) { s[7] = 0.0; hit = false; }
-        if (hit) { pending = true; rhit = r; }
-        else finish_row(constant_post(p, s, r));
-      }
       const int npend = __popc(__ballot_sync(FULL_MASK, pending));
       const int nrun = __popc(__ballot_sync(FULL_MASK, have && !pending));
       wait_iters = npend ? wait_iters + 1 : 0;
@@ -851,9 +859,27 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
         if (pending) {
           constant_bounce_fast(p, S, s, rhit, seed, first_id + (uint64_t)idx, (uint32_t)ct);
           pending = false;
-          finish_row(constant_post(p, s, rhit));
+          live = constant_post(p, s, rhit);
+          emit = true;
         }
         wait_iters = 0;
+      }
+    }
+    if (emit) {
+      if (traj) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) traj[((size_t)idx * 8 + k) * nsteps + ct] = s[k];
+      }
+      if (image) image_add(ip, G, isteps, s, image, counts);
+      const bool fresh = (ct == 0);
+      ++ct;
+      if (!fresh) curtime -= p.step_size;
+      if (!live || !(curtime > 0.0) || ct >= nsteps) {
+        if (!fresh) {                       // an unintegrated packet stays as it is
+#pragma unroll
+          for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
+        }
+        have = false;
       }
     }
   }
@@ -873,12 +899,12 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
 // loads, two packets per thread per iteration) and scatters with f64 / u64
 // atomics into the L2-resident image (800x800: 5 MB + 5 MB).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void image_one(const ImageParams& ip, const GTables& G, double step_x,
-                                          double step_z, double x, double y, double z, double v,
+__device__ __forceinline__ void image_one(const ImageParams& ip, const GTables& G,
+                                          const ImageSteps& t, double x, double y, double z, double v,
                                           double f, double* image, unsigned long long* counts) {
   if (ip.skip_dead && !(f > 0.0)) return;
   double w;
-  const int pix = image_packet<true>(ip, G, step_x, step_z, x, y, z, v, f, w);
+  const int pix = image_packet_fast(ip, G, t, x, y, z, v, f, w);
   if (pix >= 0) {
     if (w != 0.0) atomicAdd(&image[pix], w);
     atomicAdd(&counts[pix], 1ull);
@@ -899,7 +925,7 @@ k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
   for (int t = 0; t < NX_MAX_GTABLES; ++t)
     if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off); off += (size_t)Gg.f[t].nrec * 32; }
   __syncthreads();
-  const double step_x = (ip.x1 - ip.x0) / ip.nx, step_z = (ip.z1 - ip.z0) / ip.nz;
+  const ImageSteps isteps = image_steps(ip);
   const long long npair = n >> 1;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const double2* __restrict__ X2 = reinterpret_cast<const double2*>(P.c[1]);
@@ -907,27 +933,30 @@ k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
   const double2* __restrict__ Z2 = reinterpret_cast<const double2*>(P.c[3]);
   const double2* __restrict__ V2 = reinterpret_cast<const double2*>(P.c[5]);
   const double2* __restrict__ F2 = reinterpret_cast<const double2*>(P.c[7]);
+  // software pipeline: the five loads of the NEXT pair are issued before the current
+  // pair is binned (ten 16-byte loads in flight per thread); one copy of the per-packet
+  // code per lane of the pair keeps the kernel inside the instruction cache
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; i + stride < npair; i += 2 * stride) {
-    const long long j = i + stride;
-    const double2 xa = __ldcs(X2 + i), ya = __ldcs(Y2 + i), za = __ldcs(Z2 + i),
-                  va = __ldcs(V2 + i), fa = __ldcs(F2 + i);
-    const double2 xb = __ldcs(X2 + j), yb = __ldcs(Y2 + j), zb = __ldcs(Z2 + j),
-                  vb = __ldcs(V2 + j), fb = __ldcs(F2 + j);
-    image_one(ip, G, step_x, step_z, xa.x, ya.x, za.x, va.x, fa.x, image, counts);
-    image_one(ip, G, step_x, step_z, xa.y, ya.y, za.y, va.y, fa.y, image, counts);
-    image_one(ip, G, step_x, step_z, xb.x, yb.x, zb.x, vb.x, fb.x, image, counts);
-    image_one(ip, G, step_x, step_z, xb.y, yb.y, zb.y, vb.y, fb.y, image, counts);
-  }
+  double2 xa, ya, za, va, fa;
   if (i < npair) {
-    const double2 xa = __ldcs(X2 + i), ya = __ldcs(Y2 + i), za = __ldcs(Z2 + i),
-                  va = __ldcs(V2 + i), fa = __ldcs(F2 + i);
-    image_one(ip, G, step_x, step_z, xa.x, ya.x, za.x, va.x, fa.x, image, counts);
-    image_one(ip, G, step_x, step_z, xa.y, ya.y, za.y, va.y, fa.y, image, counts);
+    xa = __ldcs(X2 + i); ya = __ldcs(Y2 + i); za = __ldcs(Z2 + i);
+    va = __ldcs(V2 + i); fa = __ldcs(F2 + i);
+  }
+  while (i < npair) {
+    const long long j = i + stride;
+    double2 xb = xa, yb = ya, zb = za, vb = va, fb = fa;
+    if (j < npair) {
+      xb = __ldcs(X2 + j); yb = __ldcs(Y2 + j); zb = __ldcs(Z2 + j);
+      vb = __ldcs(V2 + j); fb = __ldcs(F2 + j);
+    }
+    image_one(ip, G, isteps, xa.x, ya.x, za.x, va.x, fa.x, image, counts);
+    image_one(ip, G, isteps, xa.y, ya.y, za.y, va.y, fa.y, image, counts);
+    xa = xb; ya = yb; za = zb; va = vb; fa = fb;
+    i = j;
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long q = n - 1;
-    image_one(ip, G, step_x, step_z, P.c[1][q], P.c[2][q], P.c[3][q], P.c[5][q], P.c[7][q],
+    image_one(ip, G, isteps, P.c[1][q], P.c[2][q], P.c[3][q], P.c[5][q], P.c[7][q],
               image, counts);
   }
 }

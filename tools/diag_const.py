@@ -13,7 +13,8 @@ from nexoclom_b200.ModelImage import image_rotation
 from nexoclom_b200.runsetup import RunSetup
 eng = Engine(0)
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 2_000_000
-for strict in (0, 1):
+stricts = (0,) if (len(sys.argv) > 2 and sys.argv[2] == 'fast') else (0, 1)
+for strict in stricts:
     setup = RunSetup(workload('Na.bounce.input'), strict_math=bool(strict))
     setup.upload(eng)
     eng.upload_gtables(setup.gtables([5891, 5897]))

@@ -21,7 +21,17 @@ setup = RunSetup(workload(wl))
 setup.upload(eng)
 eng.upload_gtables(setup.gtables([5891, 5897]))
 eng.init_state(setup.source_params(eng), 0, 0, n)
-att, acc = eng.integrate_adaptive()
+if len(sys.argv) > 3 and sys.argv[3] == 'host':
+    # the end-to-end path: streamed H2D behind one class-ordered persistent kernel
+    import torch
+    X0 = eng.export_x0()[:8]
+    host = torch.empty((8, n), dtype=torch.float64).pin_memory()
+    host.numpy()[:] = X0
+    att, acc = eng.integrate_adaptive_host([host.numpy()[k] for k in range(8)], nchunks=16)
+else:
+    if len(sys.argv) > 3 and sys.argv[3] == 'stream':
+        eng.set_option('schedule', 2)      # streaming kernel over the resident X0 slab
+    att, acc = eng.integrate_adaptive()
 ms = eng.last_kernel_ms()
 ip = ImageParams()
 M = image_rotation(0.0, np.pi / 2)
