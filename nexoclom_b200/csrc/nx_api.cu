@@ -89,7 +89,8 @@ static void free_interp(DevInterp& d) {
   d = DevInterp{};
 }
 
-static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const double* f, int n) {
+static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const double* f, int n,
+                         bool want_fast = true) {
   free_interp(d);
   if (n <= 0) return 0;
   HostInterp h = make_interp(x, f, n);
@@ -102,7 +103,17 @@ static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const doubl
   CK(cudaMemcpyAsync(d.slope, h.slope.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d.bucket, h.bucket.data(), h.nbucket * sizeof(unsigned short),
                      cudaMemcpyHostToDevice, ctx->stream));
+  if (!want_fast) {      // inverse-CDF tables are only read through the np.interp form
+    CK(cudaStreamSynchronize(ctx->stream));
+    d.view.x = d.x; d.view.f = d.f; d.view.slope = d.slope; d.view.bucket = d.bucket;
+    d.view.n = n; d.view.nbucket = h.nbucket; d.view.blo = h.blo; d.view.binvw = h.binvw;
+    return 0;
+  }
   HostFastTable hf = make_fast_table(x, f, n, 32768);
+  if (hf.max_steps > NX_FAST_TABLE_MAX_STEPS) {
+    ctx->err = "lookup table has more than two nodes within 1/2^22 of its range";
+    return -1;
+  }
   CK(cudaMalloc(&d.rec, hf.rec.size() * sizeof(double)));
   CK(cudaMalloc(&d.fbucket, hf.bucket.size() * sizeof(unsigned short)));
   CK(cudaMemcpyAsync(d.rec, hf.rec.data(), hf.rec.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -410,7 +421,7 @@ int nx_sourcemap_upload(nx_ctx* ctx, const double* fmap, int nx_, int ny_, const
 
 int nx_speedtable_upload(nx_ctx* ctx, const double* cdf, const double* v, int n) {
   CK(cudaSetDevice(ctx->device));
-  return upload_interp(ctx, ctx->speed, cdf, v, n);
+  return upload_interp(ctx, ctx->speed, cdf, v, n, false);
 }
 
 int nx_init_state(nx_ctx* ctx, const nx_source_params* sp_, uint64_t seed, uint64_t first_id,

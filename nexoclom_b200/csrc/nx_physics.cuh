@@ -161,8 +161,9 @@ struct FastTable {
   double blo, binvw, boff;
 };
 
-// np.interp through the record table: bucket -> record, then (rarely) walk to the
-// neighbouring record; clamp records make the ends branch-free.
+// np.interp through the record table: bucket -> record, then at most two steps to the
+// following records (guaranteed by the table builder, nx_tables.h); clamp records make
+// the ends branch-free and pad records keep +inf in bounds.
 NX_HD double interp_fast(const FastTable& T, double v) {
 #if defined(__CUDA_ARCH__)
   int b = __double2int_rz(fma(v, T.binvw, T.boff));    // boff = -blo*binvw; NaN -> 0
@@ -174,9 +175,9 @@ NX_HD double interp_fast(const FastTable& T, double v) {
   int idx = T.bucket[b];
 #endif
   InterpRec r = T.rec[idx];
-  if (!(v >= r.lo && v < r.hi)) {              // bucket holding a node / clamp: rare walk
-    while (v >= r.hi && idx < T.nrec - 1) r = T.rec[++idx];
-    while (v < r.lo && idx > 0) r = T.rec[--idx];
+  if (v >= r.hi) {                             // the bucket holds a node and v is past it
+    r = T.rec[idx + 1];
+    if (v >= r.hi) r = T.rec[idx + 2];         // ... a pair of near-coincident nodes
   }
   return fma(r.slope, v - r.lo, r.f);
 }
