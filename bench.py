@@ -297,7 +297,7 @@ def run_gpu(args):
     cols = [host_np[k] for k in range(8)]
     img_host = torch.empty((800, 800), dtype=torch.float64).pin_memory()
     e2e_steps, e2e_ms = 0, 0.0
-    for it in range(1 + max(1, min(args.steps, 3))):
+    for it in range(0 if args.no_e2e else 1 + max(1, min(args.steps, 3))):
         fence()
         t0 = time.perf_counter()
         # reference-facing host-buffer call: pinned H2D (64 B/packet) pipelined with K2
@@ -319,7 +319,7 @@ def run_gpu(args):
         ts = te.clone()
         dist.all_reduce(ts, op=dist.ReduceOp.SUM)
         e2e_ms, e2e_steps = float(tm[0]), float(ts[1])
-    e2e_value = e2e_steps / (e2e_ms * 1e-3)
+    e2e_value = e2e_steps / (e2e_ms * 1e-3) if e2e_ms > 0 else None
 
     # ---- line-of-sight sweep over the resident final state (not part of `value`) ----
     los_info = None
@@ -442,6 +442,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-los', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true',
+                    help='skip the end-to-end leg (its streaming kernel waits for concurrent '
+                         'copies, which a serialising profiler never runs)')
     ap.add_argument('--e2e-chunks', type=int, default=16,
                     help='segments of the streamed H2D copy of the end-to-end path')
     ap.add_argument('--los', type=int, default=100_000, help='lines of sight of the K5 sweep')

@@ -116,7 +116,11 @@ int nx_ctx_destroy(nx_ctx* ctx);
 /* adopt a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) */
 int nx_ctx_set_stream(nx_ctx* ctx, void* cuda_stream);
 int nx_ctx_sync(nx_ctx* ctx);
-/* tuning switches: "order_packets" (1 = longest-first scheduling of K2, default 1) */
+/* tuning switches: "order_packets" (cost model of the K2 work queue: 0 natural order,
+ * 1 ballistic flight time (default), 2 + radiation-pressure perturbation);
+ * "schedule" (host-buffer path: 1 one streaming class-ordered kernel (default), 0 one
+ * sort + kernel per chunk; 2 = developer mode, streaming kernel over the resident X0);
+ * "los_mode" (0 auto, 1 brute force, 2 cell grid); "los_grid" (cells per axis)         */
 int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value);
 const char* nx_last_error(nx_ctx* ctx);
 int nx_status(nx_ctx* ctx, int* invariant_bits);
@@ -154,9 +158,13 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n,
                           unsigned long long* attempted_steps,
                           unsigned long long* accepted_steps);
 
-/* End-to-end variant: imports `cols` (host, ideally pinned) and integrates in
- * `nchunks` pipelined ranges so that the H2D copy overlaps the integration.
- * Equivalent to nx_import_state + nx_integrate_adaptive.                          */
+/* End-to-end variant: imports `cols` (8 host columns time..frac, ideally pinned) and
+ * integrates them while they are still arriving: the copy engine delivers the packets
+ * in `nchunks` (<= 32) segments behind ONE persistent kernel that consumes every
+ * segment as soon as it is resident, longest packets first.  The imported initial
+ * state stays in the context's X0 columns (nx_export_x0, columns 0-7), the final state
+ * goes to the state columns.  Same results as nx_import_state + nx_integrate_adaptive
+ * (bit-identical; reference Output.py:180-182 + 221-366 on imported X0).              */
 int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* cols, int nchunks,
                                unsigned long long* attempted_steps,
                                unsigned long long* accepted_steps);
