@@ -131,16 +131,19 @@ static void free_los_work(LosGridWork& w) {
   cudaFree(w.sorted.x); cudaFree(w.sorted.y); cudaFree(w.sorted.z); cudaFree(w.sorted.vy);
   cudaFree(w.sorted.frac); cudaFree(w.sorted.idx); cudaFree(w.cell_id); cudaFree(w.count);
   cudaFree(w.start); cudaFree(w.block_sum); cudaFree(w.total); cudaFree(w.extent_bits);
-  const int G = w.G;
+  const int G = w.G_fixed;
+  const double scale = w.scale;
   w = LosGridWork{};
-  w.G = G;
+  w.G_fixed = G;
+  w.scale = scale;
 }
 
 static int alloc_los_work(nx_ctx* ctx, long long n) {
   LosGridWork& w = ctx->losw;
   if (w.cap >= n && w.sorted.x) return 0;
   free_los_work(w);
-  const size_t ncell = (size_t)w.G * w.G * w.G;
+  const int gmax = w.G_fixed > NX_LOS_GRID_MAX ? w.G_fixed : NX_LOS_GRID_MAX;
+  const size_t ncell = (size_t)gmax * gmax * gmax;
   const size_t nn = (size_t)n;
   CK(cudaMalloc(&w.sorted.x, nn * sizeof(double)));
   CK(cudaMalloc(&w.sorted.y, nn * sizeof(double)));
@@ -153,7 +156,7 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
   CK(cudaMalloc(&w.start, (ncell + 1) * sizeof(unsigned)));
   CK(cudaMalloc(&w.block_sum, ((ncell + 4095) / 4096 + 1) * sizeof(unsigned)));
   CK(cudaMalloc(&w.total, sizeof(unsigned)));
-  CK(cudaMalloc(&w.extent_bits, sizeof(unsigned long long)));
+  CK(cudaMalloc(&w.extent_bits, 2 * sizeof(unsigned long long)));
   w.cap = n;
   return 0;
 }
@@ -255,7 +258,8 @@ int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   if (name && std::strcmp(name, "order_packets") == 0) { ctx->order_packets = value; return 0; }
   if (name && std::strcmp(name, "schedule") == 0) { ctx->schedule = value; return 0; }
   if (name && std::strcmp(name, "los_mode") == 0) { ctx->los_mode = value; return 0; }
-  if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G = value; ctx->losw.cap = 0; return 0; }
+  if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G_fixed = value; ctx->losw.cap = 0; return 0; }
+  if (name && std::strcmp(name, "los_grid_scale_milli") == 0) { ctx->losw.scale = 1e-3 * value; return 0; }
   ctx->err = std::string("unknown option ") + (name ? name : "(null)");
   return -1;
 }
@@ -746,6 +750,12 @@ static void los_prepare(const double* los, long long nlos, const LosParams& lp,
   const double cd = std::cos(lp.dphi);
   lc.cos_margin2 = (cd * (1 - 1e-9)) * (cd * (1 - 1e-9));
   lc.cos_loose2 = (cd * (1 - 1e-6)) * (cd * (1 - 1e-6));
+  lc.cos_accept2 = (cd * (1 + 1e-9)) * (cd * (1 + 1e-9));
+  // nearest ball centre is <= t_k s/2 away along the axis, the cone is <= t_k (1+s) tan(dphi)
+  // wide there, the ball radius is t_k sin(2 dphi): covered if the sum of squares fits with
+  // 10 % to spare
+  const double td = std::tan(lp.dphi);
+  lc.cover = (0.25 * s * s + (1 + s) * (1 + s) * td * td <= 0.9 * s2 * s2) ? 1 : 0;
   lc.inv_log_ratio = 1.0 / std::log1p(s);
   lc.log_t0 = std::log(s);
   const double w1 = std::log1p(s2) * lc.inv_log_ratio;

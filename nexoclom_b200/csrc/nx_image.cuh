@@ -158,21 +158,31 @@ struct LosRay {            // per-LOS constants prepared by nx_los_prepare
 // the KD-tree candidate filter (:164-173): the packet must lie in at least one
 // ball |p - (x_sc + bore t_k)| <= t_k sin(2 dphi).  `ladder` = t_k, `wid2` =
 // (t_k sin 2dphi)^2, `kwin` = half-width of the ball-index window to search.
-NX_HD bool los_hit(const LosRay& L, double dphi, double cos_margin2,
-                   const double* ladder, const double* wid2, double inv_log_ratio,
+// Two shortcuts keep the common hit cheap without changing any decision:
+//  * a packet whose cos^2 exceeds cos_accept2 = (cos(dphi)(1+1e-9))^2 is inside the
+//    cone by a margin far above the rounding of acos(): no sqrt / div / acos;
+//  * if `cover` is set (host: the balls overlap enough, true for dphi up to ~20 deg),
+//    every in-cone point with t_0 <= losrad <= t_last lies in the ball whose centre is
+//    nearest, with a factor ~3 to spare: no log / window search.
+// Outputs losrad and the squared distance d2 (the weight takes its sqrt).
+NX_HD bool los_hit(const LosRay& L, double dphi, double cos_margin2, double cos_accept2,
+                   int cover, const double* ladder, const double* wid2, double inv_log_ratio,
                    double log_t0, int kwin,
-                   double px, double py, double pz, double& losrad, double& dist) {
+                   double px, double py, double pz, double& losrad, double& d2) {
   const double rx = sub_rn(px, L.xs), ry = sub_rn(py, L.ys), rz = sub_rn(pz, L.zs);
   losrad = add_rn(add_rn(mul_rn(rx, L.bx), mul_rn(ry, L.by)), mul_rn(rz, L.bz));
-  const double d2 = add_rn(add_rn(mul_rn(rx, rx), mul_rn(ry, ry)), mul_rn(rz, rz));
+  d2 = add_rn(add_rn(mul_rn(rx, rx), mul_rn(ry, ry)), mul_rn(rz, rz));
   // cheap conservative reject: cos(ang) < cos(dphi) - margin
-  if (!(losrad > 0.0) || mul_rn(losrad, losrad) < mul_rn(d2, cos_margin2)) return false;
+  const double l2 = mul_rn(losrad, losrad);
+  if (!(losrad > 0.0) || l2 < mul_rn(d2, cos_margin2)) return false;
   if (!(losrad < L.dist_plan)) return false;
-  dist = sqrt(d2);
-  double cosang = div_rn(losrad, dist);
-  if (cosang > 1.0) cosang = 1.0;
-  if (!(acos(cosang) <= dphi)) return false;
+  if (!(l2 > mul_rn(d2, cos_accept2))) {
+    double cosang = div_rn(losrad, sqrt(d2));
+    if (cosang > 1.0) cosang = 1.0;
+    if (!(acos(cosang) <= dphi)) return false;
+  }
   // KD-ball candidate filter
+  if (cover && losrad >= ladder[0] && losrad <= ladder[L.nball - 1]) return true;
   int k0 = (int)((log(losrad) - log_t0) * inv_log_ratio);
   int lo = k0 - kwin, hi = k0 + kwin;
   if (lo < 0) lo = 0;
@@ -191,7 +201,9 @@ NX_HD bool los_hit(const LosRay& L, double dphi, double cos_margin2,
 
 // Radiance weight of a hit packet (compute_iteration.py:193-206).
 NX_HD double los_weight(const LosRay& L, const LosParams& lp, const GTables& G,
-                        double sin_dphi, double frac, double vy, double losrad, double dist) {
+                        double sin_dphi, double frac, double vy, double losrad, double d2) {
+  if (!(frac != 0.0)) return frac;            // 0 * finite g-value / area = 0 (keeps NaN)
+  const double dist = sqrt(d2);
   const double rv = add_rn(vy, lp.vrplanet);
   const double gg = gvalue_sum(G, rv);
   const double w = div_rn(mul_rn(mul_rn(frac, 1.0), gg), 1e6);          // sunlit flag = 1 here (Q16)

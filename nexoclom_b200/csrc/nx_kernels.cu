@@ -1009,7 +1009,8 @@ k_los_accumulate(StateCols P, long long n, long long nlos, const double* __restr
       const double d2 = fma(rz, rz, fma(ry, ry, rx * rx));
       if (lr > 0.0 && lr * lr >= d2 * lc.cos_loose2) {
         double losrad, dist;
-        if (los_hit(L, lp.dphi, lc.cos_margin2, ladder, wid2, lc.inv_log_ratio, lc.log_t0,
+        if (los_hit(L, lp.dphi, lc.cos_margin2, lc.cos_accept2, lc.cover, ladder, wid2,
+                    lc.inv_log_ratio, lc.log_t0,
                     lc.kwin, px, py, pz, losrad, dist)) {
           ++cnt;
           double vy = P.c[5][base + j], fr = P.c[7][base + j];

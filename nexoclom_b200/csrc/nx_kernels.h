@@ -21,6 +21,8 @@ struct LosConsts {
   double sin_dphi;
   double cos_margin2;     // (cos(dphi) (1 - 1e-9))^2   conservative reject, exact-order path
   double cos_loose2;      // (cos(dphi) (1 - 1e-6))^2   conservative reject, FMA path
+  double cos_accept2;     // (cos(dphi) (1 + 1e-9))^2   sure accept, no acos needed
+  int cover;              // 1: in-cone points between the first and last ball centre are in a ball
   double inv_log_ratio;   // 1 / log(1 + sin dphi)
   double log_t0;          // log(sin dphi)
   int kwin;
@@ -28,10 +30,17 @@ struct LosConsts {
 };
 
 // ---- K5 spatial culling (nx_los_grid.cu) ----
-struct LosGrid { int G; double half, cell, inv_cell; };
+// Cell grid of K5.  Exospheric packets pile up near the planet (most of them end on its
+// surface), so the grid is uniform in u = asinh(v / scale) per axis instead of in v:
+// cell index = floor(G/2 + k * asinh(v / scale)); cells are scale/k wide at the origin and
+// grow ~ |v| / k far out, where the cone of a line of sight is wide anyway.
+struct LosGrid { int G; double half, scale, inv_scale, k; };
+#define NX_LOS_GRID_MAX 160       // cells per axis the work arrays are allocated for
 struct LosSorted { double *x, *y, *z, *vy, *frac; unsigned* idx; };
 struct LosGridWork {
-  int G = 128;
+  int G = 128;                 // cells per axis of the current grid
+  int G_fixed = 0;             // option "los_grid": > 0 pins G, 0 = sized from the packet count
+  double scale = 1.0;          // R_p: where the asinh grid turns from uniform to logarithmic
   LosGrid grid{};
   LosSorted sorted{};
   unsigned *cell_id = nullptr, *count = nullptr, *start = nullptr, *block_sum = nullptr,
