@@ -202,6 +202,31 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
                 const double* dist_from_plan, const nx_los_params* lp,
                 const long long* used_offsets, long long* used_count, uint32_t* used_indices);
 
+/* ---- K6: source maps (data_simulation/make_source_map.py:11-175) ----------------
+ * Whole-planet and per-grid-point (haversine ball of radius smear_radius*cos(lat_point),
+ * sklearn BallTree.query_radius) histograms of the initial states.  All arrays are host
+ * buffers: six packet columns of length n (longitude, latitude [rad], speed [km/s],
+ * altitude, azimuth [rad], frac); point_lon[nlon] / point_lat[nlat] = bin centres of the
+ * abundance histogram, point_radius[nlat] = smear_radius*cos(point_lat) as the caller's
+ * NumPy computed them.  Outputs (caller-allocated, overwritten): abundance_hist
+ * [nlon*nlat], speed_dist[nvel], altitude_dist[nalt], azimuth_dist[naz], n_included /
+ * n_total [nlon*nlat], abundance[nlon*nlat], speed_map[nlon*nlat*nvel], altitude_map
+ * [..*nalt], azimuth_map[..*naz]; point index = ilon*nlat + ilat.                      */
+typedef struct nx_source_map_params {
+  double smear_radius;
+  double vmax;
+  int32_t nlon, nlat, nvel, nalt, naz;
+  int32_t weight_is_frac;   /* 1: todo = 'source' (weight = frac), 0: 'available' (weight = 1) */
+} nx_source_map_params;
+int nx_source_map(nx_ctx* ctx, long long n, const nx_source_map_params* p,
+                  const double* longitude, const double* latitude, const double* speed_kms,
+                  const double* altitude, const double* azimuth, const double* frac,
+                  const double* point_lon, const double* point_lat, const double* point_radius,
+                  double* abundance_hist, double* speed_dist, double* altitude_dist,
+                  double* azimuth_dist, long long* n_included, long long* n_total,
+                  double* abundance, double* speed_map, double* altitude_map,
+                  double* azimuth_map);
+
 /* ---- measurement --------------------------------------------------------------- */
 int nx_last_kernel_ms(nx_ctx* ctx, float* ms);          /* CUDA-event time of last K* */
 int nx_kernel_launches(nx_ctx* ctx, unsigned long long* count);

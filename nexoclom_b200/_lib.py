@@ -73,6 +73,15 @@ class LosParams(C.Structure):
     ]
 
 
+class SourceMapParams(C.Structure):
+    """Mirror of ``nx_source_map_params``."""
+    _fields_ = [
+        ('smear_radius', C.c_double), ('vmax', C.c_double),
+        ('nlon', C.c_int32), ('nlat', C.c_int32), ('nvel', C.c_int32), ('nalt', C.c_int32),
+        ('naz', C.c_int32), ('weight_is_frac', C.c_int32),
+    ]
+
+
 _lib = None
 
 
@@ -121,6 +130,8 @@ def load():
         'nx_los_accumulate_dev': [vp, i64, i64, vp, vp, C.POINTER(LosParams), vp, vp, vp],
         'nx_los_used': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams), c_i64_p,
                         c_i64_p, c_u32_p],
+        'nx_source_map': [vp, i64, C.POINTER(SourceMapParams)] + [c_double_p] * 9 +
+                         [c_double_p] * 4 + [c_i64_p] * 2 + [c_double_p] * 4,
         'nx_state_device_ptr': [vp, C.c_int, C.POINTER(vp)],
         'nx_last_kernel_ms': [vp, C.POINTER(C.c_float)],
         'nx_kernel_launches': [vp, C.POINTER(u64)],

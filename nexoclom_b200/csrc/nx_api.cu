@@ -264,6 +264,84 @@ int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   return -1;
 }
 
+int nx_source_map(nx_ctx* ctx, long long n, const nx_source_map_params* p_,
+                  const double* longitude, const double* latitude, const double* speed_kms,
+                  const double* altitude, const double* azimuth, const double* frac,
+                  const double* point_lon, const double* point_lat, const double* point_radius,
+                  double* abundance_hist, double* speed_dist, double* altitude_dist,
+                  double* azimuth_dist, long long* n_included, long long* n_total,
+                  double* abundance, double* speed_map, double* altitude_map,
+                  double* azimuth_map) {
+  CK(cudaSetDevice(ctx->device));
+  SourceMapParams sp;
+  static_assert(sizeof(SourceMapParams) == sizeof(nx_source_map_params), "ABI mirror");
+  std::memcpy(&sp, p_, sizeof(sp));
+  if (sp.nlon < 1 || sp.nlat < 1 || sp.nvel < 1 || sp.nalt < 1 || sp.naz < 1 || !(sp.vmax > 0.0)) {
+    ctx->err = "nx_source_map: bad bin counts / vmax";
+    return -1;
+  }
+  const size_t npts = (size_t)sp.nlon * sp.nlat;
+  // per-row constants: cos(lat_p) and sklearn's reduced radius sin^2(r/2)
+  std::vector<double> pcos(sp.nlat), pthr(sp.nlat);
+  for (int j = 0; j < sp.nlat; ++j) {
+    pcos[j] = std::cos(point_lat[j]);
+    const double t = std::sin(0.5 * point_radius[j]);
+    pthr[j] = t * t;
+  }
+  const size_t nd = (size_t)(n > 0 ? n : 1);
+  const size_t out_doubles = npts + sp.nvel + sp.nalt + sp.naz + npts +
+                             npts * ((size_t)sp.nvel + sp.nalt + sp.naz);
+  double *d_in = nullptr, *d_pts = nullptr, *d_out = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  CK(cudaMalloc(&d_in, 6 * nd * sizeof(double)));
+  CK(cudaMalloc(&d_pts, ((size_t)sp.nlon + 3 * (size_t)sp.nlat) * sizeof(double)));
+  CK(cudaMalloc(&d_out, out_doubles * sizeof(double)));
+  CK(cudaMalloc(&d_cnt, 2 * npts * sizeof(unsigned long long)));
+  const double* cols[6] = {longitude, latitude, speed_kms, altitude, azimuth, frac};
+  for (int k = 0; k < 6; ++k)
+    if (n > 0) CK(cudaMemcpyAsync(d_in + k * nd, cols[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  double* d_plon = d_pts; double* d_plat = d_plon + sp.nlon;
+  double* d_pcos = d_plat + sp.nlat; double* d_pthr = d_pcos + sp.nlat;
+  CK(cudaMemcpyAsync(d_plon, point_lon, sp.nlon * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_plat, point_lat, sp.nlat * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_pcos, pcos.data(), sp.nlat * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_pthr, pthr.data(), sp.nlat * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_out, 0, out_doubles * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(d_cnt, 0, 2 * npts * sizeof(unsigned long long), ctx->stream));
+  SourceMapOut o;
+  double* q = d_out;
+  o.abundance_hist = q; q += npts;
+  o.speed_dist = q; q += sp.nvel;
+  o.altitude_dist = q; q += sp.nalt;
+  o.azimuth_dist = q; q += sp.naz;
+  o.abundance = q; q += npts;
+  o.speed_map = q; q += npts * sp.nvel;
+  o.altitude_map = q; q += npts * sp.nalt;
+  o.azimuth_map = q;
+  o.n_included = d_cnt; o.n_total = d_cnt + npts;
+  int r;
+  if ((r = begin_timed(ctx))) return r;
+  CK(launch_source_map(ctx->stream, n, sp, d_in, d_in + nd, d_in + 2 * nd, d_in + 3 * nd,
+                       d_in + 4 * nd, d_in + 5 * nd, d_plon, d_plat, d_pcos, d_pthr, o));
+  if ((r = end_timed(ctx, 1))) return r;
+  auto back = [&](void* dst, const void* src, size_t bytes) {
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  CK(back(abundance_hist, o.abundance_hist, npts * sizeof(double)));
+  CK(back(speed_dist, o.speed_dist, sp.nvel * sizeof(double)));
+  CK(back(altitude_dist, o.altitude_dist, sp.nalt * sizeof(double)));
+  CK(back(azimuth_dist, o.azimuth_dist, sp.naz * sizeof(double)));
+  CK(back(abundance, o.abundance, npts * sizeof(double)));
+  CK(back(speed_map, o.speed_map, npts * sp.nvel * sizeof(double)));
+  CK(back(altitude_map, o.altitude_map, npts * sp.nalt * sizeof(double)));
+  CK(back(azimuth_map, o.azimuth_map, npts * sp.naz * sizeof(double)));
+  CK(back(n_included, o.n_included, npts * sizeof(long long)));
+  CK(back(n_total, o.n_total, npts * sizeof(long long)));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_in); cudaFree(d_pts); cudaFree(d_out); cudaFree(d_cnt);
+  return 0;
+}
+
 // developer hook: K2 instrumentation words (all zero unless built with NX_STREAM_DEBUG)
 int nx_debug_queue(nx_ctx* ctx, unsigned long long* out, int count) {
   CK(cudaSetDevice(ctx->device));

@@ -429,7 +429,7 @@ k_cost_scatter(long long n, const unsigned char* __restrict__ bucket,
 #ifndef NX_SCAN_MAX
 #define NX_SCAN_MAX 3                // batches scanned per step while some lane is live
 #endif
-#define NX_STREAM_TIMEOUT_NS 4000000000ull
+#define NX_STREAM_TIMEOUT_NS 20000000000ull   // watchdog of a lane starved of segments
 
 __device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);

@@ -103,6 +103,26 @@ cudaError_t launch_los_accumulate(cudaStream_t st, int device, StateCols P, long
                                   const LosParams& lp, const LosConsts& lc, const GTables& G,
                                   double* radiance, unsigned long long* npack,
                                   unsigned char* included);
+// ---- K6 source maps (nx_source_map.cu) ----
+struct SourceMapParams {
+  double smear;            // smear_radius [rad]
+  double vmax;             // ceil(max speed) [km/s]
+  int32_t nlon, nlat, nvel, nalt, naz;
+  int32_t weight_is_frac;  // todo == 'source': weight = X0.frac; 'available': weight = 1
+};
+struct SourceMapOut {
+  double *abundance_hist;                 // [nlon][nlat]   np.histogram2d of the included packets
+  double *speed_dist, *altitude_dist, *azimuth_dist;     // whole-planet histograms
+  unsigned long long *n_included, *n_total;              // [nlon*nlat]
+  double *abundance;                      // [nlon*nlat]    smeared: sum of weights in the ball
+  double *speed_map, *altitude_map, *azimuth_map;        // [nlon*nlat][nbins]
+};
+cudaError_t launch_source_map(cudaStream_t st, long long n, const SourceMapParams& sp,
+                              const double* lon, const double* lat, const double* v,
+                              const double* alt, const double* az, const double* frac,
+                              const double* plon, const double* plat, const double* pcos,
+                              const double* pthr, const SourceMapOut& out);
+
 cudaError_t launch_fp64_peak(cudaStream_t st, int device, double* out, int iters, int* blocks,
                              int* threads);
 cudaError_t launch_copy(cudaStream_t st, int device, const double* src, double* dst,

@@ -281,6 +281,37 @@ class Engine:
             C.c_void_p(inc_dev)), 'nx_los_accumulate_dev')
 
 
+    def source_map(self, params, longitude, latitude, speed_kms, altitude, azimuth, frac,
+                   point_lon, point_lat, point_radius):
+        """K6 (reference make_source_map.py:67-160).  Returns a dict of ndarrays; per-point
+        arrays are shaped (nlon, nlat[, nbins])."""
+        cols = [as_f64(a) for a in (longitude, latitude, speed_kms, altitude, azimuth, frac)]
+        n = len(cols[0])
+        plon, plat, prad = as_f64(point_lon), as_f64(point_lat), as_f64(point_radius)
+        nlon, nlat = params.nlon, params.nlat
+        npts = nlon * nlat
+        out = {
+            'abundance_hist': np.zeros((nlon, nlat)),
+            'speed_dist': np.zeros(params.nvel), 'altitude_dist': np.zeros(params.nalt),
+            'azimuth_dist': np.zeros(params.naz),
+            'n_included': np.zeros((nlon, nlat), dtype=np.int64),
+            'n_total': np.zeros((nlon, nlat), dtype=np.int64),
+            'abundance': np.zeros((nlon, nlat)),
+            'speed_map': np.zeros((nlon, nlat, params.nvel)),
+            'altitude_map': np.zeros((nlon, nlat, params.nalt)),
+            'azimuth_map': np.zeros((nlon, nlat, params.naz)),
+        }
+        assert npts == out['abundance'].size
+        i64p = lambda a: a.ctypes.data_as(_lib.c_i64_p)     # noqa: E731
+        self._check(self.lib.nx_source_map(
+            self.ctx, n, C.byref(params), *[dptr(c) for c in cols], dptr(plon), dptr(plat),
+            dptr(prad), dptr(out['abundance_hist']), dptr(out['speed_dist']),
+            dptr(out['altitude_dist']), dptr(out['azimuth_dist']), i64p(out['n_included']),
+            i64p(out['n_total']), dptr(out['abundance']), dptr(out['speed_map']),
+            dptr(out['altitude_map']), dptr(out['azimuth_map'])), 'nx_source_map')
+        return out
+
+
 _engines = {}
 
 

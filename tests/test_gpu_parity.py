@@ -337,6 +337,39 @@ def test_los_vs_reference_golden(engine, tag, los_mode):
         assert np.array_equal(np.sort(idx[off[i]:off[i + 1]]), ridx[roff[i]:roff[i + 1]])
 
 
+@pytest.mark.parametrize('todo', ['source', 'available'])
+def test_source_map_vs_reference_golden(engine, todo):
+    """K6 through the C ABI against the reference's own make_source_map()
+    (tests/golden/source_map.npz): ball membership counts bit-exact, histograms 1e-6."""
+    from nexoclom_b200.make_source_map import source_map_arrays
+    from test_oracle_products_golden import check_source_map, source_map_inputs
+    g = np.load(os.path.join(GOLDEN, 'source_map.npz'))
+    X0, rkm, params = source_map_inputs(g)
+    res = source_map_arrays(X0, rkm, params, todo)
+    check_source_map(res, g, todo, tol=IMAGE_TOL)
+
+
+def test_source_map_large_vs_oracle(engine):
+    """Default 180 x 90 grid, 2e5 packets over the whole sphere (longitude wrap, poles)."""
+    from nexoclom_b200.make_source_map import source_map_arrays
+    from oracle import source_map
+    setup = RunSetup(workload('Ca.isotropic.flat.input'))
+    X0a = initial_state.draw_x0(setup, 200_000, 23)
+    cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac', 'v', 'longitude', 'latitude',
+            'local_time', 'altitude', 'azimuth']
+    X0 = {c: X0a[:, k].astype(np.float32).astype(np.float64) for k, c in enumerate(cols)}
+    rng = np.random.default_rng(1)
+    X0['frac'] = rng.random(len(X0['v'])) * (rng.random(len(X0['v'])) > 0.5)
+    params = {'smear_radius': np.radians(6.0), 'nlonbins': 90, 'nlatbins': 45}
+    got = source_map_arrays(X0, setup.radius_km, params, 'source')
+    ref = source_map.make_source_map(X0, setup.radius_km, params, 'source')
+    assert np.array_equal(got['n_total'], ref['n_total'].astype(np.int64))
+    assert np.array_equal(got['n_included'], ref['n_included'].astype(np.int64))
+    for k in ('abundance_hist', 'abundance', 'speed_dist', 'altitude_dist', 'azimuth_dist',
+              'speed_map', 'altitude_map', 'azimuth_map'):
+        assert np.max(np.abs(got[k] - ref[k])) <= IMAGE_TOL * max(np.max(np.abs(ref[k])), 1.0), k
+
+
 def test_public_api_end_to_end(engine):
     """Input -> Output (device-drawn packets) -> ModelImage through the
     reference-facing classes; the image equals the oracle's create_image on the

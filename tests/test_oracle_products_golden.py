@@ -166,3 +166,48 @@ def test_k1_transform_vs_reference(hc, tag):
         # nearly cancel are judged against the size of the vector, not their own
         err = np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
         assert err < 1e-14, (tag, c, err)
+
+
+SRCMAP_KEYS = {'abundance_hist': None, 'speed_dist': 'speed_dist', 'altitude_dist': 'altitude_dist',
+               'azimuth_dist': 'azimuth_dist', 'n_included': 'n_included', 'n_total': 'n_total',
+               'speed_map': 'speed_dist_map', 'altitude_map': 'altitude_dist_map',
+               'azimuth_map': 'azimuth_dist_map', 'longitude': 'longitude', 'latitude': 'latitude',
+               'speed': 'speed', 'altitude': 'altitude', 'azimuth': 'azimuth'}
+
+
+def check_source_map(result, g, todo, exact_counts=True, tol=1e-12):
+    """Compare a source-map result (oracle or CUDA) with the reference's dictionaries."""
+    for smear in ('smear', 'hist'):
+        tag = f'{todo}_{smear}'
+        ref_ab = g[f'{tag}_abundance_uncor']
+        got_ab = result['abundance'] if smear == 'smear' else result['abundance_hist']
+        assert np.max(np.abs(got_ab - ref_ab)) <= tol * max(np.max(np.abs(ref_ab)), 1.0)
+        for key, refkey in SRCMAP_KEYS.items():
+            if refkey is None:
+                continue
+            ref = g[f'{tag}_{refkey}']
+            got = np.asarray(result[key], dtype=np.float64)
+            assert got.shape == ref.shape, (key, got.shape, ref.shape)
+            if key in ('n_included', 'n_total') and exact_counts:
+                assert np.array_equal(got, ref), key            # ball membership is bit-exact
+            else:
+                assert np.max(np.abs(got - ref)) <= tol * max(np.max(np.abs(ref)), 1.0), key
+
+
+def source_map_inputs(g):
+    cols = ['longitude', 'latitude', 'v', 'altitude', 'azimuth', 'frac']
+    X0 = {c: g['X0'][:, k] for k, c in enumerate(cols)}
+    params = {k[len('param_'):]: (float(g[k]) if 'radius' in k else int(g[k]))
+              for k in g.files if k.startswith('param_')}
+    return X0, float(g['radius_km']), params
+
+
+@pytest.mark.parametrize('todo', ['source', 'available'])
+def test_source_map_vs_reference(todo):
+    """oracle.source_map == the reference's make_source_map() (run unmodified)."""
+    from oracle import source_map
+    g = np.load(os.path.join(GOLDEN, 'source_map.npz'))
+    X0, rkm, params = source_map_inputs(g)
+    res = source_map.make_source_map(X0, rkm, params, todo)
+    assert g[f'{todo}_smear_n_total'].sum() > 1e5
+    check_source_map(res, g, todo)

@@ -315,9 +315,47 @@ def golden_los():
     print('los.npz')
 
 
+def golden_source_map():
+    """reference data_simulation/make_source_map.py, unmodified, on oracle-drawn X0."""
+    from nexoclom.data_simulation import make_source_map as msm
+    from nexoclom_b200 import Input
+    from nexoclom_b200.runsetup import RunSetup
+    from oracle import initial_state
+    ns = types.SimpleNamespace
+    setup = RunSetup(Input(os.path.join(GOLD, 'source_cases', 'maxw_band.input')))
+    n = 30000
+    X0a = initial_state.draw_x0(setup, n, 17)
+    cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac', 'v', 'longitude', 'latitude',
+            'local_time', 'altitude', 'azimuth']
+    X0 = pd.DataFrame(X0a, columns=cols)
+    rng = np.random.default_rng(4)
+    X0['frac'] = rng.random(n) * (rng.random(n) > 0.3)          # some packets not seen (frac = 0)
+    X0 = X0.astype(np.float32).astype(np.float64)                # Output.save / restore (Q14)
+    rp_km = setup.radius_km
+    fake = ns(X0=X0, inputs=ns(geometry=ns(planet=ns(radius=q(rp_km, u.km)))))
+    msm.Output = ns(restore=lambda fname, _o=fake: _o)
+    params = {'smear_radius': np.radians(12.), 'nlonbins': 36, 'nlatbins': 18, 'nvelbins': 25,
+              'nazbins': 12, 'naltbins': 9}
+    out = {'X0': X0[['longitude', 'latitude', 'v', 'altitude', 'azimuth', 'frac']].values,
+           'radius_km': rp_km}
+    for k, v in params.items():
+        out['param_' + k] = v
+    for todo in ('source', 'available'):
+        for smear in (True, False):
+            d = msm.make_source_map('none', dict(params, smear_abundance=smear), todo=todo)
+            tag = f"{todo}_{'smear' if smear else 'hist'}"
+            for key, val in d.items():
+                out[f'{tag}_{key}'] = np.asarray(val, dtype=np.float64)
+            print(tag, 'n_total', d['n_total'].sum(), 'n_included', d['n_included'].sum())
+    np.savez_compressed(os.path.join(GOLD, 'source_map.npz'), **out)
+    print('source_map.npz')
+
+
 if __name__ == '__main__':
     install()
-    which = sys.argv[1:] or ['source', 'image', 'los']
+    which = sys.argv[1:] or ['source', 'image', 'los', 'map']
+    if 'map' in which:
+        golden_source_map()
     if 'source' in which:
         golden_source_distribution()
     if 'image' in which:
