@@ -428,6 +428,104 @@ def run_gpu(args):
     return 0
 
 
+def run_gpu_config3(args):
+    """Extra measurement (not the driver's contract line): BASELINE configs[2] -- Na at
+    Mercury, surface-bound packets with temperature-dependent sticking, bounce and thermal
+    accommodation, constant 30 s step, the 800x800 radiance image accumulated per step
+    INSIDE the integrator (K1 -> K3 fused), packets sharded over the ranks, one NCCL
+    all-reduce of the image per step.  `--packets` per GPU (1.25e7 x 8 = the 1e8 run)."""
+    import torch
+    import torch.distributed as dist
+    from common import workload
+    from nexoclom_b200._lib import ImageParams
+    from nexoclom_b200.engine import Engine
+    from nexoclom_b200.runsetup import RunSetup
+    from nexoclom_b200.ModelImage import image_rotation
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    eng = Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    n = args.packets
+    setup = RunSetup(workload('Na.bounce.input'))
+    setup.upload(eng)
+    eng.upload_gtables(setup.gtables([5891, 5897]))
+    sp = setup.source_params(eng)
+    M = np.asarray(image_rotation(0.0, np.pi / 2))
+    ip = ImageParams()
+    for k in range(9):
+        ip.M[k] = float(M.flat[k])
+    ip.x0, ip.x1, ip.z0, ip.z1 = -4., 4., -4., 4.
+    ip.nx = ip.nz = 800
+    rcm = setup.radius_km * 1e5
+    ip.apix = (8 / 800 * rcm) * (8 / 800 * rcm)
+    ip.vrplanet = setup.vrplanet
+    ip.quantity, ip.round_f32, ip.skip_dead = 1, 1, 1
+    image = torch.zeros((800, 800), dtype=torch.float64, device='cuda')
+    counts = torch.zeros((800, 800), dtype=torch.int64, device='cuda')
+    steps_done = []
+
+    def one_step(record):
+        image.zero_()
+        counts.zero_()
+        eng.init_state(sp, args.seed, rank * n, n)                    # K1
+        _, nsteps, psteps = eng.integrate_constant(                   # K3 + fused image
+            seed=args.seed + 1, first_id=rank * n, image_params=ip, image_dev=image.data_ptr(),
+            counts_dev=counts.data_ptr())
+        if world > 1:
+            dist.all_reduce(image)
+            dist.all_reduce(counts)
+        if record:
+            steps_done.append(psteps)
+        return nsteps
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        nsteps = one_step(False)
+    fence()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        one_step(True)
+    ev1.record(stream)
+    fence()
+    t = torch.tensor([ev0.elapsed_time(ev1), float(sum(steps_done))], dtype=torch.float64,
+                     device='cuda')
+    rows = counts.sum().item()
+    if world > 1:
+        tmax, tsum = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, all_steps = float(tmax[0]), float(tsum[1])
+    else:
+        elapsed_ms, all_steps = float(t[0]), float(t[1])
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'packet-steps/s (FP64), constant step + bounce + fused image',
+            'value': all_steps / (elapsed_ms * 1e-3), 'unit': 'packet-steps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[2]: Na at Mercury, T-dependent sticking + '
+                                   'bounce + accommodation, 30 s step, image fused into K3',
+                       'inputfile': 'Na.bounce.input', 'packets_per_gpu': n,
+                       'packets_total': n * world, 'nsteps': int(nsteps),
+                       'rows_in_image_per_step': int(rows),
+                       'step': 'K1 init -> K3 constant-step integrate with fused radiance '
+                               'image' + (' -> NCCL all-reduce(image, counts)' if world > 1 else '')}}))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -448,9 +546,13 @@ def main():
     ap.add_argument('--e2e-chunks', type=int, default=16,
                     help='segments of the streamed H2D copy of the end-to-end path')
     ap.add_argument('--los', type=int, default=100_000, help='lines of sight of the K5 sweep')
+    ap.add_argument('--config3', action='store_true',
+                    help='extra: the constant-step / bounce / fused-image workload (configs[2])')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.config3:
+        return run_gpu_config3(args)
     return run_gpu(args)
 
 
