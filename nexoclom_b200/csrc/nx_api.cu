@@ -64,6 +64,7 @@ struct nx_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[2] = {};
   int los_mode = 0;                  // 0 auto, 1 brute force, 2 cell grid
+  int los_order = 1;                 // process lines of sight in Morton order of closest approach
   cudaStream_t pipe[16] = {};                  // H2D / compute pipeline of the host-buffer path
   cudaEvent_t pipe_ev[17] = {};
   unsigned long long* pipe_scalars = nullptr;  // 4 u64 per chunk
@@ -258,6 +259,7 @@ int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   if (name && std::strcmp(name, "order_packets") == 0) { ctx->order_packets = value; return 0; }
   if (name && std::strcmp(name, "schedule") == 0) { ctx->schedule = value; return 0; }
   if (name && std::strcmp(name, "los_mode") == 0) { ctx->los_mode = value; return 0; }
+  if (name && std::strcmp(name, "los_order") == 0) { ctx->los_order = value; return 0; }
   if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G_fixed = value; ctx->losw.cap = 0; return 0; }
   if (name && std::strcmp(name, "los_grid_scale_milli") == 0) { ctx->losw.scale = 1e-3 * value; return 0; }
   ctx->err = std::string("unknown option ") + (name ? name : "(null)");
@@ -842,6 +844,36 @@ static void los_prepare(const double* los, long long nlos, const LosParams& lp,
   lc.nladder = (int)ladder.size();
 }
 
+// Processing order of the lines of sight for the cell-grid kernel: counting sort on the
+// 15-bit Morton code of the point of closest approach to the planet (0.4 R_p cells over
+// +-6.4 R_p), so that warps that run together stream the same near-planet cells.
+static std::vector<unsigned> los_order(const double* los, long long nlos) {
+  auto spread = [](unsigned v) {            // 5 bits -> every third bit
+    unsigned r = 0;
+    for (int b = 0; b < 5; ++b) r |= ((v >> b) & 1u) << (3 * b);
+    return r;
+  };
+  std::vector<unsigned> key(nlos), count(32768 + 1, 0), order(nlos);
+  for (long long i = 0; i < nlos; ++i) {
+    const double x = los[i], y = los[nlos + i], z = los[2 * nlos + i];
+    const double bx = los[3 * nlos + i], by = los[4 * nlos + i], bz = los[5 * nlos + i];
+    double t = -(x * bx + y * by + z * bz);
+    if (!(t > 0.0)) t = 0.0;
+    const double c[3] = {x + bx * t, y + by * t, z + bz * t};
+    unsigned q[3];
+    for (int a = 0; a < 3; ++a) {
+      double v = (c[a] + 6.4) / 0.4;
+      v = v < 0.0 ? 0.0 : (v > 31.0 ? 31.0 : v);
+      q[a] = (v == v) ? (unsigned)v : 0u;
+    }
+    key[i] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
+    ++count[key[i] + 1];
+  }
+  for (int k = 0; k < 32768; ++k) count[k + 1] += count[k];
+  for (long long i = 0; i < nlos; ++i) order[count[key[i]]++] = (unsigned)i;
+  return order;
+}
+
 static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_host,
                    const double* los_dev, const double* dist_dev, const LosParams& lp,
                    double* rad_dev, unsigned long long* np_dev, unsigned char* inc_dev) {
@@ -862,7 +894,14 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
                         (ctx->los_mode == 0 && (double)n * (double)nlos > 2e9 && n < (1LL << 32));
   int nlaunch = 1;
   int r = 0;
+  unsigned* d_order = nullptr;
   if (use_grid) r = alloc_los_work(ctx, n);
+  if (r == 0 && use_grid && ctx->los_order && nlos >= 1024) {
+    const std::vector<unsigned> order = los_order(los_host, nlos);
+    CK(cudaMalloc(&d_order, nlos * sizeof(unsigned)));
+    CK(cudaMemcpyAsync(d_order, order.data(), nlos * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));       // `order` is a local vector
+  }
   if (r == 0) r = begin_timed(ctx);
   if (r == 0) {
     cudaError_t e;
@@ -870,7 +909,8 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
       e = launch_los_grid_build(ctx->stream, ctx->device, state_cols(ctx), n, lp, ctx->losw);
       if (e == cudaSuccess)
         e = launch_los_grid(ctx->stream, ctx->losw, nlos, los_dev, dist_dev, d_nball, d_ladder,
-                            d_wid2, lp, lc, ctx->gtables, rad_dev, np_dev, inc_dev);
+                            d_wid2, lp, lc, ctx->gtables, rad_dev, np_dev, inc_dev, nullptr,
+                            nullptr, nullptr, nullptr, d_order);
       nlaunch = 8;
     } else {
       e = launch_los_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, nlos, los_dev,
@@ -882,7 +922,7 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
   if (r == 0) r = end_timed(ctx, nlaunch);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (r == 0 && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
-  cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2);
+  cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2); cudaFree(d_order);
   return r;
 }
 

@@ -56,7 +56,8 @@ cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlo
                             const LosConsts& lc, const GTables& G, double* radiance,
                             unsigned long long* npack, unsigned char* included,
                             unsigned long long* nused = nullptr, const long long* used_off = nullptr,
-                            unsigned long long* used_cursor = nullptr, unsigned* used_idx = nullptr);
+                            unsigned long long* used_cursor = nullptr, unsigned* used_idx = nullptr,
+                            const unsigned* order = nullptr);
 
 size_t table_smem_bytes(const InterpTable& g);
 

@@ -192,9 +192,13 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
            double* __restrict__ radiance, unsigned long long* __restrict__ npack,
            unsigned char* __restrict__ included,
            unsigned long long* __restrict__ nused, const long long* __restrict__ used_off,
-           unsigned long long* __restrict__ used_cursor, unsigned* __restrict__ used_idx) {
-  const long long l = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (l >= nlos) return;
+           unsigned long long* __restrict__ used_cursor, unsigned* __restrict__ used_idx,
+           const unsigned* __restrict__ order) {
+  const long long w_ = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w_ >= nlos) return;
+  // lines of sight are processed in a spatially coherent order (host: Morton order of the
+  // points of closest approach) so that neighbouring warps stream the same cells out of L2
+  const long long l = order ? (long long)order[w_] : w_;
   const unsigned lane = threadIdx.x & 31u;
   LosRay L;
   L.xs = los[l]; L.ys = los[nlos + l]; L.zs = los[2 * nlos + l];
@@ -325,12 +329,13 @@ cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlo
                             const LosConsts& lc, const GTables& G, double* radiance,
                             unsigned long long* npack, unsigned char* included,
                             unsigned long long* nused, const long long* used_off,
-                            unsigned long long* used_cursor, unsigned* used_idx) {
+                            unsigned long long* used_cursor, unsigned* used_idx,
+                            const unsigned* order) {
   const long long threads = nlos * 32;
   const long long blocks = (threads + 127) / 128;
   k_los_grid<<<(unsigned)blocks, 128, 0, st>>>(w.sorted, w.grid, w.start, nlos, los, dist_plan,
                                                nball, ladder, wid2, lp, lc, G, radiance, npack,
-                                               included, nused, used_off, used_cursor, used_idx);
+                                               included, nused, used_off, used_cursor, used_idx, order);
   return cudaGetLastError();
 }
 

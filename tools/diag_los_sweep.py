@@ -38,12 +38,13 @@ lp.vrplanet, lp.rp_cm = setup.vrplanet, setup.radius_km * 1e5
 lp.quantity, lp.round_f32 = 1, 1
 eng.set_option('los_mode', 2)
 combos = [tuple(int(v) for v in a.split(':')) for a in (sys.argv[3].split(',') if len(sys.argv) > 3 else ['128:1000'])]
-for skip in (0, 1):
+for skip, order in ((0, 0), (0, 1), (1, 0), (1, 1)):
     lp.skip_dead = skip
+    eng.set_option('los_order', order)
     for G, sc in combos:
         eng.set_option('los_grid', G)
         eng.set_option('los_grid_scale_milli', sc)
         for rep in range(2):
             rad, npk, inc = eng.los_accumulate(los, dist, lp)
             ms = eng.last_kernel_ms()
-        print(f'skip_dead={skip} G={G} scale={sc / 1000}: {ms:.2f} ms hits={int(npk.sum())}', flush=True)
+        print(f'skip_dead={skip} order={order} G={G} scale={sc / 1000}: {ms:.2f} ms hits={int(npk.sum())}', flush=True)
