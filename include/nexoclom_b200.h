@@ -62,7 +62,15 @@ typedef struct nx_run_params {
   int32_t loss_mode;       /* 0 none, 1 constant lifetime, 2 photo x sunlit        */
   int32_t sticktype;       /* 0 constant, 1 temperature dependent                  */
   int32_t strict_math;     /* 1: NumPy operation order without FMA contraction     */
-  int32_t reserved;
+  int32_t nmoons;          /* 0 = the reference's case (it asserts for planets with moons,
+                              Output.py:153-155); > 0: extension, see DESIGN.md           */
+  /* moons on circular prograde equatorial orbits; position at time-remaining tau:
+     a (-sin phi, cos phi, 0), phi = moon_phi - moon_omega tau (inputfiles.rst:72-77)      */
+  double moon_GM[4];       /* R_p^3/s^2, negative                                       */
+  double moon_a[4];        /* R_p                                                        */
+  double moon_omega[4];    /* rad/s                                                      */
+  double moon_phi[4];      /* rad at the time of the observation                         */
+  double moon_r2[4];       /* (moon radius / R_p)^2                                      */
 } nx_run_params;
 
 /* Initial-state distributions (source_distribution.py:37-283). */
@@ -83,6 +91,9 @@ typedef struct nx_source_params {
   int32_t map_nx, map_ny;    /* source map grid (surface map / surface spot)        */
   int32_t map_lat_is_sin;    /* 1: y-axis is sin(lat) (surface map); 0: lat (spot)  */
   double map_fmax;
+  int32_t start_is_moon;     /* extension: StartPoint is a moon (see nx_run_params)      */
+  int32_t reserved;
+  double moon_a, moon_omega, moon_phi, moon_radius;   /* R_p, rad/s, rad, R_p            */
 } nx_source_params;
 
 /* Image accumulation (ModelImage.py:229-274). */

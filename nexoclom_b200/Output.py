@@ -56,10 +56,12 @@ class Output:
             self.npackets = npackets
             self.totalsource = float(npackets)        # sum of frac == 1 (Output.py:150)
 
-            if self.planet.moons is not None:
-                assert False, 'Not set up'            # Output.py:153-155 (moons)
-            if self.planet.object != inputs.geometry.startpoint:
-                assert 0, 'Not set up yet'            # Output.py:173-175
+            # The reference stops here for planets with moons (`assert False, 'Not set up'`,
+            # Output.py:153-155) and for StartPoint != planet (:173-175).  Extension: moons
+            # listed in geometry.objects act on the packets from circular orbits at the
+            # phases geometry.phi, and a moon can be the start point.
+            if setup.moons:
+                print('Including the gravity of ' + ', '.join(m['name'] for m in setup.moons))
 
             eng = get_engine(device)
             self._engine = eng

@@ -27,7 +27,9 @@ class RunParams(C.Structure):
         ('stick_A', C.c_double * 3), ('surf_t1', C.c_double), ('planet_radius_km', C.c_double),
         ('radpres_amax', C.c_double),
         ('gravity', C.c_int32), ('radpres', C.c_int32), ('loss_mode', C.c_int32),
-        ('sticktype', C.c_int32), ('strict_math', C.c_int32), ('reserved', C.c_int32),
+        ('sticktype', C.c_int32), ('strict_math', C.c_int32), ('nmoons', C.c_int32),
+        ('moon_GM', C.c_double * 4), ('moon_a', C.c_double * 4), ('moon_omega', C.c_double * 4),
+        ('moon_phi', C.c_double * 4), ('moon_r2', C.c_double * 4),
     ]
 
 
@@ -46,6 +48,9 @@ class SourceParams(C.Structure):
         ('endtime', C.c_double), ('random_time', C.c_int32), ('map_nx', C.c_int32),
         ('map_ny', C.c_int32), ('map_lat_is_sin', C.c_int32),
         ('map_fmax', C.c_double),
+        ('start_is_moon', C.c_int32), ('reserved', C.c_int32),
+        ('moon_a', C.c_double), ('moon_omega', C.c_double), ('moon_phi', C.c_double),
+        ('moon_radius', C.c_double),
     ]
 
 

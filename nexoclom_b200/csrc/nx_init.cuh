@@ -27,6 +27,12 @@ struct SourceParams {
   int32_t map_nx, map_ny;
   int32_t map_lat_is_sin;
   double map_fmax;
+  // StartPoint = a moon (extension, see RunParams): the source sits on the moon's surface;
+  // exobase is in moon radii, the satellite-local frame of xyz_from_lonlat (:21-28: sub-planet
+  // point at (0,-1,0), leading point at (-1,0,0)) is turned by the moon's phase at the packet's
+  // ejection time and moved to the moon, whose orbital velocity is added.
+  int32_t start_is_moon, reserved;
+  double moon_a, moon_omega, moon_phi, moon_radius;     // R_p, rad/s, rad, R_p
 };
 
 // 2-D source map on a uniform (x, y) grid, row-major [nx][ny]
@@ -112,6 +118,18 @@ NX_HD void init_packet_finish(const SourceParams& sp, const InterpTable& speed, 
   x0[4] = mul_rn(d[0], v); x0[5] = mul_rn(d[1], v); x0[6] = mul_rn(d[2], v);
   x0[7] = 1.0; x0[8] = v; x0[9] = lon; x0[10] = lat; x0[11] = local_time;
   x0[12] = alt; x0[13] = az;
+  if (sp.start_is_moon) {
+    const double phi = sp.moon_phi - sp.moon_omega * time;
+    const double c = cos(phi), s = sin(phi);
+    const double lx = x0[1] * sp.moon_radius, ly = x0[2] * sp.moon_radius;
+    const double lvx = x0[4], lvy = x0[5];
+    const double vorb = sp.moon_a * sp.moon_omega;
+    x0[1] = (lx * c - ly * s) - sp.moon_a * s;
+    x0[2] = (lx * s + ly * c) + sp.moon_a * c;
+    x0[3] = x0[3] * sp.moon_radius;
+    x0[4] = (lvx * c - lvy * s) - vorb * c;
+    x0[5] = (lvx * s + lvy * c) - vorb * s;
+  }
 }
 
 // Fills x0[NCOL_X0] = time,x,y,z,vx,vy,vz,frac,v,longitude,latitude,local_time,

@@ -1160,7 +1160,7 @@ cudaError_t launch_integrate_adaptive_stream(cudaStream_t st, int device, const 
   StreamQueue Q;
   Q.seg = seg; Q.nseg = nseg; Q.model = model; Q.cursor = cursor; Q.arrived = arrived;
 #define NX_ARGS st, device, in0, in_stride, step0, P, n, p, T, F, Q, totals, att, acc, status
-  if (p.strict_math) return launch_adaptive_stream_mode<-1>(NX_ARGS);
+  if (p.strict_math || p.nmoons > 0) return launch_adaptive_stream_mode<-1>(NX_ARGS);   // moons: generic path
   const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
   switch (mode) {
     case 0: return launch_adaptive_stream_mode<0>(NX_ARGS);
@@ -1202,7 +1202,7 @@ cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, 
                                       unsigned long long* queue, unsigned long long* totals,
                                       unsigned* att, unsigned* acc, int* status) {
 #define NX_ARGS st, device, P, n, p, T, F, perm, queue, totals, att, acc, status
-  if (p.strict_math) return launch_adaptive_mode<-1>(NX_ARGS);
+  if (p.strict_math || p.nmoons > 0) return launch_adaptive_mode<-1>(NX_ARGS);          // moons: generic path
   const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
   switch (mode) {
     case 0: return launch_adaptive_mode<0>(NX_ARGS);
@@ -1254,7 +1254,7 @@ cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, 
                                       int* status) {
 #define NX_ARGS st, device, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, \
                 queue, totals, status
-  if (p.strict_math) return launch_constant_mode<-1>(NX_ARGS);
+  if (p.strict_math || p.nmoons > 0) return launch_constant_mode<-1>(NX_ARGS);
   const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
   switch (mode) {
     case 0: return launch_constant_mode<0>(NX_ARGS);

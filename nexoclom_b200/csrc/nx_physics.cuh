@@ -29,6 +29,7 @@ namespace nx {
 enum LossMode { LOSS_NONE = 0, LOSS_LIFETIME = 1, LOSS_PHOTO = 2 };
 enum StickType { STICK_CONSTANT = 0, STICK_TEMPERATURE = 1 };
 
+#define NX_MAX_MOONS 4
 struct RunParams {
   double GM;              // R_p^3 / s^2, NEGATIVE (reference SSObject.py:53)
   double vrplanet;        // R_p / s
@@ -48,7 +49,16 @@ struct RunParams {
   int32_t loss_mode;      // LossMode
   int32_t sticktype;      // StickType
   int32_t strict_math;    // 1 = STRICT kernels
-  int32_t reserved;
+  int32_t nmoons;         // moons whose gravity acts on the packets (0: the reference's case)
+  // Moons on circular, prograde, equatorial orbits (extension: the reference asserts when the
+  // planet has moons, Output.py:153-155; conventions of docs/nexoclom/inputfiles.rst:72-77).
+  // Position at time-remaining tau: a (-sin phi, cos phi, 0), phi = moon_phi - moon_omega tau
+  // (phi = 0: superior conjunction, pi/2: over the dawn terminator).
+  double moon_GM[NX_MAX_MOONS];      // R_p^3/s^2, negative
+  double moon_a[NX_MAX_MOONS];       // R_p
+  double moon_omega[NX_MAX_MOONS];   // rad/s
+  double moon_phi[NX_MAX_MOONS];     // rad, at the time of the observation (tau = 0)
+  double moon_r2[NX_MAX_MOONS];      // (moon radius / R_p)^2: impact test
 };
 
 // np.interp table + slopes + a uniform bucket index that accelerates the search
@@ -190,10 +200,17 @@ NX_HD bool out_of_shadow(double x, double y, double z) {
   return (s > NX_ONE_PLUS_ULP) || (y < 0.0);
 }
 
+// moon position / phase at time-remaining tau
+NX_HD void moon_position(const RunParams& p, int m, double tau, double& mx, double& my) {
+  const double phi = p.moon_phi[m] - p.moon_omega[m] * tau;
+  mx = -p.moon_a[m] * sin(phi);
+  my = p.moon_a[m] * cos(phi);
+}
+
 template <bool STRICT>
 NX_HD void rhs(const RunParams& p, const InterpTable& T,
                double x, double y, double z, double vy,
-               double& ax, double& ay, double& az, double& rate) {
+               double& ax, double& ay, double& az, double& rate, double tau = 0.0) {
   if (p.gravity) {
     if (STRICT) {
       const double r2 = add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z));
@@ -206,6 +223,21 @@ NX_HD void rhs(const RunParams& p, const InterpTable& T,
       const double ri = rsqrt_fast(r2);
       const double g = p.GM * (ri * ri) * ri;
       ax = g * x; ay = g * y; az = g * z;
+    }
+    // moons (state.py:5-10 docstring: sum over objects of GM (x - x_obj) / r_obj^3), in the
+    // planet-centred frame: direct term + the planet's own acceleration towards the moon
+    for (int m = 0; m < p.nmoons; ++m) {
+      double mx, my;
+      moon_position(p, m, tau, mx, my);
+      const double dx = x - mx, dy = y - my;
+      const double d2 = dx * dx + dy * dy + z * z;
+      const double di = 1.0 / sqrt(d2);
+      const double gd = p.moon_GM[m] * di * di * di;
+      const double ai = 1.0 / p.moon_a[m];
+      const double gi = p.moon_GM[m] * ai * ai * ai;
+      ax += gd * dx + gi * mx;
+      ay += gd * dy + gi * my;
+      az += gd * z;
     }
   } else {
     ax = 0.0; ay = 0.0; az = 0.0;
@@ -272,7 +304,8 @@ NX_HD void dp_step(const RunParams& p, const InterpTable& T, const double* s, do
 #pragma unroll
   for (int n = 0; n < 6; ++n) {
     kv[n][0] = vx; kv[n][1] = vy; kv[n][2] = vz;
-    rhs<STRICT>(p, T, px, py, pz, vy, ka[n][0], ka[n][1], ka[n][2], kr[n]);
+    rhs<STRICT>(p, T, px, py, pz, vy, ka[n][0], ka[n][1], ka[n][2], kr[n],
+                p.nmoons ? s[0] - DP::c(n) * h : 0.0);
     double ap[3], av[3], af;
     {
       const double ha = mul_rn(h, DP::a(n + 1, 0));
@@ -359,6 +392,12 @@ NX_HD int adaptive_attempt(const RunParams& p, const InterpTable& T, double* s, 
     const double r2 = add_rn(add_rn(mul_rn(nx[1], nx[1]), mul_rn(nx[2], nx[2])), mul_rn(nx[3], nx[3]));
     double f = nx[7];
     if (r2 < 1.0) f = 0.0;                 // impact, stickcoef == 1 (Q6)
+    for (int m = 0; m < p.nmoons; ++m) {   // impact on a moon (same rule, moon surface)
+      double mx, my;
+      moon_position(p, m, nx[0], mx, my);
+      const double dx = nx[1] - mx, dy = nx[2] - my;
+      if (dx * dx + dy * dy + nx[3] * nx[3] < p.moon_r2[m]) f = 0.0;
+    }
     if (r2 > p.outeredge) f = 0.0;         // escape: r^2 vs outeredge (Q7)
     if (f < 1e-10) f = 0.0;                // vanish (Q8)
     s[0] = (f == 0.0) ? 0.0 : nx[0];

@@ -282,6 +282,12 @@ NX_HD bool constant_step_finish(const RunParams& p, const Spline2D& S, double* n
       else bounce(p, S, nx, r, u_alt, u_az, u_prob);
     }
   }
+  for (int m = 0; m < p.nmoons; ++m) {     // extension: packets that hit a moon stick to it
+    double mx, my;
+    moon_position(p, m, nx[0], mx, my);
+    const double dx = nx[1] - mx, dy = nx[2] - my;
+    if (dx * dx + dy * dy + nx[3] * nx[3] < p.moon_r2[m]) nx[7] = 0.0;
+  }
   if (r > p.outeredge) nx[7] = 0.0;
   if (nx[7] < 1e-10) nx[7] = 0.0;
   if (nx[7] == 0.0) nx[0] = 0.0;

@@ -78,7 +78,39 @@ class RunSetup:
         p.radpres_amax = (float(np.max(np.abs(self.radpres_a)))
                           if self.radpres_a is not None else 0.0)
         p.strict_math = int(bool(strict_math))
+        self.moons = self._moons(inputs)
+        p.nmoons = len(self.moons)
+        for k, m in enumerate(self.moons):
+            p.moon_GM[k], p.moon_a[k], p.moon_omega[k] = m['GM'], m['a'], m['omega']
+            p.moon_phi[k], p.moon_r2[k] = m['phi'], m['radius']**2
         self.params = p
+
+    def _moons(self, inputs):
+        """Moons whose gravity is included (``geometry.objects``), inner first, with the
+        orbital phases ``geometry.phi`` in that order (docs/nexoclom/inputfiles.rst:62-77).
+        Extension beyond the reference, which asserts for planets with moons
+        (Output.py:153-155): circular, prograde, equatorial orbits."""
+        geo = inputs.geometry
+        objs = getattr(geo, 'objects', None) or set()
+        moons = sorted((o for o in objs if o.object != self.planet.object),
+                       key=lambda o: float(o.a.value))
+        if not moons:
+            return []
+        if len(moons) > 4:
+            raise ValueError('at most 4 moons are supported')
+        phi = getattr(geo, 'phi', None)
+        if phi is None or len(phi) != len(moons):
+            raise ValueError('geometry.phi must give one orbital phase per included moon')
+        rp_m = self.radius_km * 1e3
+        out = []
+        for m, ph in zip(moons, phi):
+            out.append(dict(name=m.object,
+                            GM=float(m.GM.value) / rp_m**3,
+                            a=float(m.a.value) / self.radius_km,
+                            omega=2 * np.pi / float(m.orbperiod.to('s').value),
+                            phi=float(value_of(ph)),
+                            radius=float(m.radius.value) / self.radius_km))
+        return out
 
     @property
     def spline_tck(self):
@@ -101,7 +133,16 @@ class RunSetup:
         inputs = self.inputs
         sp = SourceParams()
         sd, vd, ad = inputs.spatialdist, inputs.speeddist, inputs.angulardist
-        sp.is_planet = int(inputs.geometry.planet.type == 'Planet')
+        start = inputs.geometry.startpoint
+        sp.is_planet = int(start == inputs.geometry.planet.object)   # xyz_from_lonlat(isplan)
+        sp.start_is_moon = 0
+        if not sp.is_planet:
+            moon = [m for m in self.moons if m['name'] == start]
+            if not moon:
+                raise ValueError(f'StartPoint {start} must be one of geometry.objects')
+            sp.start_is_moon = 1
+            sp.moon_a, sp.moon_omega = moon[0]['a'], moon[0]['omega']
+            sp.moon_phi, sp.moon_radius = moon[0]['phi'], moon[0]['radius']
         sp.endtime = float(value_of(inputs.options.endtime))
         sp.random_time = int(inputs.options.step_size == 0)          # Output.py:136-139
         sp.v_scale = 1.0 / self.radius_km

@@ -215,6 +215,19 @@ def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None, lonlat
     out[:, 0] = time
     out[:, 1:4] = pos
     out[:, 4:7] = d * v[:, None]
+    if getattr(sp, 'start_is_moon', 0):
+        # extension (no reference code): satellite-local frame turned by the moon's phase at
+        # the ejection time, moved to the moon, orbital velocity added
+        phi = sp.moon_phi - sp.moon_omega * time
+        c, s_ = np.cos(phi), np.sin(phi)
+        lx, ly = out[:, 1] * sp.moon_radius, out[:, 2] * sp.moon_radius
+        lvx, lvy = out[:, 4].copy(), out[:, 5].copy()
+        vorb = sp.moon_a * sp.moon_omega
+        out[:, 1] = (lx * c - ly * s_) - sp.moon_a * s_
+        out[:, 2] = (lx * s_ + ly * c) + sp.moon_a * c
+        out[:, 3] = out[:, 3] * sp.moon_radius
+        out[:, 4] = (lvx * c - lvy * s_) - vorb * c
+        out[:, 5] = (lvx * s_ + lvy * c) - vorb * s_
     out[:, 7] = 1.0
     out[:, 8] = v
     out[:, 9] = lon

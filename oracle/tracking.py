@@ -65,6 +65,15 @@ class RunConstants:
     planet_radius_km: float = 2440.53
     v_interp: object = None                    # callable (T, prob) -> km/s
     extra: dict = field(default_factory=dict)
+    # EXTENSION (no reference code: it asserts for planets with moons, Output.py:153-155):
+    # moons on circular prograde equatorial orbits, dicts with GM, a, omega, phi, radius in
+    # R_p units; position at time-remaining tau = a (-sin phi, cos phi, 0), phi = phi0 - omega tau
+    moons: list = field(default_factory=list)
+
+
+def moon_xy(m, tau):
+    phi = m['phi'] - m['omega'] * tau
+    return -m['a'] * np.sin(phi), m['a'] * np.cos(phi)
 
 
 def _out_of_shadow(x):
@@ -80,6 +89,15 @@ def rhs(x, rc):
         r = np.sqrt((x[:, 1] * x[:, 1] + x[:, 2] * x[:, 2]) + x[:, 3] * x[:, 3])
         r3 = r**3
         acc = rc.GM * x[:, 1:4] / r3[:, np.newaxis]
+        for mo in rc.moons:       # extension: direct term + the planet's own acceleration
+            mx, my = moon_xy(mo, x[:, 0])
+            dx, dy, z = x[:, 1] - mx, x[:, 2] - my, x[:, 3]
+            d2 = dx * dx + dy * dy + z * z
+            di = 1.0 / np.sqrt(d2)
+            gd = mo['GM'] * di * di * di
+            ai = 1.0 / mo['a']
+            gi = mo['GM'] * ai * ai * ai
+            acc = acc + np.stack([gd * dx + gi * mx, gd * dy + gi * my, gd * z], axis=1)
     if rc.radpres:
         lit = _out_of_shadow(x)
         vv = x[:, 5] + rc.vrplanet
@@ -184,6 +202,10 @@ def integrate_adaptive(X0, rc, step0=1000., max_iter=None, return_step=False):
             gn = nxt[good]
             r2 = (gn[:, 1]**2 + gn[:, 2]**2) + gn[:, 3]**2
             gn[r2 < 1, 7] = 0
+            for mo in rc.moons:                       # extension: impact on a moon
+                mx, my = moon_xy(mo, gn[:, 0])
+                dx, dy = gn[:, 1] - mx, gn[:, 2] - my
+                gn[dx * dx + dy * dy + gn[:, 3] * gn[:, 3] < mo['radius']**2, 7] = 0
             gn[r2 > rc.outeredge, 7] = 0
             gn[gn[:, 7] < 1e-10, 7] = 0.
             gn[gn[:, 7] == 0, 0] = 0

@@ -35,7 +35,8 @@ def oracle_constants(setup):
         taa=float(np.asarray(setup.inputs.geometry.taa)),
         planet_radius_km=p.planet_radius_km,
         v_interp=(setup.surfaceint.v_interp if setup.surfaceint is not None and
-                  setup.surfaceint.tck is not None else None))
+                  setup.surfaceint.tck is not None else None),
+        moons=list(getattr(setup, 'moons', [])))
 
 
 def vec_rel(a, b):

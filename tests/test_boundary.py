@@ -30,8 +30,9 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_struct_layouts_match_header():
     # sizes the static_asserts in nx_api.cu also pin against the kernels' structs
-    assert C.sizeof(_lib.RunParams) == 15 * 8 + 6 * 4
-    assert C.sizeof(_lib.SourceParams) == 4 * 4 + 14 * 8 + 4 * 4 + 8
+    assert C.sizeof(_lib.RunParams) == 15 * 8 + 6 * 4 + 5 * 4 * 8          # + 4 moons x 5 doubles
+    assert C.sizeof(_lib.SourceParams) == 4 * 4 + 14 * 8 + 4 * 4 + 8 + 2 * 4 + 4 * 8
+    assert C.sizeof(_lib.SourceMapParams) == 2 * 8 + 6 * 4
     assert C.sizeof(_lib.ImageParams) == 15 * 8 + 6 * 4
     assert C.sizeof(_lib.LosParams) == 4 * 8 + 4 * 4
 
