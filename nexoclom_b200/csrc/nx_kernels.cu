@@ -126,11 +126,12 @@ __global__ void k_fill(double* p, long long n, double v) {
 // of their use, so a lane that finishes its packet picks the next one out of
 // shared memory instead of stalling the whole warp on a chain of dependent
 // global loads (queue index -> permutation -> 9 state columns).
-// Layout per warp: 2 buffers x (9 columns x 32 doubles + 32 indices).
+// Layout per warp: 2 buffers x (8 columns x 32 doubles + 32 indices).
 // ---------------------------------------------------------------------------
-#define NX_FEED_COLS 9
+#define NX_FEED_COLS 8     // time,x,y,z,vx,vy,vz,frac; the step size starts at 1000 s (Output.py:246)
 #define NX_FEED_BYTES_PER_WARP (2 * (NX_FEED_COLS * 32 * 8 + 32 * 4))
 #define NX_INVALID 0xffffffffu
+#define NX_INITIAL_STEP 1000.0        // every packet starts with a 1000 s step (Output.py:246)
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -246,7 +247,7 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
         const double* v = feed.vals + (size_t)feed.buf * NX_FEED_COLS * 32 + slot;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s[k] = v[k * 32];
-        step = v[8 * 32];
+        step = NX_INITIAL_STEP;
         idx = feed.ids[feed.buf * 32 + slot];
         att = 0; acc = 0;
         have = (s[0] > p.resolution) && (s[7] > 0.0);

@@ -9,7 +9,11 @@
 #include "nx_surface.cuh"
 
 #define NX_INT_THREADS 128
+#ifdef NX_INT_MINBLOCKS_OVERRIDE
+#define NX_INT_MINBLOCKS NX_INT_MINBLOCKS_OVERRIDE
+#else
 #define NX_INT_MINBLOCKS 4
+#endif
 #define NX_LOS_THREADS 128
 
 namespace nx {
