@@ -370,6 +370,33 @@ def test_source_map_large_vs_oracle(engine):
         assert np.max(np.abs(got[k] - ref[k])) <= IMAGE_TOL * max(np.max(np.abs(ref[k])), 1.0), k
 
 
+def test_maxwellian_speeds_histogram(engine, tmp_path):
+    """The reference's own sampler test (tests/unit_tests/math/test_randomdeviates.py:34-43),
+    on K1: 1e7 Maxwellian speeds (Na, 1500 K) histogrammed against MaxwellianDist, both
+    normalised to mean 1; mean and std of the squared deviation below 1e-3."""
+    from nexoclom_b200 import Input
+    from nexoclom_b200.surfaceinteraction import MaxwellianDist, thermal_speed_kms
+    src = open(os.path.join(os.path.dirname(__file__), '..', 'nexoclom_b200', 'workloads',
+                            'Na.maxwellian.radpres.input')).read()
+    f = tmp_path / 'maxw1500.input'
+    f.write_text(src.replace('SpeedDist.temperature = 1200.', 'SpeedDist.temperature = 1500.'))
+    setup = RunSetup(Input(str(f)))
+    setup.upload(engine)
+    n = 10_000_000
+    engine.init_state(setup.source_params(engine), 3, 0, n)
+    v = engine.export_x0()[8] * setup.radius_km                     # km/s
+    vth = thermal_speed_kms(1500., 'Na')
+    edges = np.linspace(0.1, 5 * vth, 201)                          # the sampler's own range
+    hist, _ = np.histogram(v, bins=edges)
+    assert hist.sum() == n
+    x = edges[:-1] + (edges[1] - edges[0]) / 2
+    h = hist / hist.mean()
+    f1 = MaxwellianDist(x, 1500., 'Na')
+    f1 = f1 / f1.mean()
+    d2 = (h - f1)**2
+    assert d2.mean() < 1e-3 and d2.std() < 1e-3, (d2.mean(), d2.std())
+
+
 def test_public_api_end_to_end(engine):
     """Input -> Output (device-drawn packets) -> ModelImage through the
     reference-facing classes; the image equals the oracle's create_image on the
