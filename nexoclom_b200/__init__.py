@@ -9,8 +9,10 @@ from .Input import Input
 from .Output import Output
 from .ModelImage import ModelImage
 from .LOSResult import LOSResult
+from .LOSResultFitted import LOSResultFitted
 from .solarsystem import SSObject
 from .input_classes import InputError
 
-__all__ = ['Input', 'Output', 'ModelImage', 'LOSResult', 'SSObject', 'InputError']
+__all__ = ['Input', 'Output', 'ModelImage', 'LOSResult', 'LOSResultFitted', 'SSObject',
+           'InputError']
 __version__ = '0.1.0'

@@ -1,0 +1,94 @@
+"""LOSResultFitted: the vectorised CSR reductions against the loop restatement of the
+reference (oracle/losfit.py), and the public class on the GPU."""
+import numpy as np
+import pytest
+
+from nexoclom_b200.LOSResultFitted import fit_packet_weights, fitted_radiance
+from oracle import losfit
+
+
+@pytest.mark.parametrize('use_weight', [None, 'dist2', 'dist', 'sigma'])
+def test_reweighting_matches_loop_restatement(use_weight):
+    rng = np.random.default_rng(8)
+    npk, n0, nspec = 4000, 5000, 60
+    index0 = rng.choice(n0, npk, replace=False)
+    xyz = rng.normal(size=(npk, 3)) * 3
+    frac = rng.random(npk)
+    gsum = rng.random(npk) * 5
+    sc = rng.normal(size=(nspec, 3)) * 6
+    used = [sorted(rng.choice(npk, rng.integers(0, 200), replace=False).tolist())
+            for _ in range(nspec)]
+    used[7] = []
+    data_rad = rng.random(nspec) * 10
+    model_rad = rng.random(nspec) * 10
+    model_rad[3] = 0.0                                  # inf ratio -> reference keeps inf
+    data_rad[3] = 0.0                                   # 0/0 -> NaN -> 0
+    mask = rng.random(nspec) > 0.2
+    sigma = 0.1 + rng.random(nspec)
+    w_ref, frac_ref, rad_ref = losfit.fit(used, index0, xyz, frac, gsum, n0, sc, data_rad,
+                                          model_rad, mask, sigma, use_weight,
+                                          np.radians(1.0), 2.44e8)
+    off = np.zeros(nspec + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(u) for u in used])
+    rows = np.concatenate([np.asarray(u, dtype=np.int64) for u in used])
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ratio = data_rad / model_rad
+    ratio[np.isnan(ratio)] = 0
+    w = fit_packet_weights(off, rows, index0, n0, sc, xyz, ratio, mask, sigma, use_weight)
+    assert np.allclose(w, w_ref, rtol=1e-12, atol=0)
+    new_frac = frac * w[index0]
+    rad = fitted_radiance(off, rows, sc, xyz, new_frac * gsum / 1e6, np.radians(1.0), 2.44e8)
+    assert np.allclose(new_frac, frac_ref, rtol=1e-12)
+    assert np.allclose(rad, rad_ref, rtol=1e-12)
+    assert rad[7] == 0.0
+
+
+@pytest.mark.gpu
+def test_losresultfitted_public_api(engine):
+    """LOSResult -> LOSResultFitted through the reference-facing classes: the re-weighted
+    packets reproduce the loop restatement on the K5 `used` sets, the fitted output is
+    catalogued under the fitted Input, and the fit moves the model towards the data."""
+    from common import workload
+    from nexoclom_b200 import Output, LOSResult, LOSResultFitted
+    from nexoclom_b200.runsetup import RunSetup
+    from nexoclom_b200.units import Quantity
+    from test_gpu_parity import _FakeSCData, _synthetic_los
+    inputs = workload('Ca.isotropic.flat.input')
+    inputs.delete_files()
+    out = Output(inputs, 40000, seed=5)
+    los = _synthetic_los(150, seed=9)
+    truth = 1.0 + np.abs(np.sin(np.arange(150) * 0.3)) * 4
+    sc = _FakeSCData(los, truth)
+    unfit = LOSResult(sc, inputs, dphi=Quantity(2.0, 'deg'), label='unfit')
+    unfit.simulate_data_from_inputs(sc)
+    sc.model_result = {'unfit': unfit}
+    sc.data['mask_unfit'] = unfit.mask
+
+    fitted = LOSResultFitted(sc, 'unfit', dphi=Quantity(2.0, 'deg'), label='fitted')
+    assert fitted.inputs.options.fitted and not unfit.inputs.options.fitted
+    fitted.determine_source_from_data(sc, use_weight='dist2')
+    assert len(fitted.outputfiles) == 1 and fitted.outputfiles[0] != out.filename
+    # loop restatement on the same `used` sets
+    P = Output.restore(out.filename)
+    it = unfit._iterations[out.filename]
+    off, idx0, labels = it.used_csr
+    rows = P.X.index.get_indexer(labels)
+    used = [rows[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+    setup = RunSetup(inputs)
+    gsum = np.zeros(len(P.X))
+    for v, g in setup.gtables([4227]):
+        gsum += np.interp(P.X.vy.values + setup.vrplanet, v, g)
+    w_ref, frac_ref, rad_ref = losfit.fit(
+        used, P.X['Index'].values, P.X[['x', 'y', 'z']].values, P.X.frac.values, gsum, len(P.X0),
+        los[:, :3], truth, unfit.radiance.values, unfit.mask, sc.data.sigma.values, 'dist2',
+        np.radians(2.0), setup.radius_km * 1e5)
+    res = fitted._iterations[fitted.outputfiles[0]]
+    assert np.allclose(res.weighting, w_ref, rtol=1e-10)
+    Pf = Output.restore(fitted.outputfiles[0])
+    assert np.allclose(Pf.X0.frac.values, (P.X0.frac.values * w_ref).astype(np.float32), rtol=1e-6)
+    assert np.allclose(res.radiance.values, rad_ref, rtol=1e-10)
+    # better agreement with the data than the unfitted model (both scaled by their source rate)
+    m = unfit.mask & (unfit.radiance.values > 0)
+    err0 = np.mean((unfit.radiance.values[m] - truth[m])**2)
+    err1 = np.mean((fitted.radiance.values[m] - truth[m])**2)
+    assert err1 < err0
