@@ -156,16 +156,50 @@ NX_HD double exp_step(double d) {
   return exp(d);
 }
 
+// sin / cos of a small angle (|d| < ~0.2 rad: moon phase advanced over one step)
+NX_HD void sincos_small(double d, double& sn, double& cs) {
+  const double d2 = d * d;
+  double ps = -1.0 / 39916800.0;                       // -1/11!
+  ps = fma(ps, d2, 1.0 / 362880.0);
+  ps = fma(ps, d2, -1.0 / 5040.0);
+  ps = fma(ps, d2, 1.0 / 120.0);
+  ps = fma(ps, d2, -1.0 / 6.0);
+  sn = fma(ps * d2, d, d);
+  double pc = 1.0 / 479001600.0;                       // 1/12!
+  pc = fma(pc, d2, -1.0 / 3628800.0);
+  pc = fma(pc, d2, 1.0 / 40320.0);
+  pc = fma(pc, d2, -1.0 / 720.0);
+  pc = fma(pc, d2, 1.0 / 24.0);
+  pc = fma(pc, d2, -0.5);
+  cs = fma(pc, d2, 1.0);
+}
+
 // The six Dormand-Prince stages in Nystrom form.  Inputs s[0..7], step h.
 // Outputs: nx[6] = new position / velocity, fn = new frac; if ERR also the error
 // vector d[6] = |h sum_{i<6} bd_i k_i| (stage 7 not included: quirk Q1) and
 // delta_f for the log-frac component.
-template <int GR, int RP, int LOSS, bool ERR>
+// MO = 1: one moon (the extension of RunParams) acts on the packets: its phase at the stage
+// time tau - c_n h is phi_0 + omega c_n h, evaluated by angle addition from one sincos per
+// step; `moon_end` receives the moon's position at the end of the step (impact test).
+template <int GR, int RP, int LOSS, bool ERR, int MO = 0>
 NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, double h,
-                       double* nx, double& fn, double* d, double& delta_f) {
+                       double* nx, double& fn, double* d, double& delta_f,
+                       double* moon_end = nullptr) {
   double K[6][3];                      // K_j = h * accel_j  (the only per-stage storage)
   const double hv0 = h * s[4], hv1 = h * s[5], hv2 = h * s[6];
   const double hGM = h * p.GM;
+  double ms0 = 0.0, mc0 = 1.0, hGMm = 0.0, hGMi = 0.0, mx = 0.0, my = 0.0;
+  if (MO) {
+    const double phi0 = p.moon_phi[0] - p.moon_omega[0] * s[0];
+#if defined(__CUDA_ARCH__)
+    sincos(phi0, &ms0, &mc0);
+#else
+    ms0 = sin(phi0); mc0 = cos(phi0);
+#endif
+    hGMm = h * p.moon_GM[0];
+    const double ai = 1.0 / p.moon_a[0];
+    hGMi = hGMm * (ai * ai) * ai;
+  }
   unsigned litmask = 0;
   double px = s[1], py = s[2], pz = s[3], vx = s[4], vy = s[5], vz = s[6];
 #pragma unroll
@@ -178,6 +212,18 @@ NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, 
       const double ri = rsqrt_h(r2);
       const double g = (hGM * ri) * (ri * ri);
       kx = g * px; ky = g * py; kz = g * pz;
+      if (MO) {
+        double sd, cd;
+        sincos_small(p.moon_omega[0] * (dp_c(n) * h), sd, cd);
+        const double sn = fma(ms0, cd, mc0 * sd), cs = fma(mc0, cd, -(ms0 * sd));
+        mx = -p.moon_a[0] * sn; my = p.moon_a[0] * cs;
+        const double dx = px - mx, dy = py - my;
+        const double di = rsqrt_h(fma(pz, pz, fma(dy, dy, dx * dx)));
+        const double gm = (hGMm * di) * (di * di);
+        kx = fma(gm, dx, fma(hGMi, mx, kx));
+        ky = fma(gm, dy, fma(hGMi, my, ky));
+        kz = fma(gm, pz, kz);
+      }
     }
     bool lit = true;
     if (RP || LOSS == LOSS_PHOTO)
@@ -207,6 +253,7 @@ NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, 
     px = ap0; py = ap1; pz = ap2; vx = av0; vy = av1; vz = av2;
   }
   nx[0] = px; nx[1] = py; nx[2] = pz; nx[3] = vx; nx[4] = vy; nx[5] = vz;
+  if (MO && moon_end) { moon_end[0] = mx; moon_end[1] = my; }     // stage 5 sits at tau - h
 
   // fractional content: dlogf = -h sum b_i rate_i ; error term h sum bd_i rate_i
   double sb = 0.0, sbd = 0.0;
@@ -245,14 +292,14 @@ NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, 
 
 // One attempted adaptive step, fast arithmetic.  Same contract as
 // adaptive_attempt<>(): s[0..7] = time,x,y,z,vx,vy,vz,frac; returns AttemptFlags.
-template <int GR, int RP, int LOSS>
+template <int GR, int RP, int LOSS, int MO = 0>
 NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* s,
                                 double& step) {
   const double res = p.resolution;
   const double resv = 0.1 * res;
   const double h = fmin(s[0], step);
-  double nx[6], d[6], fn, delta_f;
-  fast_stages<GR, RP, LOSS, true>(p, T, s, h, nx, fn, d, delta_f);
+  double nx[6], d[6], fn, delta_f, moon_end[2] = {0.0, 0.0};
+  fast_stages<GR, RP, LOSS, true, MO>(p, T, s, h, nx, fn, d, delta_f, moon_end);
   const double px = nx[0], py = nx[1], pz = nx[2], vx = nx[3], vy = nx[4], vz = nx[5];
   // accept  <=>  every delta_j < scale_j  (== max_j fl(delta_j/scale_j) < 1).  The
   // quotient itself (Newton reciprocal, ~2^-40) only sizes the next step after a
@@ -288,6 +335,10 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
     double f = fn;
     if (fn < 0.0) flags |= ATT_NEG_FRAC;
     if (r2 < 1.0) f = 0.0;                 // impact, stickcoef == 1 (Q6)
+    if (MO) {                              // impact on the moon
+      const double dx = px - moon_end[0], dy = py - moon_end[1];
+      if (fma(pz, pz, fma(dy, dy, dx * dx)) < p.moon_r2[0]) f = 0.0;
+    }
     if (r2 > p.outeredge) f = 0.0;         // escape: r^2 vs outeredge (Q7)
     if (f < 1e-10) f = 0.0;                // vanish (Q8)
     s[0] = (f == 0.0) ? 0.0 : s[0] - h;
@@ -305,6 +356,16 @@ NX_HD int adaptive_attempt_fast(const RunParams& p, const FastTable& T, double* 
 // runtime dispatch over the compile-time force / loss combinations
 NX_HD int adaptive_attempt_fast_rt(const RunParams& p, const FastTable& T, double* s,
                                    double& step) {
+  if (p.nmoons == 1 && p.gravity) {
+    if (p.radpres) {
+      if (p.loss_mode == LOSS_PHOTO) return adaptive_attempt_fast<1, 1, LOSS_PHOTO, 1>(p, T, s, step);
+      if (p.loss_mode == LOSS_LIFETIME) return adaptive_attempt_fast<1, 1, LOSS_LIFETIME, 1>(p, T, s, step);
+      return adaptive_attempt_fast<1, 1, LOSS_NONE, 1>(p, T, s, step);
+    }
+    if (p.loss_mode == LOSS_PHOTO) return adaptive_attempt_fast<1, 0, LOSS_PHOTO, 1>(p, T, s, step);
+    if (p.loss_mode == LOSS_LIFETIME) return adaptive_attempt_fast<1, 0, LOSS_LIFETIME, 1>(p, T, s, step);
+    return adaptive_attempt_fast<1, 0, LOSS_NONE, 1>(p, T, s, step);
+  }
   const int key = (p.gravity ? 4 : 0) | (p.radpres ? 2 : 0);
 #define NX_CASE(G, R)                                                                    \
   if (key == ((G) * 4 + (R) * 2)) {                                                      \

@@ -264,7 +264,7 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
     if (have) {
       int fl;
       if (MODE < 0) fl = adaptive_attempt<true>(p, T, s, step);
-      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s, step);
+      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3, (MODE >> 4) & 1>(p, F, s, step);
       ++att;
       if (fl & ATT_ACCEPTED) ++acc;
       st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
@@ -724,7 +724,7 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
     if (have) {
       int fl;
       if (MODE < 0) fl = adaptive_attempt<true>(p, T, s, step);
-      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s, step);
+      else fl = adaptive_attempt_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3, (MODE >> 4) & 1>(p, F, s, step);
       ++att;
       if (fl & ATT_ACCEPTED) ++acc;
       st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
@@ -1161,9 +1161,18 @@ cudaError_t launch_integrate_adaptive_stream(cudaStream_t st, int device, const 
   StreamQueue Q;
   Q.seg = seg; Q.nseg = nseg; Q.model = model; Q.cursor = cursor; Q.arrived = arrived;
 #define NX_ARGS st, device, in0, in_stride, step0, P, n, p, T, F, Q, totals, att, acc, status
-  if (p.strict_math || p.nmoons > 0) return launch_adaptive_stream_mode<-1>(NX_ARGS);   // moons: generic path
-  const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
+  // one moon + gravity: fast path with MO = 1 (MODE bit 4); more moons: generic kernel
+  if (p.strict_math || p.nmoons > 1 || (p.nmoons == 1 && !p.gravity))
+    return launch_adaptive_stream_mode<-1>(NX_ARGS);
+  const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3) |
+                   (p.nmoons == 1 ? 16 : 0);
   switch (mode) {
+    case 24: return launch_adaptive_stream_mode<24>(NX_ARGS);
+    case 25: return launch_adaptive_stream_mode<25>(NX_ARGS);
+    case 26: return launch_adaptive_stream_mode<26>(NX_ARGS);
+    case 28: return launch_adaptive_stream_mode<28>(NX_ARGS);
+    case 29: return launch_adaptive_stream_mode<29>(NX_ARGS);
+    case 30: return launch_adaptive_stream_mode<30>(NX_ARGS);
     case 0: return launch_adaptive_stream_mode<0>(NX_ARGS);
     case 1: return launch_adaptive_stream_mode<1>(NX_ARGS);
     case 2: return launch_adaptive_stream_mode<2>(NX_ARGS);
@@ -1203,9 +1212,17 @@ cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, 
                                       unsigned long long* queue, unsigned long long* totals,
                                       unsigned* att, unsigned* acc, int* status) {
 #define NX_ARGS st, device, P, n, p, T, F, perm, queue, totals, att, acc, status
-  if (p.strict_math || p.nmoons > 0) return launch_adaptive_mode<-1>(NX_ARGS);          // moons: generic path
-  const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
+  if (p.strict_math || p.nmoons > 1 || (p.nmoons == 1 && !p.gravity))
+    return launch_adaptive_mode<-1>(NX_ARGS);
+  const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3) |
+                   (p.nmoons == 1 ? 16 : 0);
   switch (mode) {
+    case 24: return launch_adaptive_mode<24>(NX_ARGS);
+    case 25: return launch_adaptive_mode<25>(NX_ARGS);
+    case 26: return launch_adaptive_mode<26>(NX_ARGS);
+    case 28: return launch_adaptive_mode<28>(NX_ARGS);
+    case 29: return launch_adaptive_mode<29>(NX_ARGS);
+    case 30: return launch_adaptive_mode<30>(NX_ARGS);
     case 0: return launch_adaptive_mode<0>(NX_ARGS);
     case 1: return launch_adaptive_mode<1>(NX_ARGS);
     case 2: return launch_adaptive_mode<2>(NX_ARGS);

@@ -96,15 +96,17 @@ def hc():
     return C.CDLL(path)
 
 
-def test_kernel_code_matches_oracle_with_moons(hc):
-    """The kernels' own physics (csrc/*.cuh compiled for the host) against the NumPy
+@pytest.mark.parametrize('strict', [1, 0])
+def test_kernel_code_matches_oracle_with_moons(hc, strict):
+    """The kernels' own physics (csrc/*.cuh compiled for the host; strict = generic path,
+    0 = the single-moon fast path with angle-addition moon phases) against the NumPy
     restatement: same accept / reject sequences, states within 1e-10."""
     from test_hostcheck import run_adaptive
     setup = RunSetup(workload('Na.Io.Jupiter.input'))
     X0 = initial_state.draw_x0(setup, 200, 3)[:, :8]
     X0[:, 0] *= 0.2
     Xo, a_o, c_o = tracking.integrate_adaptive(X0, oracle_constants(setup))
-    Xh, a_h, c_h, _ = run_adaptive(hc, setup, X0, 1)
+    Xh, a_h, c_h, _ = run_adaptive(hc, setup, X0, strict)
     par = state_parity(Xh, Xo)
     assert par['alive_mismatch'] == 0
     assert np.array_equal(a_h, a_o) and np.array_equal(c_h, c_o)
@@ -124,9 +126,11 @@ def test_init_state_matches_oracle_with_moon_start(hc):
 
 
 @pytest.mark.gpu
-def test_gpu_moons_vs_oracle(engine):
-    """K1 + K2 through the C ABI on the Io / Jupiter workload against the oracle."""
-    setup = RunSetup(workload('Na.Io.Jupiter.input'))
+@pytest.mark.parametrize('strict', [False, True])
+def test_gpu_moons_vs_oracle(engine, strict):
+    """K1 + K2 through the C ABI on the Io / Jupiter workload against the oracle (fast
+    single-moon kernels and the generic ones)."""
+    setup = RunSetup(workload('Na.Io.Jupiter.input'), strict_math=strict)
     setup.upload(engine)
     n = 1500
     engine.init_state(setup.source_params(engine), 4, 0, n)
