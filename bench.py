@@ -404,6 +404,14 @@ def run_gpu(args):
                                '(MEASURED_PEAKS.json has no FP64 entry); nominal 37.2',
                 'flop_per_packet_step': FLOP_PER_STEP,
             },
+            # second kernel of the step, in the task's own schema (HBM-bound image accumulation;
+            # 40 B per packet = x, y, z, vy, frac; ncu: DRAM traffic == algorithmic bytes)
+            'roofline_hbm': {
+                'bound': 'hbm', 'kernel': 'k_image_accumulate',
+                'achieved': 40.0 * n / (k4 * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
+                'unit': 'GB/s', 'frac': 40.0 * n / (k4 * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                'traffic': int(40.18 * n), 'peak_source': peak_kind + ' (MEASURED_PEAKS.json)',
+                'bytes_per_packet': 40},
             'e2e': {'value': e2e_value, 'unit': 'packet-steps/s',
                     'h2d_bytes_per_step': 64 * n, 'd2h_bytes_per_step': 8 * 800 * 800,
                     'ms_per_step': e2e_ms / max(1, min(args.steps, 3)),
