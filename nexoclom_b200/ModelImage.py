@@ -133,6 +133,8 @@ class ModelImage(ModelResult):
         eng = get_engine(self._device)
         setup = RunSetup(self.inputs)
         self._upload_weighting_tables(eng, setup)
+        if not getattr(output, 'trajectory_kept', True):
+            return self._create_image_fused(output, eng, setup)
         eng.import_state([packets[c].values for c in
                           ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac')])
         img, cnt = eng.image_accumulate(self.image_params(setup))
@@ -140,6 +142,35 @@ class ModelImage(ModelResult):
         zr = [float(z) for z in self.zrange]
         image = _Hist2d(img, xr, zr, self.dims)
         packim = _Hist2d(cnt.astype(float), xr, zr, self.dims)
+        self.xaxis = Quantity(image.x, self.unit)
+        self.zaxis = Quantity(image.y, self.unit)
+        return image, packim
+
+    def _create_image_fused(self, output, eng, setup):
+        """Constant-step output whose (N, 8, nsteps) rows were not kept: run K1 + K3 again
+        with this image fused into the integrator.  The packets (Philox keyed by seed and
+        packet id) and every bounce (keyed by packet id and step) are reproduced exactly, the
+        rows are binned as the reference would bin the saved ones: rounded to float32
+        (Output.save, quirk Q14) and without the frac == 0 rows that `compress` drops."""
+        import torch
+        if getattr(output, 'imported_x0', False) or not output.compress:
+            raise NotImplementedError('fused images need device-drawn packets and compress=True; '
+                                      'run Output(..., keep_trajectory=True)')
+        setup.upload(eng)
+        self._upload_weighting_tables(eng, setup)
+        eng.init_state(setup.source_params(eng), output.seed, 0, output.npackets)
+        ip = self.image_params(setup)
+        ip.round_f32, ip.skip_dead = 1, 1
+        img = torch.zeros(tuple(self.dims), dtype=torch.float64, device=f'cuda:{eng.device}')
+        cnt = torch.zeros(tuple(self.dims), dtype=torch.int64, device=f'cuda:{eng.device}')
+        eng.integrate_constant(seed=output.seed, first_id=0, image_params=ip,
+                               image_dev=img.data_ptr(), counts_dev=cnt.data_ptr(),
+                               n=output.npackets)
+        eng.sync()
+        xr = [float(x) for x in self.xrange]
+        zr = [float(z) for z in self.zrange]
+        image = _Hist2d(img.cpu().numpy(), xr, zr, self.dims)
+        packim = _Hist2d(cnt.cpu().numpy().astype(float), xr, zr, self.dims)
         self.xaxis = Quantity(image.x, self.unit)
         self.zaxis = Quantity(image.y, self.unit)
         return image, packim

@@ -76,6 +76,7 @@ class Output:
                     self._host_cols = cols
                 else:
                     eng.import_state(cols)
+                    self._imported = True
                 self.X0 = pd.DataFrame({c: cols[k] for k, c in enumerate(STATE_COLS)})
             else:
                 if self.inputs.spatialdist.type not in ('uniform', 'surface map',
@@ -149,8 +150,10 @@ class Output:
         """Constant-step driver + bounce on the GPU (K3).  Semantics of reference
         Output.py:368-455: every step of every packet becomes a row of ``X``
         (``totalsource *= nsteps``).  The dense (N, 8, nsteps) tensor is only
-        materialised on request / for small runs; large runs use
-        ``ModelImage(..., fused=True)`` which accumulates inside the integrator."""
+        materialised on request / for small runs.  For large runs only the final state
+        is kept (``trajectory_kept = False``) and ``ModelImage`` regenerates the rows
+        inside the integrator: packets and bounce deviates are pure functions of
+        (seed, packet id, step), so K1 + K3 with the image fused reproduce the same rows."""
         eng = self._engine
         p = self._setup.params
         self.nsteps = int(np.ceil(p.endtime / p.step_size + 1))
@@ -160,6 +163,8 @@ class Output:
             seed=self.seed, first_id=0, trajectory=keep_trajectory, n=self.npackets)
         self.kernel_ms = eng.last_kernel_ms()
         self.totalsource *= self.nsteps
+        self.trajectory_kept = bool(keep_trajectory)
+        self.imported_x0 = getattr(self, '_imported', False)
         if keep_trajectory:
             n = self.npackets * self.nsteps
             X = pd.DataFrame()

@@ -397,6 +397,27 @@ def test_maxwellian_speeds_histogram(engine, tmp_path):
     assert d2.mean() < 1e-3 and d2.std() < 1e-3, (d2.mean(), d2.std())
 
 
+def test_model_image_of_large_constant_step_run_is_regenerated(engine):
+    """Public API, BASELINE configs[2] pattern: an Output whose dense trajectory tensor was
+    not kept gives the same ModelImage as one that kept every row."""
+    from nexoclom_b200 import Output, ModelImage
+    params = {'quantity': 'radiance', 'dims': '200,200'}
+    inputs = workload('Na.bounce.input')
+    inputs.delete_files()
+    Output(inputs, 3000, seed=21, keep_trajectory=True)
+    dense = ModelImage(inputs, params)
+    inputs.delete_files()
+    out = Output(inputs, 3000, seed=21, keep_trajectory=False)
+    assert not out.trajectory_kept and len(out.X) <= 3000
+    fused = ModelImage(inputs, params)
+    inputs.delete_files()
+    assert np.array_equal(fused.packet_image, dense.packet_image) and dense.packet_image.sum() > 1e5
+    nz = dense.image > 0
+    assert np.max(np.abs(fused.image[nz] - dense.image[nz]) / dense.image[nz]) < IMAGE_TOL
+    assert np.all(fused.image[~nz] == 0)
+    assert fused.atoms_per_packet == pytest.approx(dense.atoms_per_packet, rel=1e-12)
+
+
 def test_public_api_end_to_end(engine):
     """Input -> Output (device-drawn packets) -> ModelImage through the
     reference-facing classes; the image equals the oracle's create_image on the
