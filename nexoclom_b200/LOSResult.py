@@ -77,6 +77,10 @@ def compute_iteration(self, outputfile, scdata, delay=False):
     dist_from_plan = dist_from_planet_cut(data)
 
     output = Output.restore(outputfile)
+    if not getattr(output, 'trajectory_kept', True):
+        raise NotImplementedError(
+            'this constant-step Output kept only the final packet states; lines of sight need '
+            'every step: run Output(..., keep_trajectory=True) (ModelImage can regenerate them)')
     X0_index = output.X0.index
     packets = output.X
     if 'Index' not in packets.columns:
