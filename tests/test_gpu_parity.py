@@ -397,6 +397,32 @@ def test_maxwellian_speeds_histogram(engine, tmp_path):
     assert d2.mean() < 1e-3 and d2.std() < 1e-3, (d2.mean(), d2.std())
 
 
+@pytest.mark.parametrize('smear_deg, nlon, nlat', [(100.0, 12, 6), (0.5, 24, 12), (30.0, 7, 5)])
+def test_source_map_edge_cases(engine, smear_deg, nlon, nlat):
+    """Smear radius larger than a hemisphere (every point reaches every packet), smaller than
+    a grid cell, odd grids; packets at the poles and on the longitude seam; empty input."""
+    from nexoclom_b200.make_source_map import source_map_arrays
+    from oracle import source_map
+    rng = np.random.default_rng(2)
+    n = 5000
+    X0 = {'longitude': rng.random(n) * 2 * np.pi, 'latitude': np.arcsin(rng.random(n) * 2 - 1),
+          'v': rng.random(n) * 1e-3 + 1e-4, 'altitude': rng.random(n) * np.pi / 2,
+          'azimuth': rng.random(n) * 2 * np.pi, 'frac': rng.random(n) * (rng.random(n) > 0.3)}
+    X0['latitude'][:4] = [np.pi / 2, -np.pi / 2, 0.0, 1e-9]
+    X0['longitude'][:4] = [0.0, np.pi, 0.0, 2 * np.pi - 1e-12]
+    params = {'smear_radius': np.radians(smear_deg), 'nlonbins': nlon, 'nlatbins': nlat,
+              'nvelbins': 10, 'nazbins': 8, 'naltbins': 5}
+    got = source_map_arrays(X0, 2440.53, params, 'available')
+    ref = source_map.make_source_map(X0, 2440.53, params, 'available')
+    assert np.array_equal(got['n_total'], ref['n_total'].astype(np.int64))
+    assert np.array_equal(got['n_included'], ref['n_included'].astype(np.int64))
+    for k in ('abundance_hist', 'abundance', 'speed_dist', 'altitude_dist', 'azimuth_dist',
+              'speed_map', 'altitude_map', 'azimuth_map'):
+        assert np.max(np.abs(got[k] - ref[k])) <= IMAGE_TOL * max(np.max(np.abs(ref[k])), 1.0), k
+    if smear_deg >= 100:
+        assert np.all(got['n_total'][:, nlat // 2] > 0.5 * n)
+
+
 def test_model_image_of_large_constant_step_run_is_regenerated(engine):
     """Public API, BASELINE configs[2] pattern: an Output whose dense trajectory tensor was
     not kept gives the same ModelImage as one that kept every row."""
