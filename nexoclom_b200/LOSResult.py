@@ -255,3 +255,91 @@ fitted = {self.fitted}'''
             self.sourcerate = Quantity(0., '')
         self.goodness_of_fit = None
         self.mask = mask
+
+    def make_source_map(self, grid_params=None, normalize=True, do_source=True,
+                        do_available=True, distribute=None):
+        """Source maps of the modelled (`source`) and of all launched (`available`) packets,
+        summed over the output files of this result and optionally converted to fluxes
+        (reference LOSResult.py:310-491).  The per-file maps come from K6
+        (``make_source_map.make_source_map``); what is done here is the reference's host
+        arithmetic, statement by statement -- including its habit of adding ``speed_dist`` of
+        the file with the largest speed range twice (:349-353).  Quantities are plain arrays:
+        abundance in atoms cm^-2 s^-1, speed distributions per km/s, angular ones per rad."""
+        from .make_source_map import make_source_map
+        from .sourcemap import SourceMap
+        if distribute in (True, 'delay', 'delayed'):
+            assert False, "Don't do this"                              # :328
+        sourcemap = availablemap = None
+        todo = (['source'] if do_source else []) + (['available'] if do_available else [])
+        rate_per_s = float(value_of(self.sourcerate)) * 1e23         # sourcerate.to(1/u.s)
+        r_cm = float(self.inputs.geometry.planet.radius.value) * 1e5
+        for todo_ in todo:
+            sources = [make_source_map(outputfile, grid_params, todo=todo_, device=self._device)
+                       for outputfile in self.modelfiles]
+            sources = [{k: np.asarray(value_of(v), dtype=float) for k, v in s_.items()}
+                       for s_ in sources]
+            dist = {key: np.zeros_like(value) for key, value in sources[0].items()}
+            vmaxes = [s_['speed'].max() for s_ in sources]
+            vmax = max(vmaxes)
+            dist['speed'] = sources[int(np.where(np.asarray(vmaxes) == vmax)[0][0])]['speed']
+            for s_ in sources:
+                for key in ('abundance_uncor', 'n_included', 'n_total', 'altitude_dist',
+                            'altitude_dist_map', 'azimuth_dist', 'azimuth_dist_map',
+                            'speed_dist', 'speed_dist_map'):
+                    dist[key] += s_[key]
+                if s_['speed'].max() == vmax:
+                    dist['speed_dist'] += s_['speed_dist']
+                    dist['speed_dist_map'] += s_['speed_dist_map']
+                else:
+                    dist['speed_dist'] += np.interp(dist['speed'], s_['speed'], s_['speed_dist'])
+                    for i in range(len(dist['longitude'])):
+                        for j in range(len(dist['latitude'])):
+                            dist['speed_dist_map'] += np.interp(dist['speed'], s_['speed'],
+                                                                s_['speed_dist_map'][i, j, :])
+            for key in ('longitude', 'latitude', 'azimuth', 'altitude'):
+                dist[key] = sources[0][key]
+            with np.errstate(divide='ignore', invalid='ignore'):
+                dist['fraction_observed'] = dist['n_included'] / dist['n_total']
+                q = np.isnan(dist['fraction_observed'])
+                dist['fraction_observed'][q] = 1
+                dist['abundance'] = dist['abundance_uncor'] / dist['fraction_observed']
+            dist['fraction_observed'][q] = 0
+            dist['abundance'][np.isnan(dist['abundance'])] = 0
+
+            if normalize:
+                dx = dist['longitude'][1] - dist['longitude'][0]
+                dy = dist['latitude'][1] - dist['latitude'][0]
+                _, gridlatitude = np.meshgrid(dist['longitude'], dist['latitude'])
+                d_area = np.abs(dx * (np.sin(gridlatitude + dy / 2) - np.sin(gridlatitude - dy / 2)))
+                area = r_cm**2 * d_area
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    dist['abundance'] = dist['abundance'] / dist['abundance'].sum() / area.T * rate_per_s
+                    dist['abundance_uncor'] = (dist['abundance_uncor'] /
+                                               dist['abundance_uncor'].sum() / area.T * rate_per_s)
+                    dv = dist['speed'][1] - dist['speed'][0]
+                    dist['speed_dist'] = (rate_per_s * dist['speed_dist'] /
+                                          dist['speed_dist'].sum() / dv)
+                    dist['speed_dist_map'] = (dist['abundance'][:, :, np.newaxis] *
+                                              dist['speed_dist_map'] /
+                                              dist['speed_dist_map'].sum(axis=2)[:, :, np.newaxis] / dv)
+                    # the reference normalises the AXES 'altitude' / 'azimuth' here, not the
+                    # distributions (:452-455, :464-467); kept
+                    dalt = dist['altitude'][1] - dist['altitude'][0]
+                    dist['altitude_dist_map'] = (dist['abundance'][:, :, np.newaxis] *
+                                                 dist['altitude_dist_map'] /
+                                                 dist['altitude_dist_map'].sum(axis=2)[:, :, np.newaxis] / dalt)
+                    dist['altitude'] = rate_per_s * dist['altitude'] / dist['altitude'].sum() / dalt
+                    daz = dist['azimuth'][1] - dist['azimuth'][0]
+                    dist['azimuth_dist_map'] = (dist['abundance'][:, :, np.newaxis] *
+                                                dist['azimuth_dist_map'] /
+                                                dist['azimuth_dist_map'].sum(axis=2)[:, :, np.newaxis] / daz)
+                    dist['azimuth'] = rate_per_s * dist['azimuth'] / dist['azimuth'].sum() / daz
+            source_ = SourceMap(dist)
+            for key in ('abundance_uncor', 'n_included', 'n_total', 'speed_dist_map',
+                        'altitude_dist_map', 'azimuth_dist_map'):
+                setattr(source_, key, dist[key])
+            if todo_ == 'source':
+                sourcemap = source_
+            else:
+                availablemap = source_
+        return sourcemap, availablemap

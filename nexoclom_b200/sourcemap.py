@@ -9,8 +9,9 @@ from .units import value_of
 
 
 class SourceMap:
-    _fields = ('abundance', 'longitude', 'latitude', 'speed', 'speed_dist', 'altitude',
-               'azimuth', 'fraction_observed', 'coordinate_system')
+    _fields = ('abundance', 'longitude', 'latitude', 'speed', 'speed_dist', 'azimuth',
+               'azimuth_dist', 'altitude', 'altitude_dist', 'fraction_observed',
+               'coordinate_system')
 
     def __init__(self, sourcemap=None):
         for f in self._fields:

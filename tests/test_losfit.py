@@ -92,3 +92,38 @@ def test_losresultfitted_public_api(engine):
     err0 = np.mean((unfit.radiance.values[m] - truth[m])**2)
     err1 = np.mean((fitted.radiance.values[m] - truth[m])**2)
     assert err1 < err0
+
+
+@pytest.mark.gpu
+def test_losresult_make_source_map(engine):
+    """LOSResult.make_source_map (reference LOSResult.py:310-491) on top of K6: sums over the
+    output files, observed-fraction correction, flux normalisation."""
+    from common import workload
+    from nexoclom_b200 import Output, LOSResult
+    from nexoclom_b200.units import Quantity
+    from test_gpu_parity import _FakeSCData, _synthetic_los
+    inputs = workload('Ca.isotropic.flat.input')
+    inputs.delete_files()
+    Output(inputs, 20000, seed=1)
+    Output(inputs, 20000, seed=2)
+    los = _synthetic_los(80, seed=4)
+    sc = _FakeSCData(los, np.linspace(1.0, 2.0, 80))
+    res = LOSResult(sc, inputs, dphi=Quantity(2.0, 'deg'))
+    res.simulate_data_from_inputs(sc)
+    assert len(res.modelfiles) == 2
+    grid = {'nlonbins': 36, 'nlatbins': 18, 'nvelbins': 20, 'nazbins': 8, 'naltbins': 6}
+    raw_s, raw_a = res.make_source_map(grid, normalize=False)
+    assert raw_a.n_total.sum() > 0 and np.array_equal(raw_a.n_total, raw_s.n_total)
+    assert raw_a.abundance_uncor.shape == (36, 18)
+    # 'available' weights every packet by 1: smeared abundance == number of packets in the ball
+    assert np.allclose(raw_a.abundance_uncor, raw_a.n_total)
+    assert np.all(raw_a.fraction_observed <= 1) and np.all(raw_a.fraction_observed >= 0)
+    src, avail = res.make_source_map(grid, normalize=True)
+    # normalised abundance integrates to the source rate over the sphere
+    lon, lat = np.asarray(src.longitude), np.asarray(src.latitude)
+    dx, dy = lon[1] - lon[0], lat[1] - lat[0]
+    r_cm = 2440.53e5
+    area = r_cm**2 * np.abs(dx * (np.sin(lat + dy / 2) - np.sin(lat - dy / 2)))[np.newaxis, :]
+    total = np.nansum(np.asarray(src.abundance) * area)
+    assert total == pytest.approx(float(res.sourcerate) * 1e23, rel=1e-9)
+    inputs.delete_files()
