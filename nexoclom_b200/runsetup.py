@@ -198,6 +198,7 @@ class RunSetup:
             sp.map_nx, sp.map_ny = fmap.shape
             sp.map_lat_is_sin = 1
             sp.map_fmax = float(fmap.max())
+            self.sourcemap = (fmap, xa, ya)
             if engine is not None:
                 engine.upload_sourcemap(fmap, np.linspace(xa.min(), xa.max(), fmap.shape[0]),
                                         np.linspace(ya.min(), ya.max(), fmap.shape[1]))

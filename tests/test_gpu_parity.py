@@ -423,6 +423,36 @@ def test_source_map_edge_cases(engine, smear_deg, nlon, nlat):
         assert np.all(got['n_total'][:, nlat // 2] > 0.5 * n)
 
 
+def test_surface_map_source_on_gpu(engine, tmp_path):
+    """`SpatialDist.type = surface map` (source_distribution.py:63-95) with a map pickle in the
+    layout the reference ships (longitude / latitude edges, abundance one shorter per axis):
+    K1 follows the oracle draw for draw."""
+    import pickle
+    from nexoclom_b200 import Input
+    lon = np.linspace(0, 2 * np.pi, 73)
+    lat = np.linspace(-np.pi / 2, np.pi / 2, 37)
+    lc, bc = 0.5 * (lon[1:] + lon[:-1]), 0.5 * (lat[1:] + lat[:-1])
+    ab = 1.0 + 40 * np.exp(-((lc[:, None] - 1.0)**2 + (bc[None, :] - 0.3)**2) / 0.2)
+    mapfile = tmp_path / 'map.pkl'
+    with open(mapfile, 'wb') as f:
+        pickle.dump({'longitude': lon, 'latitude': lat, 'abundance': ab,
+                     'coordinate_system': 'solar-fixed'}, f)
+    src = open(os.path.join(os.path.dirname(__file__), '..', 'nexoclom_b200', 'workloads',
+                            'Ca.isotropic.flat.input')).read()
+    inp = tmp_path / 'map.input'
+    inp.write_text(src.replace('SpatialDist.type = uniform',
+                               f'SpatialDist.type = surface map\nSpatialDist.mapfile = {mapfile}'))
+    setup = RunSetup(Input(str(inp)))
+    setup.upload(engine)
+    n = 50000
+    engine.init_state(setup.source_params(engine), 8, 0, n)
+    got = engine.export_x0().T
+    ref = initial_state.draw_x0(setup, n, 8)
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-12
+    near = (np.abs(ref[:, 9] - 1.0) < 0.5) & (np.abs(ref[:, 10] - 0.3) < 0.5)
+    assert near.mean() > 0.25                      # the spot of the map attracts the packets
+
+
 def test_model_image_of_large_constant_step_run_is_regenerated(engine):
     """Public API, BASELINE configs[2] pattern: an Output whose dense trajectory tensor was
     not kept gives the same ModelImage as one that kept every row."""

@@ -98,3 +98,55 @@ def test_ssobject():
     assert {x.object for x in j.moons} >= {'Io', 'Europa', 'Ganymede', 'Callisto'}
     io = SSObject('Io')
     assert io.type == 'Moon' and io.orbits == 'Jupiter' and io.GM.value < 0
+
+
+MAPFILE = os.path.join(os.path.dirname(INPUTS), 'surface_maps', 'Orbit3576.Ca.pkl')
+
+
+@pytest.mark.skipif(not os.path.exists(MAPFILE), reason='reference surface map not present')
+def test_surface_map_source_with_the_references_own_map(tmp_path):
+    """`SpatialDist.type = surface map` driven by a map file the reference ships
+    (tests/test_data/surface_maps/Orbit3576.Ca.pkl, written with astropy Quantities inside):
+    it loads without astropy, the kernel's sampler (host build) follows the oracle draw for
+    draw, and the sampled surface density follows the map (source_distribution.py:63-95,
+    randomdeviates.py:41-83)."""
+    import ctypes as C
+    from nexoclom_b200._lib import as_f64, dptr
+    from nexoclom_b200.runsetup import RunSetup
+    from nexoclom_b200.sourcemap import SourceMap
+    from oracle import initial_state
+    src = open(os.path.join(INPUTS, 'Ca.surfacemap.maxwellian.input')).read()
+    f = tmp_path / 'map.input'
+    f.write_text(src + f'\nSpatialDist.mapfile = {MAPFILE}\n')
+    setup = RunSetup(Input(str(f)))
+    sp = setup.source_params(None)
+    smap = SourceMap(MAPFILE)
+    assert sp.spatial_type == 1 and sp.map_lat_is_sin == 1 and (sp.map_nx, sp.map_ny) == (72, 36)
+    n = 60000
+    ref = initial_state.draw_x0(setup, n, 5)
+    hc_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_hostcheck',
+                           'libnexo_hostcheck.so')
+    if not os.path.exists(hc_path):
+        import subprocess
+        subprocess.run(['sh', os.path.join(os.path.dirname(hc_path), 'build.sh')], check=True)
+    hc = C.CDLL(hc_path)
+    fmap, xa, ya = setup.sourcemap if hasattr(setup, 'sourcemap') and setup.sourcemap else (None,) * 3
+    if fmap is None:
+        fmap = np.asarray(smap.abundance, dtype=float)
+        xa = np.linspace(np.min(smap.longitude), np.max(smap.longitude), fmap.shape[0])
+        ya = np.linspace(np.sin(np.min(smap.latitude)), np.sin(np.max(smap.latitude)), fmap.shape[1])
+    fm = as_f64(fmap)
+    axes = as_f64(np.array([xa.min(), xa.max(), ya.min(), ya.max()]))
+    cdf, vt = (as_f64(a) for a in setup.speed_table)
+    out = np.zeros((n, 14))
+    hc.hc_init_state(C.c_long(n), C.byref(sp), C.c_ulonglong(5), C.c_ulonglong(0), dptr(fm),
+                     dptr(axes), dptr(cdf), dptr(vt), C.c_int(len(cdf)), dptr(out))
+    assert np.max(np.abs(out - ref) / np.maximum(np.abs(ref), 1e-3)) < 1e-12
+    # the sampled (lon, sin lat) density follows the map
+    H, _, _ = np.histogram2d(ref[:, 9], np.sin(ref[:, 10]), bins=(18, 9),
+                             range=[[0, 2 * np.pi], [-1, 1]])
+    coarse = fmap.reshape(18, 4, 9, 4).sum(axis=(1, 3))
+    expect = coarse / coarse.sum() * n
+    big = expect > 200
+    assert big.sum() > 20
+    assert np.max(np.abs(H[big] - expect[big]) / np.sqrt(expect[big])) < 6.0
