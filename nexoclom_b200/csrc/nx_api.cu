@@ -129,7 +129,7 @@ static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const doubl
 }
 
 static void free_los_work(LosGridWork& w) {
-  cudaFree(w.sorted.x); cudaFree(w.sorted.y); cudaFree(w.sorted.z); cudaFree(w.sorted.vy);
+  cudaFree(w.sorted.pos);
   cudaFree(w.sorted.frac); cudaFree(w.sorted.idx); cudaFree(w.cell_id); cudaFree(w.count);
   cudaFree(w.start); cudaFree(w.block_sum); cudaFree(w.total); cudaFree(w.extent_bits);
   const int G = w.G_fixed;
@@ -141,15 +141,12 @@ static void free_los_work(LosGridWork& w) {
 
 static int alloc_los_work(nx_ctx* ctx, long long n) {
   LosGridWork& w = ctx->losw;
-  if (w.cap >= n && w.sorted.x) return 0;
+  if (w.cap >= n && w.sorted.pos) return 0;
   free_los_work(w);
   const int gmax = w.G_fixed > NX_LOS_GRID_MAX ? w.G_fixed : NX_LOS_GRID_MAX;
   const size_t ncell = (size_t)gmax * gmax * gmax;
   const size_t nn = (size_t)n;
-  CK(cudaMalloc(&w.sorted.x, nn * sizeof(double)));
-  CK(cudaMalloc(&w.sorted.y, nn * sizeof(double)));
-  CK(cudaMalloc(&w.sorted.z, nn * sizeof(double)));
-  CK(cudaMalloc(&w.sorted.vy, nn * sizeof(double)));
+  CK(cudaMalloc(&w.sorted.pos, nn * sizeof(double4)));
   CK(cudaMalloc(&w.sorted.frac, nn * sizeof(double)));
   CK(cudaMalloc(&w.sorted.idx, nn * sizeof(unsigned)));
   CK(cudaMalloc(&w.cell_id, nn * sizeof(unsigned)));

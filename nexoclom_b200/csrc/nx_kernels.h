@@ -40,7 +40,9 @@ struct LosConsts {
 // grow ~ |v| / k far out, where the cone of a line of sight is wide anyway.
 struct LosGrid { int G; double half, scale, inv_scale, k; };
 #define NX_LOS_GRID_MAX 160       // cells per axis the work arrays are allocated for
-struct LosSorted { double *x, *y, *z, *vy, *frac; unsigned* idx; };
+// packets in cell order: one 32-byte record (x, y, z, vy) per packet -- a candidate costs
+// exactly one DRAM sector -- plus frac and the original index for the (rare) hits
+struct LosSorted { double4* pos; double* frac; unsigned* idx; };
 struct LosGridWork {
   int G = 128;                 // cells per axis of the current grid
   int G_fixed = 0;             // option "los_grid": > 0 pins G, 0 = sized from the packet count

@@ -178,7 +178,7 @@ k_los_cell_scatter(StateCols P, long long n, int round32, const unsigned* __rest
     const unsigned pos = start[id] + atomicAdd(&cursor[id], 1u);
     double x = P.c[1][i], y = P.c[2][i], z = P.c[3][i], vy = P.c[5][i], fr = P.c[7][i];
     if (round32) { x = round_f32(x); y = round_f32(y); z = round_f32(z); vy = round_f32(vy); fr = round_f32(fr); }
-    S.x[pos] = x; S.y[pos] = y; S.z[pos] = z; S.vy[pos] = vy; S.frac[pos] = fr;
+    S.pos[pos] = make_double4(x, y, z, vy); S.frac[pos] = fr;
     S.idx[pos] = (unsigned)i;
   }
 }
@@ -245,7 +245,8 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
         const unsigned row = (unsigned)((ix * g.G + iy) * g.G);
         const unsigned p0 = start[row + iz0], p1 = start[row + iz1 + 1];
         for (unsigned q = p0 + lane; q < p1; q += 32) {
-          const double px = S.x[q], py = S.y[q], pz = S.z[q];
+          const double4 rec = S.pos[q];
+          const double px = rec.x, py = rec.y, pz = rec.z;
           // ownership: the segment that contains the packet's axial coordinate
           // (same arithmetic as los_hit so that every packet has one owner)
           const double rx = sub_rn(px, L.xs), ry = sub_rn(py, L.ys), rz = sub_rn(pz, L.zs);
@@ -256,7 +257,7 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
                     lc.inv_log_ratio, lc.log_t0,
                       lc.kwin, px, py, pz, losrad, dist)) {
             ++cnt;
-            const double w = los_weight(L, lp, G, lc.sin_dphi, S.frac[q], S.vy[q], losrad, dist);
+            const double w = los_weight(L, lp, G, lc.sin_dphi, S.frac[q], rec.w, losrad, dist);
             rad += w;
             if (included) included[S.idx[q]] = 1;
             if (w > 0.0) {                    // `used` packets (compute_iteration.py:210-211)
