@@ -70,6 +70,9 @@ constexpr double dpc_bd2(int j) {
   return s;
 }
 constexpr double dpc_bsum() { double s = 0; for (int i = 0; i < 6; ++i) s += dpc_a(6, i); return s; }
+// evaluated once at compile time (usable from device code without relaxed constexpr)
+constexpr double kDpcBsum = dpc_bsum();
+constexpr double kDpcBds = dpc_bds();
 
 #define NX_ROW(f, m) f(m, 0), f(m, 1), f(m, 2), f(m, 3), f(m, 4), f(m, 5), 0., 0.
 #define NX_TAB(f) {NX_ROW(f, 0), NX_ROW(f, 1), NX_ROW(f, 2), NX_ROW(f, 3), NX_ROW(f, 4), \
@@ -258,8 +261,8 @@ NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, 
   // fractional content: dlogf = -h sum b_i rate_i ; error term h sum bd_i rate_i
   double sb = 0.0, sbd = 0.0;
   if (LOSS == LOSS_LIFETIME) {
-    sb = p.loss_rate * dpc_bsum();
-    sbd = p.loss_rate * dpc_bds();
+    sb = p.loss_rate * kDpcBsum;
+    sbd = p.loss_rate * kDpcBds;
   } else if (LOSS == LOSS_PHOTO) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -272,7 +275,7 @@ NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, 
   fn = (LOSS == LOSS_NONE) ? s[7] : s[7] * exp_step(-(h * sb));
   if (ERR) {
     delta_f = fabs(h * sbd);
-    const double bds = dpc_bds();
+    const double bds = kDpcBds;
     double ep0 = bds * hv0, ep1 = bds * hv1, ep2 = bds * hv2;
     double ev0 = dp_bd(0) * K[0][0], ev1 = dp_bd(0) * K[0][1], ev2 = dp_bd(0) * K[0][2];
 #pragma unroll
