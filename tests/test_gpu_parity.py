@@ -640,6 +640,35 @@ def test_losresult_public_api(engine):
     assert sum(len(u) for u in used) > 0 and (used.apply(len) <= np_o).all()
 
 
+def test_losresult_on_constant_step_output(engine):
+    """Lines of sight through a constant-step (bounce) Output: every step of every packet is
+    a row (Output.py:434-449), several rows share one 'Index'."""
+    from nexoclom_b200 import Output, LOSResult
+    inputs = workload('Na.bounce.input')
+    inputs.delete_files()
+    out = Output(inputs, 1500, seed=2, keep_trajectory=True)
+    assert out.trajectory_kept
+    los = _synthetic_los(120, seed=6)
+    sc = _FakeSCData(los, np.linspace(1.0, 2.0, 120))
+    sc.species = 'Na'
+    res = LOSResult(sc, inputs, dphi=Quantity(3.0, 'deg'))
+    res.simulate_data_from_inputs(sc)
+    P = Output.restore(out.filename).X
+    assert len(P) > 1500 and P['Index'].nunique() <= 1500
+    setup = RunSetup(inputs)
+    rad_o, np_o, inc_o, _ = imaging.los_iteration(
+        P.x.values, P.y.values, P.z.values, P.vy.values, P.frac.values, los,
+        vrplanet=setup.vrplanet, dphi=np.radians(3.0), outeredge=float(inputs.options.outeredge),
+        rp_cm=setup.radius_km * 1e5, gtables=setup.gtables([5891, 5897]))
+    assert np.array_equal(res.npackets_los.values, np_o) and np_o.sum() > 500
+    it = res._iterations[out.filename]
+    assert it.included.sum() == len(np.unique(P['Index'].values[inc_o]))
+    kR = rad_o * res.atoms_per_packet / 1e3 * float(res.sourcerate)
+    nz = kR > 0
+    assert np.max(np.abs(res.radiance.values[nz] - kR[nz]) / kR[nz]) < IMAGE_TOL
+    inputs.delete_files()
+
+
 def test_pipelined_host_path_equals_resident_path(engine):
     """nx_integrate_adaptive_host (chunked H2D/compute pipeline) == import + integrate."""
     setup = RunSetup(workload('Na.maxwellian.radpres.input'))
