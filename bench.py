@@ -339,6 +339,7 @@ def run_gpu(args):
         dplan = x_sc.norm(dim=0)
         ang = torch.arccos(-(x_sc * bore).sum(dim=0) / dplan)
         dplan = torch.where(ang > torch.arcsin(1. / dplan), torch.full_like(dplan, 1e30), dplan)
+        los_host = torch.cat([x_sc, bore], dim=0).T.contiguous().numpy()
         los_dev = torch.cat([x_sc, bore], dim=0).contiguous().cuda()
         dist_dev = dplan.contiguous().cuda()
         rad_dev = torch.zeros(nlos, dtype=torch.float64, device='cuda')
@@ -429,11 +430,46 @@ def run_gpu(args):
                           f'{steps} steps in {wall:.1f} s, NumPy oracle port of the '
                           'reference driver, 1 process (host has '
                           f'{os.cpu_count()} cores)'}
+            # the image / line-of-sight products on the same final state (SURVEY 8d ii-iii)
+            m = min(n, args.cpu_product_packets)
+            fin = torch.stack([state_cols[k][:m] for k in (1, 2, 3, 5, 7)]).cpu().numpy()
+            line['config']['cpu_products'] = cpu_products(
+                fin, setup, gt, M, ip.apix,
+                los_host[:args.cpu_product_los] if los_info is not None else None)
         print(json.dumps(line))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def cpu_products(fin, setup, gtables, M, apix, los):
+    """CPU timings of the two products of the path on a bounded sample of the bench's final
+    state: the NumPy oracle port of create_image (two np.histogram2d passes) and of the
+    compute_iteration loop (sklearn KDTree), one process each."""
+    from oracle import imaging
+    x, y, z, vy, frac = (np.ascontiguousarray(fin[k].astype(np.float32).astype(np.float64))
+                         for k in range(5))
+    m = len(x)
+    t0 = time.time()
+    imaging.create_image(x, y, z, vy, frac, vrplanet=setup.vrplanet, M=M, dims=[800, 800],
+                         xrange=(-4., 4.), zrange=(-4., 4.), apix=apix, quantity='radiance',
+                         gtables=gtables)
+    t_img = time.time() - t0
+    out = {'image': {'packets': m, 'ms': t_img * 1e3, 'ms_per_1e8_packets': t_img * 1e3 * 1e8 / m,
+                     'kind': 'port', 'cores': 1}}
+    if los is not None and len(los):
+        t0 = time.time()
+        _, npk, _, _ = imaging.los_iteration(
+            x, y, z, vy, frac, los, vrplanet=setup.vrplanet, dphi=float(np.radians(1.0)),
+            outeredge=25.0, rp_cm=setup.radius_km * 1e5, gtables=gtables)
+        t_los = time.time() - t0
+        out['los'] = {'packets': m, 'lines_of_sight': int(len(los)), 's': t_los,
+                      'ms_per_line_of_sight': t_los * 1e3 / len(los), 'hits': int(npk.sum()),
+                      'kind': 'port', 'cores': 1,
+                      'note': 'KD-tree build included; the GPU los_sweep above is '
+                              '1e5 lines of sight over 10x the packets'}
+    return out
 
 
 def run_gpu_config3(args):
@@ -542,6 +578,10 @@ def main():
     ap.add_argument('--packets', type=int, default=10_000_000, help='packets per GPU')
     ap.add_argument('--cpu-packets', type=int, default=100000,
                     help='packets of the bounded CPU sample (about 15 s on one core)')
+    ap.add_argument('--cpu-product-packets', type=int, default=1_000_000,
+                    help='packets of the CPU image / line-of-sight timing sample')
+    ap.add_argument('--cpu-product-los', type=int, default=200,
+                    help='lines of sight of the CPU line-of-sight timing sample')
     ap.add_argument('--ref-packets', type=int, default=20000,
                     help='packets per host process and step of the --impl reference arm')
     ap.add_argument('--seed', type=int, default=0)
