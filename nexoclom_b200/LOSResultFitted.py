@@ -67,6 +67,30 @@ def fitted_radiance(off, rows, spectrum_xyz, packet_xyz, weight, dphi, rp_cm):
     return np.bincount(sp, weights=np.asarray(weight)[r] / apix, minlength=nspec)
 
 
+def select_one_step(X, npackets, rng):
+    """`use_selected`: keep, of every trajectory, the row of ONE step time drawn at random
+    from the step times present in the output (reference LOSResultFitted.py:95-113: the
+    set of (packet, drawn time) pairs intersected with the (Index, time) rows).  Row labels
+    are preserved, so `used` sets recorded on the full output still address the rows."""
+    times = pd.unique(X['time'].values)
+    pick = rng.choice(times, npackets)
+    ind0 = X['Index'].values.astype(np.int64)
+    return X[X['time'].values == pick[ind0]]
+
+
+def restrict_csr(off, rows):
+    """Drop the entries of a CSR `used` structure whose row is gone (rows < 0): the
+    reference's ``[x for x in used_packets if x in packets.index]`` (:135-136, :189-190)."""
+    rows = np.asarray(rows)
+    ok = rows >= 0
+    if ok.all():
+        return np.asarray(off), rows
+    nspec = len(off) - 1
+    sp = np.repeat(np.arange(nspec), np.diff(off))
+    cnt = np.bincount(sp[ok], minlength=nspec)
+    return np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64), rows[ok]
+
+
 class LOSResultFitted(LOSResult):
     def __init__(self, scdata, label_for_fitted, params=None, dphi=Quantity(1., 'deg'),
                  **kwargs):
@@ -87,9 +111,6 @@ class LOSResultFitted(LOSResult):
         data = scdata.data
         if overwrite:
             self.inputs.delete_files()
-        if use_selected:
-            raise NotImplementedError('use_selected (one random step per trajectory) is not '
-                                      'supported')
         setup = RunSetup(self.inputs)
         gtables = setup.gtables(self.wavelength) if self.g is None else None
         rp_cm = setup.radius_km * 1e5
@@ -106,8 +127,15 @@ class LOSResultFitted(LOSResult):
                 output.X['Index'] = output.X.index
             it_unfit = unfit._iterations[ufit_outfile]
             off, idx0, labels = it_unfit.used_csr
+            print(f'use_selected = {use_selected}')
+            if use_selected:
+                rng = getattr(output, 'randgen', None)
+                if rng is None:
+                    rng = np.random.default_rng(getattr(output, 'seed', None))
+                output.X = select_one_step(output.X, output.npackets, rng)
             rows = output.X.index.get_indexer(labels)          # positions of the used rows in X
-            assert np.all(rows >= 0)
+            assert use_selected or np.all(rows >= 0)
+            off, rows = restrict_csr(off, rows)
             xyz = output.X[['x', 'y', 'z']].values
             weighting = fit_packet_weights(off, rows, output.X['Index'].values,
                                            len(output.X0), sc_xyz, xyz, ratio, mask,

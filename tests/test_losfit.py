@@ -43,6 +43,38 @@ def test_reweighting_matches_loop_restatement(use_weight):
     assert rad[7] == 0.0
 
 
+def test_use_selected_restatement():
+    """`use_selected` keeps one step per trajectory; literal restatement of the reference's
+    set / MultiIndex selection (LOSResultFitted.py:95-113) and of its `to_use` filter."""
+    import pandas as pd
+    from nexoclom_b200.LOSResultFitted import restrict_csr, select_one_step
+    npk, nst = 40, 7
+    rng0 = np.random.default_rng(3)
+    X = pd.DataFrame({'Index': np.repeat(np.arange(npk), nst),
+                      'time': np.tile(np.arange(nst, 0, -1) * 30.0, npk).astype(np.float32),
+                      'x': rng0.normal(size=npk * nst)})
+    X = X[rng0.random(len(X)) > 0.3]                       # some steps are missing
+    sel = select_one_step(X, npk, np.random.default_rng(11))
+    # the reference's way
+    Xr = X.copy()
+    Xr['ind_'] = Xr.index
+    times = Xr.time.unique()
+    Xr.set_index(['Index', 'time'], inplace=True)
+    steps = set(zip(np.arange(npk), np.random.default_rng(11).choice(times, npk)))
+    steps = steps.intersection(set(Xr.index))
+    ref = Xr.loc[pd.MultiIndex.from_tuples(sorted(steps), names=['Index', 'time'])]
+    assert sorted(ref.ind_.values) == sorted(sel.index.values) and 0 < len(sel) <= npk
+    assert sel['Index'].is_unique
+
+    labels = rng0.choice(X.index.values, 60)
+    off = np.array([0, 10, 10, 35, 60])
+    rows = sel.index.get_indexer(labels)
+    off2, rows2 = restrict_csr(off, rows)
+    for i in range(4):
+        to_use = [x for x in labels[off[i]:off[i + 1]] if x in sel.index]
+        assert list(sel.index[rows2[off2[i]:off2[i + 1]]]) == to_use
+
+
 @pytest.mark.gpu
 def test_losresultfitted_public_api(engine):
     """LOSResult -> LOSResultFitted through the reference-facing classes: the re-weighted
