@@ -669,6 +669,69 @@ def test_losresult_on_constant_step_output(engine):
     inputs.delete_files()
 
 
+def test_full_size_config1_properties(engine):
+    """BASELINE configs[1] at its FULL size (1e7 packets, Na, radiation pressure + photo-loss,
+    adaptive RK5(4)), checked through size-independent properties: two shards == one run
+    bit for bit (state, step counts, image counts; the Philox counter is the global packet
+    id and packets do not interact), the image is additive over shards, physical invariants
+    hold for every packet, and a sample of the very same run matches the oracle."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    gt = setup.gtables([5891, 5897])
+    engine.upload_gtables(gt)
+    sp = setup.source_params(engine)
+    n, half = 10_000_000, 5_000_000
+    ip = _image_params(setup, 1, round_f32=1)
+
+    def run(first, count):
+        engine.init_state(sp, 0, first, count)
+        X0 = engine.export_state()
+        att, acc = engine.integrate_adaptive()
+        X = engine.export_state()
+        a, c = engine.export_stats()
+        img, cnt = engine.image_accumulate(ip)
+        assert att == int(a.sum()) and acc == int(c.sum())
+        return X0, X, a, c, img, cnt
+
+    X0, X, a, c, img, cnt = run(0, n)
+    parts = [run(0, half), run(half, half)]
+    assert np.array_equal(X0, np.concatenate([q[0] for q in parts], axis=1))
+    assert np.array_equal(X, np.concatenate([q[1] for q in parts], axis=1))
+    assert np.array_equal(a, np.concatenate([q[2] for q in parts]))
+    assert np.array_equal(c, np.concatenate([q[3] for q in parts]))
+    assert np.array_equal(cnt, parts[0][5] + parts[1][5])           # hit counts: exact
+    s = parts[0][4] + parts[1][4]
+    nz = s > 0
+    assert np.array_equal(nz, img > 0)
+    assert np.max(np.abs(img[nz] - s[nz]) / s[nz]) < 1e-12          # f64 sums, other order
+
+    # every packet
+    assert np.all(np.isfinite(X))
+    assert np.all((c >= 0) & (c <= a)) and a.min() >= 0 and a.max() < 100000
+    alive = X[7] > 0
+    assert 0.001 < alive.mean() < 0.5
+    # photo-loss only removes -- up to the step tolerance: a step across the shadow edge mixes
+    # stages with and without loss, one tableau weight is negative (Q9 accepts such steps)
+    print('largest frac increase', float((X[7] - X0[7]).max()))
+    assert np.all(X[7] <= X0[7] * (1 + 10 * float(setup.params.resolution)))
+    assert np.all(X[0][~alive] == 0)                                # Q8
+    assert np.all((X[0] >= 0) & (X[0] <= X0[0]))
+    r2 = X[1]**2 + X[2]**2 + X[3]**2
+    assert np.all(r2[alive] > 1.0) and np.all(r2[alive] <= float(setup.params.outeredge))  # Q7
+    assert 0.5 * n < cnt.sum() <= n            # packet_image counts dead packets too
+    assert (img > 0).sum() <= alive.sum() and img.sum() > 0
+
+    # a sample of the same run against the oracle (first / last packets and a stride)
+    sel = np.unique(np.concatenate([np.arange(700), np.arange(n - 700, n),
+                                    np.arange(0, n, 16661)]))
+    Xo, a_o, c_o = tracking.integrate_adaptive(np.ascontiguousarray(X0[:, sel].T),
+                                               oracle_constants(setup))
+    par = state_parity(np.ascontiguousarray(X[:, sel].T), Xo)
+    assert par['alive_mismatch'] == 0, par
+    assert max(par['pos'], par['vel'], par['frac']) < STATE_TOL, par
+    assert np.array_equal(a[sel], a_o) and np.array_equal(c[sel], c_o)
+
+
 def test_pipelined_host_path_equals_resident_path(engine):
     """nx_integrate_adaptive_host (chunked H2D/compute pipeline) == import + integrate."""
     setup = RunSetup(workload('Na.maxwellian.radpres.input'))
