@@ -732,6 +732,52 @@ def test_full_size_config1_properties(engine):
     assert np.array_equal(a[sel], a_o) and np.array_equal(c[sel], c_o)
 
 
+def test_full_size_config3_properties(engine):
+    """BASELINE configs[2] (Na, temperature-dependent sticking + bounce + accommodation,
+    constant 30 s step, 361 steps, image accumulated inside the integrator) on the LAST
+    1.25e7-packet shard of the 1e8-packet run: the fused image is additive over sub-shards
+    with exact counts (initial states and bounce deviates are keyed by the global packet
+    id), and a slice at the top of the id range matches the oracle step by step."""
+    import torch
+    setup = RunSetup(workload('Na.bounce.input'))
+    setup.upload(engine)
+    engine.upload_gtables(setup.gtables([5891, 5897]))
+    sp = setup.source_params(engine)
+    ip = _image_params(setup, 1, round_f32=1)
+    ip.skip_dead = 1
+    first, n = 87_500_000, 12_500_000
+
+    def run(f, count):
+        img = torch.zeros((800, 800), dtype=torch.float64, device='cuda')
+        cnt = torch.zeros((800, 800), dtype=torch.int64, device='cuda')
+        engine.init_state(sp, 0, f, count)
+        _, ns, steps = engine.integrate_constant(seed=1, first_id=f, image_params=ip,
+                                                 image_dev=img.data_ptr(),
+                                                 counts_dev=cnt.data_ptr())
+        torch.cuda.synchronize()
+        return img.cpu().numpy(), cnt.cpu().numpy(), ns, steps
+
+    img, cnt, ns, steps = run(first, n)
+    a = run(first, 5_000_000)
+    b = run(first + 5_000_000, n - 5_000_000)
+    assert ns == 361 and steps == a[3] + b[3] and 0.05 * n * ns < steps <= n * ns
+    assert np.array_equal(cnt, a[1] + b[1]) and cnt.sum() > 0
+    ssum = a[0] + b[0]
+    nz = ssum > 0
+    assert np.array_equal(nz, img > 0)
+    assert np.max(np.abs(img[nz] - ssum[nz]) / ssum[nz]) < 1e-10
+
+    m, f = 400, 99_999_000
+    engine.init_state(sp, 0, f, m)
+    X0 = np.ascontiguousarray(engine.export_state().T)
+    traj, ns2, st2 = engine.integrate_constant(seed=1, first_id=f, trajectory=True)
+    ref, nsteps, natt = tracking.integrate_constant(
+        X0, oracle_constants(setup), uniforms=initial_state.bounce_uniforms(1, f))
+    assert ns2 == nsteps == 361 and st2 == int(natt.sum())
+    assert np.array_equal(traj[:, 7, :] > 0, ref[:, 7, :] > 0)
+    assert np.max(np.abs(traj - ref) / np.maximum(np.abs(ref), 1e-3)) < STATE_TOL
+
+
 def test_pipelined_host_path_equals_resident_path(engine):
     """nx_integrate_adaptive_host (chunked H2D/compute pipeline) == import + integrate."""
     setup = RunSetup(workload('Na.maxwellian.radpres.input'))
