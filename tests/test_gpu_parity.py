@@ -778,6 +778,58 @@ def test_full_size_config3_properties(engine):
     assert np.max(np.abs(traj - ref) / np.maximum(np.abs(ref), 1e-3)) < STATE_TOL
 
 
+def test_full_size_los_properties(engine):
+    """1e5 lines of sight x 1e7 packets (BASELINE's line-of-sight size) through the cell-grid
+    path: additive over packet shards (each shard builds its own grid) with exact hit counts
+    and `included` masks, and equal to the brute-force kernel on a subset of the lines."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    engine.upload_gtables(setup.gtables([5891, 5897]))
+    rng = np.random.default_rng(17)
+    n, half, nlos = 10_000_000, 4_000_000, 100_000
+    X = np.zeros((n, 8))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    X[:, 1:4] = d * (1 + 9 * rng.random(n)**2)[:, None]
+    X[:, 5] = rng.normal(size=n) * 2 / setup.radius_km
+    X[:, 7] = rng.random(n) * (rng.random(n) > 0.2)            # 20 % dead
+    X = X.astype(np.float32).astype(np.float64)
+    los = _synthetic_los(nlos, seed=4)
+    sx = los[:, :3]
+    dist = np.linalg.norm(sx, axis=1)
+    ang = np.arccos(-(sx * los[:, 3:]).sum(axis=1) / dist)
+    dist[ang > np.arcsin(1. / dist)] = 1e30
+    lp = LosParams()
+    lp.dphi, lp.outeredge = np.radians(1.0), 25.
+    lp.vrplanet, lp.rp_cm, lp.quantity = setup.vrplanet, setup.radius_km * 1e5, 1
+    lt = los.T.copy()
+
+    def run(P, mode, lines=slice(None)):
+        engine.import_state(P)
+        engine.set_option('los_mode', mode)
+        try:
+            return engine.los_accumulate(np.ascontiguousarray(lt[:, lines]), dist[lines], lp)
+        finally:
+            engine.set_option('los_mode', 0)
+
+    rad, npk, inc = run(X, 2)
+    ra, na, ia = run(X[:half], 2)
+    rb, nb, ib = run(X[half:], 2)
+    assert npk.sum() > 1e7
+    assert np.array_equal(npk, na + nb)
+    assert np.array_equal(inc, np.concatenate([ia, ib]))
+    ssum = ra + rb
+    nz = ssum > 0
+    assert np.array_equal(nz, rad > 0)
+    assert np.max(np.abs(rad[nz] - ssum[nz]) / ssum[nz]) < 1e-10
+    sub = slice(0, nlos, 211)
+    r1, n1, i1 = run(X, 1, sub)                                   # brute force
+    assert np.array_equal(n1, npk[sub])
+    assert not np.any(i1 & ~inc)
+    nz = r1 > 0
+    assert np.max(np.abs(rad[sub][nz] - r1[nz]) / r1[nz]) < 1e-10
+
+
 def test_pipelined_host_path_equals_resident_path(engine):
     """nx_integrate_adaptive_host (chunked H2D/compute pipeline) == import + integrate."""
     setup = RunSetup(workload('Na.maxwellian.radpres.input'))
