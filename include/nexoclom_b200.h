@@ -131,6 +131,7 @@ int nx_ctx_sync(nx_ctx* ctx);
  * 1 ballistic flight time (default), 2 + radiation-pressure perturbation);
  * "schedule" (host-buffer path: 1 one streaming class-ordered kernel (default), 0 one
  * sort + kernel per chunk; 2 = developer mode, streaming kernel over the resident X0);
+ * "class_cache" (streaming kernel: 1 keep each packet's cost class between passes (default));
  * "los_mode" (0 auto, 1 brute force, 2 cell grid); "los_grid" (cells per axis)         */
 int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value);
 const char* nx_last_error(nx_ctx* ctx);

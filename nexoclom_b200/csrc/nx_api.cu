@@ -64,6 +64,7 @@ struct nx_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[2] = {};
   int los_mode = 0;                  // 0 auto, 1 brute force, 2 cell grid
+  int class_cache = 1;               // streaming schedule: remember each packet's cost class
   int los_order = 1;                 // process lines of sight in Morton order of closest approach
   cudaStream_t pipe[16] = {};                  // H2D / compute pipeline of the host-buffer path
   cudaEvent_t pipe_ev[17] = {};
@@ -257,6 +258,7 @@ int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   if (name && std::strcmp(name, "schedule") == 0) { ctx->schedule = value; return 0; }
   if (name && std::strcmp(name, "los_mode") == 0) { ctx->los_mode = value; return 0; }
   if (name && std::strcmp(name, "los_order") == 0) { ctx->los_order = value; return 0; }
+  if (name && std::strcmp(name, "class_cache") == 0) { ctx->class_cache = value; return 0; }
   if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G_fixed = value; ctx->losw.cap = 0; return 0; }
   if (name && std::strcmp(name, "los_grid_scale_milli") == 0) { ctx->losw.scale = 1e-3 * value; return 0; }
   ctx->err = std::string("unknown option ") + (name ? name : "(null)");
@@ -553,14 +555,15 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
                          ctx->stream));
       CK(cudaMemsetAsync(ctx->att, 0, (size_t)n * sizeof(unsigned), ctx->stream));
       CK(cudaMemsetAsync(ctx->acc, 0, (size_t)n * sizeof(unsigned), ctx->stream));
+      CK(cudaMemsetAsync(ctx->cost, 0xFF, (size_t)ctx->cap, ctx->stream));
       long long seg = (n + 15) / 16;
       seg = (seg + NX_STREAM_GROUP - 1) / NX_STREAM_GROUP * NX_STREAM_GROUP;
       CK(launch_integrate_adaptive_stream(ctx->stream, ctx->device, ctx->x0, (size_t)ctx->cap,
                                           1000.0, state_cols(ctx), n, ctx->params,
                                           ctx->radpres.view, ctx->radpres.fast, seg,
                                           (int)((n + seg - 1) / seg), ctx->order_packets,
-                                          ctx->squeue, nullptr, ctx->scalars + 1, ctx->att,
-                                          ctx->acc, ctx->status));
+                                          ctx->squeue, nullptr, ctx->class_cache ? ctx->cost : nullptr,
+                                          ctx->scalars + 1, ctx->att, ctx->acc, ctx->status));
       if ((r = end_timed(ctx, 1))) return r;
     } else {
       const bool order = ctx->order_packets && n >= 4096;
@@ -614,6 +617,7 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
                        ctx->stream));
     CK(cudaMemsetAsync(ctx->att, 0, (size_t)n * sizeof(unsigned), ctx->stream));
     CK(cudaMemsetAsync(ctx->acc, 0, (size_t)n * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->cost, 0xFF, (size_t)ctx->cap, ctx->stream));   // classes: unknown
     CK(debug_begin(ctx->stream));
     if ((r = begin_timed(ctx))) return r;
     CK(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
@@ -626,6 +630,7 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
                                         ctx->params,
                                         ctx->radpres.view, ctx->radpres.fast, seg, nseg,
                                         ctx->order_packets, ctx->squeue, arrived,
+                                        ctx->class_cache ? ctx->cost : nullptr,
                                         ctx->scalars + 1, ctx->att, ctx->acc, ctx->status));
     for (int c = 0; c < nseg; ++c) {
       const long long first = (long long)c * seg, count = std::min(seg, n - first);

@@ -494,6 +494,7 @@ struct StreamQueue {
   int model;                         // cost model (ctx option order_packets)
   unsigned long long* cursor;        // [NX_NCLASS][32], zeroed before the launch
   const unsigned* arrived;           // segments [0, *arrived) are on the device; nullptr: all
+  unsigned char* cls;                // class of every packet once known (0xFF: not yet), or nullptr
 };
 
 // Feeder state of one warp.  It lives in SHARED memory and is advanced by ONE
@@ -502,6 +503,7 @@ struct StreamQueue {
 // the 32 KB instruction cache like the sorted kernel's does (ncu: the inlined
 // version spent 1.7 cycles per issue waiting for instructions).
 struct StreamShared {
+  unsigned char clsb[2][32];         // cached classes of the batch in staging buffer 0 / 1
   unsigned base_cur, base_pend;      // packet index of slot 0 of the current / pending batch
   int cnt_pend;                      // packets in the pending batch (0: none in flight)
   int cls_pend;
@@ -511,7 +513,7 @@ struct StreamShared {
   unsigned exh[NX_NCLASS];           // bit s: cursor (class, segment s) is exhausted
   unsigned char order[32];           // slots of the current batch that belong to its class
 };
-#define NX_SFEED_STATE_BYTES 96      // >= sizeof(StreamShared), multiple of 16
+#define NX_SFEED_STATE_BYTES 160     // >= sizeof(StreamShared), multiple of 16
 #undef NX_SFEED_BYTES_PER_WARP
 #define NX_SFEED_BYTES_PER_WARP (2 * NX_SFEED_COLS * 32 * 8 + NX_SFEED_STATE_BYTES)
 
@@ -521,6 +523,7 @@ struct StreamArgs {                  // everything the feeder needs, passed by v
   long long n, seg;
   unsigned long long* cursor;
   const unsigned* arrived;
+  unsigned char* cls;
   double resolution;
   float res, mu, amax;
   int nseg, model, gravity, radpres;
@@ -550,12 +553,17 @@ __device__ __noinline__ int stream_advance(StreamShared* S, double* vals, Stream
       const double* v = vals + (size_t)buf * NX_SFEED_COLS * 32 + lane;
       int cls = -1;
       if ((int)lane < cnt_pend) {
+        // the class found by an earlier pass came in with the rows (a stale 0xFF only
+        // means the deterministic model is evaluated again)
+        const int cached = A.cls ? (int)S->clsb[buf][lane] : 0xFF;
         if (NX_NCLASS == 1) cls = 0;
+        else if (cached < NX_NCLASS) cls = cached;
         else {
           RunParams pp;               // only the fields cost_class reads
           pp.resolution = A.resolution; pp.gravity = A.gravity; pp.radpres = A.radpres;
           cls = cost_class(pp, A.model, A.res, A.mu, A.amax, v[0], v[32], v[64], v[96], v[128],
                            v[160], v[192], v[224]);
+          if (A.cls) A.cls[base_cur + lane] = (unsigned char)cls;
         }
       }
       const unsigned match = __ballot_sync(FULL_MASK, cls == cls_pend);
@@ -620,6 +628,8 @@ __device__ __noinline__ int stream_advance(StreamShared* S, double* vals, Stream
         const unsigned col = j >> 4, part = (j & 15u) * 2u;
         cp_async16_cg(dst + col * 32u + part, A.col0 + (size_t)col * A.stride + base_pend + part);
       }
+      if (A.cls && lane < 2u)
+        cp_async16_cg(&S->clsb[buf ^ 1][lane * 16u], A.cls + base_pend + lane * 16u);
       cp_async_commit();
     }
     if (result != -3) break;          // a batch became current, or nothing can be had
@@ -651,10 +661,11 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
   double* const vals = reinterpret_cast<double*>(smem_raw + table_bytes +
                                                  (size_t)(threadIdx.x >> 5) * NX_SFEED_BYTES_PER_WARP);
   StreamShared* const S = reinterpret_cast<StreamShared*>(vals + 2 * NX_SFEED_COLS * 32);
-  if (lane < NX_SFEED_STATE_BYTES / 4) reinterpret_cast<unsigned*>(S)[lane] = 0u;
+  for (unsigned i = lane; i < NX_SFEED_STATE_BYTES / 4; i += 32u)
+    reinterpret_cast<unsigned*>(S)[i] = 0u;
   StreamArgs A;
   A.col0 = col0; A.stride = stride; A.n = n; A.seg = Q.seg; A.cursor = Q.cursor;
-  A.arrived = Q.arrived; A.resolution = p.resolution; A.res = (float)p.resolution;
+  A.arrived = Q.arrived; A.cls = Q.cls; A.resolution = p.resolution; A.res = (float)p.resolution;
   A.mu = (float)fabs(p.GM); A.amax = (float)p.radpres_amax; A.nseg = Q.nseg; A.model = Q.model;
   A.gravity = p.gravity; A.radpres = p.radpres;
   __syncthreads();
@@ -1162,10 +1173,11 @@ cudaError_t launch_integrate_adaptive_stream(cudaStream_t st, int device, const 
                                              const InterpTable& T, const FastTable& F,
                                              long long seg, int nseg, int model,
                                              unsigned long long* cursor, const unsigned* arrived,
-                                             unsigned long long* totals, unsigned* att,
-                                             unsigned* acc, int* status) {
+                                             unsigned char* cls, unsigned long long* totals,
+                                             unsigned* att, unsigned* acc, int* status) {
   StreamQueue Q;
   Q.seg = seg; Q.nseg = nseg; Q.model = model; Q.cursor = cursor; Q.arrived = arrived;
+  Q.cls = cls;
 #define NX_ARGS st, device, in0, in_stride, step0, P, n, p, T, F, Q, totals, att, acc, status
   // one moon + gravity: fast path with MO = 1 (MODE bit 4); more moons: generic kernel
   if (p.strict_math || p.nmoons > 1 || (p.nmoons == 1 && !p.gravity))

@@ -89,15 +89,17 @@ cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, 
 #define NX_STREAM_CURSORS 256        // >= NX_NCLASS x 32 u64 cursors
 cudaError_t debug_begin(cudaStream_t st);                       // no-ops unless NX_STREAM_DEBUG
 cudaError_t debug_read(unsigned long long* out, int count);
-// in0/in_stride: the 8 immutable input columns (time..frac); P: where the final state goes
+// in0/in_stride: the 8 immutable input columns (time..frac); P: where the final state goes;
+// cls: nullptr, or one byte per packet (padded to 32) preset to 0xFF -- the cost class is
+// computed by the first pass that meets a packet and read back by the later ones
 cudaError_t launch_integrate_adaptive_stream(cudaStream_t st, int device, const double* in0,
                                              size_t in_stride, double step0, StateCols P,
                                              long long n, const RunParams& p,
                                              const InterpTable& T, const FastTable& F,
                                              long long seg, int nseg, int model,
                                              unsigned long long* cursor, const unsigned* arrived,
-                                             unsigned long long* totals, unsigned* att,
-                                             unsigned* acc, int* status);
+                                             unsigned char* cls, unsigned long long* totals,
+                                             unsigned* att, unsigned* acc, int* status);
 cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,
                                       const RunParams& p, const InterpTable& T,
                                       const FastTable& F,
