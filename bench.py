@@ -156,7 +156,7 @@ def run_reference(args):
         'e2e': {'value': sps, 'unit': 'packet-steps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -436,7 +436,7 @@ def run_gpu(args):
             line['config']['cpu_products'] = cpu_products(
                 fin, setup, gt, M, ip.apix,
                 los_host[:args.cpu_product_los] if los_info is not None else None)
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -552,7 +552,7 @@ def run_gpu_config3(args):
     else:
         elapsed_ms, all_steps = float(t[0]), float(t[1])
     if rank == 0:
-        print(json.dumps({
+        emit({
             'metric': 'packet-steps/s (FP64), constant step + bounce + fused image',
             'value': all_steps / (elapsed_ms * 1e-3), 'unit': 'packet-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
@@ -563,14 +563,34 @@ def run_gpu_config3(args):
                        'packets_total': n * world, 'nsteps': int(nsteps),
                        'rows_in_image_per_step': int(rows),
                        'step': 'K1 init -> K3 constant-step integrate with fused radiance '
-                               'image' + (' -> NCCL all-reduce(image, counts)' if world > 1 else '')}}))
+                               'image' + (' -> NCCL all-reduce(image, counts)' if world > 1 else '')}})
     eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: whatever libraries print there while the bench runs
+    (NCCL writes its version banner to stdout) is sent to stderr instead."""
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
