@@ -3,11 +3,15 @@
 TEST INFRASTRUCTURE -- see oracle/__init__.py for who may import this.
 
 Loop-for-loop restatement of reference nexoclom/data_simulation/LOSResultFitted.py:123-203
-(dictionaries / per-spectrum Python loops, pandas replaced by plain arrays).  The reference
-method cannot be executed here (it is one 200-line method that talks to PostgreSQL and to the
-private MESSENGERuvvs data object), so this restatement is **parity unpinned**: it pins the
-vectorised implementation in nexoclom_b200/LOSResultFitted.py to the reference's loop
-structure as read, not to outputs of the reference.
+(dictionaries / per-spectrum Python loops, pandas replaced by plain arrays).
+
+Pinned: tools/make_golden_products.py (`losfit`) EXECUTES the unmodified reference method
+``LOSResultFitted.determine_source_from_data`` (its PostgreSQL search answered "nothing saved",
+Output.restore / the unfitted-iteration pickle / IterationResultFitted replaced by in-memory
+stand-ins) for use_weight in (None, 'dist', 'dist2', 'sigma') on the packets, lines of sight and
+`used` sets of tests/golden/los.npz -> tests/golden/losfit.npz; this restatement and the
+vectorised product code reproduce the re-weighted packets and the fitted radiances to 1e-12
+(tests/test_losfit.py::test_reweighting_vs_reference_golden).
 """
 import numpy as np
 

@@ -43,6 +43,48 @@ def test_reweighting_matches_loop_restatement(use_weight):
     assert rad[7] == 0.0
 
 
+@pytest.mark.parametrize('tag, use_weight', [('none', None), ('dist', 'dist'),
+                                             ('dist2', 'dist2'), ('sigma', 'sigma')])
+def test_reweighting_vs_reference_golden(tag, use_weight):
+    """tests/golden/losfit.npz: outputs of the UNMODIFIED reference method
+    LOSResultFitted.determine_source_from_data (tools/make_golden_products.py losfit) on the
+    packets, lines of sight and `used` sets of los.npz.  The oracle restatement and the
+    vectorised product code both reproduce the re-weighted packets and the fitted radiance."""
+    import os
+    from common import GOLDEN, workload
+    from nexoclom_b200.LOSResultFitted import fit_packet_weights, fitted_radiance
+    from nexoclom_b200.runsetup import RunSetup
+    g = np.load(os.path.join(GOLDEN, 'los.npz'))
+    f = np.load(os.path.join(GOLDEN, 'losfit.npz'))
+    X, los = g['X'], g['los']
+    n, nlos = len(X), len(los)
+    off, idx = g['d3_used_off'], g['d3_used_idx']
+    used = [idx[off[i]:off[i + 1]].tolist() for i in range(nlos)]
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    gsum = np.zeros(n)
+    for v, gv in setup.gtables([5891, 5897]):
+        gsum += np.interp(X[:, 5] + setup.vrplanet, v, gv)
+    index0 = np.arange(n)
+    dphi, rp_cm = float(f['dphi']), setup.radius_km * 1e5
+    w_o, frac_o, rad_o = losfit.fit(used, index0, X[:, 1:4], X[:, 7], gsum, n, los[:, :3],
+                                    f['data_radiance'], f['model_radiance'], f['mask'],
+                                    f['sigma'], use_weight, dphi, rp_cm)
+    assert np.allclose(w_o, f[f'{tag}_frac0'], rtol=1e-12, atol=0)      # X0.frac was 1
+    assert np.allclose(frac_o, f[f'{tag}_frac'], rtol=1e-12, atol=0)
+    ref = f[f'{tag}_radiance']
+    assert (ref > 0).sum() > 50
+    assert np.allclose(rad_o, ref, rtol=1e-11, atol=0)
+    assert abs(frac_o.sum() * 0 + w_o.sum() - float(f[f'{tag}_totalsource'])) < 1e-9 * n
+
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ratio = np.nan_to_num(f['data_radiance'] / f['model_radiance'], nan=0.0, posinf=np.inf)
+    w = fit_packet_weights(off, idx, index0, n, los[:, :3], X[:, 1:4], ratio, f['mask'],
+                           f['sigma'], use_weight)
+    assert np.allclose(w, f[f'{tag}_frac0'], rtol=1e-12, atol=0)
+    rad = fitted_radiance(off, idx, los[:, :3], X[:, 1:4], X[:, 7] * w * gsum / 1e6, dphi, rp_cm)
+    assert np.allclose(rad, ref, rtol=1e-11, atol=0)
+
+
 def test_use_selected_restatement():
     """`use_selected` keeps one step per trajectory; literal restatement of the reference's
     set / MultiIndex selection (LOSResultFitted.py:95-113) and of its `to_use` filter."""

@@ -12,7 +12,10 @@ reference code (build container only; needs /root/reference):
         Histogram2d();
   tests/golden/los.npz                   reference compute_iteration()
         (compute_iteration.py:90-240) incl. the KD-tree candidate ladder, cone test,
-        planet truncation, foot-point shadow test and the used / included sets.
+        planet truncation, foot-point shadow test and the used / included sets;
+  tests/golden/losfit.npz                reference LOSResultFitted.determine_source_from_data()
+        (LOSResultFitted.py:66-262) on the packets / lines of sight / used sets of los.npz
+        (run `los` first), for use_weight in (None, 'dist', 'dist2', 'sigma').
 
 astropy / periodictable / sqlalchemy are absent here: tools/refunits.py supplies a
 functional miniature of astropy.units, the g-value tables come from this repo's host
@@ -315,6 +318,95 @@ def golden_los():
     print('los.npz')
 
 
+def golden_losfit():
+    """Execute the UNMODIFIED LOSResultFitted.determine_source_from_data (reference
+    LOSResultFitted.py:66-262) on the packets / lines of sight / `used` sets of los.npz:
+    PostgreSQL search -> "no saved result", Output.restore / the unfitted iteration pickle /
+    IterationResultFitted replaced by in-memory stand-ins that capture what the method
+    computes."""
+    import pickle
+    import tempfile
+    from nexoclom.data_simulation import LOSResultFitted as lf
+    from nexoclom.data_simulation.ModelResult import ModelResult
+    ns = types.SimpleNamespace
+    g = np.load(os.path.join(GOLD, 'los.npz'))
+    X = g['X']
+    n = len(X)
+    los = g['los']
+    nlos = len(los)
+    setup, _ = _final_packets(8, 8, True)
+    unit = u.def_unit('R_Mercury', q(setup.radius_km, u.km))
+    cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac']
+    off, idx = g['d3_used_off'], g['d3_used_idx']
+    used = pd.Series([set(int(k) for k in idx[off[i]:off[i + 1]]) for i in range(nlos)])
+    model_rad = g['d3_radiance'] * 3.0e-7                 # any positive scale: a ratio enters
+    rng = np.random.default_rng(12)
+    truth = model_rad * (1.0 + 0.8 * np.sin(np.arange(nlos) * 0.37)) + 0.02 * rng.random(nlos)
+    sigma = 0.05 + 0.1 * rng.random(nlos)
+    mask = (model_rad > 0) & (rng.random(nlos) > 0.15)
+    data = pd.DataFrame({'x': los[:, 0], 'y': los[:, 1], 'z': los[:, 2], 'xbore': los[:, 3],
+                         'ybore': los[:, 4], 'zbore': los[:, 5], 'radiance': truth,
+                         'sigma': sigma, 'mask_unfit': mask})
+    out = {'model_radiance': model_rad, 'data_radiance': truth, 'sigma': sigma, 'mask': mask,
+           'dphi': g['d3_dphi'], 'endtime': 50000.0}
+    tmp = tempfile.mkdtemp()
+    modelfile = os.path.join(tmp, 'unfit_iteration.pkl')
+    with open(modelfile, 'wb') as f:
+        pickle.dump(ns(used_packets=used), f)
+    captured = {}
+
+    class Capture:
+        def __init__(self, iteration, losresult):
+            captured.update(iteration)
+            self.radiance = pd.Series(iteration['radiance'])
+            self.totalsource = iteration['totalsource']
+            self.outputfile = iteration['outputfile']
+            self.modelfile = 'fitted_iteration.pkl'
+
+        def save_iteration(self):
+            pass
+    lf.IterationResultFitted = Capture
+    for tag, use_weight in (('none', None), ('dist', 'dist'), ('dist2', 'dist2'),
+                            ('sigma', 'sigma')):
+        packets = pd.DataFrame(X, columns=cols)
+        saved = {}
+        fake_out = ns(X=packets, X0=pd.DataFrame({'frac': np.ones(n)}), npackets=n, nsteps=1,
+                      vrplanet=q(setup.vrplanet, unit / u.s), aplanet=setup.aplanet,
+                      totalsource=float(n), idnum=2, filename='fitted_output.pkl', unit=unit,
+                      inputs=None)
+        fake_out.save = lambda _o=fake_out: saved.update(frac=_o.X['frac'].values.copy(),
+                                                         frac0=_o.X0['frac'].values.copy(),
+                                                         totalsource=float(_o.totalsource))
+        lf.Output = ns(restore=lambda fname, _o=fake_out: _o)
+        unfit = ns(outid=[1], outputfiles=['unfit_output.pkl'],
+                   modelfiles={'unfit_output.pkl': modelfile}, radiance=pd.Series(model_rad))
+        self = ns(unfitted_label='unfit', unit=unit, quantity='radiance', g=None,
+                  mechanism=['resonant scattering'], dphi=float(g['d3_dphi']), query='golden',
+                  wavelength=(q(5891, u.AA), q(5897, u.AA)), radiance=pd.Series(np.zeros(nlos)),
+                  totalsource=0., fitted=True,
+                  inputs=ns(delete_files=lambda: None,
+                            options=ns(endtime=q(50000., u.s), species='Na', outeredge=25.0)),
+                  fitted_iteration_search=lambda ufit_id: None)
+        self.packet_weighting = types.MethodType(ModelResult.packet_weighting, self)
+        self.determine_source_rate = lambda scdata, use_weight=False: setattr(
+            self, 'sourcerate', q(1.0, 1 / u.s))
+        scdata = ns(data=data.copy(), model_result={'unfit': unfit}, query='golden')
+        captured.clear()
+        try:
+            lf.LOSResultFitted.determine_source_from_data(self, scdata, use_weight=use_weight)
+        except Exception as exc:                      # unit bookkeeping of the epilogue (:253-259)
+            print('  epilogue stopped at:', type(exc).__name__, exc)
+        assert 'radiance' in captured and saved, 'the per-file body did not complete'
+        out[f'{tag}_radiance'] = np.asarray(captured['radiance'], dtype=np.float64)
+        out[f'{tag}_frac'] = saved['frac']
+        out[f'{tag}_frac0'] = saved['frac0']
+        out[f'{tag}_totalsource'] = saved['totalsource']
+        print(tag, 'fitted radiance sum', float(out[f'{tag}_radiance'].sum()), 'packets used',
+              int((saved['frac0'] > 0).sum()))
+    np.savez_compressed(os.path.join(GOLD, 'losfit.npz'), **out)
+    print('losfit.npz')
+
+
 def golden_source_map():
     """reference data_simulation/make_source_map.py, unmodified, on oracle-drawn X0."""
     from nexoclom.data_simulation import make_source_map as msm
@@ -362,3 +454,5 @@ if __name__ == '__main__':
         golden_image()
     if 'los' in which:
         golden_los()
+    if 'losfit' in which:
+        golden_losfit()
