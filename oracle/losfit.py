@@ -9,7 +9,8 @@ Pinned: tools/make_golden_products.py (`losfit`) EXECUTES the unmodified referen
 ``LOSResultFitted.determine_source_from_data`` (its PostgreSQL search answered "nothing saved",
 Output.restore / the unfitted-iteration pickle / IterationResultFitted replaced by in-memory
 stand-ins) for use_weight in (None, 'dist', 'dist2', 'sigma') on the packets, lines of sight and
-`used` sets of tests/golden/los.npz -> tests/golden/losfit.npz; this restatement and the
+`used` sets of tests/golden/los.npz, and once with use_selected=True on a constant-step-like
+output -> tests/golden/losfit.npz; this restatement and the
 vectorised product code reproduce the re-weighted packets and the fitted radiances to 1e-12
 (tests/test_losfit.py::test_reweighting_vs_reference_golden).
 """

@@ -85,6 +85,48 @@ def test_reweighting_vs_reference_golden(tag, use_weight):
     assert np.allclose(rad, ref, rtol=1e-11, atol=0)
 
 
+def test_use_selected_vs_reference_golden():
+    """`use_selected=True` of the unmodified reference method on a constant-step-like output
+    (several rows per packet, its own generator seeded): same rows kept, same re-weighted
+    packets, same fitted radiance."""
+    import os
+    import pandas as pd
+    from common import GOLDEN, workload
+    from nexoclom_b200.LOSResultFitted import (fit_packet_weights, fitted_radiance,
+                                               restrict_csr, select_one_step)
+    from nexoclom_b200.runsetup import RunSetup
+    g = np.load(os.path.join(GOLDEN, 'los.npz'))
+    f = np.load(os.path.join(GOLDEN, 'losfit.npz'))
+    los = g['los']
+    cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac', 'Index']
+    X = pd.DataFrame(f['sel_rows'], columns=cols, index=f['sel_row_labels'])
+    n0 = int(f['sel_npackets0'])
+    sel = select_one_step(X, n0, np.random.default_rng(int(f['sel_seed'])))
+    assert np.array_equal(np.sort(sel.index.values), f['sel_kept_labels'])
+    sel = sel.sort_index()
+    off, rows = restrict_csr(f['sel_used_off'], sel.index.get_indexer(f['sel_used_idx']))
+    assert 0 < len(rows) < len(f['sel_used_idx'])
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    gsum = np.zeros(len(sel))
+    for v, gv in setup.gtables([5891, 5897]):
+        gsum += np.interp(sel.vy.values + setup.vrplanet, v, gv)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ratio = np.nan_to_num(f['sel_data_radiance'] / f['sel_model_radiance'], nan=0.0,
+                              posinf=np.inf)
+    ind0 = sel['Index'].values.astype(np.int64)
+    xyz = sel[['x', 'y', 'z']].values
+    w = fit_packet_weights(off, rows, ind0, n0, los[:, :3], xyz, ratio, f['sel_mask'],
+                           f['sigma'], 'dist2')
+    assert np.allclose(w, f['sel_frac0'], rtol=1e-12, atol=0)
+    frac = sel.frac.values * w[ind0]
+    assert np.allclose(frac, f['sel_frac'], rtol=1e-12, atol=0)
+    assert abs(w.sum() * 4 - float(f['sel_totalsource'])) < 1e-9 * n0      # x nsteps (:186)
+    rad = fitted_radiance(off, rows, los[:, :3], xyz, frac * gsum / 1e6, float(f['dphi']),
+                          setup.radius_km * 1e5)
+    assert (f['sel_radiance'] > 0).sum() > 30
+    assert np.allclose(rad, f['sel_radiance'], rtol=1e-11, atol=0)
+
+
 def test_use_selected_restatement():
     """`use_selected` keeps one step per trajectory; literal restatement of the reference's
     set / MultiIndex selection (LOSResultFitted.py:95-113) and of its `to_use` filter."""

@@ -403,6 +403,70 @@ def golden_losfit():
         out[f'{tag}_totalsource'] = saved['totalsource']
         print(tag, 'fitted radiance sum', float(out[f'{tag}_radiance'].sum()), 'packets used',
               int((saved['frac0'] > 0).sum()))
+    # use_selected=True (:95-113): a constant-step-like output (several rows per packet on a
+    # common time grid), one random step per trajectory drawn with the output's own generator
+    from oracle import imaging
+    n0, nst = 4000, 4
+    _, R = _final_packets(n0 * nst, 21, True)
+    R[:, 0] = np.tile(np.array([90., 60., 30., 0.]), n0)
+    rows = pd.DataFrame(R, columns=cols)
+    rows['Index'] = np.repeat(np.arange(n0), nst)
+    keep = np.random.default_rng(4).random(len(rows)) > 0.25          # packets die on the way
+    rows = rows[keep]
+    gt = setup.gtables([5891, 5897])
+    used_rows = []
+    rad_sel, _, _, _ = imaging.los_iteration(
+        rows.x.values, rows.y.values, rows.z.values, rows.vy.values, rows.frac.values, los,
+        vrplanet=setup.vrplanet, dphi=float(g['d3_dphi']), outeredge=25.,
+        rp_cm=setup.radius_km * 1e5, gtables=gt, used=used_rows)
+    labels = rows.index.values
+    used_s = pd.Series([set(int(labels[k]) for k in u_) for u_ in used_rows])
+    model_s = rad_sel * 3.0e-7
+    truth_s = model_s * (1.0 + 0.8 * np.cos(np.arange(nlos) * 0.21)) + 1e-22
+    mask_s = model_s > 0
+    data_s = data.copy()
+    data_s['radiance'] = truth_s
+    data_s['mask_unfit'] = mask_s
+    with open(modelfile, 'wb') as f:
+        pickle.dump(ns(used_packets=used_s), f)
+    saved = {}
+    fake_out = ns(X=rows.copy(), X0=pd.DataFrame({'frac': np.ones(n0)}), npackets=n0, nsteps=nst,
+                  vrplanet=q(setup.vrplanet, unit / u.s), aplanet=setup.aplanet,
+                  totalsource=float(n0), idnum=3, filename='fitted_output.pkl', unit=unit,
+                  inputs=None, randgen=np.random.default_rng(5))
+    fake_out.save = lambda _o=fake_out: saved.update(
+        labels=_o.X.index.values.copy(), frac=_o.X['frac'].values.copy(),
+        frac0=_o.X0['frac'].values.copy(), totalsource=float(_o.totalsource))
+    lf.Output = ns(restore=lambda fname, _o=fake_out: _o)
+    unfit = ns(outid=[1], outputfiles=['unfit_output.pkl'],
+               modelfiles={'unfit_output.pkl': modelfile}, radiance=pd.Series(model_s))
+    self = ns(unfitted_label='unfit', unit=unit, quantity='radiance', g=None,
+              mechanism=['resonant scattering'], dphi=float(g['d3_dphi']), query='golden',
+              wavelength=(q(5891, u.AA), q(5897, u.AA)), radiance=pd.Series(np.zeros(nlos)),
+              totalsource=0., fitted=True,
+              inputs=ns(delete_files=lambda: None,
+                        options=ns(endtime=q(50000., u.s), species='Na', outeredge=25.0)),
+              fitted_iteration_search=lambda ufit_id: None)
+    self.packet_weighting = types.MethodType(ModelResult.packet_weighting, self)
+    self.determine_source_rate = lambda scdata, use_weight=False: setattr(
+        self, 'sourcerate', q(1.0, 1 / u.s))
+    captured.clear()
+    lf.LOSResultFitted.determine_source_from_data(
+        self, ns(data=data_s, model_result={'unfit': unfit}, query='golden'),
+        use_selected=True, use_weight='dist2')
+    order = np.argsort(saved['labels'])
+    out.update(sel_rows=rows[cols + ['Index']].values, sel_row_labels=labels,
+               sel_used_off=np.concatenate([[0], np.cumsum([len(u_) for u_ in used_rows])]),
+               sel_used_idx=np.concatenate([np.sort(labels[np.asarray(u_, dtype=np.int64)])
+                                            if len(u_) else np.zeros(0, dtype=np.int64)
+                                            for u_ in (list(x) for x in used_rows)]),
+               sel_model_radiance=model_s, sel_data_radiance=truth_s, sel_mask=mask_s,
+               sel_kept_labels=saved['labels'][order], sel_frac=saved['frac'][order],
+               sel_frac0=saved['frac0'], sel_totalsource=saved['totalsource'],
+               sel_radiance=np.asarray(captured['radiance'], dtype=np.float64),
+               sel_npackets0=n0, sel_seed=5)
+    print('selected: rows kept', len(saved['labels']), 'of', len(rows), 'fitted radiance sum',
+          float(out['sel_radiance'].sum()), 'lines with signal', int((out['sel_radiance'] > 0).sum()))
     np.savez_compressed(os.path.join(GOLD, 'losfit.npz'), **out)
     print('losfit.npz')
 
