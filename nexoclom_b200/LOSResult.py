@@ -232,8 +232,14 @@ fitted = {self.fitted}'''
 
     def determine_source_rate(self, scdata, use_weight=True):
         """Linear least-squares scale factor model -> data (reference
-        LOSResult.py:278-308; astropy's LinearLSQFitter on a Multiply model is the
-        closed form sum(w m d) / sum(w m m))."""
+        LOSResult.py:278-308).  astropy's LinearLSQFitter (5.3, pinned by the reference's
+        poetry.lock) multiplies both sides of the design equation by `weights` before
+        np.linalg.lstsq, i.e. it minimises sum((w (d - f m))**2): on a Multiply model that is
+        the closed form f = sum(w^2 m d) / sum(w^2 m m).  The reference passes
+        w = 1/sigma**2 (:281), so its weighted fit is a 1/sigma^4 fit -- kept.  With
+        `siglimit` the reference refits with the weights of the FIRST mask (:296-298, astropy
+        raises on the length mismatch whenever a point was clipped); here the weights follow
+        the clipped mask."""
         mask, sigmalimit = self.make_mask(scdata.data)
         d = scdata.data.radiance.values
         m = self.radiance.values
@@ -241,7 +247,7 @@ fitted = {self.fitted}'''
         def fit(msk):
             w = (1. / scdata.data.sigma.values[msk]**2 if use_weight
                  else np.ones_like(scdata.data.sigma.values[msk]))
-            return np.sum(w * m[msk] * d[msk]) / np.sum(w * m[msk] * m[msk])
+            return np.sum(w * w * m[msk] * d[msk]) / np.sum(w * w * m[msk] * m[msk])
 
         if not np.all(m == 0):
             factor = fit(mask)

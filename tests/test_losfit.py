@@ -85,6 +85,41 @@ def test_reweighting_vs_reference_golden(tag, use_weight):
     assert np.allclose(rad, ref, rtol=1e-11, atol=0)
 
 
+@pytest.mark.parametrize('use_weight', [False, True])
+@pytest.mark.parametrize('masking', [None, 'minsnr3; minalt0.5', 'siglimit2'])
+def test_determine_source_rate_is_astropy_linear_lsq(use_weight, masking):
+    """reference LOSResult.py:171-200, 278-308 with astropy's LinearLSQFitter restated as what
+    it does: scale both sides by the weights, np.linalg.lstsq."""
+    import types
+    import pandas as pd
+    from nexoclom_b200.LOSResult import LOSResult
+    rng = np.random.default_rng(2)
+    n = 300
+    model = rng.random(n) * (rng.random(n) > 0.1)
+    data = pd.DataFrame({'radiance': 2.5 * model + rng.normal(0, 0.05, n),
+                         'sigma': 0.02 + 0.2 * rng.random(n), 'alttan': rng.random(n) * 2})
+    me = types.SimpleNamespace(masking=masking, radiance=pd.Series(model.copy()))
+    me.make_mask = types.MethodType(LOSResult.make_mask, me)
+    LOSResult.determine_source_rate(me, types.SimpleNamespace(data=data), use_weight=use_weight)
+
+    mask = np.ones(n, dtype=bool)
+    if masking and 'minsnr' in masking:
+        mask = (data.radiance / data.sigma > 3).values & (data.alttan >= 0.5).values
+
+    def lsq(msk):
+        w = 1 / data.sigma.values[msk]**2 if use_weight else np.ones(msk.sum())
+        lhs = (model[msk] * w)[:, None]
+        return np.linalg.lstsq(lhs, data.radiance.values[msk] * w, rcond=None)[0][0]
+    f = lsq(mask)
+    if masking == 'siglimit2':
+        mask = mask & (np.abs((data.radiance.values - f * model) / data.sigma.values) < 2)
+        assert mask.sum() < n
+        f = lsq(mask)
+    assert float(me.sourcerate) == pytest.approx(f, rel=1e-12)
+    assert np.array_equal(np.asarray(me.mask), mask)
+    assert np.allclose(me.radiance.values, model * f, rtol=1e-12)
+
+
 def test_use_selected_vs_reference_golden():
     """`use_selected=True` of the unmodified reference method on a constant-step-like output
     (several rows per packet, its own generator seeded): same rows kept, same re-weighted
