@@ -171,7 +171,11 @@ fit_method = {self.fit_method}
 fitted = {self.fitted}'''
 
     def make_mask(self, data):
-        """reference LOSResult.py:171-200."""
+        """reference LOSResult.py:171-200.  `middleNN`: the reference hands the WHOLE data
+        frame to astropy's PercentileInterval.get_limits (:181-182), which ravel()s every
+        column (positions, boresights, sigma, ...) into one sample -- and fails on the
+        non-numeric columns a MESSENGERuvvs frame carries; here the limits are the
+        percentiles of the radiances, which the comparison on :183-185 is then applied to."""
         mask = np.array([True for _ in data.radiance])
         sigmalimit = None
         if self.masking is not None:
