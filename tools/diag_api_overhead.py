@@ -1,5 +1,8 @@
-import sys, time, cProfile, pstats, io
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+#!/usr/bin/env python
+"""Host-side overhead of the public Output API (wall time and cProfile of Output(inputs, n))."""
+import os, sys, time, cProfile, pstats, io
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
 import numpy as np
 from common import workload
 from nexoclom_b200 import Output

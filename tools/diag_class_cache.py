@@ -1,5 +1,9 @@
+#!/usr/bin/env python
+"""A/B of the streaming kernel's per-packet class cache (option `class_cache`): end-to-end
+host-buffer time and the resident streaming kernel, 1e7 packets."""
 import os, sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.join(os.path.dirname(HERE), 'tests'))
 import numpy as np, torch
 from common import workload
 from nexoclom_b200.engine import Engine
