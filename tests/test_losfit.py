@@ -120,6 +120,55 @@ def test_determine_source_rate_is_astropy_linear_lsq(use_weight, masking):
     assert np.allclose(me.radiance.values, model * f, rtol=1e-12)
 
 
+@pytest.mark.parametrize('tag, normalize', [('norm', True), ('raw', False)])
+def test_losresult_make_source_map_vs_reference_golden(monkeypatch, tag, normalize):
+    """tests/golden/losresult_source_map.npz: the UNMODIFIED reference
+    LOSResult.make_source_map (LOSResult.py:310-491) over two output files with different
+    speed ranges.  The per-file maps (K6 in the product) come from the oracle here, so the
+    host arithmetic of the port -- sums, the interp branch, observed-fraction correction,
+    flux normalisation, the reference's habits included -- is pinned on the CPU."""
+    import os
+    import types
+    from common import GOLDEN
+    from nexoclom_b200 import make_source_map as msm_mod
+    from nexoclom_b200.LOSResult import LOSResult
+    from nexoclom_b200.units import Quantity
+    from oracle import source_map as osm
+    g = np.load(os.path.join(GOLDEN, 'losresult_source_map.npz'))
+    keep = ['longitude', 'latitude', 'v', 'altitude', 'azimuth', 'frac']
+    files = {f: {k: g[f + '_X0'][:, i] for i, k in enumerate(keep)} for f in ('f1', 'f2')}
+    params = {k[6:]: (float(g[k]) if k == 'param_smear_radius' else int(g[k]))
+              for k in g.files if k.startswith('param_')}
+    rp = float(g['radius_km'])
+
+    def arrays(X0, R_planet_km, grid_params, todo, device=0):       # stands in for K6
+        return osm.make_source_map(X0, R_planet_km, grid_params, todo)
+    monkeypatch.setattr(msm_mod, 'source_map_arrays', arrays)
+    radius = Quantity(rp, 'km')
+    monkeypatch.setattr(msm_mod, 'Output', types.SimpleNamespace(
+        restore=lambda fname: types.SimpleNamespace(X0=files[fname], inputs=types.SimpleNamespace(
+            geometry=types.SimpleNamespace(planet=types.SimpleNamespace(radius=radius))))))
+    me = types.SimpleNamespace(
+        modelfiles={'f1': 'm1', 'f2': 'm2'}, sourcerate=Quantity(float(g['sourcerate_1e23']), ''),
+        _device=0, inputs=types.SimpleNamespace(geometry=types.SimpleNamespace(
+            planet=types.SimpleNamespace(radius=Quantity(rp, 'km')))))
+    src, avail = LOSResult.make_source_map(me, params, normalize=normalize)
+    checked = 0
+    for which, m in (('source', src), ('available', avail)):
+        for key in ('abundance', 'abundance_uncor', 'longitude', 'latitude', 'speed',
+                    'speed_dist', 'altitude', 'altitude_dist', 'azimuth', 'azimuth_dist',
+                    'n_included', 'n_total', 'fraction_observed', 'speed_dist_map',
+                    'altitude_dist_map', 'azimuth_dist_map'):
+            ref = g[f'{tag}_{which}_{key}']
+            got = np.asarray(getattr(m, key), dtype=float)
+            assert got.shape == ref.shape, key
+            assert np.array_equal(np.isnan(got), np.isnan(ref)), key
+            ok = ~np.isnan(ref)
+            assert np.allclose(got[ok], ref[ok], rtol=1e-10, atol=0), (which, key)
+            checked += 1
+    assert checked == 32 and np.nansum(g[f'{tag}_source_abundance']) > 0
+
+
 def test_use_selected_vs_reference_golden():
     """`use_selected=True` of the unmodified reference method on a constant-step-like output
     (several rows per packet, its own generator seeded): same rows kept, same re-weighted

@@ -15,7 +15,9 @@ reference code (build container only; needs /root/reference):
         planet truncation, foot-point shadow test and the used / included sets;
   tests/golden/losfit.npz                reference LOSResultFitted.determine_source_from_data()
         (LOSResultFitted.py:66-262) on the packets / lines of sight / used sets of los.npz
-        (run `los` first), for use_weight in (None, 'dist', 'dist2', 'sigma').
+        (run `los` first), for use_weight in (None, 'dist', 'dist2', 'sigma');
+  tests/golden/losresult_source_map.npz  reference LOSResult.make_source_map()
+        (LOSResult.py:310-491) over two output files, normalised and raw.
 
 astropy / periodictable / sqlalchemy are absent here: tools/refunits.py supplies a
 functional miniature of astropy.units, the g-value tables come from this repo's host
@@ -507,6 +509,51 @@ def golden_source_map():
     print('source_map.npz')
 
 
+def golden_losresult_source_map():
+    """reference LOSResult.make_source_map (LOSResult.py:310-491), unmodified, summing the
+    reference's own make_source_map() of two output files with different speed ranges
+    (the np.interp branch) and converting to fluxes with astropy-style units."""
+    from nexoclom.data_simulation import LOSResult as lr
+    from nexoclom.data_simulation import make_source_map as msm
+    from nexoclom_b200 import Input
+    from nexoclom_b200.runsetup import RunSetup
+    from oracle import initial_state
+    ns = types.SimpleNamespace
+    cols = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac', 'v', 'longitude', 'latitude',
+            'local_time', 'altitude', 'azimuth']
+    keep = ['longitude', 'latitude', 'v', 'altitude', 'azimuth', 'frac']
+    files, out = {}, {}
+    setup = RunSetup(Input(os.path.join(GOLD, 'source_cases', 'maxw_band.input')))
+    for name, seed, n in (('f1', 17, 20000), ('f2', 23, 12000)):
+        X0 = pd.DataFrame(initial_state.draw_x0(setup, n, seed), columns=cols)
+        rng = np.random.default_rng(seed)
+        X0['frac'] = rng.random(n) * (rng.random(n) > 0.3)
+        if name == 'f2':
+            X0['v'] *= 0.8                  # smaller speed range -> the np.interp branch (:361-369)
+        X0 = X0.astype(np.float32).astype(np.float64)
+        files[name] = ns(X0=X0, inputs=ns(geometry=ns(planet=ns(radius=q(setup.radius_km, u.km)))))
+        out[f'{name}_X0'] = X0[keep].values
+    msm.Output = ns(restore=lambda fname: files[fname])
+    lr.SourceMap = lambda d: ns(**d)
+    params = {'smear_radius': np.radians(12.), 'nlonbins': 24, 'nlatbins': 12, 'nvelbins': 15,
+              'nazbins': 8, 'naltbins': 6}
+    for k, v in params.items():
+        out['param_' + k] = v
+    out['radius_km'] = setup.radius_km
+    out['sourcerate_1e23'] = 2.5
+    rate_unit = u.def_unit('10**23 atoms/s', 1e23 / u.s)
+    for tag, normalize in (('norm', True), ('raw', False)):
+        self = ns(modelfiles={'f1': 'm1', 'f2': 'm2'}, sourcerate=q(2.5, rate_unit),
+                  inputs=ns(geometry=ns(planet=ns(radius=q(setup.radius_km, u.km)))))
+        src, avail = lr.LOSResult.make_source_map(self, params, normalize=normalize)
+        for which, m in (('source', src), ('available', avail)):
+            for key, val in vars(m).items():
+                out[f'{tag}_{which}_{key}'] = np.asarray(val, dtype=np.float64)
+        print(tag, 'abundance sum', float(np.asarray(src.abundance).sum()))
+    np.savez_compressed(os.path.join(GOLD, 'losresult_source_map.npz'), **out)
+    print('losresult_source_map.npz')
+
+
 if __name__ == '__main__':
     install()
     which = sys.argv[1:] or ['source', 'image', 'los', 'map']
@@ -520,3 +567,5 @@ if __name__ == '__main__':
         golden_los()
     if 'losfit' in which:
         golden_losfit()
+    if 'losmap' in which:
+        golden_losresult_source_map()

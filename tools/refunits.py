@@ -117,7 +117,13 @@ class Quantity(np.ndarray):
         v = np.asarray(self)
         return float(v) if v.ndim == 0 else v
 
+    def __getitem__(self, key):
+        r = super().__getitem__(key)
+        return r if isinstance(r, Quantity) else Quantity(r, self.unit)
+
     def to(self, unit):
+        if isinstance(unit, Quantity):               # astropy: 1 / u.s is a unit
+            unit = Unit(float(np.asarray(unit)) * unit.unit.scale, unit.unit.dims)
         return Quantity(np.asarray(self) * (self.unit.scale / unit.scale), unit) \
             if self.unit._same_dims(unit) else self.unit.to(unit)
 
@@ -129,7 +135,10 @@ class Quantity(np.ndarray):
         name = ufunc.__name__
         if method != '__call__':
             res = getattr(ufunc, method)(*raw, **kwargs)
-            return Quantity(res, _unit_of(inputs[0])) if isinstance(res, np.ndarray) else res
+            if isinstance(res, np.ndarray) or (method == 'reduce' and name in
+                                               ('add', 'maximum', 'minimum')):
+                return Quantity(res, _unit_of(inputs[0]))
+            return res
         if name in ('add', 'subtract', 'maximum', 'minimum', 'remainder', 'fmod', 'less',
                     'less_equal', 'greater', 'greater_equal', 'equal', 'not_equal'):
             ua = _unit_of(inputs[0])
