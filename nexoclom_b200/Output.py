@@ -20,6 +20,14 @@ from .runsetup import RunSetup
 from .units import Quantity, def_unit
 
 
+class RadPres:
+    """Radiation-pressure table the reference attaches as ``output.radpres``
+    (velocity [R_p/s], accel [R_p/s^2]; reference Output.py:113-121).  Module level: saved
+    Outputs are pickles."""
+    velocity = None
+    accel = None
+
+
 class Output:
     def __init__(self, inputs, npackets, compress=True, run_model=True, seed=None,
                  X0=None, device=0, strict_math=False, keep_trajectory=None):
@@ -47,7 +55,7 @@ class Output:
             self.loss_info = setup.loss_info
             self.radpres = None
             if inputs.forces.radpres:
-                self.radpres = type('RadPres', (), {})()
+                self.radpres = RadPres()
                 self.radpres.velocity = setup.radpres_v
                 self.radpres.accel = setup.radpres_a
             if setup.surfaceint is not None:

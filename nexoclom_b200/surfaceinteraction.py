@@ -59,20 +59,28 @@ def sputdist(velocity, U_eV, alpha, beta, species):
     return f_v
 
 
+class TemperatureDependentSticking:
+    """stickcoef(lon, lat) = clip(A0 exp(A1 T_surf) + A2, 0, 1) (reference
+    SurfaceInteraction.py:15-20).  A class rather than the reference's closure so that an
+    Output carrying it can be pickled."""
+
+    def __init__(self, geometry, A):
+        self.geometry = geometry
+        self.A = A
+
+    def __call__(self, lon, lat):
+        tsurf = surface_temperature(self.geometry, lon, lat)
+        coef = self.A[0] * np.exp(self.A[1] * tsurf) + self.A[2]
+        coef[coef > 1.] = 1.
+        coef[coef < 0.] = 0.
+        return coef
+
+
 class SurfaceInteraction:
     def __init__(self, inputs, **kwargs):
         sint = inputs.surfaceinteraction
         if sint.sticktype == 'temperature dependent':
-            A = sint.A
-
-            def stickcoef(lon, lat):
-                tsurf = surface_temperature(inputs.geometry, lon, lat)
-                coef = A[0] * np.exp(A[1] * tsurf) + A[2]
-                coef[coef > 1.] = 1.
-                coef[coef < 0.] = 0.
-                return coef
-
-            self.stickcoef = stickcoef
+            self.stickcoef = TemperatureDependentSticking(inputs.geometry, sint.A)
         elif sint.sticktype == 'surface map':
             assert 0
 
