@@ -45,14 +45,20 @@ def vec_rel(a, b):
 
 
 def state_parity(X_gpu, X_ref):
-    """Relative differences (position vector, velocity vector, frac) over packets
-    alive in both; X_* are (N,8).  Returns dict of maxima and mismatch counts."""
+    """Relative differences between two (N,8) packet tables.  `pos` / `vel` (vector norms)
+    and `time` cover EVERY packet whose alive flag agrees -- the dead ones too: their last
+    position decides a pixel of `packet_image` when compress=False -- `frac` the packets
+    alive in both (it is exactly 0 for the dead).  Returns maxima and mismatch counts."""
     alive_g, alive_r = X_gpu[:, 7] > 0, X_ref[:, 7] > 0
     both = alive_g & alive_r
-    out = dict(alive_mismatch=int((alive_g != alive_r).sum()), n_both=int(both.sum()))
+    same = alive_g == alive_r
+    out = dict(alive_mismatch=int((~same).sum()), n_both=int(both.sum()),
+               n_dead_both=int((same & ~alive_g).sum()))
+    if same.any():
+        out['pos'] = float(vec_rel(X_gpu[same, 1:4], X_ref[same, 1:4]).max())
+        out['vel'] = float(vec_rel(X_gpu[same, 4:7], X_ref[same, 4:7]).max())
+        out['time'] = float(np.abs(X_gpu[same, 0] - X_ref[same, 0]).max())
+        out['frac'] = 0.0
     if both.any():
-        out['pos'] = float(vec_rel(X_gpu[both, 1:4], X_ref[both, 1:4]).max())
-        out['vel'] = float(vec_rel(X_gpu[both, 4:7], X_ref[both, 4:7]).max())
         out['frac'] = float((np.abs(X_gpu[both, 7] - X_ref[both, 7]) / X_ref[both, 7]).max())
-        out['time'] = float(np.abs(X_gpu[both, 0] - X_ref[both, 0]).max())
     return out

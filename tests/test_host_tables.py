@@ -97,3 +97,54 @@ def test_xyz_from_lonlat_known_answers():
     z_ = np.array([0, s2, 1, s2, 0])
     assert xyz == approx(np.array([np.array([0, s2, 1., s2, 0]) * z_,
                                    np.array([-1, -s2, 0., s2, 1]) * z_, z]) * 2., abs=1e-15)
+
+
+# ---------------------------------------------------------------------------
+# host tables pinned to outputs of the UNMODIFIED reference builders
+# (tools/make_golden_tables.py -> tests/golden/host_tables.npz)
+# ---------------------------------------------------------------------------
+@pytest.fixture(scope='module')
+def tables_gold():
+    return np.load(os.path.join(GOLDEN, 'host_tables.npz'))
+
+
+@pytest.mark.parametrize('tag, wl, taa', [('tdep314', 'Na.bounce.input', None),
+                                           ('tdep130', 'Na.bounce.input', 1.3),
+                                           ('c05', 'Na.bounce.stick05.input', None)])
+def test_surface_interaction_table_vs_reference(tables_gold, tag, wl, taa):
+    """probgrid / accommodation spline / sticking closure of the port are bit-identical to
+    what the reference's SurfaceInteraction.__init__ (SurfaceInteraction.py:10-61) built."""
+    from common import workload
+    from nexoclom_b200.surfaceinteraction import SurfaceInteraction
+    from nexoclom_b200.units import Quantity
+    g = tables_gold
+    inputs = workload(wl)
+    if taa is not None:
+        inputs.geometry.taa = Quantity(float(taa), 'rad')
+    si = SurfaceInteraction(inputs)
+    assert np.array_equal(si.probgrid, g[f'{tag}_probgrid'])
+    assert np.array_equal(si.temperature, g[f'{tag}_temperature'])
+    assert np.array_equal(si.probability, g[f'{tag}_probability'])
+    v = si.v_interp(g[f'{tag}_sample_T'], g[f'{tag}_sample_P'])
+    assert np.array_equal(v, g[f'{tag}_v_interp'])
+    if f'{tag}_stickcoef' in g.files:
+        assert np.array_equal(si.stickcoef(g[f'{tag}_lon'], g[f'{tag}_lat']),
+                              g[f'{tag}_stickcoef'])
+    else:
+        assert not hasattr(si, 'stickcoef')
+
+
+def test_planet_dist_vs_reference(tables_gold):
+    """(r, v_r) of the port == the reference's planet_dist (planet_dist.py:29-74) at the
+    workloads' true anomalies 0 / 1.3 / 3.14 and on a sweep; vrplanet shifts every
+    radiation-pressure and g-value lookup, so this is bit-exact, not approximate."""
+    g = tables_gold
+    for planet, key in (('Mercury', 'mercury'), ('Jupiter', 'jupiter'), ('Mars', 'mars')):
+        got = np.array([[float(q.value) for q in planet_dist(planet, float(t))]
+                        for t in g[f'{key}_taa']])
+        assert np.array_equal(got, g[f'{key}_r_vr']), planet
+    for name in ('Mercury', 'Jupiter', 'Io'):
+        o = SSObject(name)
+        got = np.array([o.radius.value, o.mass.value, o.a.value, o.e, o.orbperiod.value,
+                        o.GM.value])
+        assert got == approx(g[f'ss_{name.lower()}'], rel=1e-15), name

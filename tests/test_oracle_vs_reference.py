@@ -65,3 +65,28 @@ def test_constant_driver_bounce_bit_exact(ref):
                                   gen.random(len(idx))))
     got = fo.X[COLS].values.reshape(len(x0), nsteps, 8).transpose(0, 2, 1)
     assert np.array_equal(got, traj)
+
+
+def test_host_tables_live_vs_reference():
+    """The port's SurfaceInteraction table and planet_dist against the reference classes
+    executed here (tools/reftables.py), beyond the committed sample points."""
+    import reftables
+    from nexoclom_b200.solarsystem import planet_dist
+    from nexoclom_b200.surfaceinteraction import SurfaceInteraction
+    try:
+        inputs = workload('Na.bounce.input')
+        inputs.geometry.taa = Quantity(0.7, 'rad')
+        theirs = reftables.surface_interaction(inputs)
+        mine = SurfaceInteraction(inputs)
+        assert np.array_equal(mine.probgrid, np.asarray(theirs.probgrid))
+        rng = np.random.default_rng(5)
+        T = rng.uniform(100., float(np.max(mine.temperature)), 500)
+        P = rng.random(500)
+        assert np.array_equal(mine.v_interp(T, P), theirs.v_interp(T, P))
+        lon, lat = rng.random(500) * 2 * np.pi, np.arcsin(rng.random(500) * 2 - 1)
+        assert np.array_equal(mine.stickcoef(lon, lat), theirs.stickcoef(lon, lat))
+        for taa in rng.random(20) * 2 * np.pi:
+            r, v = planet_dist('Mercury', float(taa))
+            assert (float(r.value), float(v.value)) == reftables.planet_dist('Mercury', taa)
+    finally:
+        reftables.purge()

@@ -29,7 +29,7 @@ COLS = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac']
 GOLD = os.path.join(REPO, 'tests', 'golden')
 
 
-def fake_from_setup(setup, seed=0):
+def fake_from_setup(setup, seed=0, ref_surfaceint=None):
     p = setup.params
     sint = setup.inputs.surfaceinteraction
     fo = refimport.fake_output(
@@ -43,11 +43,26 @@ def fake_from_setup(setup, seed=0):
         taa=float(np.asarray(setup.inputs.geometry.taa)), planet_radius_km=p.planet_radius_km,
         seed=seed)
     if setup.surfaceint is not None:
-        fo.surfaceint = setup.surfaceint
+        # the accommodation table / sticking closure of the REFERENCE's own
+        # SurfaceInteraction.__init__ when the caller built one (reference_surfaceint),
+        # else this repo's port (bit-identical: tests/test_host_tables.py)
+        fo.surfaceint = ref_surfaceint if ref_surfaceint is not None else setup.surfaceint
     return fo
 
 
+def reference_surfaceints():
+    """{workload: reference SurfaceInteraction} built by the unmodified reference class
+    (tools/reftables.py) BEFORE the lighter refimport stubs are installed."""
+    import reftables
+    out = {}
+    for wl in ('Na.bounce.input', 'Na.bounce.stick05.input'):
+        out[wl] = reftables.surface_interaction(workload(wl))
+    reftables.purge()
+    return out
+
+
 def main():
+    surfaceints = reference_surfaceints()
     ref = refimport.install()
     os.makedirs(GOLD, exist_ok=True)
 
@@ -100,7 +115,7 @@ def main():
             inputs.options.endtime = type(inputs.options.endtime)(3000., 's')
         setup = RunSetup(inputs)
         seed = 31
-        fo = fake_from_setup(setup, seed=seed)
+        fo = fake_from_setup(setup, seed=seed, ref_surfaceint=surfaceints.get(wl))
         x0 = initial_state.draw_x0(setup, n, 9)[:, :8]
         fo.X0 = pd.DataFrame(x0.copy(), columns=COLS)
         fo.npackets = n
