@@ -28,12 +28,17 @@ extern "C" {
 #endif
 
 typedef struct nx_ctx nx_ctx;
+typedef struct nx_packets nx_packets;   /* a compacted packet table resident on the GPU   */
+typedef struct nx_comm nx_comm;         /* the ranks of one sharded run (NCCL communicator) */
 
 /* invariant bits (positive return values / nx_status) */
 #define NX_INV_BAD_ERRMAX 4   /* non-finite errmax        (Output.py:284)      */
 #define NX_INV_NEG_FRAC   8   /* accepted negative frac   (Output.py:287-288)  */
 #define NX_INV_BAD_STEP   16  /* non-finite step size     (Output.py:337-339)  */
 #define NX_INV_BAD_STATE  32  /* non-finite packet state  (Output.py:388-389)  */
+#define NX_INV_STARVED    64  /* host-buffer path: a segment never arrived (20 s watchdog) */
+#define NX_INV_NO_PROGRESS 128 /* adaptive driver: a packet used 2^22 attempted steps; the
+                                 reference's loop (Output.py:248-353) would never end   */
 
 /* packet-state columns (Output.py:247, :370) */
 enum { NX_COL_TIME = 0, NX_COL_X, NX_COL_Y, NX_COL_Z, NX_COL_VX, NX_COL_VY, NX_COL_VZ,
@@ -74,7 +79,7 @@ typedef struct nx_run_params {
 } nx_run_params;
 
 /* Initial-state distributions (source_distribution.py:37-283). */
-enum { NX_SPATIAL_UNIFORM = 0, NX_SPATIAL_MAP = 1 };
+enum { NX_SPATIAL_UNIFORM = 0, NX_SPATIAL_MAP = 1, NX_SPATIAL_LON1D = 2 };
 enum { NX_SPEED_FLAT = 0, NX_SPEED_GAUSSIAN = 1, NX_SPEED_TABLE = 2 };
 enum { NX_ANGULAR_RADIAL = 0, NX_ANGULAR_ISOTROPIC = 1, NX_ANGULAR_2D = 2 };
 typedef struct nx_source_params {
@@ -162,8 +167,25 @@ int nx_state_device_ptr(nx_ctx* ctx, int column, void** dev_ptr);
 int nx_sourcemap_upload(nx_ctx* ctx, const double* fmap, int nx, int ny,
                         const double* xaxis, const double* yaxis);
 int nx_speedtable_upload(nx_ctx* ctx, const double* cdf, const double* v, int n);
+/* inverse CDF of a longitude-only source map (source_distribution.py:72-76 ->
+ * random_deviates_1d, randomdeviates.py:29-33): spatial_type NX_SPATIAL_LON1D           */
+int nx_lontable_upload(nx_ctx* ctx, const double* cdf, const double* lon, int n);
+/* Draws n packets with global ids [first_id, first_id + n) into the context's X0 columns
+ * (112 B per packet).  The packets' current state IS X0[0:8] until an integrator has run;
+ * nx_export_state / nx_state_device_ptr / K4 / K5 materialise a copy on demand.          */
 int nx_init_state(nx_ctx* ctx, const nx_source_params* sp, uint64_t seed,
                   uint64_t first_id, long long n);
+/* Import mode for reference-generated DEVIATES: the same deviate -> state transform as
+ * nx_init_state (source_distribution.py:47-62, 137-283) on caller-supplied host columns of
+ * length n.  lon_in / lat_in: surface points sampled elsewhere (map rejection sampling), or
+ * both NULL for the uniform band drawn from u_sinlat / u_lon; unused deviates may be NULL. */
+int nx_init_state_deviates(nx_ctx* ctx, const nx_source_params* sp, long long n,
+                           const double* u_time, const double* u_sinlat, const double* u_lon,
+                           const double* lon_in, const double* lat_in, const double* u_speed,
+                           const double* z_normal, const double* u_alt, const double* u_az);
+/* Make the resident initial state (X0[0:8], from nx_init_state or the host-buffer path) the
+ * packets' current state again, without copying: the next integrator call re-runs it.      */
+int nx_rewind_state(nx_ctx* ctx);
 
 /* ---- K2: adaptive driver (Output.py:221-366 + rk5.py + state.py) ------------- */
 int nx_integrate_adaptive(nx_ctx* ctx, long long n,
@@ -188,6 +210,16 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
 int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
                           const nx_image_params* img, void* image_dev, void* counts_dev,
                           double* traj_host, unsigned long long* packet_steps);
+
+/* Row-table variant: every row of the reference's results[N, 8, nsteps] tensor (Output.py:
+ * 376-449) that Output.save would keep (frac > 0 when skip_dead; float32-rounded when
+ * round_f32) is appended to a NEW resident packet table (index = packet number within the
+ * launch, step = step number; row order is unspecified).  ModelImage / LOSResult then run K4
+ * / K5 over the bound table -- any Output of a constant-step run, at any size, without the
+ * dense tensor ever existing (compute_iteration.py:118-222 works on these rows).           */
+int nx_integrate_constant_rows(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
+                               int skip_dead, int round_f32, nx_packets** out, long long* nrows,
+                               unsigned long long* packet_steps);
 
 /* ---- K4: image (ModelImage.create_image + packet_weighting + Histogram2d) ---- */
 int nx_image_accumulate(nx_ctx* ctx, long long n, const nx_image_params* ip,
@@ -238,6 +270,44 @@ int nx_source_map(nx_ctx* ctx, long long n, const nx_source_map_params* p,
                   double* azimuth_dist, long long* n_included, long long* n_total,
                   double* abundance, double* speed_map, double* altitude_map,
                   double* azimuth_map);
+
+/* ---- resident packet tables: Output.save on the device (Output.py:522-543) ------
+ * nx_compact_state copies the current state of the first n packets into a new table:
+ * rows with frac == 0 dropped when skip_dead (compress=True, :526-527; the f64 value is
+ * tested, as the reference does before its down-cast), every column rounded to float32 when
+ * round_f32 (:528-543; kept as f64 bit patterns so K4 / K5 read what Output.restore would
+ * hand them), original packet index kept; row order is the packet order.  The table stays
+ * on the GPU until nx_packets_free; nx_packets_bind makes K4 / K5 / nx_export_state read it
+ * instead of the context's slab (NULL: back to the slab; integrators unbind).
+ * nx_packets_export writes the columns time,x,y,z,vx,vy,vz,frac as float32 (entries of
+ * cols[8] may be NULL) and the indices as int32 -- the only packet bytes that cross PCIe
+ * when a run is saved.  nx_packets_upload is the inverse (a restored Output file).          */
+int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_packets** out,
+                     long long* count);
+int nx_packets_upload(nx_ctx* ctx, long long n, const double* const* cols /* 8 */,
+                      const uint32_t* index, nx_packets** out);
+int nx_packets_bind(nx_ctx* ctx, nx_packets* table);
+int nx_packets_count(nx_ctx* ctx, nx_packets* table, long long* count);
+int nx_packets_export(nx_ctx* ctx, nx_packets* table, float* const* cols /* 8 */, int32_t* index,
+                      uint16_t* step /* constant-step row tables; may be NULL */);
+int nx_packets_free(nx_ctx* ctx, nx_packets* table);
+
+/* ---- multi-GPU: one all-reduce (sum) per product (the reference has no
+ * collective: Input.py:243-249 loops chunks serially).  Packets are sharded by global id
+ * (first_id of nx_init_state / nx_integrate_constant), per-rank images and LOS columns are
+ * summed in place.  Rank 0 calls nx_comm_unique_id and hands the 128 bytes to the other ranks
+ * (file, socket, MPI, torch.distributed store ...); every rank then calls nx_comm_create.
+ * NCCL (libnccl.so.2) is loaded on first use.                                                */
+#define NX_COMM_ID_BYTES 128
+#define NX_DTYPE_F64 0
+#define NX_DTYPE_I64 1
+int nx_comm_unique_id(void* out128);
+int nx_comm_create(int device, const void* unique_id128, int rank, int world, nx_comm** out);
+int nx_allreduce(nx_comm* comm, void* dev_buffer, long long count, int dtype, void* cuda_stream);
+int nx_allreduce_host(nx_comm* comm, void* host_buffer, long long count, int dtype);
+int nx_comm_rank(nx_comm* comm, int* rank, int* world);
+int nx_comm_destroy(nx_comm* comm);
+const char* nx_comm_last_error(void);
 
 /* ---- measurement --------------------------------------------------------------- */
 int nx_last_kernel_ms(nx_ctx* ctx, float* ms);          /* CUDA-event time of last K* */

@@ -123,6 +123,9 @@ def load():
         'nx_sourcemap_upload': [vp, c_double_p, C.c_int, C.c_int, c_double_p, c_double_p],
         'nx_speedtable_upload': [vp, c_double_p, c_double_p, C.c_int],
         'nx_init_state': [vp, C.POINTER(SourceParams), u64, u64, i64],
+        'nx_lontable_upload': [vp, c_double_p, c_double_p, C.c_int],
+        'nx_init_state_deviates': [vp, C.POINTER(SourceParams), i64] + [c_double_p] * 9,
+        'nx_rewind_state': [vp],
         'nx_integrate_adaptive': [vp, i64, C.POINTER(u64), C.POINTER(u64)],
         'nx_integrate_adaptive_host': [vp, i64, C.POINTER(c_double_p), C.c_int, C.POINTER(u64),
                                        C.POINTER(u64)],
@@ -138,6 +141,22 @@ def load():
         'nx_source_map': [vp, i64, C.POINTER(SourceMapParams)] + [c_double_p] * 9 +
                          [c_double_p] * 4 + [c_i64_p] * 2 + [c_double_p] * 4,
         'nx_state_device_ptr': [vp, C.c_int, C.POINTER(vp)],
+        'nx_compact_state': [vp, i64, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(i64)],
+        'nx_packets_upload': [vp, i64, C.POINTER(c_double_p), c_u32_p, C.POINTER(vp)],
+        'nx_packets_bind': [vp, vp],
+        'nx_packets_count': [vp, vp, C.POINTER(i64)],
+        'nx_packets_export': [vp, vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int32),
+                              C.POINTER(C.c_uint16)],
+        'nx_integrate_constant_rows': [vp, i64, u64, u64, C.c_int, C.c_int, C.POINTER(vp),
+                                       C.POINTER(i64), C.POINTER(u64)],
+        'nx_packets_free': [vp, vp],
+        'nx_comm_unique_id': [vp],
+        'nx_comm_create': [C.c_int, vp, C.c_int, C.c_int, C.POINTER(vp)],
+        'nx_allreduce': [vp, vp, i64, C.c_int, vp],
+        'nx_allreduce_host': [vp, vp, i64, C.c_int],
+        'nx_comm_rank': [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        'nx_comm_destroy': [vp],
+        'nx_comm_last_error': [],
         'nx_last_kernel_ms': [vp, C.POINTER(C.c_float)],
         'nx_kernel_launches': [vp, C.POINTER(u64)],
         'nx_measure_fp64_peak': [vp, C.POINTER(C.c_double)],
@@ -146,7 +165,8 @@ def load():
     for name, args in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = args
-        fn.restype = C.c_char_p if name == 'nx_last_error' else C.c_int
+        fn.restype = (C.c_char_p if name in ('nx_last_error', 'nx_comm_last_error')
+                      else C.c_int)
     _lib = lib
     return lib
 

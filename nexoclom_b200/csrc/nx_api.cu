@@ -30,6 +30,19 @@ struct DevInterp {
   FastTable fast{};
 };
 
+// A compacted packet table that stays on the GPU (device-side Output.save, nx_compact.cu)
+struct nx_packets {
+  long long n = 0, cap = 0;          // rows, column stride (multiple of 32)
+  double* cols = nullptr;            // 8 columns time..frac
+  unsigned* index = nullptr;         // original packet index of every row
+  unsigned short* step = nullptr;    // constant-step rows: step number (else nullptr)
+};
+static void free_packets(nx_packets* h) {
+  if (!h) return;
+  cudaFree(h->cols); cudaFree(h->index); cudaFree(h->step);
+  delete h;
+}
+
 struct nx_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -43,6 +56,7 @@ struct nx_ctx {
   bool have_params = false;
   DevInterp radpres;
   DevInterp speed;
+  DevInterp lon1d;             // inverse CDF of a longitude-only source map
   DevInterp gtab[NX_MAX_GTABLES];
   GTables gtables{};
   double *spl_tx = nullptr, *spl_ty = nullptr, *spl_c = nullptr;
@@ -53,6 +67,13 @@ struct nx_ctx {
   long long cap = 0;           // column stride (multiple of 32)
   double* state = nullptr;     // 9 columns
   double* x0 = nullptr;        // 14 columns
+  // K1 writes the X0 slab only; until an integrator (or materialize()) has filled the state
+  // slab, the packets' current state IS columns 0-7 of X0 (`fresh`).
+  bool fresh = false;
+  bool x0_valid = false;
+  nx_packets* bound = nullptr; // K4 / K5 / K6 inputs come from this table instead of the slab
+  unsigned* cmp_tiles = nullptr;     // compaction scratch (tile counts)
+  long long cmp_tiles_cap = 0;       // X0 columns 0-7 hold an initial state (K1 or the host-buffer path)
   unsigned *att = nullptr, *acc = nullptr;
   unsigned* perm = nullptr;          // longest-first processing order
   unsigned char* cost = nullptr;     // cost bucket per packet
@@ -64,6 +85,7 @@ struct nx_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[2] = {};
   int los_mode = 0;                  // 0 auto, 1 brute force, 2 cell grid
+  int image_mode = 0;                // K4: 0 auto, 1 global atomics only, 2 privatised counts
   int class_cache = 1;               // streaming schedule: remember each packet's cost class
   int los_order = 1;                 // process lines of sight in Morton order of closest approach
   cudaStream_t pipe[16] = {};                  // H2D / compute pipeline of the host-buffer path
@@ -162,13 +184,44 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
 
 static StateCols state_cols(nx_ctx* ctx) {
   StateCols P;
+  if (ctx->bound) {
+    for (int k = 0; k < 8; ++k) P.c[k] = ctx->bound->cols + (size_t)k * ctx->bound->cap;
+    P.c[8] = nullptr;
+    return P;
+  }
   for (int k = 0; k < 9; ++k) P.c[k] = ctx->state + (size_t)k * ctx->cap;
   return P;
 }
+// rows the product kernels (K4 / K5) may read
+static long long resident_rows(nx_ctx* ctx) { return ctx->bound ? ctx->bound->n : ctx->cap; }
 static X0Cols x0_cols(nx_ctx* ctx) {
   X0Cols X;
   for (int k = 0; k < 14; ++k) X.c[k] = ctx->x0 + (size_t)k * ctx->cap;
   return X;
+}
+
+// columns the packets' CURRENT state is read from
+static StateCols in_cols(nx_ctx* ctx) {
+  StateCols P = state_cols(ctx);
+  if (ctx->fresh && !ctx->bound)
+    for (int k = 0; k < 8; ++k) P.c[k] = ctx->x0 + (size_t)k * ctx->cap;
+  return P;
+}
+// make the state slab hold the current state (consumers that are not integrators)
+static int materialize(nx_ctx* ctx) {
+  if (!ctx->fresh || ctx->bound) return 0;
+  StateCols P = state_cols(ctx);
+  for (int k = 0; k < 8; ++k) {
+    cudaError_t e = cudaMemcpyAsync(P.c[k], ctx->x0 + (size_t)k * ctx->cap,
+                                    (size_t)ctx->cap * sizeof(double), cudaMemcpyDeviceToDevice,
+                                    ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return -(int)e; }
+  }
+  cudaError_t e = launch_fill(ctx->stream, P.c[8], ctx->cap, 1000.0);     // Output.py:246
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return -(int)e; }
+  ctx->launches += 1;
+  ctx->fresh = false;
+  return 0;
 }
 
 static int begin_timed(nx_ctx* ctx) { CK(cudaEventRecord(ctx->ev0, ctx->stream)); return 0; }
@@ -219,6 +272,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_interp(ctx->radpres);
   free_interp(ctx->speed);
+  free_interp(ctx->lon1d);
   for (auto& g : ctx->gtab) free_interp(g);
   cudaFree(ctx->spl_tx); cudaFree(ctx->spl_ty); cudaFree(ctx->spl_c);
   cudaFree(ctx->srcmap);
@@ -228,7 +282,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   for (auto& s : ctx->pipe) if (s) cudaStreamDestroy(s);
   for (auto& e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
   cudaFree(ctx->pipe_scalars); cudaFree(ctx->pipe_hist);
-  cudaFree(ctx->scalars); cudaFree(ctx->status);
+  cudaFree(ctx->scalars); cudaFree(ctx->status); cudaFree(ctx->cmp_tiles);
   cudaFree(ctx->squeue); cudaFreeHost(ctx->seq_host);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
@@ -257,6 +311,7 @@ int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   if (name && std::strcmp(name, "order_packets") == 0) { ctx->order_packets = value; return 0; }
   if (name && std::strcmp(name, "schedule") == 0) { ctx->schedule = value; return 0; }
   if (name && std::strcmp(name, "los_mode") == 0) { ctx->los_mode = value; return 0; }
+  if (name && std::strcmp(name, "image_mode") == 0) { ctx->image_mode = value; return 0; }
   if (name && std::strcmp(name, "los_order") == 0) { ctx->los_order = value; return 0; }
   if (name && std::strcmp(name, "class_cache") == 0) { ctx->class_cache = value; return 0; }
   if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G_fixed = value; ctx->losw.cap = 0; return 0; }
@@ -410,12 +465,14 @@ int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* 
 
 int nx_packets_resize(nx_ctx* ctx, long long n) {
   CK(cudaSetDevice(ctx->device));
+  ctx->bound = nullptr;
   if (n <= ctx->cap && ctx->state) return 0;
   const long long cap = ((std::max(n, 1LL) + 31) / 32) * 32;
   cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
   cudaFree(ctx->perm); cudaFree(ctx->cost);
   ctx->state = ctx->x0 = nullptr; ctx->att = ctx->acc = nullptr; ctx->cap = 0;
   ctx->perm = nullptr; ctx->cost = nullptr;
+  ctx->fresh = ctx->x0_valid = false;
   if (n >= (1LL << 32)) { ctx->err = "more than 2^32 packets per GPU"; return -1; }
   CK(cudaMalloc(&ctx->state, (size_t)9 * cap * sizeof(double)));
   CK(cudaMalloc(&ctx->x0, (size_t)14 * cap * sizeof(double)));
@@ -433,6 +490,8 @@ int nx_packets_resize(nx_ctx* ctx, long long n) {
 int nx_import_state(nx_ctx* ctx, long long n, const double* const* cols) {
   int r = nx_packets_resize(ctx, n);
   if (r) return r;
+  ctx->fresh = false;
+  ctx->x0_valid = false;
   StateCols P = state_cols(ctx);
   for (int k = 0; k < 8; ++k)
     CK(cudaMemcpyAsync(P.c[k], cols[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice,
@@ -446,8 +505,8 @@ int nx_import_state(nx_ctx* ctx, long long n, const double* const* cols) {
 
 int nx_export_state(nx_ctx* ctx, long long n, double* const* cols) {
   CK(cudaSetDevice(ctx->device));
-  if (n > ctx->cap) { ctx->err = "export: n exceeds resident packets"; return -1; }
-  StateCols P = state_cols(ctx);
+  if (n > resident_rows(ctx)) { ctx->err = "export: n exceeds resident packets"; return -1; }
+  StateCols P = in_cols(ctx);
   for (int k = 0; k < 8; ++k)
     CK(cudaMemcpyAsync(cols[k], P.c[k], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost,
                        ctx->stream));
@@ -478,6 +537,7 @@ int nx_export_stats(nx_ctx* ctx, long long n, uint32_t* attempted, uint32_t* acc
 int nx_export_step(nx_ctx* ctx, long long n, double* step) {
   CK(cudaSetDevice(ctx->device));
   if (n > ctx->cap) { ctx->err = "export: n exceeds resident packets"; return -1; }
+  { int r = materialize(ctx); if (r) return r; }
   CK(cudaMemcpyAsync(step, state_cols(ctx).c[8], (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -485,6 +545,7 @@ int nx_export_step(nx_ctx* ctx, long long n, double* step) {
 
 int nx_state_device_ptr(nx_ctx* ctx, int column, void** dev_ptr) {
   if (column < 0 || column >= 9 || !ctx->state) { ctx->err = "bad column / no packets"; return -1; }
+  { int r = materialize(ctx); if (r) return r; }
   *dev_ptr = state_cols(ctx).c[column];
   return 0;
 }
@@ -507,6 +568,11 @@ int nx_speedtable_upload(nx_ctx* ctx, const double* cdf, const double* v, int n)
   return upload_interp(ctx, ctx->speed, cdf, v, n, false);
 }
 
+int nx_lontable_upload(nx_ctx* ctx, const double* cdf, const double* lon, int n) {
+  CK(cudaSetDevice(ctx->device));
+  return upload_interp(ctx, ctx->lon1d, cdf, lon, n, false);
+}
+
 int nx_init_state(nx_ctx* ctx, const nx_source_params* sp_, uint64_t seed, uint64_t first_id,
                   long long n) {
   int r = nx_packets_resize(ctx, n);
@@ -514,12 +580,55 @@ int nx_init_state(nx_ctx* ctx, const nx_source_params* sp_, uint64_t seed, uint6
   SourceParams sp;
   std::memcpy(&sp, sp_, sizeof(sp));
   if (sp.spatial_type == SPATIAL_MAP && !ctx->srcmap) { ctx->err = "no source map uploaded"; return -1; }
+  if (sp.spatial_type == SPATIAL_LON1D && ctx->lon1d.view.n == 0) { ctx->err = "no longitude table uploaded"; return -1; }
   if (sp.speed_type == SPEED_TABLE && ctx->speed.view.n == 0) { ctx->err = "no speed table uploaded"; return -1; }
   if (n == 0) return 0;
   if ((r = begin_timed(ctx))) return r;
-  CK(launch_init_state(ctx->stream, state_cols(ctx), x0_cols(ctx), n, sp, ctx->map,
-                       ctx->speed.view, seed, first_id));
+  CK(launch_init_state(ctx->stream, x0_cols(ctx), n, sp, ctx->map, ctx->speed.view,
+                       ctx->lon1d.view, seed, first_id));
+  ctx->fresh = ctx->x0_valid = true;
   return end_timed(ctx, 1);
+}
+
+int nx_init_state_deviates(nx_ctx* ctx, const nx_source_params* sp_, long long n,
+                           const double* u_time, const double* u_sinlat, const double* u_lon,
+                           const double* lon_in, const double* lat_in, const double* u_speed,
+                           const double* z_normal, const double* u_alt, const double* u_az) {
+  int r = nx_packets_resize(ctx, n);
+  if (r) return r;
+  SourceParams sp;
+  std::memcpy(&sp, sp_, sizeof(sp));
+  if (sp.speed_type == SPEED_TABLE && ctx->speed.view.n == 0) { ctx->err = "no speed table uploaded"; return -1; }
+  if ((lon_in == nullptr) != (lat_in == nullptr)) { ctx->err = "lon_in and lat_in go together"; return -1; }
+  if (sp.spatial_type == SPATIAL_LON1D && !lon_in && ctx->lon1d.view.n == 0) { ctx->err = "no longitude table uploaded"; return -1; }
+  if (n == 0) return 0;
+  const double* host[9] = {u_time, u_sinlat, u_lon, lon_in, lat_in, u_speed, z_normal, u_alt, u_az};
+  double* slab = nullptr;
+  CK(cudaMalloc(&slab, (size_t)9 * n * sizeof(double)));
+  const double* dev[9];
+  cudaError_t e = cudaMemsetAsync(slab, 0, (size_t)9 * n * sizeof(double), ctx->stream);
+  for (int k = 0; k < 9 && e == cudaSuccess; ++k) {
+    dev[k] = host[k] ? slab + (size_t)k * n : nullptr;
+    if (k != 3 && k != 4) dev[k] = slab + (size_t)k * n;        // absent deviates read as 0
+    if (host[k])
+      e = cudaMemcpyAsync(slab + (size_t)k * n, host[k], (size_t)n * sizeof(double),
+                          cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess)
+    e = launch_init_from_deviates(ctx->stream, x0_cols(ctx), n, sp, ctx->speed.view,
+                                  ctx->lon1d.view, dev);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(slab);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return -(int)e; }
+  ctx->launches += 1;
+  ctx->fresh = ctx->x0_valid = true;
+  return 0;
+}
+
+int nx_rewind_state(nx_ctx* ctx) {
+  if (!ctx->x0_valid) { ctx->err = "no initial state resident (nx_init_state first)"; return -1; }
+  ctx->fresh = true;
+  return 0;
 }
 
 static int check_status(nx_ctx* ctx) {
@@ -538,6 +647,7 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
                           unsigned long long* accepted) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->have_params) { ctx->err = "nx_tables_upload not called"; return -1; }
+  ctx->bound = nullptr;            // integrators work on the slab
   if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
   if (!(ctx->params.sticktype == STICK_CONSTANT && ctx->params.stickcoef == 1.0)) {
     ctx->err = "Not set up";      // reference Output.py:315 (adaptive needs stickcoef == 1)
@@ -548,6 +658,10 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
   if (n > 0) {
     CK(debug_begin(ctx->stream));
     if ((r = begin_timed(ctx))) return r;
+    if (ctx->schedule == 2 && !ctx->x0_valid) {
+      ctx->err = "schedule 2 reads the X0 slab: nx_init_state first";
+      return -1;
+    }
     if (ctx->schedule == 2) {
       // developer option (profiling the streaming kernel with kernel replay, which cannot
       // run the concurrent copies): class-ordered passes over the X0 slab, nothing in flight
@@ -568,14 +682,16 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
     } else {
       const bool order = ctx->order_packets && n >= 4096;
       if (order)
-        CK(launch_cost_order(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
+        CK(launch_cost_order(ctx->stream, ctx->device, in_cols(ctx), n, ctx->params,
                              ctx->order_packets, ctx->cost, ctx->hist, ctx->perm));
-      CK(launch_integrate_adaptive(ctx->stream, ctx->device, state_cols(ctx), n, ctx->params,
+      CK(launch_integrate_adaptive(ctx->stream, ctx->device, in_cols(ctx), state_cols(ctx), n,
+                                   ctx->params,
                                    ctx->radpres.view, ctx->radpres.fast,
                                    order ? ctx->perm : nullptr, ctx->scalars, ctx->scalars + 1,
                                    ctx->att, ctx->acc, ctx->status));
       if ((r = end_timed(ctx, order ? 4 : 1))) return r;
     }
+    ctx->fresh = false;
   }
   unsigned long long h[3] = {0, 0, 0};
   CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
@@ -644,6 +760,8 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
     CK(cudaEventRecord(ctx->copy_ev[1], ctx->copy_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[1], 0));
     if ((r = end_timed(ctx, 2))) return r;
+    ctx->fresh = false;
+    ctx->x0_valid = true;
     unsigned long long h[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
     r = check_status(ctx);
@@ -665,6 +783,7 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
   CK(cudaEventRecord(ctx->pipe_ev[16], ctx->stream));
   for (int s = 0; s < nchunks; ++s) CK(cudaStreamWaitEvent(ctx->pipe[s], ctx->pipe_ev[16], 0));
   StateCols P = state_cols(ctx);
+  ctx->fresh = ctx->x0_valid = false;
   int nlaunch = 0;
   for (int c = 0; c < nchunks; ++c) {
     const long long first = n * c / nchunks, count = n * (c + 1) / nchunks - first;
@@ -681,7 +800,7 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
       CK(launch_cost_order(st, ctx->device, Pc, count, ctx->params, ctx->order_packets,
                            ctx->cost + first, ctx->pipe_hist + 64 * c, ctx->perm + first));
     unsigned long long* sc = ctx->pipe_scalars + 4 * c;
-    CK(launch_integrate_adaptive(st, ctx->device, Pc, count, ctx->params, ctx->radpres.view,
+    CK(launch_integrate_adaptive(st, ctx->device, Pc, Pc, count, ctx->params, ctx->radpres.view,
                                  ctx->radpres.fast, order ? ctx->perm + first : nullptr, sc, sc + 1,
                                  ctx->att + first, ctx->acc + first, ctx->status));
     nlaunch += order ? 5 : 2;
@@ -703,11 +822,13 @@ int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* co
   return r;
 }
 
-int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
-                          const nx_image_params* img, void* image_dev, void* counts_dev,
-                          double* traj_host, unsigned long long* packet_steps) {
+static int integrate_constant_core(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
+                                   const nx_image_params* img, void* image_dev, void* counts_dev,
+                                   double* traj_host, const RowSink& rows,
+                                   unsigned long long* packet_steps) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->have_params) { ctx->err = "nx_tables_upload not called"; return -1; }
+  ctx->bound = nullptr;            // integrators work on the slab
   if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
   const RunParams& p = ctx->params;
   if (!(p.step_size > 0.0)) { ctx->err = "constant driver needs step_size > 0"; return -1; }
@@ -728,36 +849,109 @@ int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t firs
   const size_t traj_bytes = (size_t)n * 8 * nsteps * sizeof(double);
   if (traj_host) {
     CK(cudaMalloc(&traj, traj_bytes));
-    CK(cudaMemsetAsync(traj, 0, traj_bytes, ctx->stream));
+    cudaError_t e = cudaMemsetAsync(traj, 0, traj_bytes, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(traj); ctx->err = cudaGetErrorString(e); return -(int)e; }
   }
-  CK(cudaMemsetAsync(ctx->scalars, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  auto fail = [&](cudaError_t e) {
+    cudaFree(traj);
+    ctx->err = cudaGetErrorString(e);
+    return -(int)e;
+  };
+  cudaError_t e = cudaMemsetAsync(ctx->scalars, 0, 8 * sizeof(unsigned long long), ctx->stream);
+  if (e != cudaSuccess) return fail(e);
   int r;
   if (n > 0) {
-    if ((r = begin_timed(ctx))) return r;
-    CK(launch_integrate_constant(ctx->stream, ctx->device, state_cols(ctx), n, p,
-                                 ctx->radpres.view, ctx->radpres.fast, ctx->spline, seed,
-                                 first_id, nsteps, ip,
-                                 ctx->gtables, (double*)image_dev,
-                                 (unsigned long long*)counts_dev, traj, ctx->scalars,
-                                 ctx->scalars + 1, ctx->status));
-    if ((r = end_timed(ctx, 1))) return r;
+    if ((r = begin_timed(ctx))) { cudaFree(traj); return r; }
+    e = launch_integrate_constant(ctx->stream, ctx->device, in_cols(ctx), state_cols(ctx), n, p,
+                                  ctx->radpres.view, ctx->radpres.fast, ctx->spline, seed,
+                                  first_id, nsteps, ip, ctx->gtables, (double*)image_dev,
+                                  (unsigned long long*)counts_dev, traj, rows, ctx->scalars,
+                                  ctx->scalars + 1, ctx->status);
+    if (e != cudaSuccess) return fail(e);
+    if ((r = end_timed(ctx, 1))) { cudaFree(traj); return r; }
+    ctx->fresh = false;
   }
   unsigned long long h[2] = {0, 0};
-  CK(cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  if (traj_host) {
-    CK(cudaMemcpyAsync(traj_host, traj, traj_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  }
+  e = cudaMemcpyAsync(h, ctx->scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && traj_host)
+    e = cudaMemcpyAsync(traj_host, traj, traj_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e != cudaSuccess) return fail(e);
   r = check_status(ctx);
-  if (traj) cudaFree(traj);
+  cudaFree(traj);
   if (r < 0) return r;
   if (packet_steps) *packet_steps = h[1];
+  return r;
+}
+
+int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
+                          const nx_image_params* img, void* image_dev, void* counts_dev,
+                          double* traj_host, unsigned long long* packet_steps) {
+  return integrate_constant_core(ctx, n, seed, first_id, img, image_dev, counts_dev, traj_host,
+                                 RowSink{}, packet_steps);
+}
+
+int nx_integrate_constant_rows(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
+                               int skip_dead, int round_f32, nx_packets** out, long long* nrows,
+                               unsigned long long* packet_steps) {
+  CK(cudaSetDevice(ctx->device));
+  if (!out) { ctx->err = "nx_integrate_constant_rows: null output"; return -1; }
+  *out = nullptr;
+  if (!ctx->have_params || !(ctx->params.step_size > 0.0)) {
+    ctx->err = "constant driver needs nx_tables_upload with step_size > 0";
+    return -1;
+  }
+  const int nsteps = (int)std::ceil(ctx->params.endtime / ctx->params.step_size + 1);
+  if (nsteps > 65535) { ctx->err = "more than 65535 steps per packet"; return -1; }
+  unsigned long long* cursor = ctx->scalars + 5;
+  RowSink rows{};
+  rows.cursor = cursor;
+  rows.skip_dead = skip_dead; rows.to_f32 = round_f32;
+  unsigned long long need = (unsigned long long)n * (unsigned long long)nsteps;
+  int r;
+  if (ctx->fresh && ctx->x0_valid) {
+    // the initial state is immutable (X0 slab): count the rows first, allocate exactly
+    r = integrate_constant_core(ctx, n, seed, first_id, nullptr, nullptr, nullptr, nullptr, rows,
+                                nullptr);
+    if (r < 0) return r;
+    CK(cudaMemcpyAsync(&need, cursor, sizeof(need), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->fresh = true;               // rewind: second pass over the same packets
+  }
+  nx_packets* h = new nx_packets();
+  h->cap = (((long long)std::max<unsigned long long>(need, 1ull) + 31) / 32) * 32;
+  cudaError_t e = cudaMalloc(&h->cols, (size_t)8 * h->cap * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->index, (size_t)h->cap * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&h->step, (size_t)h->cap * sizeof(unsigned short));
+  if (e != cudaSuccess) {
+    ctx->err = std::string("row table allocation (") + std::to_string(need) + " rows): " + cudaGetErrorString(e);
+    free_packets(h);
+    return -(int)e;
+  }
+  rows.cols = h->cols; rows.index = h->index; rows.step = h->step;
+  rows.cap = (unsigned long long)h->cap; rows.stride = (size_t)h->cap;
+  unsigned long long steps = 0;
+  r = integrate_constant_core(ctx, n, seed, first_id, nullptr, nullptr, nullptr, nullptr, rows,
+                              &steps);
+  if (r < 0) { free_packets(h); return r; }
+  unsigned long long got = 0;
+  e = cudaMemcpyAsync(&got, cursor, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess || got > (unsigned long long)h->cap) {
+    ctx->err = e != cudaSuccess ? cudaGetErrorString(e) : "row table overflow";
+    free_packets(h);
+    return e != cudaSuccess ? -(int)e : -1;
+  }
+  h->n = (long long)got;
+  *out = h;
+  if (nrows) *nrows = h->n;
+  if (packet_steps) *packet_steps = steps;
   return r;
 }
 
 int nx_image_accumulate_dev(nx_ctx* ctx, long long n, const nx_image_params* ip_, void* image_dev,
                             void* counts_dev) {
   CK(cudaSetDevice(ctx->device));
-  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
   ImageParams ip;
   std::memcpy(&ip, ip_, sizeof(ip));
   if (ip.quantity == 1 && ctx->gtables.n == 0) {
@@ -766,9 +960,11 @@ int nx_image_accumulate_dev(nx_ctx* ctx, long long n, const nx_image_params* ip_
   }
   if (n == 0) return 0;
   int r;
+  if ((r = materialize(ctx))) return r;
   if ((r = begin_timed(ctx))) return r;
   CK(launch_image_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, ip, ctx->gtables,
-                             (double*)image_dev, (unsigned long long*)counts_dev));
+                             (double*)image_dev, (unsigned long long*)counts_dev,
+                             ctx->image_mode));
   return end_timed(ctx, 1);
 }
 
@@ -879,6 +1075,7 @@ static std::vector<unsigned> los_order(const double* los, long long nlos) {
 static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_host,
                    const double* los_dev, const double* dist_dev, const LosParams& lp,
                    double* rad_dev, unsigned long long* np_dev, unsigned char* inc_dev) {
+  { int r0 = materialize(ctx); if (r0) return r0; }
   std::vector<int> nball;
   std::vector<double> ladder, wid2;
   LosConsts lc;
@@ -932,7 +1129,7 @@ int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_de
                           const nx_los_params* lp_, void* radiance_dev, void* npackets_dev,
                           void* included_dev) {
   CK(cudaSetDevice(ctx->device));
-  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
   LosParams lp;
   std::memcpy(&lp, lp_, sizeof(lp));
   if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }   // compute_iteration.py:213
@@ -950,7 +1147,7 @@ int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* lo
                       const double* dist_from_plan, const nx_los_params* lp_, double* radiance,
                       long long* npackets, uint8_t* included) {
   CK(cudaSetDevice(ctx->device));
-  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
   LosParams lp;
   std::memcpy(&lp, lp_, sizeof(lp));
   if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }
@@ -986,7 +1183,7 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
                 const double* dist_from_plan, const nx_los_params* lp_, const long long* used_offsets,
                 long long* used_count, uint32_t* used_indices) {
   CK(cudaSetDevice(ctx->device));
-  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
   LosParams lp;
   std::memcpy(&lp, lp_, sizeof(lp));
   if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }
@@ -994,6 +1191,7 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
   if (nlos <= 0) return 0;
   if (n <= 0) { for (long long i = 0; i < nlos; ++i) used_count[i] = 0; return 0; }
   if (n >= (1LL << 32)) { ctx->err = "more than 2^32 packets per GPU"; return -1; }
+  { int r0 = materialize(ctx); if (r0) return r0; }
   std::vector<int> nball;
   std::vector<double> ladder, wid2;
   LosConsts lc;
@@ -1043,6 +1241,124 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
   cudaFree(d_los); cudaFree(d_dist); cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2);
   cudaFree(d_nused); cudaFree(d_cursor); cudaFree(d_off); cudaFree(d_idx);
   return r;
+}
+
+// ---- resident packet tables (device-side Output.save, Output.py:522-543) -----------------
+int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_packets** out,
+                     long long* count) {
+  CK(cudaSetDevice(ctx->device));
+  if (!out) { ctx->err = "nx_compact_state: null output"; return -1; }
+  *out = nullptr;
+  ctx->bound = nullptr;
+  if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
+  nx_packets* h = new nx_packets();
+  if (n > 0) {
+    const long long nt = compact_tiles(n);
+    if (nt + 2 > ctx->cmp_tiles_cap) {
+      cudaFree(ctx->cmp_tiles);
+      ctx->cmp_tiles = nullptr; ctx->cmp_tiles_cap = 0;
+      CK(cudaMalloc(&ctx->cmp_tiles, (size_t)(nt + 2) * sizeof(unsigned)));
+      ctx->cmp_tiles_cap = nt + 2;
+    }
+    StateCols P = in_cols(ctx);
+    int r;
+    if ((r = begin_timed(ctx))) { delete h; return r; }
+    cudaError_t e = launch_compact_count(ctx->stream, P.c[7], n, skip_dead, ctx->cmp_tiles,
+                                         ctx->scalars + 4);
+    unsigned long long total = 0;
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(&total, ctx->scalars + 4, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && total > 0) {
+      h->n = (long long)total;
+      h->cap = ((h->n + 31) / 32) * 32;
+      e = cudaMalloc(&h->cols, (size_t)8 * h->cap * sizeof(double));
+      if (e == cudaSuccess) e = cudaMalloc(&h->index, (size_t)h->cap * sizeof(unsigned));
+      if (e == cudaSuccess)
+        e = launch_compact_scatter(ctx->stream, P, n, skip_dead, round_f32, ctx->cmp_tiles,
+                                   h->cols, (size_t)h->cap, h->index);
+    }
+    if (e != cudaSuccess) {
+      ctx->err = std::string("nx_compact_state: ") + cudaGetErrorString(e);
+      free_packets(h);
+      return -(int)e;
+    }
+    if ((r = end_timed(ctx, total > 0 ? 3 : 2))) { free_packets(h); return r; }
+  }
+  *out = h;
+  if (count) *count = h->n;
+  return 0;
+}
+
+int nx_packets_upload(nx_ctx* ctx, long long n, const double* const* cols, const uint32_t* index,
+                      nx_packets** out) {
+  CK(cudaSetDevice(ctx->device));
+  if (!out) { ctx->err = "nx_packets_upload: null output"; return -1; }
+  nx_packets* h = new nx_packets();
+  h->n = n;
+  h->cap = ((std::max(n, 1LL) + 31) / 32) * 32;
+  cudaError_t e = cudaMalloc(&h->cols, (size_t)8 * h->cap * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->index, (size_t)h->cap * sizeof(unsigned));
+  for (int k = 0; k < 8 && e == cudaSuccess && n > 0; ++k)
+    e = cudaMemcpyAsync(h->cols + (size_t)k * h->cap, cols[k], (size_t)n * sizeof(double),
+                        cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && n > 0 && index)
+    e = cudaMemcpyAsync(h->index, index, (size_t)n * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->err = std::string("nx_packets_upload: ") + cudaGetErrorString(e);
+    free_packets(h);
+    return -(int)e;
+  }
+  *out = h;
+  return 0;
+}
+
+int nx_packets_bind(nx_ctx* ctx, nx_packets* h) {
+  ctx->bound = h;
+  return 0;
+}
+
+int nx_packets_count(nx_ctx* ctx, nx_packets* h, long long* count) {
+  if (!h) { ctx->err = "null packet table"; return -1; }
+  if (count) *count = h->n;
+  return 0;
+}
+
+int nx_packets_export(nx_ctx* ctx, nx_packets* h, float* const* cols, int32_t* index,
+                      uint16_t* step) {
+  CK(cudaSetDevice(ctx->device));
+  if (!h) { ctx->err = "null packet table"; return -1; }
+  if (h->n == 0) return 0;
+  float* tmp = nullptr;
+  CK(cudaMalloc(&tmp, (size_t)8 * h->n * sizeof(float)));
+  cudaError_t e = launch_to_f32(ctx->stream, h->cols, (size_t)h->cap, h->n, 8, tmp);
+  for (int k = 0; k < 8 && e == cudaSuccess; ++k)
+    if (cols[k])
+      e = cudaMemcpyAsync(cols[k], tmp + (size_t)k * h->n, (size_t)h->n * sizeof(float),
+                          cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && index)
+    e = cudaMemcpyAsync(index, h->index, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && step) {
+    if (h->step)
+      e = cudaMemcpyAsync(step, h->step, (size_t)h->n * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
+    else
+      std::memset(step, 0, (size_t)h->n * sizeof(uint16_t));
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  ctx->launches += 1;
+  if (e != cudaSuccess) { ctx->err = std::string("nx_packets_export: ") + cudaGetErrorString(e); return -(int)e; }
+  return 0;
+}
+
+int nx_packets_free(nx_ctx* ctx, nx_packets* h) {
+  if (!h) return 0;
+  cudaSetDevice(ctx->device);
+  if (ctx->bound == h) ctx->bound = nullptr;
+  cudaStreamSynchronize(ctx->stream);
+  free_packets(h);
+  return 0;
 }
 
 int nx_last_kernel_ms(nx_ctx* ctx, float* ms) {

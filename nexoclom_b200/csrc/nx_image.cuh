@@ -124,7 +124,7 @@ NX_HD int image_packet(const ImageParams& ip, const GTables& G, double step_x, d
 // instead of the two divisions (<= 2 ulp from the form above; the gate is 1e-6).
 NX_HD int image_packet_fast(const ImageParams& ip, const GTables& G, const ImageSteps& t,
                             double x, double y, double z, double vy, double frac,
-                            double& weight) {
+                            double& weight, int* ix_out = nullptr, int* iz_out = nullptr) {
   if (ip.round_f32) { x = round_f32(x); y = round_f32(y); z = round_f32(z);
                       vy = round_f32(vy); frac = round_f32(frac); }
   const double xo = fma(ip.M[2], z, fma(ip.M[1], y, ip.M[0] * x));
@@ -141,6 +141,7 @@ NX_HD int image_packet_fast(const ImageParams& ip, const GTables& G, const Image
   const int ix = hist_bin_fast(xo, ip.nx, ip.x0, ip.x1, t.step_x, t.inv_step_x);
   const int iz = hist_bin_fast(zo, ip.nz, ip.z0, ip.z1, t.step_z, t.inv_step_z);
   if (ix < 0 || iz < 0) return -1;
+  if (ix_out) { *ix_out = ix; *iz_out = iz; }
   return ix * ip.nz + iz;
 }
 

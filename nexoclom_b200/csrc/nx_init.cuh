@@ -9,7 +9,7 @@
 
 namespace nx {
 
-enum SpatialType { SPATIAL_UNIFORM = 0, SPATIAL_MAP = 1 };
+enum SpatialType { SPATIAL_UNIFORM = 0, SPATIAL_MAP = 1, SPATIAL_LON1D = 2 };
 enum SpeedType { SPEED_FLAT = 0, SPEED_GAUSSIAN = 1, SPEED_TABLE = 2 };
 enum AngularType { ANGULAR_RADIAL = 0, ANGULAR_ISOTROPIC = 1, ANGULAR_2D = 2 };
 
@@ -134,8 +134,11 @@ NX_HD void init_packet_finish(const SourceParams& sp, const InterpTable& speed, 
 
 // Fills x0[NCOL_X0] = time,x,y,z,vx,vy,vz,frac,v,longitude,latitude,local_time,
 // altitude,azimuth for packet `id`.
+// lon1d: inverse CDF of a longitude-only source map (source_distribution.py:72-76 ->
+// random_deviates_1d, randomdeviates.py:29-33); latitude is 0 for those maps.
 NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const InterpTable& speed,
-                       uint64_t seed, uint64_t id, double* x0) {
+                       uint64_t seed, uint64_t id, double* x0,
+                       const InterpTable& lon1d = InterpTable{}) {
   double u_time, u_sinlat, u_lon, u_speed, u_alt, u_az;
   uniform_pair(seed, id, STREAM_INIT, 0, u_time, u_sinlat);
   uniform_pair(seed, id, STREAM_INIT, 1, u_lon, u_speed);
@@ -145,6 +148,9 @@ NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const Inter
   double lon, lat;
   if (sp.spatial_type == SPATIAL_UNIFORM) {
     uniform_lonlat(sp, u_sinlat, u_lon, lon, lat);
+  } else if (sp.spatial_type == SPATIAL_LON1D) {
+    lon = interp(lon1d, u_lon);
+    lat = 0.0;
   } else {
     // acceptance / rejection on the map (randomdeviates.py:61-72)
     uint32_t draw = 4;

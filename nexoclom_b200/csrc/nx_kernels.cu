@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+
 #include "nx_fast.cuh"
 #include "nx_image.cuh"
 #include "nx_init.cuh"
@@ -94,18 +96,58 @@ size_t table_smem_bytes(const InterpTable& g) {
 // ---------------------------------------------------------------------------
 // K1: initial state
 // ---------------------------------------------------------------------------
+// Only the 14 X0 columns are written (112 B per packet, the algorithmic minimum): the
+// integrators read their input straight from the first eight of them and write the final
+// state to the state slab, so the initial state is never stored twice.  A lane computes one
+// packet; lanes 2j / 2j+1 then swap halves with one shuffle per column pair so that every
+// store is a 16-byte STG of two consecutive packets (even lanes: columns 0,2,..,12, odd
+// lanes: columns 1,3,..,13; 16 lanes x 16 B = one full 256-byte row segment per column).
 __global__ void __launch_bounds__(256)
-k_init_state(StateCols P, X0Cols X, long long n, SourceParams sp, SourceMap map,
-             InterpTable speed, uint64_t seed, uint64_t first_id) {
+k_init_state(X0Cols X, long long n, SourceParams sp, SourceMap map, InterpTable speed,
+             InterpTable lon1d, uint64_t seed, uint64_t first_id) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ic = i < n ? i : n - 1;            // whole warps run the shuffles
+  const unsigned lane = threadIdx.x & 31u;
+  double x0[14];
+  init_packet(sp, map, speed, seed, first_id + (uint64_t)ic, x0, lon1d);
+  const bool odd = lane & 1u;
+  const long long pair0 = i & ~1LL;                  // first packet of this lane pair
+  const bool full = pair0 + 1 < n;                   // both packets of the pair exist
+#pragma unroll
+  for (int k = 0; k < 14; k += 2) {
+    const double mine = odd ? x0[k] : x0[k + 1];
+    const double other = __shfl_xor_sync(FULL_MASK, mine, 1);
+    if (full) {
+      if (!odd) __stcs(reinterpret_cast<double2*>(X.c[k] + pair0), make_double2(x0[k], other));
+      else __stcs(reinterpret_cast<double2*>(X.c[k + 1] + pair0), make_double2(other, x0[k + 1]));
+    } else if (i < n) {                              // last packet of an odd n
+      X.c[k][i] = x0[k]; X.c[k + 1][i] = x0[k + 1];
+    }
+  }
+}
+
+// The pure deviate -> state transform of K1 on caller-supplied deviates (import mode for
+// reference-generated draws; the parity tests replay the reference's recorded deviates
+// through this entry on the device).  lon_in / lat_in: surface points sampled elsewhere
+// (rejection sampling on a map), or null for the uniform band.
+__global__ void __launch_bounds__(256)
+k_init_from_deviates(X0Cols X, long long n, SourceParams sp, InterpTable speed,
+                     InterpTable lon1d, const double* __restrict__ u_time, const double* __restrict__ u_sinlat,
+                     const double* __restrict__ u_lon, const double* __restrict__ lon_in,
+                     const double* __restrict__ lat_in, const double* __restrict__ u_speed,
+                     const double* __restrict__ z_normal, const double* __restrict__ u_alt,
+                     const double* __restrict__ u_az) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  double lon, lat;
+  if (lon_in) { lon = lon_in[i]; lat = lat_in[i]; }
+  else if (sp.spatial_type == SPATIAL_LON1D) { lon = interp(lon1d, u_lon[i]); lat = 0.0; }
+  else uniform_lonlat(sp, u_sinlat[i], u_lon[i], lon, lat);
   double x0[14];
-  init_packet(sp, map, speed, seed, first_id + (uint64_t)i, x0);
+  init_packet_finish(sp, speed, u_time[i], lon, lat, u_speed[i], z_normal[i], u_alt[i], u_az[i],
+                     x0);
 #pragma unroll
   for (int k = 0; k < 14; ++k) X.c[k][i] = x0[k];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) P.c[k][i] = x0[k];
-  P.c[8][i] = 1000.0;            // initial step size (Output.py:246)
 }
 
 __global__ void k_fill(double* p, long long n, double v) {
@@ -131,6 +173,13 @@ __global__ void k_fill(double* p, long long n, double v) {
 #define NX_FEED_COLS 8     // time,x,y,z,vx,vy,vz,frac; the step size starts at 1000 s (Output.py:246)
 #define NX_FEED_BYTES_PER_WARP (2 * (NX_FEED_COLS * 32 * 8 + 32 * 4))
 #define NX_INVALID 0xffffffffu
+// The reference's adaptive loop never ends for a packet that makes no progress (errmax == 0
+// on every attempt: no forces, no loss, v = 0 -- Output.py:294-300 rejects the step and grows
+// it forever).  On the GPU that would be a kernel that cannot be interrupted, so a packet is
+// retired as it is after this many attempted steps and status bit NX_INV_NO_PROGRESS is set
+// (the longest packet of the 1e7-packet Na run needs 5 434).
+#define NX_ATTEMPT_CAP (1u << 22)
+#define NX_ST_NO_PROGRESS 128
 #define NX_INITIAL_STEP 1000.0        // every packet starts with a 1000 s step (Output.py:246)
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
@@ -210,8 +259,8 @@ struct PacketFeeder {
 //       MODE = GR*8 + RP*4 + LOSS.
 template <int MODE>
 __global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
-k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, FastTable Fg,
-                     const unsigned* __restrict__ perm,
+k_integrate_adaptive(StateCols In, StateCols P, long long n, RunParams p, InterpTable Tg,
+                     FastTable Fg, const unsigned* __restrict__ perm,
                      unsigned long long* __restrict__ queue,
                      unsigned long long* __restrict__ totals,
                      unsigned* __restrict__ att_out, unsigned* __restrict__ acc_out,
@@ -222,9 +271,13 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
   if (MODE < 0) stage_table(Tg, T, smem_raw);
   else stage_fast_table(Fg, F, smem_raw);
   PacketFeeder feed;
-  feed.init(smem_raw + table_bytes, &P, perm, queue, n);
+  feed.init(smem_raw + table_bytes, &In, perm, queue, n);
   __syncthreads();
 
+  // In: where the initial state is read (the X0 slab right after K1, else the state slab
+  // itself); P: where the final state goes.  Packets that need no integration are passed
+  // through when the two differ.
+  const bool pass_through = In.c[0] != P.c[0];
   const unsigned lane = threadIdx.x & 31u;
   bool have = false, drained = false;
   unsigned idx = 0;
@@ -251,7 +304,14 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
         idx = feed.ids[feed.buf * 32 + slot];
         att = 0; acc = 0;
         have = (s[0] > p.resolution) && (s[7] > 0.0);
-        if (!have) { att_out[idx] = 0; acc_out[idx] = 0; }
+        if (!have) {
+          att_out[idx] = 0; acc_out[idx] = 0;
+          if (pass_through) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
+            __stcs(P.c[8] + idx, step);
+          }
+        }
       }
       feed.pos += take;
       need = __ballot_sync(FULL_MASK, !have);
@@ -268,6 +328,7 @@ k_integrate_adaptive(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
       ++att;
       if (fl & ATT_ACCEPTED) ++acc;
       st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
+      if (att >= NX_ATTEMPT_CAP) { st |= NX_ST_NO_PROGRESS; fl &= ~ATT_LIVE; }
       if (!(fl & ATT_LIVE)) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
@@ -739,6 +800,7 @@ k_integrate_adaptive_stream(const double* __restrict__ col0, size_t stride, doub
       ++att;
       if (fl & ATT_ACCEPTED) ++acc;
       st |= fl & ~(ATT_ACCEPTED | ATT_LIVE);
+      if (att >= NX_ATTEMPT_CAP) { st |= NX_ST_NO_PROGRESS; fl &= ~ATT_LIVE; }
       if (!(fl & ATT_LIVE)) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
@@ -794,10 +856,10 @@ __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& 
 // MODE as in k_integrate_adaptive: -1 strict, else fast with MODE = GR*8 + RP*4 + LOSS.
 template <int MODE>
 __global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
-k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, FastTable Fg,
-                     Spline2D S, uint64_t seed, uint64_t first_id, int nsteps,
+k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, InterpTable Tg,
+                     FastTable Fg, Spline2D S, uint64_t seed, uint64_t first_id, int nsteps,
                      ImageParams ip, GTables G, double* image, unsigned long long* counts,
-                     double* traj,
+                     double* traj, RowSink rows,
                      unsigned long long* __restrict__ queue,
                      unsigned long long* __restrict__ totals, int* __restrict__ status,
                      unsigned table_bytes) {
@@ -807,8 +869,9 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
   if (MODE < 0) stage_table(Tg, T, smem_raw);
   else stage_fast_table(Fg, F, smem_raw);
   PacketFeeder feed;
-  feed.init(smem_raw + table_bytes, &P, nullptr, queue, n);
+  feed.init(smem_raw + table_bytes, &In, nullptr, queue, n);
   __syncthreads();
+  const bool pass_through = In.c[0] != P.c[0];     // see k_integrate_adaptive
   const unsigned lane = threadIdx.x & 31u;
   const ImageSteps isteps = image_steps(ip);
 
@@ -889,11 +952,40 @@ k_integrate_constant(StateCols P, long long n, RunParams p, InterpTable Tg, Fast
         for (int k = 0; k < 8; ++k) traj[((size_t)idx * 8 + k) * nsteps + ct] = s[k];
       }
       if (image) image_add(ip, G, isteps, s, image, counts);
+    }
+    if (rows.cursor) {
+      // Row sink: what the reference keeps of a constant-step run (Output.py:434-449 flattens
+      // results[N, 8, nsteps]; Output.save drops the frac == 0 rows and rounds to float32),
+      // appended to a device table with one warp-aggregated atomic per iteration
+      // (cap == 0: the rows are only counted).
+      const bool want = emit && (!rows.skip_dead || s[7] > 0.0);
+      const unsigned m = __ballot_sync(FULL_MASK, want);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(rows.cursor, (unsigned long long)__popc(m));
+        base = __shfl_sync(FULL_MASK, base, leader);
+        if (want) {
+          const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
+          if (o < rows.cap) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              double v = s[k];
+              if (rows.to_f32) v = (double)(float)v;
+              rows.cols[(size_t)k * rows.stride + o] = v;
+            }
+            rows.index[o] = idx;
+            rows.step[o] = (unsigned short)ct;
+          }
+        }
+      }
+    }
+    if (emit) {
       const bool fresh = (ct == 0);
       ++ct;
       if (!fresh) curtime -= p.step_size;
       if (!live || !(curtime > 0.0) || ct >= nsteps) {
-        if (!fresh) {                       // an unintegrated packet stays as it is
+        if (!fresh || pass_through) {       // an unintegrated packet stays as it is
 #pragma unroll
           for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
         }
@@ -976,6 +1068,81 @@ k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
     const long long q = n - 1;
     image_one(ip, G, isteps, P.c[1][q], P.c[2][q], P.c[3][q], P.c[5][q], P.c[7][q],
               image, counts);
+  }
+}
+
+// K4, privatised variant (north_star: "shared-memory-privatised histograms").  Shared-memory
+// atomics are native only for 32-bit operands on sm_100a (64-bit ones, f64 and u64 alike,
+// compile to ATOMS.CAST.SPIN loops), so what is privatised is the PACKET-COUNT histogram: one
+// 1024-thread block per SM keeps a u32 tile of counts for the pixel rectangle around the
+// projected planet -- where the packets of an exosphere run pile up -- in ~200 KB of shared
+// memory (ATOMS.POPC.INC.32), and only the f64 weight of a packet goes to the L2-resident
+// image as a RED.  That halves the global atomics per live packet; the tile is flushed with
+// one u64 RED per non-empty pixel at the end.  Pixels outside the tile take the global path.
+struct ImageTile { int ix0, iz0, w, h; };
+
+__global__ void __launch_bounds__(1024, 1)
+k_image_accumulate_tile(StateCols P, long long n, ImageParams ip, GTables Gg, ImageTile tile,
+                        double* __restrict__ image, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GTables G;
+  G.n = Gg.n;
+  size_t off = 0;
+#pragma unroll
+  for (int t = 0; t < NX_MAX_GTABLES; ++t)
+    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off); off += (size_t)Gg.f[t].nrec * 32; }
+  unsigned* __restrict__ tcnt = reinterpret_cast<unsigned*>(smem_raw + off);
+  const int tsize = tile.w * tile.h;
+  for (int i = threadIdx.x; i < tsize; i += blockDim.x) tcnt[i] = 0u;
+  __syncthreads();
+  const ImageSteps isteps = image_steps(ip);
+  const long long npair = n >> 1;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const double2* __restrict__ X2 = reinterpret_cast<const double2*>(P.c[1]);
+  const double2* __restrict__ Y2 = reinterpret_cast<const double2*>(P.c[2]);
+  const double2* __restrict__ Z2 = reinterpret_cast<const double2*>(P.c[3]);
+  const double2* __restrict__ V2 = reinterpret_cast<const double2*>(P.c[5]);
+  const double2* __restrict__ F2 = reinterpret_cast<const double2*>(P.c[7]);
+  auto one = [&](double x, double y, double z, double v, double f) {
+    if (ip.skip_dead && !(f > 0.0)) return;
+    double w;
+    int ix, iz;
+    const int pix = image_packet_fast(ip, G, isteps, x, y, z, v, f, w, &ix, &iz);
+    if (pix < 0) return;
+    if (w != 0.0) atomicAdd(&image[pix], w);
+    const unsigned tx = (unsigned)(ix - tile.ix0), tz = (unsigned)(iz - tile.iz0);
+    if (tx < (unsigned)tile.w && tz < (unsigned)tile.h) atomicAdd(&tcnt[tx * tile.h + tz], 1u);
+    else atomicAdd(&counts[pix], 1ull);
+  };
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double2 xa, ya, za, va, fa;
+  if (i < npair) {
+    xa = __ldcs(X2 + i); ya = __ldcs(Y2 + i); za = __ldcs(Z2 + i);
+    va = __ldcs(V2 + i); fa = __ldcs(F2 + i);
+  }
+  while (i < npair) {
+    const long long j = i + stride;
+    double2 xb = xa, yb = ya, zb = za, vb = va, fb = fa;
+    if (j < npair) {
+      xb = __ldcs(X2 + j); yb = __ldcs(Y2 + j); zb = __ldcs(Z2 + j);
+      vb = __ldcs(V2 + j); fb = __ldcs(F2 + j);
+    }
+    one(xa.x, ya.x, za.x, va.x, fa.x);
+    one(xa.y, ya.y, za.y, va.y, fa.y);
+    xa = xb; ya = yb; za = zb; va = vb; fa = fb;
+    i = j;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long q = n - 1;
+    one(P.c[1][q], P.c[2][q], P.c[3][q], P.c[5][q], P.c[7][q]);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < tsize; t += blockDim.x) {
+    const unsigned c = tcnt[t];
+    if (c) {
+      const int tx = t / tile.h, tz = t - tx * tile.h;
+      atomicAdd(&counts[(size_t)(tile.ix0 + tx) * ip.nz + (tile.iz0 + tz)], (unsigned long long)c);
+    }
   }
 }
 
@@ -1076,12 +1243,22 @@ static int sm_count(int device) {
   return v;
 }
 
-cudaError_t launch_init_state(cudaStream_t st, StateCols P, X0Cols X, long long n,
+cudaError_t launch_init_state(cudaStream_t st, X0Cols X, long long n,
                               const SourceParams& sp, const SourceMap& map,
-                              const InterpTable& speed, uint64_t seed, uint64_t first_id) {
+                              const InterpTable& speed, const InterpTable& lon1d, uint64_t seed,
+                              uint64_t first_id) {
   const int threads = 256;
   const long long blocks = (n + threads - 1) / threads;
-  k_init_state<<<(unsigned)blocks, threads, 0, st>>>(P, X, n, sp, map, speed, seed, first_id);
+  k_init_state<<<(unsigned)blocks, threads, 0, st>>>(X, n, sp, map, speed, lon1d, seed, first_id);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_init_from_deviates(cudaStream_t st, X0Cols X, long long n,
+                                      const SourceParams& sp, const InterpTable& speed,
+                                      const InterpTable& lon1d,
+                                      const double* const* dev /* 9 device columns */) {
+  k_init_from_deviates<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+      X, n, sp, speed, lon1d, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8]);
   return cudaGetLastError();
 }
 
@@ -1105,7 +1282,8 @@ static cudaError_t persistent_grid(K kernel, int device, size_t smem, int* block
 }
 
 template <int MODE>
-static cudaError_t launch_adaptive_mode(cudaStream_t st, int device, StateCols P, long long n,
+static cudaError_t launch_adaptive_mode(cudaStream_t st, int device, StateCols In, StateCols P,
+                                        long long n,
                                         const RunParams& p, const InterpTable& T,
                                         const FastTable& F,
                                         const unsigned* perm, unsigned long long* queue,
@@ -1118,7 +1296,7 @@ static cudaError_t launch_adaptive_mode(cudaStream_t st, int device, StateCols P
   if (e != cudaSuccess) return e;
   const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
   if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-  k_integrate_adaptive<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(P, n, p, T, F, perm, queue,
+  k_integrate_adaptive<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(In, P, n, p, T, F, perm, queue,
                                                                    totals, att, acc, status,
                                                                    (unsigned)tbytes);
   return cudaGetLastError();
@@ -1224,12 +1402,12 @@ cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long lon
   return cudaGetLastError();
 }
 
-cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
-                                      const RunParams& p, const InterpTable& T,
+cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols In, StateCols P,
+                                      long long n, const RunParams& p, const InterpTable& T,
                                       const FastTable& F, const unsigned* perm,
                                       unsigned long long* queue, unsigned long long* totals,
                                       unsigned* att, unsigned* acc, int* status) {
-#define NX_ARGS st, device, P, n, p, T, F, perm, queue, totals, att, acc, status
+#define NX_ARGS st, device, In, P, n, p, T, F, perm, queue, totals, att, acc, status
   if (p.strict_math || p.nmoons > 1 || (p.nmoons == 1 && !p.gravity))
     return launch_adaptive_mode<-1>(NX_ARGS);
   const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3) |
@@ -1259,12 +1437,14 @@ cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, 
 }
 
 template <int MODE>
-static cudaError_t launch_constant_mode(cudaStream_t st, int device, StateCols P, long long n,
+static cudaError_t launch_constant_mode(cudaStream_t st, int device, StateCols In, StateCols P,
+                                        long long n,
                                         const RunParams& p, const InterpTable& T,
                                         const FastTable& F, const Spline2D& S, uint64_t seed,
                                         uint64_t first_id, int nsteps, const ImageParams& ip,
                                         const GTables& G, double* image,
                                         unsigned long long* counts, double* traj,
+                                        const RowSink& rows,
                                         unsigned long long* queue, unsigned long long* totals,
                                         int* status) {
   const size_t tbytes = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
@@ -1275,21 +1455,22 @@ static cudaError_t launch_constant_mode(cudaStream_t st, int device, StateCols P
   const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
   if (need < blocks) blocks = (int)(need > 0 ? need : 1);
   k_integrate_constant<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(
-      P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, queue, totals, status,
-      (unsigned)tbytes);
+      In, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, rows, queue,
+      totals, status, (unsigned)tbytes);
   return cudaGetLastError();
 }
 
-cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,
-                                      const RunParams& p, const InterpTable& T,
+cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols In, StateCols P,
+                                      long long n, const RunParams& p, const InterpTable& T,
                                       const FastTable& F, const Spline2D& S, uint64_t seed,
                                       uint64_t first_id, int nsteps, const ImageParams& ip,
                                       const GTables& G, double* image,
                                       unsigned long long* counts, double* traj,
+                                      const RowSink& rows,
                                       unsigned long long* queue, unsigned long long* totals,
                                       int* status) {
-#define NX_ARGS st, device, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, \
-                queue, totals, status
+#define NX_ARGS st, device, In, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, \
+                traj, rows, queue, totals, status
   if (p.strict_math || p.nmoons > 0) return launch_constant_mode<-1>(NX_ARGS);
   const int mode = (p.gravity ? 8 : 0) | (p.radpres ? 4 : 0) | (p.loss_mode & 3);
   switch (mode) {
@@ -1312,9 +1493,37 @@ cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, 
 
 cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, long long n,
                                     const ImageParams& ip, const GTables& G, double* image,
-                                    unsigned long long* counts) {
+                                    unsigned long long* counts, int mode) {
   size_t smem = 0;
   for (int t = 0; t < G.n; ++t) smem += fast_table_smem_bytes(G.f[t]);
+  // privatised counts (mode 2; mode 0 = auto: when there are enough packets to amortise the
+  // tile flush): a square tile around the pixel of the projected planet centre
+  const bool tiled = mode == 2 || (mode == 0 && n >= (1LL << 22));
+  if (tiled) {
+    const size_t budget = 227 * 1024 - 1024 - smem;
+    int side = (int)std::sqrt((double)(budget / 4));
+    side &= ~7;
+    ImageTile tile;
+    tile.w = side < ip.nx ? side : ip.nx;
+    tile.h = side < ip.nz ? side : ip.nz;
+    const double cx = (0.0 - ip.x0) / (ip.x1 - ip.x0) * ip.nx;
+    const double cz = (0.0 - ip.z0) / (ip.z1 - ip.z0) * ip.nz;
+    int ix0 = (int)cx - tile.w / 2, iz0 = (int)cz - tile.h / 2;
+    if (!(cx == cx) || ix0 < 0) ix0 = 0;
+    if (!(cz == cz) || iz0 < 0) iz0 = 0;
+    if (ix0 > ip.nx - tile.w) ix0 = ip.nx - tile.w;
+    if (iz0 > ip.nz - tile.h) iz0 = ip.nz - tile.h;
+    tile.ix0 = ix0; tile.iz0 = iz0;
+    const size_t total = smem + (size_t)tile.w * tile.h * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_image_accumulate_tile,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+    if (e != cudaSuccess) return e;
+    long long blocks = sm_count(device);
+    const long long need = ((n >> 1) + 1023) / 1024;
+    if (need < blocks) blocks = need > 0 ? need : 1;
+    k_image_accumulate_tile<<<(unsigned)blocks, 1024, total, st>>>(P, n, ip, G, tile, image, counts);
+    return cudaGetLastError();
+  }
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_image_accumulate,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

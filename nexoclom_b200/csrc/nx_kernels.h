@@ -25,6 +25,17 @@ namespace nx {
 
 struct StateCols { double* c[9]; };    // time,x,y,z,vx,vy,vz,frac,step_size
 struct X0Cols { double* c[14]; };
+// Device table K3 appends the rows of a constant-step run to (cursor == nullptr: no sink;
+// cap == 0: count the rows only)
+struct RowSink {
+  double* cols;                  // 8 columns time..frac, stride `stride`
+  unsigned* index;               // packet index of the row (within the launch)
+  unsigned short* step;          // step number of the row
+  unsigned long long* cursor;    // rows appended so far (may run past cap: overflow)
+  unsigned long long cap;
+  size_t stride;
+  int skip_dead, to_f32;
+};
 
 struct LosConsts {
   double sin_dphi;
@@ -72,15 +83,22 @@ cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlo
 
 size_t table_smem_bytes(const InterpTable& g);
 
-cudaError_t launch_init_state(cudaStream_t st, StateCols P, X0Cols X, long long n,
+cudaError_t launch_init_state(cudaStream_t st, X0Cols X, long long n,
                               const SourceParams& sp, const SourceMap& map,
-                              const InterpTable& speed, uint64_t seed, uint64_t first_id);
+                              const InterpTable& speed, const InterpTable& lon1d, uint64_t seed,
+                              uint64_t first_id);
+// deviate columns: u_time, u_sinlat, u_lon, lon_in, lat_in (both null: uniform band), u_speed,
+// z_normal, u_alt, u_az
+cudaError_t launch_init_from_deviates(cudaStream_t st, X0Cols X, long long n,
+                                      const SourceParams& sp, const InterpTable& speed,
+                                      const InterpTable& lon1d, const double* const* dev);
 cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v);
 cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long long n,
                               const RunParams& p, int model, unsigned char* bucket,
                               unsigned* hist_cursor, unsigned* perm);
-cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols P, long long n,
-                                      const RunParams& p, const InterpTable& T,
+// In: columns the initial state is read from (X0 slab right after K1, else == P)
+cudaError_t launch_integrate_adaptive(cudaStream_t st, int device, StateCols In, StateCols P,
+                                      long long n, const RunParams& p, const InterpTable& T,
                                       const FastTable& F, const unsigned* perm,
                                       unsigned long long* queue, unsigned long long* totals,
                                       unsigned* att, unsigned* acc, int* status);
@@ -100,17 +118,18 @@ cudaError_t launch_integrate_adaptive_stream(cudaStream_t st, int device, const 
                                              unsigned long long* cursor, const unsigned* arrived,
                                              unsigned char* cls, unsigned long long* totals,
                                              unsigned* att, unsigned* acc, int* status);
-cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols P, long long n,
-                                      const RunParams& p, const InterpTable& T,
+cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols In, StateCols P,
+                                      long long n, const RunParams& p, const InterpTable& T,
                                       const FastTable& F,
                                       const Spline2D& S, uint64_t seed, uint64_t first_id,
                                       int nsteps, const ImageParams& ip, const GTables& G,
                                       double* image, unsigned long long* counts, double* traj,
+                                      const RowSink& rows,
                                       unsigned long long* queue, unsigned long long* totals,
                                       int* status);
 cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, long long n,
                                     const ImageParams& ip, const GTables& G, double* image,
-                                    unsigned long long* counts);
+                                    unsigned long long* counts, int mode = 0);
 cudaError_t launch_los_accumulate(cudaStream_t st, int device, StateCols P, long long n,
                                   long long nlos, const double* los, const double* dist_plan,
                                   const int* nball, const double* ladder, const double* wid2,
@@ -142,4 +161,16 @@ cudaError_t launch_fp64_peak(cudaStream_t st, int device, double* out, int iters
 cudaError_t launch_copy(cudaStream_t st, int device, const double* src, double* dst,
                         long long n);
 
+}  // namespace nx
+
+namespace nx {
+// ---- device-side Output.save: stable compaction + f32 rounding (nx_compact.cu) ----
+long long compact_tiles(long long n);
+cudaError_t launch_compact_count(cudaStream_t st, const double* frac, long long n, int skip_dead,
+                                 unsigned* tile_count, unsigned long long* total);
+cudaError_t launch_compact_scatter(cudaStream_t st, StateCols P, long long n, int skip_dead,
+                                   int to_f32, const unsigned* tile_offset, double* out,
+                                   size_t out_stride, unsigned* index);
+cudaError_t launch_to_f32(cudaStream_t st, const double* src, size_t src_stride, long long n,
+                          int ncols, float* dst);
 }  // namespace nx

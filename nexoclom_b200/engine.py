@@ -61,6 +61,11 @@ class Engine:
                 msgs.append('\n\tInfinite values of step_size')             # Output.py:338
             if rc & 32:
                 msgs.append('non-finite packet state')                      # Output.py:389
+            if rc & 64:
+                msgs.append('a packet segment never arrived on the device')
+            if rc & 128:
+                msgs.append('a packet made no progress in 2**22 attempted steps '
+                            '(the reference loop, Output.py:248-353, would not end)')
             raise AssertionError('; '.join(msgs) or f'invariant bits {rc}')
         return rc
 
@@ -133,6 +138,12 @@ class Engine:
         self._check(self.lib.nx_speedtable_upload(self.ctx, dptr(c), dptr(vv), len(c)),
                     'nx_speedtable_upload')
 
+    def upload_lontable(self, cdf, lon):
+        """Inverse CDF of a longitude-only source map (random_deviates_1d)."""
+        c, ll = as_f64(cdf), as_f64(lon)
+        self._check(self.lib.nx_lontable_upload(self.ctx, dptr(c), dptr(ll), len(c)),
+                    'nx_lontable_upload')
+
     # -- packets --------------------------------------------------------------
     def import_state(self, cols):
         """cols: sequence of 8 arrays (time,x,y,z,vx,vy,vz,frac) or an (N,8) array."""
@@ -180,6 +191,55 @@ class Engine:
                                            int(first_id), int(n)), 'nx_init_state')
         self.n = int(n)
 
+    def init_state_deviates(self, source_params, n, u_time=None, u_sinlat=None, u_lon=None,
+                            lon=None, lat=None, u_speed=None, z_normal=None, u_alt=None,
+                            u_az=None):
+        """K1's deviate -> state transform on caller-supplied deviates (host arrays of
+        length n; ``lon`` / ``lat``: surface points sampled elsewhere)."""
+        arrs = [None if a is None else as_f64(a)
+                for a in (u_time, u_sinlat, u_lon, lon, lat, u_speed, z_normal, u_alt, u_az)]
+        ptrs = [None if a is None else dptr(a) for a in arrs]
+        self._check(self.lib.nx_init_state_deviates(self.ctx, C.byref(source_params), int(n),
+                                                    *ptrs), 'nx_init_state_deviates')
+        self.n = int(n)
+
+    def rewind_state(self):
+        """The resident initial state becomes the current state again (no copy)."""
+        self._check(self.lib.nx_rewind_state(self.ctx), 'nx_rewind_state')
+
+    # -- resident packet tables (device-side Output.save) -----------------------
+    def compact_state(self, skip_dead=True, round_f32=True, n=None):
+        """Copy the current state into a packet table that stays on the GPU: frac == 0 rows
+        dropped when ``skip_dead``, columns rounded to float32 when ``round_f32``
+        (reference Output.save, Output.py:522-543).  Returns a ``PacketTable``."""
+        n = self.n if n is None else n
+        h, cnt = C.c_void_p(), C.c_longlong()
+        self._check(self.lib.nx_compact_state(self.ctx, int(n), int(bool(skip_dead)),
+                                              int(bool(round_f32)), C.byref(h), C.byref(cnt)),
+                    'nx_compact_state')
+        return PacketTable(self, h, int(cnt.value))
+
+    def upload_packets(self, cols, index=None):
+        """Host columns (8 arrays time..frac, or (N, 8)) -> resident ``PacketTable``."""
+        if isinstance(cols, np.ndarray) and cols.ndim == 2:
+            cols = [cols[:, k] for k in range(8)]
+        arrs = [as_f64(c) for c in cols]
+        n = len(arrs[0])
+        idx = (np.arange(n, dtype=np.uint32) if index is None
+               else np.ascontiguousarray(index, dtype=np.uint32))
+        ptrs = (c_double_p * 8)(*[dptr(a) for a in arrs])
+        h = C.c_void_p()
+        self._check(self.lib.nx_packets_upload(self.ctx, n, ptrs, idx.ctypes.data_as(_lib.c_u32_p),
+                                               C.byref(h)), 'nx_packets_upload')
+        return PacketTable(self, h, n)
+
+    def bind_packets(self, table):
+        """K4 / K5 read ``table`` (None: the context's own slab) until the next bind."""
+        self._check(self.lib.nx_packets_bind(self.ctx, table.handle if table is not None else None),
+                    'nx_packets_bind')
+        if table is not None:
+            self.n = table.n
+
     # -- hot kernels ----------------------------------------------------------
     def integrate_adaptive(self, n=None):
         att, acc = C.c_ulonglong(), C.c_ulonglong()
@@ -217,6 +277,17 @@ class Engine:
             C.c_void_p(counts_dev) if counts_dev else None,
             dptr(traj) if traj is not None else None, C.byref(steps)), 'nx_integrate_constant')
         return traj, nsteps, int(steps.value)
+
+    def integrate_constant_rows(self, seed=0, first_id=0, skip_dead=True, round_f32=True, n=None):
+        """K3 with the row sink: returns (PacketTable of the kept rows, nsteps, packet-steps)."""
+        n = self.n if n is None else n
+        p = self.params
+        nsteps = int(np.ceil(p.endtime / p.step_size + 1))
+        h, nrows, steps = C.c_void_p(), C.c_longlong(), C.c_ulonglong()
+        self._check(self.lib.nx_integrate_constant_rows(
+            self.ctx, int(n), int(seed), int(first_id), int(bool(skip_dead)), int(bool(round_f32)),
+            C.byref(h), C.byref(nrows), C.byref(steps)), 'nx_integrate_constant_rows')
+        return PacketTable(self, h, int(nrows.value)), nsteps, int(steps.value)
 
     def image_accumulate(self, image_params, n=None):
         n = self.n if n is None else n
@@ -310,6 +381,43 @@ class Engine:
             i64p(out['n_total']), dptr(out['abundance']), dptr(out['speed_map']),
             dptr(out['altitude_map']), dptr(out['azimuth_map'])), 'nx_source_map')
         return out
+
+
+class PacketTable:
+    """A compacted packet table resident on one GPU (``nx_packets``): what a saved Output
+    holds -- float32-rounded time, x, y, z, vx, vy, vz, frac of the rows that survive
+    ``compress`` plus their packet index -- without having left the device."""
+
+    def __init__(self, engine, handle, n):
+        self.engine, self.handle, self.n = engine, handle, int(n)
+
+    def export(self, with_step=False):
+        """(dict of float32 columns, int32 packet index[, uint16 step]): the D2H copy of a
+        save."""
+        cols = np.empty((8, self.n), dtype=np.float32)
+        index = np.empty(self.n, dtype=np.int32)
+        step = np.zeros(self.n, dtype=np.uint16)
+        if self.n:
+            fp = C.POINTER(C.c_float)
+            ptrs = (fp * 8)(*[cols[k].ctypes.data_as(fp) for k in range(8)])
+            eng = self.engine
+            eng._check(eng.lib.nx_packets_export(
+                eng.ctx, self.handle, ptrs, index.ctypes.data_as(C.POINTER(C.c_int32)),
+                step.ctypes.data_as(C.POINTER(C.c_uint16)) if with_step else None),
+                'nx_packets_export')
+        out = {c: cols[k] for k, c in enumerate(STATE_COLS)}
+        return (out, index, step) if with_step else (out, index)
+
+    def free(self):
+        if self.handle is not None and getattr(self.engine, 'ctx', None):
+            self.engine.lib.nx_packets_free(self.engine.ctx, self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 _engines = {}

@@ -190,7 +190,19 @@ class RunSetup:
                     assert False, 'Need to verify this works'        # source_distribution.py:90
                 raise ValueError('inputs.spatialdist.subsolarlon is None')
             if smap.latitude is None:
-                raise NotImplementedError('1-D longitude source maps')
+                # longitude-only map: lat = 0, lon by inverse CDF (source_distribution.py:72-76,
+                # random_deviates_1d: randomdeviates.py:29-33)
+                x = np.asarray(smap.longitude, dtype=float)
+                f_x = np.asarray(smap.abundance, dtype=float)
+                x_ = np.linspace(x.min(), x.max(), f_x.shape[0])
+                cumsum = f_x.cumsum()
+                cumsum -= cumsum.min()
+                cumsum /= cumsum.max()
+                sp.spatial_type = 2
+                self.lon_table = (cumsum, x_)
+                if engine is not None:
+                    engine.upload_lontable(cumsum, x_)
+                return self._speed_and_direction(sp, engine)
             sp.spatial_type = 1
             fmap = np.asarray(smap.abundance, dtype=float)
             xa = np.asarray(smap.longitude, dtype=float)
@@ -205,6 +217,11 @@ class RunSetup:
         else:
             assert 0, 'Not a valid spatial distribution type'        # Output.py:164
 
+        return self._speed_and_direction(sp, engine)
+
+    def _speed_and_direction(self, sp, engine):
+        inputs = self.inputs
+        vd, ad = inputs.speeddist, inputs.angulardist
         species = inputs.options.species
         vtype = vd.type.lower()
         table = None

@@ -123,7 +123,8 @@ def pooled_rejection(fmap, xa, ya, fmax, rounds, n):
     return np.array(xs[:n]), np.array(ys[:n])
 
 
-def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None, lonlat=None):
+def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None, lonlat=None,
+              lon_table=None):
     """Uniform deviates -> X0 (N,14).
 
     sp: the SourceParams numbers (nexoclom_b200._lib.SourceParams or any object
@@ -140,6 +141,12 @@ def transform(sp, u, sourcemap=None, speed_table=None, map_uniforms=None, lonlat
         sinlat = sp.sinlat0 + (sp.sinlat1 - sp.sinlat0) * u['sinlat']
         lat = np.arcsin(sinlat)
         lon = (sp.lon0 + (sp.lon1 - sp.lon0) * u['lon']) % (2 * np.pi)
+    elif sp.spatial_type == 2:
+        # longitude-only source map (source_distribution.py:72-76): lat = 0,
+        # lon = random_deviates_1d = np.interp(U, cumsum, linspace) (randomdeviates.py:29-33)
+        cdf, xl = lon_table
+        lon = np.interp(u['lon'], cdf, xl)
+        lat = np.zeros(n)
     else:
         fmap, xa, ya = sourcemap
         xa_ = np.linspace(xa.min(), xa.max(), fmap.shape[0])
@@ -263,4 +270,5 @@ def draw_x0(setup, n, seed, first_id=0, rng='philox'):
         def map_uniforms(k):
             return g.random(n), g.random(n), g.random(n)
     return transform(sp, u, getattr(setup, 'sourcemap', None),
-                     getattr(setup, 'speed_table', None), map_uniforms)
+                     getattr(setup, 'speed_table', None), map_uniforms,
+                     lon_table=getattr(setup, 'lon_table', None))

@@ -127,12 +127,16 @@ extern "C" void hc_init_from_deviates(long n, const SourceParams* sp, const doub
                                       const double* lon_in, const double* lat_in,
                                       const double* u_speed, const double* z_normal,
                                       const double* u_alt, const double* u_az,
-                                      double* out /* n x 14 */) {
+                                      double* out /* n x 14 */, const double* lon_cdf,
+                                      const double* lon_tab, int nlon) {
   HostInterp hs; InterpTable speed{};
   if (ntab > 0) { hs = make_interp(cdf, vtab, ntab); speed = view(hs); }
+  HostInterp hl; InterpTable lon1d{};
+  if (nlon > 0) { hl = make_interp(lon_cdf, lon_tab, nlon); lon1d = view(hl); }
   for (long i = 0; i < n; ++i) {
     double lon, lat;
     if (lon_in) { lon = lon_in[i]; lat = lat_in[i]; }
+    else if (sp->spatial_type == SPATIAL_LON1D) { lon = interp(lon1d, u_lon[i]); lat = 0.0; }
     else uniform_lonlat(*sp, u_sinlat[i], u_lon[i], lon, lat);
     init_packet_finish(*sp, speed, u_time[i], lon, lat, u_speed[i], z_normal[i], u_alt[i],
                        u_az[i], out + 14 * i);

@@ -62,3 +62,15 @@ def state_parity(X_gpu, X_ref):
     if both.any():
         out['frac'] = float((np.abs(X_gpu[both, 7] - X_ref[both, 7]) / X_ref[both, 7]).max())
     return out
+
+
+def source_case_input(tag):
+    """Parsed tests/golden/source_cases/<tag>.input; table files named relative to the repo
+    root are made absolute so the tests run from any directory."""
+    from nexoclom_b200.Input import Input
+    inputs = Input(os.path.join(GOLDEN, 'source_cases', tag + '.input'))
+    for group, attr in ((inputs.spatialdist, 'mapfile'), (inputs.speeddist, 'vdistfile')):
+        path = getattr(group, attr, None)
+        if isinstance(path, str) and path != 'default' and not os.path.isabs(path):
+            setattr(group, attr, os.path.join(REPO, path))
+    return inputs

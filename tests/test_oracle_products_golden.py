@@ -8,12 +8,12 @@ import os
 import numpy as np
 import pytest
 
-from common import GOLDEN
+from common import GOLDEN, source_case_input
 from nexoclom_b200 import Input
 from nexoclom_b200.runsetup import RunSetup
 from oracle import initial_state, imaging
 
-CASES = ['flat_iso', 'maxw_band', 'gauss_radial', 'sput_2d', 'spot_flat']
+CASES = ['flat_iso', 'maxw_band', 'gauss_radial', 'sput_2d', 'spot_flat', 'lon1d_user']
 COLS = ['time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'v', 'longitude', 'latitude', 'local_time', 'altitude',
         'azimuth']
 IDX = {'time': 0, 'x': 1, 'y': 2, 'z': 3, 'vx': 4, 'vy': 5, 'vz': 6, 'v': 8, 'longitude': 9, 'latitude': 10,
@@ -23,7 +23,7 @@ IDX = {'time': 0, 'x': 1, 'y': 2, 'z': 3, 'vx': 4, 'vy': 5, 'vz': 6, 'v': 8, 'lo
 def _replay(tag, g, device=None):
     """Map the reference's recorded draws (in its call order) onto the oracle's inputs
     (or, with ``device`` = the host build of the kernels' code, onto K1's transform)."""
-    setup = RunSetup(Input(os.path.join(GOLDEN, 'source_cases', tag + '.input')))
+    setup = RunSetup(source_case_input(tag))
     sp = setup.source_params(None)
     uni = list(g[f'{tag}_uniform'])
     legacy = list(g[f'{tag}_legacy'])
@@ -33,6 +33,8 @@ def _replay(tag, g, device=None):
     lonlat = None
     if sp.spatial_type == 0:                       # source_distribution.py:52, 61
         u['sinlat'], u['lon'] = uni.pop(0), uni.pop(0)
+    elif sp.spatial_type == 2:                     # random_deviates_1d: one legacy draw (:74)
+        u['lon'] = legacy.pop(0)
     else:                                          # random_deviates_2d: pooled rounds of 3 draws
         fmap, xa, ya = setup.sourcemap
         rounds = [(legacy[k], legacy[k + 1], legacy[k + 2]) for k in range(0, len(legacy), 3)]
@@ -59,15 +61,20 @@ def _replay(tag, g, device=None):
         tab = getattr(setup, 'speed_table', None)
         cdf, vt = (as_f64(tab[0]), as_f64(tab[1])) if tab is not None else (None, None)
         out = np.zeros((n, 14))
+        ltab = getattr(setup, 'lon_table', None)
+        lcdf, lx = (as_f64(ltab[0]), as_f64(ltab[1])) if ltab is not None else (None, None)
         device.hc_init_from_deviates(
             C.c_long(n), C.byref(sp), dptr(cdf) if tab is not None else None,
             dptr(vt) if tab is not None else None, C.c_int(len(cdf) if tab is not None else 0),
             dptr(arr['time']), dptr(arr['sinlat']), dptr(arr['lon']),
             dptr(ll[0]) if ll else None, dptr(ll[1]) if ll else None, dptr(arr['speed']),
-            dptr(arr['normal']), dptr(arr['alt']), dptr(arr['az']), dptr(out))
+            dptr(arr['normal']), dptr(arr['alt']), dptr(arr['az']), dptr(out),
+            dptr(lcdf) if ltab is not None else None, dptr(lx) if ltab is not None else None,
+            C.c_int(len(lcdf) if ltab is not None else 0))
         return out
     return initial_state.transform(sp, u, getattr(setup, 'sourcemap', None),
-                                   getattr(setup, 'speed_table', None), None, lonlat=lonlat)
+                                   getattr(setup, 'speed_table', None), None, lonlat=lonlat,
+                                   lon_table=getattr(setup, 'lon_table', None))
 
 
 @pytest.mark.parametrize('tag', CASES)

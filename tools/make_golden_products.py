@@ -102,6 +102,18 @@ def install():
     _stub('nexoclom.math.smooth', smooth=None, smooth2d=None)
 
 
+def write_source_case_tables(cdir):
+    """The two tables of the `lon1d_user` source case, as unit-free pickled dicts."""
+    import pickle
+    lon = np.linspace(0, 2 * np.pi, 73)
+    with open(os.path.join(cdir, 'lon1d_map.pkl'), 'wb') as f:
+        pickle.dump({'longitude': lon, 'abundance': 1.0 + 0.8 * np.cos(lon - 1.0) ** 2,
+                     'latitude': None, 'coordinate_system': 'solar-fixed'}, f, protocol=4)
+    v = np.linspace(0.2, 8.0, 400)
+    with open(os.path.join(cdir, 'user_speed.pkl'), 'wb') as f:
+        pickle.dump({'speed': v, 'speed_dist': v ** 2 * np.exp(-v / 1.5)}, f, protocol=4)
+
+
 class RecordingRNG:
     """numpy Generator that keeps every deviate it hands out, in call order."""
 
@@ -148,8 +160,25 @@ def golden_source_distribution():
         return ns(**{k: conv(v) for k, v in vars(obj).items()})
     cases = {}
     cdir = os.path.join(GOLD, 'source_cases')
-    for fn in sorted(os.listdir(cdir)):
-        inp = Input(os.path.join(cdir, fn))
+    write_source_case_tables(cdir)
+    from common import source_case_input
+    from nexoclom_b200.sourcemap import load_pickle
+
+    def RefSourceMap(filename):
+        """What the reference's SourceMap(filename) holds for a pickled dict (SourceMap.py:
+        19-30, 73-85): the dict's entries as astropy Quantities.  The committed pickles are
+        unit-free so that the product reads them without astropy."""
+        d = load_pickle(filename)
+        units = {'longitude': u.rad, 'latitude': u.rad, 'speed': u.km / u.s,
+                 'abundance': u.dimensionless, 'speed_dist': u.dimensionless}
+        m = ns(coordinate_system=d.get('coordinate_system', 'solar-fixed'))
+        for key, unit_ in units.items():
+            v = d.get(key, None)
+            setattr(m, key, None if v is None else q(np.asarray(v, dtype=float), unit_))
+        return m
+    sd.SourceMap = RefSourceMap
+    for fn in sorted(f for f in os.listdir(cdir) if f.endswith('.input')):
+        inp = source_case_input(fn[:-len('.input')])
         cases[fn[:-len('.input')]] = dict(spatial=group(inp.spatialdist),
                                           speed=group(inp.speeddist),
                                           angular=group(inp.angulardist),
