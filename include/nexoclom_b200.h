@@ -226,6 +226,14 @@ int nx_image_accumulate(nx_ctx* ctx, long long n, const nx_image_params* ip,
                         double* image /* nx*nz */, long long* counts /* nx*nz */);
 int nx_image_accumulate_dev(nx_ctx* ctx, long long n, const nx_image_params* ip,
                             void* image_dev, void* counts_dev);
+/* The same through an image the CONTEXT owns: begin allocates / zeroes nx * nz pixels, every
+ * add bins the bound packet table (or the slab) into it -- ModelImage sums its output files
+ * this way (ModelImage.py:92-99) --, fetch copies image f64 / counts i64 to the host (either
+ * may be NULL).  nx_image_device_ptrs exposes the buffers (fused K3 image, NCCL).          */
+int nx_image_begin(nx_ctx* ctx, int nx, int nz);
+int nx_image_add(nx_ctx* ctx, long long n, const nx_image_params* ip);
+int nx_image_fetch(nx_ctx* ctx, double* image, long long* counts);
+int nx_image_device_ptrs(nx_ctx* ctx, void** image_dev, void** counts_dev);
 
 /* ---- K5: lines of sight (compute_iteration.py:151-222) ------------------------
  * los[6*nlos] SoA: x,y,z,xbore,ybore,zbore; dist_from_plan[nlos] as computed at
@@ -279,8 +287,9 @@ int nx_source_map(nx_ctx* ctx, long long n, const nx_source_map_params* p,
  * hand them), original packet index kept; row order is the packet order.  The table stays
  * on the GPU until nx_packets_free; nx_packets_bind makes K4 / K5 / nx_export_state read it
  * instead of the context's slab (NULL: back to the slab; integrators unbind).
- * nx_packets_export writes the columns time,x,y,z,vx,vy,vz,frac as float32 (entries of
- * cols[8] may be NULL) and the indices as int32 -- the only packet bytes that cross PCIe
+ * nx_packets_export writes the columns time,x,y,z,vx,vy,vz,frac,step_size as float32 (cols
+ * has 9 entries, any may be NULL; step_size exists for tables made by nx_compact_state) and
+ * the indices as int32 -- the only packet bytes that cross PCIe
  * when a run is saved.  nx_packets_upload is the inverse (a restored Output file).          */
 int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_packets** out,
                      long long* count);
@@ -288,7 +297,7 @@ int nx_packets_upload(nx_ctx* ctx, long long n, const double* const* cols /* 8 *
                       const uint32_t* index, nx_packets** out);
 int nx_packets_bind(nx_ctx* ctx, nx_packets* table);
 int nx_packets_count(nx_ctx* ctx, nx_packets* table, long long* count);
-int nx_packets_export(nx_ctx* ctx, nx_packets* table, float* const* cols /* 8 */, int32_t* index,
+int nx_packets_export(nx_ctx* ctx, nx_packets* table, float* const* cols /* 9 */, int32_t* index,
                       uint16_t* step /* constant-step row tables; may be NULL */);
 int nx_packets_free(nx_ctx* ctx, nx_packets* table);
 

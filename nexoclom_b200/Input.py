@@ -74,41 +74,63 @@ class Input:
 
     def run(self, npackets, packs_per_it=None, overwrite=False, compress=True,
             distribute=False, seed=None):
-        """Run the model (reference Input.py:175-268): packets already in the
-        catalogue are not re-run; the rest is integrated in chunks of
-        ``packs_per_it`` (default 1e6 adaptive, 1 GiB / nsteps / 8 constant-step)."""
+        """Run the model (reference Input.py:175-268): packets already in the catalogue are
+        not re-run; the rest is integrated in chunks of ``packs_per_it``.
+
+        Under ``torch.distributed`` (``sharding.init()``, one process per GPU) ``npackets`` is
+        the size of the WHOLE run: the packets still to do are split into contiguous
+        global-id ranges, one per rank, and every rank integrates its own range on its own
+        GPU.  A packet is identified by its global id (the Philox counter), so the products
+        do not depend on the number of GPUs nor on ``packs_per_it``; the reference hands the
+        same ``seed`` to every chunk (Input.py:247), which repeats the packets when a seed is
+        given -- here chunks continue the id sequence instead.
+
+        Default ``packs_per_it``: the rank's whole share (the slabs of 1e8 packets are 20 GB
+        of the 180 GB; the reference's 1e6 / 1 GiB-dense-tensor defaults are host-memory
+        limits that do not apply)."""
         from .Output import Output
+        from . import sharding
         t0_ = time.time()
         distribute = distribute in (True, 'delay', 'delayed')
+        rank, world = sharding.rank_world()
+
+        def global_packets():
+            _, files, n_local, _ = self.search()
+            if world == 1:
+                return files, n_local
+            tot = np.array([n_local], dtype=np.int64)
+            sharding.allreduce_sum(tot)
+            return files, int(tot[0])
         if overwrite:
             self.delete_files()
             totalpackets = 0
         else:
-            _, outputfiles, totalpackets, _ = self.search()
+            outputfiles, totalpackets = global_packets()
             print(f'Found {len(outputfiles)} files with {totalpackets} packets.')
 
         npackets = int(npackets)
         ntodo = npackets - totalpackets
+        if seed is None and ntodo > 0:
+            seed = sharding.broadcast_object(
+                int(np.random.SeedSequence().entropy & ((1 << 63) - 1)))
         while ntodo > 0:
-            if (packs_per_it is None) and (self.options.step_size == 0):
-                packs_per_it = 1000000
-            elif packs_per_it is None:
-                nsteps = int(np.ceil(self.options.endtime.value / self.options.step_size) + 1)
-                packs_per_it = np.ceil(1024**3 / nsteps / 8)
-            packs_per_it = int(np.min([ntodo, packs_per_it]))
-            nits = int(np.ceil(ntodo / packs_per_it))
+            first, mine = sharding.shard_range(ntodo, rank, world)
+            first += totalpackets                       # ids continue after earlier runs
+            chunk = mine if packs_per_it is None else int(min(mine, packs_per_it))
+            nits = int(np.ceil(mine / chunk)) if mine > 0 else 0
             print('Running Model')
-            print(f'Will complete {nits} iterations of {packs_per_it} packets.')
+            print(f'Will complete {nits} iterations of {chunk} packets.')
             if distribute:
                 assert False, 'Dont do this'          # Input.py:235-236
+            done = 0
             for it in range(nits):
                 tit0_ = time.time()
                 print(f'Starting iteration #{it + 1} of {nits}')
-                # distinct packets per chunk: offset the seed like a fresh default_rng would
-                chunk_seed = None if seed is None else int(seed) + it
-                Output(self, packs_per_it, compress=compress, seed=chunk_seed)
+                m = min(chunk, mine - done)
+                Output(self, m, compress=compress, seed=seed, first_id=first + done)
+                done += m
                 print(f'Completed iteration #{it + 1} in {time.time() - tit0_} seconds.')
-            _, outputfiles, totalpackets, _ = self.search()
+            outputfiles, totalpackets = global_packets()
             print(f'Found {len(outputfiles)} files with {totalpackets} packets.')
             ntodo = npackets - totalpackets
         print(f'Model run completed in {time.time() - t0_} sec.')

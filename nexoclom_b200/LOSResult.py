@@ -14,10 +14,11 @@ the same membership rule.  The SQL model cache is replaced by an in-memory one.
 import numpy as np
 import pandas as pd
 
+from . import catalogue
 from .engine import get_engine
 from .ModelResult import ModelResult
 from .Output import Output
-from .runsetup import RunSetup
+from .runsetup import get_setup
 from ._lib import LosParams
 from .units import Quantity, value_of
 
@@ -72,27 +73,19 @@ def dist_from_planet_cut(data):
 
 
 def compute_iteration(self, outputfile, scdata, delay=False):
-    """One output file against all spectra (reference compute_iteration.py:90-240)."""
+    """One output file against all spectra (reference compute_iteration.py:90-240).  The
+    packets are the Output's resident table (the rows the reference reads back from its
+    pickle); a constant-step run that was too large to keep its rows regenerates them chunk
+    by chunk (``Output.tables``), so ANY Output works here, as in the reference."""
     data = scdata.data
     dist_from_plan = dist_from_planet_cut(data)
 
-    output = Output.restore(outputfile)
-    if not getattr(output, 'trajectory_kept', True):
-        raise NotImplementedError(
-            'this constant-step Output kept only the final packet states; lines of sight need '
-            'every step: run Output(..., keep_trajectory=True) (ModelImage can regenerate them)')
-    X0_index = output.X0.index
-    packets = output.X
-    if 'Index' not in packets.columns:
-        packets['Index'] = list(packets.index)
+    output = catalogue.fetch(outputfile)
     totalsource = output.totalsource
     idnum = output.idnum
 
     eng = get_engine(self._device)
-    setup = RunSetup(self.inputs)
-    self._upload_weighting_tables(eng, setup)
-    eng.import_state([packets[c].values for c in
-                      ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac')])
+    setup = get_setup(self.inputs, strict_math=getattr(output, 'strict_math', False))
     lp = LosParams()
     lp.dphi = self.dphi
     lp.outeredge = float(self.inputs.options.outeredge)
@@ -104,22 +97,37 @@ def compute_iteration(self, outputfile, scdata, delay=False):
     los = np.stack([data[c].values.astype(float) for c in
                     ('x', 'y', 'z', 'xbore', 'ybore', 'zbore')])
     print(f'{data.shape[0]} spectra taken.')
-    rad_, npack_, inc_ = eng.los_accumulate(los, dist_from_plan.values, lp)
-    self.kernel_ms = eng.last_kernel_ms()
+
+    rad_ = np.zeros(len(data))
+    npack_ = np.zeros(len(data), dtype=np.int64)
+    included_ = np.zeros(output.npackets, dtype=bool)
+    used_csr = None
+    resident = getattr(output, 'trajectory_kept', True)
+    self.kernel_ms = 0.0
+    for table, first in output.tables():
+        # (re)upload per chunk: regenerating a chunk re-uploads the run tables
+        self._upload_weighting_tables(eng, setup)
+        eng.bind_packets(table)
+        try:
+            r_, n_, inc_ = eng.los_accumulate(los, dist_from_plan.values, lp, n=table.n)
+            self.kernel_ms += eng.last_kernel_ms()
+            index = table.index_host() + first
+            included_[index[inc_]] = True
+            rad_ += r_
+            npack_ += n_
+            # `used` / `used0` (compute_iteration.py:143-144, 210-211): packets with weight
+            # > 0 per spectrum, delivered by the kernel as CSR and kept in that form (the
+            # sets the reference stores are built on demand by IterationResult.used_sets())
+            if resident and getattr(self, 'keep_used', True):
+                off, idx = eng.los_used(los, dist_from_plan.values, lp, n=table.n)
+                used_csr = (off, index[idx], output.row_labels()[idx])
+        finally:
+            eng.bind_packets(None)
+    assert np.all(np.isfinite(rad_))
 
     rad = pd.Series(rad_, index=data.index)
     npack = pd.Series(npack_, index=data.index, dtype=int)
-    included = pd.Series(False, index=X0_index, dtype=bool)
-    included[packets['Index'].values[inc_]] = True
-    assert np.all(np.isfinite(rad_))
-
-    # `used` / `used0` (compute_iteration.py:143-144, 210-211): packets with weight > 0
-    # per spectrum, delivered by the kernel as CSR and kept in that form (the sets
-    # the reference stores are built on demand by IterationResult.used_sets()).
-    used_csr = None
-    if getattr(self, 'keep_used', True):
-        off, idx = eng.los_used(los, dist_from_plan.values, lp)
-        used_csr = (off, packets['Index'].values[idx], packets.index.values[idx])
+    included = pd.Series(included_, index=pd.RangeIndex(output.npackets), dtype=bool)
     iteration_ = {'radiance': rad, 'npackets': npack, 'totalsource': totalsource,
                   'outputfile': outputfile, 'out_idnum': idnum, 'query': scdata.query,
                   'used': None, 'used0': None, 'included': included}
@@ -130,7 +138,7 @@ def compute_iteration(self, outputfile, scdata, delay=False):
 
 
 class LOSResult(ModelResult):
-    def __init__(self, scdata, inputs, params=None, dphi=Quantity(1., 'deg'), device=0,
+    def __init__(self, scdata, inputs, params=None, dphi=Quantity(1., 'deg'), device=None,
                  **kwargs):
         if params is None:
             params = {'quantity': 'radiance'}
@@ -153,7 +161,8 @@ class LOSResult(ModelResult):
         self.masking = kwargs.get('masking', None)
         self.fit_method = kwargs.get('fit_method', None)
         self.label = kwargs.get('label', 'LOSResult')
-        self._device = device
+        from .sharding import local_device
+        self._device = local_device() if device is None else device
         self._iterations = {}
 
     def __repr__(self):
@@ -206,7 +215,8 @@ fitted = {self.fitted}'''
 
         (self.outid, self.outputfiles, self.npackets, self.totalsource) = self.inputs.search()
         print(f'LOSResult: {len(self.outid)} output files found.')
-        if self.npackets == 0:
+        from .sharding import rank_world
+        if self.npackets == 0 and rank_world()[1] == 1:
             raise RuntimeError('No packets found for these Inputs.')
         if distribute in (True, 'delay', 'delayed'):
             assert False, "Don't do this"                       # LOSResult.py:230
@@ -226,6 +236,18 @@ fitted = {self.fitted}'''
             self.radiance += it.radiance
             self.npackets_los += it.npackets
             self.modelfiles[it.outputfile] = it.modelfile
+
+        # sharded run: every rank holds the columns of its own packets; ONE all-reduce per
+        # product (radiance, hit counts, packet / source totals) makes them complete
+        from .sharding import allreduce_sum, rank_world
+        if rank_world()[1] > 1:
+            rad = np.ascontiguousarray(self.radiance.values, dtype=np.float64)
+            cnt = np.ascontiguousarray(self.npackets_los.values, dtype=np.int64)
+            tot = np.array([float(self.totalsource), float(self.npackets)])
+            allreduce_sum(rad, cnt, tot)
+            self.radiance = pd.Series(rad, index=data.index)
+            self.npackets_los = pd.Series(cnt, index=data.index)
+            self.totalsource, self.npackets = float(tot[0]), int(round(tot[1]))
 
         model_rate = self.totalsource / float(value_of(self.inputs.options.endtime))
         self.atoms_per_packet = 1e23 / model_rate

@@ -10,10 +10,11 @@ import json
 
 import numpy as np
 
+from . import catalogue
 from .engine import get_engine
 from .ModelResult import ModelResult
 from .Output import Output
-from .runsetup import RunSetup
+from .runsetup import get_setup
 from ._lib import ImageParams
 from .units import Quantity, def_unit
 
@@ -56,7 +57,8 @@ class _Hist2d:
 
 
 class ModelImage(ModelResult):
-    def __init__(self, inputs, params, overwrite=False, distribute=None, device=0):
+    def __init__(self, inputs, params, overwrite=False, distribute=None, device=None):
+        from .sharding import local_device, allreduce_sum
         super().__init__(inputs, params)
         self.type = 'image'
         self.origin = self.params.get('origin', inputs.geometry.planet)
@@ -84,20 +86,29 @@ class ModelImage(ModelResult):
         scale = tuple(float(w) / d for w, d in zip(self.width, self.dims))
         r_cm = float(self.origin.radius.value) * 1e5
         self.Apix = Quantity((scale[0] * r_cm) * (scale[1] * r_cm), 'cm2')
-        self.xaxis = None
-        self.zaxis = None
-        self._device = device
+        self._device = local_device() if device is None else device
+        xr = [float(x) for x in self.xrange]
+        zr = [float(z) for z in self.zrange]
+        axes = _Hist2d(None, xr, zr, self.dims)
+        self.xaxis = R(axes.x)
+        self.zaxis = R(axes.y)
 
+        # Every output file of this rank is binned into ONE image that stays on the device
+        # (the reference adds the per-file histograms on the host, ModelImage.py:92-99) ...
         self.outid, self.outputfiles, _, _ = self.inputs.search()
-        for fname in self.outputfiles:
-            print(f'Output filename: {fname}')
-            output = Output.restore(fname)
-            image, packets = self.create_image(fname)
-            self.image += image.histogram
-            self.packet_image += packets.histogram
-            self.totalsource += output.totalsource
-            self.xaxis = R(image.x)
-            self.zaxis = R(image.y)
+        if self.outputfiles:
+            eng = get_engine(self._device)
+            eng.image_begin(*self.dims)
+            for fname in self.outputfiles:
+                print(f'Output filename: {fname}')
+                self.totalsource += self._accumulate(catalogue.fetch(fname), eng)
+            img, cnt = eng.image_fetch(*self.dims)
+            self.image += img
+            self.packet_image += cnt
+        # ... and the ranks of a sharded run are combined with one all-reduce per product
+        tot = np.array([float(self.totalsource)])
+        allreduce_sum(self.image, self.packet_image, tot)
+        self.totalsource = float(tot[0])
 
         mod_rate = self.totalsource / self.inputs.options.endtime.value
         self.atoms_per_packet = 1e23 / mod_rate
@@ -122,58 +133,52 @@ class ModelImage(ModelResult):
         ip.skip_dead = 0
         return ip
 
-    def create_image(self, fname):
-        """reference ModelImage.py:229-274, one K4 launch.  The restored Output
-        holds exactly what the reference would read from disk (f32-rounded,
+    def _accumulate(self, output, eng):
+        """K4 of one Output into the context-owned device image; returns its totalsource.
+        The packet table holds exactly what the reference would read from disk (f32-rounded,
         frac == 0 rows removed when ``compress``)."""
-        output = Output.restore(fname)
-        packets = output.X
         if self.origin != self.inputs.geometry.planet:
             raise NotImplementedError('transform_reference_frame')   # ModelResult base stub
-        eng = get_engine(self._device)
-        setup = RunSetup(self.inputs)
+        setup = get_setup(self.inputs, strict_math=getattr(output, 'strict_math', False))
         self._upload_weighting_tables(eng, setup)
-        if not getattr(output, 'trajectory_kept', True):
-            return self._create_image_fused(output, eng, setup)
-        eng.import_state([packets[c].values for c in
-                          ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac')])
-        img, cnt = eng.image_accumulate(self.image_params(setup))
-        xr = [float(x) for x in self.xrange]
-        zr = [float(z) for z in self.zrange]
-        image = _Hist2d(img, xr, zr, self.dims)
-        packim = _Hist2d(cnt.astype(float), xr, zr, self.dims)
-        self.xaxis = Quantity(image.x, self.unit)
-        self.zaxis = Quantity(image.y, self.unit)
-        return image, packim
+        ip = self.image_params(setup)
+        if getattr(output, 'trajectory_kept', True):
+            table = output.device_table()
+            eng.bind_packets(table)
+            try:
+                eng.image_add(ip, n=table.n)
+            finally:
+                eng.bind_packets(None)
+        else:
+            self._accumulate_fused(output, eng, setup, ip)
+        return output.totalsource
 
-    def _create_image_fused(self, output, eng, setup):
-        """Constant-step output whose (N, 8, nsteps) rows were not kept: run K1 + K3 again
-        with this image fused into the integrator.  The packets (Philox keyed by seed and
-        packet id) and every bounce (keyed by packet id and step) are reproduced exactly, the
-        rows are binned as the reference would bin the saved ones: rounded to float32
+    def _accumulate_fused(self, output, eng, setup, ip):
+        """Recipe-only constant-step output (its rows were too many to keep): run K1 + K3
+        again with this image fused into the integrator.  The packets (Philox keyed by seed
+        and packet id) and every bounce (keyed by packet id and step) are reproduced exactly,
+        the rows are binned as the reference would bin the saved ones: rounded to float32
         (Output.save, quirk Q14) and without the frac == 0 rows that `compress` drops."""
-        import torch
-        if getattr(output, 'imported_x0', False) or not output.compress:
-            raise NotImplementedError('fused images need device-drawn packets and compress=True; '
-                                      'run Output(..., keep_trajectory=True)')
         setup.upload(eng)
         self._upload_weighting_tables(eng, setup)
-        eng.init_state(setup.source_params(eng), output.seed, 0, output.npackets)
-        ip = self.image_params(setup)
+        eng.init_state(setup.source_params(eng), output.seed, output.first_id, output.npackets)
         ip.round_f32, ip.skip_dead = 1, 1
-        img = torch.zeros(tuple(self.dims), dtype=torch.float64, device=f'cuda:{eng.device}')
-        cnt = torch.zeros(tuple(self.dims), dtype=torch.int64, device=f'cuda:{eng.device}')
-        eng.integrate_constant(seed=output.seed, first_id=0, image_params=ip,
-                               image_dev=img.data_ptr(), counts_dev=cnt.data_ptr(),
-                               n=output.npackets)
-        eng.sync()
+        img_dev, cnt_dev = eng.image_device_ptrs()
+        eng.integrate_constant(seed=output.seed, first_id=output.first_id, image_params=ip,
+                               image_dev=img_dev, counts_dev=cnt_dev, n=output.npackets)
+
+    def create_image(self, fname):
+        """reference ModelImage.py:229-274 for ONE output file: (image, packet image) as
+        ``Histogram2d``-like objects."""
+        output = fname if isinstance(fname, Output) else catalogue.fetch(fname)
+        eng = get_engine(self._device)
+        eng.image_begin(*self.dims)
+        self._accumulate(output, eng)
+        img, cnt = eng.image_fetch(*self.dims)
         xr = [float(x) for x in self.xrange]
         zr = [float(z) for z in self.zrange]
-        image = _Hist2d(img.cpu().numpy(), xr, zr, self.dims)
-        packim = _Hist2d(cnt.cpu().numpy().astype(float), xr, zr, self.dims)
-        self.xaxis = Quantity(image.x, self.unit)
-        self.zaxis = Quantity(image.y, self.unit)
-        return image, packim
+        return (_Hist2d(img, xr, zr, self.dims),
+                _Hist2d(cnt.astype(float), xr, zr, self.dims))
 
     def export(self, filename='image.json'):
         if filename.endswith('.json'):

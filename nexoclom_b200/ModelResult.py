@@ -74,6 +74,9 @@ class ModelResult:
         if self.quantity in ('column', 'density'):
             return 0
         if self.quantity in ('radiance', 'difrad'):
+            key = (id(setup), self.g, tuple(float(w) for w in self.wavelength))
+            if getattr(engine, '_uploaded_gtables', None) == key:
+                return 1
             if self.g is not None:
                 # user-supplied constant g-value (ModelResult.py:158-159): a two-point
                 # table whose clamped ends make np.interp return g everywhere
@@ -82,5 +85,6 @@ class ModelResult:
                 engine.upload_gtables([(np.array([-1.0, 1.0]), np.array([g, g]))])
             else:
                 engine.upload_gtables(setup.gtables(self.wavelength))
+            engine._uploaded_gtables = key
             return 1
         raise InputError('ModelResults.packet_weighting', f'{self.quantity} is invalid.')

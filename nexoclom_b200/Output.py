@@ -4,19 +4,30 @@ Drop-in for the reference ``particle_tracking/Output.py:23-202`` -- same
 constructor, same attributes (``X0, X, npackets, totalsource, unit, GM, aplanet,
 vrplanet, radpres, loss_info, compress, filename, idnum``) -- with the bodies of
 ``surface/speed/angular_distribution`` (:160-170), ``variable_step_size_driver``
-(:221-366) and ``constant_step_size_driver`` (:368-455) replaced by calls through
-the C ABI (``nx_init_state``, ``nx_integrate_adaptive``, ``nx_integrate_constant``).
+(:221-366), ``constant_step_size_driver`` (:368-455) and the frac > 0 / float32 part of
+``save`` (:522-543) replaced by calls through the C ABI (``nx_init_state``,
+``nx_integrate_adaptive``, ``nx_integrate_constant[_rows]``, ``nx_compact_state``).
 
-Extension (import mode, north star): ``X0=`` accepts a reference-generated
-initial state (DataFrame / dict / (N,8) array with time,x,y,z,vx,vy,vz,frac) that
-is uploaded instead of being drawn on the device.
+What differs from the reference is WHERE the packets live, not what they are: after the run
+the rows the reference would pickle (frac > 0 when ``compress``, float32) stay on the GPU as
+a compacted ``PacketTable``; ``ModelImage`` / ``LOSResult`` of the same process read it
+there.  ``X`` and ``X0`` are built on first access (``X0`` by re-running K1: the packets are
+a pure function of (seed, global packet id)), and only when the run is written to disk
+(``NEXOCLOM_B200_SAVEPATH``) do the surviving rows cross PCIe, as float32.
+
+Extensions: ``X0=`` accepts a reference-generated initial state (import mode);
+``first_id=`` is the global id of the first packet (sharded runs: the Philox counter of
+packet i is ``first_id + i``, so products do not depend on the number of GPUs).
 """
+import copy
+import os
+
 import numpy as np
 import pandas as pd
 
 from . import catalogue
 from .engine import get_engine, STATE_COLS, X0_COLS
-from .runsetup import RunSetup
+from .runsetup import get_setup
 from .units import Quantity, def_unit
 
 
@@ -28,12 +39,25 @@ class RadPres:
     accel = None
 
 
+def _max_rows():
+    """Rows of a constant-step run that are kept resident as one table (about 70 B each)."""
+    return int(float(os.environ.get('NEXOCLOM_B200_MAX_ROWS', '4e8')))
+
+
 class Output:
     def __init__(self, inputs, npackets, compress=True, run_model=True, seed=None,
-                 X0=None, device=0, strict_math=False, keep_trajectory=None):
+                 X0=None, device=None, strict_math=False, keep_trajectory=None, first_id=0):
+        from .sharding import local_device
         self.inputs = inputs
         self.planet = inputs.geometry.planet
         npackets = int(npackets)
+        self._X = self._X0 = None
+        self._table = None           # resident PacketTable (what save() would pickle)
+        self._host = None            # the same rows as float32 host arrays (evicted / unpickled)
+        self._upcast = False
+        self.first_id = int(first_id)
+        self.strict_math = bool(strict_math)
+        self.device = local_device() if device is None else int(device)
         if run_model:
             # the reference seeds numpy's PCG64 (Output.py:92); here the seed keys the
             # per-packet Philox streams.  seed=None -> fresh entropy, like default_rng(None)
@@ -47,8 +71,7 @@ class Output:
             self.unit = def_unit('R_' + self.planet.object, 'length',
                                  float(self.planet.radius.value) * 1e3)
 
-            setup = RunSetup(inputs, strict_math=strict_math)
-            self._setup = setup
+            setup = get_setup(inputs, strict_math=strict_math)
             self.GM = setup.GM
             self.aplanet = setup.aplanet
             self.vrplanet = setup.vrplanet
@@ -71,41 +94,39 @@ class Output:
             if setup.moons:
                 print('Including the gravity of ' + ', '.join(m['name'] for m in setup.moons))
 
-            eng = get_engine(device)
-            self._engine = eng
+            eng = get_engine(self.device)
             setup.upload(eng)
 
+            self.imported_x0 = X0 is not None
+            host_cols = None
             if X0 is not None:
                 cols = self._coerce_x0(X0, npackets)
-                self._host_cols = None
                 if self.inputs.options.step_size == 0:
                     # adaptive run on imported packets: the copy is streamed behind the
                     # integrator (nx_integrate_adaptive_host), see variable_step_size_driver
-                    self._host_cols = cols
+                    host_cols = cols
                 else:
                     eng.import_state(cols)
-                    self._imported = True
-                self.X0 = pd.DataFrame({c: cols[k] for k, c in enumerate(STATE_COLS)})
+                self._X0 = pd.DataFrame({c: cols[k] for k, c in enumerate(STATE_COLS)})
+                self._imported_cols = cols
             else:
                 if self.inputs.spatialdist.type not in ('uniform', 'surface map',
                                                         'surface spot'):
                     assert 0, 'Not a valid spatial distribution type'
-                sp = setup.source_params(eng)
-                eng.init_state(sp, self.seed, 0, npackets)
-                x0 = eng.export_x0()
-                self.X0 = pd.DataFrame({c: x0[k] for k, c in enumerate(X0_COLS)})
+                eng.init_state(setup.source_params(eng), self.seed, self.first_id, npackets)
 
             if self.inputs.options.step_size == 0:
                 print('Running variable step size integrator.')
-                self.variable_step_size_driver()
+                self.variable_step_size_driver(eng, host_cols)
             else:
                 print('Running constant step size integrator.')
-                self.constant_step_size_driver(keep_trajectory)
+                self.constant_step_size_driver(eng, setup, keep_trajectory)
+            self._finish_units()
         else:
             print('Not running anything')
             self.compress = False
-            self.X0 = pd.DataFrame()
-            self.X = pd.DataFrame()
+            self._X0 = pd.DataFrame()
+            self._X = pd.DataFrame()
             self.npackets = npackets
             self.totalsource = npackets
 
@@ -131,64 +152,48 @@ class Output:
         self.X = self.X.iloc[keys]
 
     # ------------------------------------------------------------------
-    def variable_step_size_driver(self):
+    def variable_step_size_driver(self, eng, host_cols=None):
         """Adaptive driver on the GPU (K2).  Semantics of reference
         Output.py:221-366, including quirks Q1-Q9."""
-        eng = self._engine
-        host_cols = getattr(self, '_host_cols', None)
         if host_cols is not None:
             self.attempted_steps, self.accepted_steps = eng.integrate_adaptive_host(
                 host_cols, nchunks=16)
-            self._host_cols = None
         else:
             self.attempted_steps, self.accepted_steps = eng.integrate_adaptive(self.npackets)
         self.kernel_ms = eng.last_kernel_ms()
-        x = eng.export_state()
-        X = pd.DataFrame({c: x[k] for k, c in enumerate(STATE_COLS)})
-        for c in ('v', 'altitude', 'azimuth'):
-            if c in self.X0:
-                X[c] = self.X0[c].values
-        X['lossfrac'] = np.zeros(self.npackets)
-        X['step_size'] = eng.export_step()
-        X['Index'] = X.index
-        self.X = X
-        self._finish_units()
+        # Output.save on the device: frac > 0 rows (if compress), float32, packet index
+        self._table = eng.compact_state(skip_dead=self.compress, round_f32=True,
+                                        n=self.npackets)
+        self.trajectory_kept = True
 
-    def constant_step_size_driver(self, keep_trajectory=None):
+    def constant_step_size_driver(self, eng, setup, keep_trajectory=None):
         """Constant-step driver + bounce on the GPU (K3).  Semantics of reference
-        Output.py:368-455: every step of every packet becomes a row of ``X``
-        (``totalsource *= nsteps``).  The dense (N, 8, nsteps) tensor is only
-        materialised on request / for small runs.  For large runs only the final state
-        is kept (``trajectory_kept = False``) and ``ModelImage`` regenerates the rows
-        inside the integrator: packets and bounce deviates are pure functions of
-        (seed, packet id, step), so K1 + K3 with the image fused reproduce the same rows."""
-        eng = self._engine
-        p = self._setup.params
+        Output.py:368-455: every step of every packet is a row of ``X``
+        (``totalsource *= nsteps``).  The dense (N, 8, nsteps) tensor never exists: the rows
+        ``save`` would keep are appended to a resident table inside the integrator.  A run
+        whose rows exceed ``NEXOCLOM_B200_MAX_ROWS`` keeps only its recipe (seed, first
+        packet id, count): packets and bounce deviates are pure functions of (seed, packet
+        id, step), so ``tables()`` regenerates the same rows chunk by chunk for
+        ``ModelImage`` / ``LOSResult``."""
+        p = setup.params
         self.nsteps = int(np.ceil(p.endtime / p.step_size + 1))
         if keep_trajectory is None:
-            keep_trajectory = self.npackets * self.nsteps <= 50_000_000
-        traj, nsteps, self.attempted_steps = eng.integrate_constant(
-            seed=self.seed, first_id=0, trajectory=keep_trajectory, n=self.npackets)
+            keep_trajectory = self.npackets * self.nsteps <= _max_rows()
+        if keep_trajectory:
+            self._table, _, self.attempted_steps = eng.integrate_constant_rows(
+                seed=self.seed, first_id=self.first_id, skip_dead=self.compress, round_f32=True,
+                n=self.npackets)
+        else:
+            if self.imported_x0 or not self.compress:
+                raise NotImplementedError(
+                    'a constant-step run that is too large to keep its rows resident needs '
+                    'device-drawn packets and compress=True (raise NEXOCLOM_B200_MAX_ROWS or '
+                    'run fewer packets per Output)')
+            _, _, self.attempted_steps = eng.integrate_constant(
+                seed=self.seed, first_id=self.first_id, n=self.npackets)
         self.kernel_ms = eng.last_kernel_ms()
         self.totalsource *= self.nsteps
         self.trajectory_kept = bool(keep_trajectory)
-        self.imported_x0 = getattr(self, '_imported', False)
-        if keep_trajectory:
-            n = self.npackets * self.nsteps
-            X = pd.DataFrame()
-            X['Index'] = np.repeat(np.arange(self.npackets), self.nsteps)
-            for k, c in enumerate(STATE_COLS):
-                X[c] = traj[:, k, :].reshape(n)
-            frac = traj[:, 7, :]
-            lossfrac = np.zeros_like(frac)
-            lossfrac[:, 1:] = np.cumsum(frac[:, :-1] - frac[:, 1:], axis=1)   # Q13: base = 0
-            X['lossfrac'] = lossfrac.reshape(n)
-            self.X = X
-        else:
-            x = eng.export_state()
-            self.X = pd.DataFrame({c: x[k] for k, c in enumerate(STATE_COLS)})
-            self.X['Index'] = self.X.index
-        self._finish_units()
 
     def _finish_units(self):
         # "Add units back in" (Output.py:361-366, 451-455)
@@ -196,41 +201,221 @@ class Output:
         self.vrplanet = Quantity(self.vrplanet * float(self.planet.radius.value), 'km/s')
         self.GM = Quantity(self.GM, '')
 
+    # ---- packets on the device -------------------------------------------------------
+    def _engine(self):
+        return get_engine(self.device)
+
+    def _device_bytes(self):
+        t = self._table
+        return 0 if t is None or t.handle is None else t.n * 84
+
+    def _release_device(self):
+        if self._table is not None:
+            self._table.free()
+            self._table = None
+
+    def _evict_to_host(self):
+        """Residency budget exceeded: keep the rows as float32 host arrays instead."""
+        if self._table is not None and self._table.handle is not None:
+            self._host = self._table.export(with_step=True)
+            self._release_device()
+
+    def _rows_host(self):
+        """(float32 columns, int32 packet index, uint16 step) of the saved rows."""
+        if self._host is not None:
+            return self._host
+        if self._table is not None:
+            return self._table.export(with_step=True)
+        if self._X is not None:                  # unpickled: rebuild from the frame
+            X = self._X
+            cols = {c: np.ascontiguousarray(X[c].values, dtype=np.float32)
+                    for c in STATE_COLS}
+            cols['step_size'] = (np.ascontiguousarray(X['step_size'].values, dtype=np.float32)
+                                 if 'step_size' in X else np.full(len(X), 1000., np.float32))
+            index = (X['Index'].values if 'Index' in X else np.asarray(X.index)).astype(np.int32)
+            step = np.zeros(len(X), dtype=np.uint16)
+            nsteps = getattr(self, 'nsteps', None)
+            if nsteps:
+                step = (np.asarray(X.index) - index.astype(np.int64) * nsteps).astype(np.uint16)
+            return cols, index, step
+        raise RuntimeError('this Output holds no packets')
+
+    def device_table(self):
+        """The saved rows as a resident ``PacketTable`` (uploaded again if they were evicted
+        or came from a file).  Not available for recipe-only constant-step runs: iterate
+        ``tables()`` instead."""
+        live = getattr(self, '_live', None)
+        if live is not None:                      # a restore()d copy: the registered object
+            return live.device_table()            # owns the table
+        if self._table is None or self._table.handle is None:
+            if not getattr(self, 'trajectory_kept', True):
+                raise RuntimeError('recipe-only Output: use tables()')
+            cols, index, _ = self._rows_host()
+            eng = self._engine()
+            self._table = eng.upload_packets([cols[c].astype(np.float64) for c in STATE_COLS],
+                                             index.astype(np.uint32))
+            self._host = (cols, index, _)
+        catalogue.touch(self)
+        return self._table
+
+    def row_labels(self):
+        """Row label of every row of the resident table, as ``X.index`` has them: the packet
+        index (adaptive), packet * nsteps + step (constant step)."""
+        table = self.device_table()
+        index = table.index_host()
+        if self.inputs.options.step_size != 0:
+            return index * self.nsteps + table.export_steps().astype(np.int64)
+        return index
+
+    def tables(self, max_rows=None):
+        """Iterate ``(PacketTable, packet offset)`` over the saved rows: one resident table, or
+        -- recipe-only constant-step runs -- tables regenerated chunk by chunk (K1 + K3 with
+        the row sink; freed after use).  ``table.index + offset`` is the 'Index' column."""
+        if getattr(self, 'trajectory_kept', True):
+            yield self.device_table(), 0
+            return
+        eng = self._engine()
+        setup = get_setup(self.inputs, strict_math=self.strict_math)
+        setup.upload(eng)
+        sp = setup.source_params(eng)
+        max_rows = max_rows or _max_rows()
+        chunk = max(1, int(max_rows // self.nsteps))
+        for first in range(0, self.npackets, chunk):
+            m = min(chunk, self.npackets - first)
+            eng.init_state(sp, self.seed, self.first_id + first, m)
+            table, _, _ = eng.integrate_constant_rows(
+                seed=self.seed, first_id=self.first_id + first, skip_dead=True, round_f32=True,
+                n=m)
+            try:
+                yield table, first
+            finally:
+                table.free()
+
+    # ---- X0 / X as DataFrames (built on access) -----------------------------------------
+    def _cast(self, frame):
+        """float32 / int32 as saved (Output.py:528-543), or 64 bit for a restore()d copy
+        (:555-570)."""
+        f_t, i_t = (np.float64, np.int64) if self._upcast else (np.float32, np.int32)
+        for column in frame:
+            kind = frame[column].dtype.kind
+            if kind == 'f' and frame[column].dtype != f_t:
+                frame[column] = frame[column].astype(f_t)
+            elif kind in 'iu' and frame[column].dtype != i_t:
+                frame[column] = frame[column].astype(i_t)
+        return frame
+
+    def _build_X0(self):
+        if getattr(self, 'imported_x0', False):
+            cols = self._imported_cols
+            return pd.DataFrame({c: cols[k] for k, c in enumerate(STATE_COLS)})
+        eng = self._engine()
+        setup = get_setup(self.inputs, strict_math=self.strict_math)
+        setup.upload(eng)
+        eng.init_state(setup.source_params(eng), self.seed, self.first_id, self.npackets)
+        x0 = eng.export_x0()
+        return pd.DataFrame({c: x0[k] for k, c in enumerate(X0_COLS)})
+
+    @property
+    def X0(self):
+        if self._X0 is None:
+            self._X0 = self._build_X0()
+        return self._cast(self._X0)
+
+    @X0.setter
+    def X0(self, frame):
+        self._X0 = frame
+
+    def _build_X(self):
+        constant = self.inputs.options.step_size != 0
+        if constant and not getattr(self, 'trajectory_kept', True):
+            parts = []
+            for table, first in self.tables():
+                cols, index, step = table.export(with_step=True)
+                parts.append((cols, index + first, step))
+            cols = {c: np.concatenate([p[0][c] for p in parts]) for c in parts[0][0]}
+            index = np.concatenate([p[1] for p in parts])
+            step = np.concatenate([p[2] for p in parts])
+        else:
+            cols, index, step = self._rows_host()
+        if constant:
+            order = np.lexsort((step, index))
+            X = pd.DataFrame({'Index': index[order]})
+            for c in STATE_COLS:
+                X[c] = cols[c][order]
+            # running loss of each packet (Output.py:420-421 summed from 0, quirk Q13):
+            # sum_{j<k} (frac_j - frac_{j+1}) = frac_0 - frac_k with frac_0 = 1
+            X['lossfrac'] = (1.0 - X['frac'].values.astype(np.float64)).astype(np.float32)
+            X.index = index[order].astype(np.int64) * self.nsteps + step[order]
+        else:
+            X = pd.DataFrame({c: cols[c] for c in STATE_COLS})
+            if not getattr(self, 'imported_x0', False):
+                X0 = self.X0
+                for c in ('v', 'altitude', 'azimuth'):
+                    X[c] = X0[c].values[index]
+            X['lossfrac'] = np.zeros(len(index), dtype=np.float32)
+            X['step_size'] = cols['step_size']
+            X['Index'] = index
+            X.index = index.astype(np.int64)
+        return X
+
+    @property
+    def X(self):
+        if self._X is None:
+            self._X = self._build_X()
+        return self._cast(self._X)
+
+    @X.setter
+    def X(self, frame):
+        self._X = frame
+
+    def _drop_host_frames(self):
+        """After the run was pickled: the frames can be rebuilt from the device table."""
+        if self._table is not None or self._host is not None:
+            self._X = None
+        if not getattr(self, 'imported_x0', False) and hasattr(self, 'seed'):
+            self._X0 = None
+
     # ------------------------------------------------------------------
     def save(self):
-        """Register in the local catalogue; drop frac == 0 rows if ``compress``;
-        down-cast every float64 column to float32 exactly like the reference
-        (Output.py:522-543, quirk Q14)."""
-        if len(self.X) > 0 and self.compress:
-            self.X = self.X[self.X.frac > 0]
-        for frame in (self.X0, self.X):
-            for column in frame:
-                if frame[column].dtype == np.int64:
-                    frame[column] = frame[column].astype(np.int32)
-                elif frame[column].dtype == np.float64:
-                    frame[column] = frame[column].astype(np.float32)
-        eng = self.__dict__.pop('_engine', None)
-        setup = self.__dict__.pop('_setup', None)
+        """Register in the local catalogue.  The reference's save (Output.py:522-543) drops
+        the frac == 0 rows if ``compress`` and down-casts every column to float32 (quirk
+        Q14) -- both already happened on the device (``nx_compact_state`` /
+        ``nx_integrate_constant_rows``); the pickle is only written when
+        ``NEXOCLOM_B200_SAVEPATH`` is set."""
         catalogue.register(self.inputs, self)
-        self._engine, self._setup = eng, setup
 
     def __getstate__(self):
+        """The pickle holds what the reference's holds: X0 / X as float32 DataFrames."""
         d = dict(self.__dict__)
-        d.pop('_engine', None)
-        d.pop('_setup', None)
+        for k in ('_table', '_host', '_X', '_X0', '_imported_cols', '_upcast', '_live'):
+            d.pop(k, None)
+        up, self._upcast = self._upcast, False
+        try:
+            d['X0'] = self.X0
+            d['X'] = self.X
+        finally:
+            self._upcast = up
         return d
+
+    def __setstate__(self, d):
+        d = dict(d)
+        self._X0 = d.pop('X0', None)
+        self._X = d.pop('X', None)
+        self._table = self._host = None
+        self._upcast = False
+        self.__dict__.update(d)
+        if getattr(self, 'imported_x0', False) and self._X0 is not None:
+            self._imported_cols = [np.ascontiguousarray(self._X0[c].values, dtype=np.float64)
+                                   for c in STATE_COLS]
 
     @classmethod
     def restore(cls, filename):
-        """Fetch a saved Output and up-cast to 64 bit (Output.py:550-572)."""
-        import copy
-        output = copy.copy(catalogue.fetch(filename))
-        output.X0 = output.X0.copy()
-        output.X = output.X.copy()
-        for frame in (output.X0, output.X):
-            for column in frame:
-                if frame[column].dtype == np.int32:
-                    frame[column] = frame[column].astype(np.int64)
-                elif frame[column].dtype == np.float32:
-                    frame[column] = frame[column].astype(np.float64)
+        """Fetch a saved Output; its X0 / X read as 64 bit (Output.py:550-572).  The copy
+        shares the resident packet table with the registered object."""
+        live = catalogue.fetch(filename)
+        output = copy.copy(live)
+        output._upcast = True
+        output._X0 = None if live._X0 is None else live._X0.copy()
+        output._X = None if live._X is None else live._X.copy()
+        output._live = live
         return output

@@ -133,6 +133,10 @@ def load():
                                   c_double_p, C.POINTER(u64)],
         'nx_image_accumulate': [vp, i64, C.POINTER(ImageParams), c_double_p, c_i64_p],
         'nx_image_accumulate_dev': [vp, i64, C.POINTER(ImageParams), vp, vp],
+        'nx_image_begin': [vp, C.c_int, C.c_int],
+        'nx_image_add': [vp, i64, C.POINTER(ImageParams)],
+        'nx_image_fetch': [vp, c_double_p, c_i64_p],
+        'nx_image_device_ptrs': [vp, C.POINTER(vp), C.POINTER(vp)],
         'nx_los_accumulate': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams),
                               c_double_p, c_i64_p, c_u8_p],
         'nx_los_accumulate_dev': [vp, i64, i64, vp, vp, C.POINTER(LosParams), vp, vp, vp],

@@ -33,7 +33,8 @@ struct DevInterp {
 // A compacted packet table that stays on the GPU (device-side Output.save, nx_compact.cu)
 struct nx_packets {
   long long n = 0, cap = 0;          // rows, column stride (multiple of 32)
-  double* cols = nullptr;            // 8 columns time..frac
+  int ncols = 8;                     // 9: + the adaptive driver's step size
+  double* cols = nullptr;            // ncols columns time..frac[, step_size]
   unsigned* index = nullptr;         // original packet index of every row
   unsigned short* step = nullptr;    // constant-step rows: step number (else nullptr)
 };
@@ -72,6 +73,11 @@ struct nx_ctx {
   bool fresh = false;
   bool x0_valid = false;
   nx_packets* bound = nullptr; // K4 / K5 / K6 inputs come from this table instead of the slab
+  // grow-only device scratch, one slot per temporary of the product calls: no cudaMalloc /
+  // cudaFree (an implicit device synchronisation each) on the calls LOSResult / ModelImage
+  // make once per output file, and nothing to leak on an error path
+  struct Scratch { void* p = nullptr; size_t bytes = 0; } scr[24];
+  int img_nx = 0, img_nz = 0;  // shape of the context-owned image scratch (nx_image_begin)
   unsigned* cmp_tiles = nullptr;     // compaction scratch (tile counts)
   long long cmp_tiles_cap = 0;       // X0 columns 0-7 hold an initial state (K1 or the host-buffer path)
   unsigned *att = nullptr, *acc = nullptr;
@@ -114,7 +120,7 @@ static void free_interp(DevInterp& d) {
 }
 
 static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const double* f, int n,
-                         bool want_fast = true) {
+                         bool want_fast = true, int fast_nbucket = 32768) {
   free_interp(d);
   if (n <= 0) return 0;
   HostInterp h = make_interp(x, f, n);
@@ -133,7 +139,7 @@ static int upload_interp(nx_ctx* ctx, DevInterp& d, const double* x, const doubl
     d.view.n = n; d.view.nbucket = h.nbucket; d.view.blo = h.blo; d.view.binvw = h.binvw;
     return 0;
   }
-  HostFastTable hf = make_fast_table(x, f, n, 32768);
+  HostFastTable hf = make_fast_table(x, f, n, fast_nbucket);
   if (hf.max_steps > NX_FAST_TABLE_MAX_STEPS) {
     ctx->err = "lookup table has more than two nodes within 1/2^22 of its range";
     return -1;
@@ -182,11 +188,35 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
   return 0;
 }
 
+enum { SCR_IMG, SCR_CNT, SCR_LOS, SCR_DIST, SCR_RAD, SCR_NP, SCR_INC, SCR_NBALL, SCR_LADDER,
+       SCR_WID2, SCR_ORDER, SCR_NUSED, SCR_CURSOR, SCR_OFF, SCR_IDX, SCR_SM_IN, SCR_SM_PTS,
+       SCR_SM_OUT, SCR_SM_CNT, SCR_TMP, SCR_NSLOTS };
+static int scratch_bytes(nx_ctx* ctx, int slot, size_t bytes, void** out) {
+  nx_ctx::Scratch& sc = ctx->scr[slot];
+  if (bytes > sc.bytes) {
+    cudaFree(sc.p);
+    sc.p = nullptr; sc.bytes = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&sc.p, want);
+    if (e != cudaSuccess) { ctx->err = std::string("scratch allocation: ") + cudaGetErrorString(e); return -(int)e; }
+    sc.bytes = want;
+  }
+  *out = sc.p;
+  return 0;
+}
+#define SCR(slot, ptr, count)                                                              \
+  do {                                                                                     \
+    void* p_ = nullptr;                                                                    \
+    int r_ = scratch_bytes(ctx, slot, (size_t)(count) * sizeof(*(ptr)), &p_);              \
+    if (r_) return r_;                                                                     \
+    (ptr) = reinterpret_cast<decltype(ptr)>(p_);                                           \
+  } while (0)
+
 static StateCols state_cols(nx_ctx* ctx) {
   StateCols P;
   if (ctx->bound) {
     for (int k = 0; k < 8; ++k) P.c[k] = ctx->bound->cols + (size_t)k * ctx->bound->cap;
-    P.c[8] = nullptr;
+    P.c[8] = ctx->bound->ncols > 8 ? ctx->bound->cols + (size_t)8 * ctx->bound->cap : nullptr;
     return P;
   }
   for (int k = 0; k < 9; ++k) P.c[k] = ctx->state + (size_t)k * ctx->cap;
@@ -283,6 +313,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   for (auto& e : ctx->pipe_ev) if (e) cudaEventDestroy(e);
   cudaFree(ctx->pipe_scalars); cudaFree(ctx->pipe_hist);
   cudaFree(ctx->scalars); cudaFree(ctx->status); cudaFree(ctx->cmp_tiles);
+  for (auto& sc : ctx->scr) cudaFree(sc.p);
   cudaFree(ctx->squeue); cudaFreeHost(ctx->seq_host);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
@@ -349,10 +380,10 @@ int nx_source_map(nx_ctx* ctx, long long n, const nx_source_map_params* p_,
                              npts * ((size_t)sp.nvel + sp.nalt + sp.naz);
   double *d_in = nullptr, *d_pts = nullptr, *d_out = nullptr;
   unsigned long long* d_cnt = nullptr;
-  CK(cudaMalloc(&d_in, 6 * nd * sizeof(double)));
-  CK(cudaMalloc(&d_pts, ((size_t)sp.nlon + 3 * (size_t)sp.nlat) * sizeof(double)));
-  CK(cudaMalloc(&d_out, out_doubles * sizeof(double)));
-  CK(cudaMalloc(&d_cnt, 2 * npts * sizeof(unsigned long long)));
+  SCR(SCR_SM_IN, d_in, 6 * nd);
+  SCR(SCR_SM_PTS, d_pts, (size_t)sp.nlon + 3 * (size_t)sp.nlat);
+  SCR(SCR_SM_OUT, d_out, out_doubles);
+  SCR(SCR_SM_CNT, d_cnt, 2 * npts);
   const double* cols[6] = {longitude, latitude, speed_kms, altitude, azimuth, frac};
   for (int k = 0; k < 6; ++k)
     if (n > 0) CK(cudaMemcpyAsync(d_in + k * nd, cols[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -394,7 +425,6 @@ int nx_source_map(nx_ctx* ctx, long long n, const nx_source_map_params* p_,
   CK(back(n_included, o.n_included, npts * sizeof(long long)));
   CK(back(n_total, o.n_total, npts * sizeof(long long)));
   CK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_in); cudaFree(d_pts); cudaFree(d_out); cudaFree(d_cnt);
   return 0;
 }
 
@@ -453,7 +483,9 @@ int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* 
   ctx->gtables.n = 0;
   size_t off = 0;
   for (int t = 0; t < ntables; ++t) {
-    int r = upload_interp(ctx, ctx->gtab[t], v + off, g + off, sizes[t]);
+    // small bucket index (doubled by the builder until <= 2 nodes per bucket): K4 stages it
+    // in shared memory together with the records
+    int r = upload_interp(ctx, ctx->gtab[t], v + off, g + off, sizes[t], true, 256);
     if (r) return r;
     ctx->gtables.t[t] = ctx->gtab[t].view;
     ctx->gtables.f[t] = ctx->gtab[t].fast;
@@ -604,7 +636,7 @@ int nx_init_state_deviates(nx_ctx* ctx, const nx_source_params* sp_, long long n
   if (n == 0) return 0;
   const double* host[9] = {u_time, u_sinlat, u_lon, lon_in, lat_in, u_speed, z_normal, u_alt, u_az};
   double* slab = nullptr;
-  CK(cudaMalloc(&slab, (size_t)9 * n * sizeof(double)));
+  SCR(SCR_TMP, slab, (size_t)9 * n);
   const double* dev[9];
   cudaError_t e = cudaMemsetAsync(slab, 0, (size_t)9 * n * sizeof(double), ctx->stream);
   for (int k = 0; k < 9 && e == cudaSuccess; ++k) {
@@ -618,7 +650,6 @@ int nx_init_state_deviates(nx_ctx* ctx, const nx_source_params* sp_, long long n
     e = launch_init_from_deviates(ctx->stream, x0_cols(ctx), n, sp, ctx->speed.view,
                                   ctx->lon1d.view, dev);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(slab);
   if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return -(int)e; }
   ctx->launches += 1;
   ctx->fresh = ctx->x0_valid = true;
@@ -962,30 +993,62 @@ int nx_image_accumulate_dev(nx_ctx* ctx, long long n, const nx_image_params* ip_
   int r;
   if ((r = materialize(ctx))) return r;
   if ((r = begin_timed(ctx))) return r;
+  // auto: privatised counts pay off when most rows are live -- a compacted table, or a slab
+  // binned without skip_dead; a raw slab of an adaptive run is ~99 % dead packets, where the
+  // plain kernel streams faster (measured 1e7 packets: 0.075 vs 0.092 ms)
+  int mode = ctx->image_mode;
+  if (mode == 0) mode = (n >= (1LL << 20) && (ctx->bound || !ip.skip_dead)) ? 2 : 1;
   CK(launch_image_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, ip, ctx->gtables,
-                             (double*)image_dev, (unsigned long long*)counts_dev,
-                             ctx->image_mode));
+                             (double*)image_dev, (unsigned long long*)counts_dev, mode));
   return end_timed(ctx, 1);
+}
+
+// Context-owned image scratch: begin (allocate + zero), add (K4 into it, any number of packet
+// tables), fetch (D2H).  ModelImage sums its output files on the device this way.
+int nx_image_begin(nx_ctx* ctx, int nx_, int nz_) {
+  CK(cudaSetDevice(ctx->device));
+  if (nx_ < 1 || nz_ < 1) { ctx->err = "nx_image_begin: bad dims"; return -1; }
+  const size_t npix = (size_t)nx_ * nz_;
+  double* d_img = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  SCR(SCR_IMG, d_img, npix);
+  SCR(SCR_CNT, d_cnt, npix);
+  CK(cudaMemsetAsync(d_img, 0, npix * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(d_cnt, 0, npix * sizeof(unsigned long long), ctx->stream));
+  ctx->img_nx = nx_; ctx->img_nz = nz_;
+  return 0;
+}
+
+int nx_image_device_ptrs(nx_ctx* ctx, void** image_dev, void** counts_dev) {
+  if (!ctx->img_nx) { ctx->err = "nx_image_begin not called"; return -1; }
+  if (image_dev) *image_dev = ctx->scr[SCR_IMG].p;
+  if (counts_dev) *counts_dev = ctx->scr[SCR_CNT].p;
+  return 0;
+}
+
+int nx_image_add(nx_ctx* ctx, long long n, const nx_image_params* ip) {
+  if (!ctx->img_nx || ip->nx != ctx->img_nx || ip->nz != ctx->img_nz) {
+    ctx->err = "nx_image_add: dims differ from nx_image_begin";
+    return -1;
+  }
+  return nx_image_accumulate_dev(ctx, n, ip, ctx->scr[SCR_IMG].p, ctx->scr[SCR_CNT].p);
+}
+
+int nx_image_fetch(nx_ctx* ctx, double* image, long long* counts) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->img_nx) { ctx->err = "nx_image_begin not called"; return -1; }
+  const size_t npix = (size_t)ctx->img_nx * ctx->img_nz;
+  if (image) CK(cudaMemcpyAsync(image, ctx->scr[SCR_IMG].p, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (counts) CK(cudaMemcpyAsync(counts, ctx->scr[SCR_CNT].p, npix * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 int nx_image_accumulate(nx_ctx* ctx, long long n, const nx_image_params* ip, double* image,
                         long long* counts) {
-  CK(cudaSetDevice(ctx->device));
-  const size_t npix = (size_t)ip->nx * ip->nz;
-  double* d_img = nullptr;
-  unsigned long long* d_cnt = nullptr;
-  CK(cudaMalloc(&d_img, npix * sizeof(double)));
-  CK(cudaMalloc(&d_cnt, npix * sizeof(unsigned long long)));
-  CK(cudaMemsetAsync(d_img, 0, npix * sizeof(double), ctx->stream));
-  CK(cudaMemsetAsync(d_cnt, 0, npix * sizeof(unsigned long long), ctx->stream));
-  int r = nx_image_accumulate_dev(ctx, n, ip, d_img, d_cnt);
-  if (r == 0) {
-    cudaMemcpyAsync(image, d_img, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(counts, d_cnt, npix * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
-  }
-  cudaFree(d_img); cudaFree(d_cnt);
+  int r = nx_image_begin(ctx, ip->nx, ip->nz);
+  if (r == 0) r = nx_image_add(ctx, n, ip);
+  if (r == 0) r = nx_image_fetch(ctx, image, counts);
   return r;
 }
 
@@ -1082,9 +1145,9 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
   los_prepare(los_host, nlos, lp, nball, ladder, wid2, lc);
   int* d_nball = nullptr;
   double *d_ladder = nullptr, *d_wid2 = nullptr;
-  CK(cudaMalloc(&d_nball, nlos * sizeof(int)));
-  CK(cudaMalloc(&d_ladder, ladder.size() * sizeof(double)));
-  CK(cudaMalloc(&d_wid2, wid2.size() * sizeof(double)));
+  SCR(SCR_NBALL, d_nball, nlos);
+  SCR(SCR_LADDER, d_ladder, ladder.size());
+  SCR(SCR_WID2, d_wid2, wid2.size());
   CK(cudaMemcpyAsync(d_nball, nball.data(), nlos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_ladder, ladder.data(), ladder.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_wid2, wid2.data(), wid2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -1097,7 +1160,7 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
   if (use_grid) r = alloc_los_work(ctx, n);
   if (r == 0 && use_grid && ctx->los_order && nlos >= 1024) {
     const std::vector<unsigned> order = los_order(los_host, nlos);
-    CK(cudaMalloc(&d_order, nlos * sizeof(unsigned)));
+    SCR(SCR_ORDER, d_order, nlos);
     CK(cudaMemcpyAsync(d_order, order.data(), nlos * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));       // `order` is a local vector
   }
@@ -1121,7 +1184,6 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
   if (r == 0) r = end_timed(ctx, nlaunch);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (r == 0 && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
-  cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2); cudaFree(d_order);
   return r;
 }
 
@@ -1156,11 +1218,11 @@ int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* lo
   unsigned long long* d_np = nullptr;
   unsigned char* d_inc = nullptr;
   const size_t nl = (size_t)(nlos > 0 ? nlos : 1), nn = (size_t)(n > 0 ? n : 1);
-  CK(cudaMalloc(&d_los, 6 * nl * sizeof(double)));
-  CK(cudaMalloc(&d_dist, nl * sizeof(double)));
-  CK(cudaMalloc(&d_rad, nl * sizeof(double)));
-  CK(cudaMalloc(&d_np, nl * sizeof(unsigned long long)));
-  CK(cudaMalloc(&d_inc, nn));
+  SCR(SCR_LOS, d_los, 6 * nl);
+  SCR(SCR_DIST, d_dist, nl);
+  SCR(SCR_RAD, d_rad, nl);
+  SCR(SCR_NP, d_np, nl);
+  SCR(SCR_INC, d_inc, nn);
   CK(cudaMemcpyAsync(d_los, los, 6 * (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_dist, dist_from_plan, (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(d_rad, 0, nl * sizeof(double), ctx->stream));
@@ -1175,7 +1237,6 @@ int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* lo
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
   }
-  cudaFree(d_los); cudaFree(d_dist); cudaFree(d_rad); cudaFree(d_np); cudaFree(d_inc);
   return r;
 }
 
@@ -1202,21 +1263,21 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
   unsigned long long *d_nused = nullptr, *d_cursor = nullptr;
   long long* d_off = nullptr;
   unsigned* d_idx = nullptr;
-  CK(cudaMalloc(&d_los, 6 * (size_t)nlos * sizeof(double)));
-  CK(cudaMalloc(&d_dist, (size_t)nlos * sizeof(double)));
-  CK(cudaMalloc(&d_nball, (size_t)nlos * sizeof(int)));
-  CK(cudaMalloc(&d_ladder, ladder.size() * sizeof(double)));
-  CK(cudaMalloc(&d_wid2, wid2.size() * sizeof(double)));
-  CK(cudaMalloc(&d_nused, (size_t)nlos * sizeof(unsigned long long)));
+  SCR(SCR_LOS, d_los, 6 * (size_t)nlos);
+  SCR(SCR_DIST, d_dist, (size_t)nlos);
+  SCR(SCR_NBALL, d_nball, (size_t)nlos);
+  SCR(SCR_LADDER, d_ladder, ladder.size());
+  SCR(SCR_WID2, d_wid2, wid2.size());
+  SCR(SCR_NUSED, d_nused, (size_t)nlos);
   CK(cudaMemcpyAsync(d_los, los, 6 * (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_dist, dist_from_plan, (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_nball, nball.data(), (size_t)nlos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_ladder, ladder.data(), ladder.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_wid2, wid2.data(), wid2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (used_indices) {
-    CK(cudaMalloc(&d_cursor, (size_t)nlos * sizeof(unsigned long long)));
-    CK(cudaMalloc(&d_off, (size_t)(nlos + 1) * sizeof(long long)));
-    CK(cudaMalloc(&d_idx, (size_t)(total > 0 ? total : 1) * sizeof(unsigned)));
+    SCR(SCR_CURSOR, d_cursor, (size_t)nlos);
+    SCR(SCR_OFF, d_off, (size_t)(nlos + 1));
+    SCR(SCR_IDX, d_idx, (size_t)(total > 0 ? total : 1));
     CK(cudaMemsetAsync(d_cursor, 0, (size_t)nlos * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemcpyAsync(d_off, used_offsets, (size_t)(nlos + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   }
@@ -1238,8 +1299,6 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
   }
-  cudaFree(d_los); cudaFree(d_dist); cudaFree(d_nball); cudaFree(d_ladder); cudaFree(d_wid2);
-  cudaFree(d_nused); cudaFree(d_cursor); cudaFree(d_off); cudaFree(d_idx);
   return r;
 }
 
@@ -1272,11 +1331,13 @@ int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_
     if (e == cudaSuccess && total > 0) {
       h->n = (long long)total;
       h->cap = ((h->n + 31) / 32) * 32;
-      e = cudaMalloc(&h->cols, (size_t)8 * h->cap * sizeof(double));
+      h->ncols = 9;
+      e = cudaMalloc(&h->cols, (size_t)9 * h->cap * sizeof(double));
       if (e == cudaSuccess) e = cudaMalloc(&h->index, (size_t)h->cap * sizeof(unsigned));
       if (e == cudaSuccess)
-        e = launch_compact_scatter(ctx->stream, P, n, skip_dead, round_f32, ctx->cmp_tiles,
-                                   h->cols, (size_t)h->cap, h->index);
+        e = launch_compact_scatter(ctx->stream, P, n, skip_dead, round_f32,
+                                   ctx->fresh ? 0 : 1, ctx->cmp_tiles, h->cols,
+                                   (size_t)h->cap, h->index);
     }
     if (e != cudaSuccess) {
       ctx->err = std::string("nx_compact_state: ") + cudaGetErrorString(e);
@@ -1330,10 +1391,15 @@ int nx_packets_export(nx_ctx* ctx, nx_packets* h, float* const* cols, int32_t* i
   CK(cudaSetDevice(ctx->device));
   if (!h) { ctx->err = "null packet table"; return -1; }
   if (h->n == 0) return 0;
+  bool any = false;
+  for (int k = 0; k < h->ncols; ++k) any |= cols && cols[k];
   float* tmp = nullptr;
-  CK(cudaMalloc(&tmp, (size_t)8 * h->n * sizeof(float)));
-  cudaError_t e = launch_to_f32(ctx->stream, h->cols, (size_t)h->cap, h->n, 8, tmp);
-  for (int k = 0; k < 8 && e == cudaSuccess; ++k)
+  cudaError_t e = cudaSuccess;
+  if (any) {
+    SCR(SCR_TMP, tmp, (size_t)h->ncols * h->n);
+    e = launch_to_f32(ctx->stream, h->cols, (size_t)h->cap, h->n, h->ncols, tmp);
+  }
+  for (int k = 0; any && k < h->ncols && e == cudaSuccess; ++k)
     if (cols[k])
       e = cudaMemcpyAsync(cols[k], tmp + (size_t)k * h->n, (size_t)h->n * sizeof(float),
                           cudaMemcpyDeviceToHost, ctx->stream);
@@ -1346,7 +1412,6 @@ int nx_packets_export(nx_ctx* ctx, nx_packets* h, float* const* cols, int32_t* i
       std::memset(step, 0, (size_t)h->n * sizeof(uint16_t));
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(tmp);
   ctx->launches += 1;
   if (e != cudaSuccess) { ctx->err = std::string("nx_packets_export: ") + cudaGetErrorString(e); return -(int)e; }
   return 0;

@@ -81,7 +81,7 @@ k_compact_scan(unsigned* __restrict__ tile_count, long long ntiles,
 }
 
 __global__ void __launch_bounds__(NX_CMP_THREADS)
-k_compact_scatter(StateCols P, long long n, int skip_dead, int to_f32,
+k_compact_scatter(StateCols P, long long n, int skip_dead, int to_f32, int have_step,
                   const unsigned* __restrict__ tile_offset, double* __restrict__ out,
                   size_t out_stride, unsigned* __restrict__ index) {
   __shared__ unsigned warp_cnt[NX_CMP_THREADS / 32];
@@ -107,6 +107,11 @@ k_compact_scatter(StateCols P, long long n, int skip_dead, int to_f32,
         double v = (k == 7) ? f : P.c[k][i];
         if (to_f32) v = (double)(float)v;
         out[(size_t)k * out_stride + o] = v;
+      }
+      {                              // 9th column: the adaptive driver's step size (Output.py:246)
+        double v = have_step ? P.c[8][i] : 1000.0;
+        if (to_f32) v = (double)(float)v;
+        out[(size_t)8 * out_stride + o] = v;
       }
       index[o] = (unsigned)i;
     }
@@ -139,10 +144,10 @@ cudaError_t launch_compact_count(cudaStream_t st, const double* frac, long long 
 }
 
 cudaError_t launch_compact_scatter(cudaStream_t st, StateCols P, long long n, int skip_dead,
-                                   int to_f32, const unsigned* tile_offset, double* out,
-                                   size_t out_stride, unsigned* index) {
+                                   int to_f32, int have_step, const unsigned* tile_offset,
+                                   double* out, size_t out_stride, unsigned* index) {
   k_compact_scatter<<<(unsigned)compact_tiles(n), NX_CMP_THREADS, 0, st>>>(
-      P, n, skip_dead, to_f32, tile_offset, out, out_stride, index);
+      P, n, skip_dead, to_f32, have_step, tile_offset, out, out_stride, index);
   return cudaGetLastError();
 }
 

@@ -88,7 +88,7 @@ NX_HD double gvalue_sum_fast(const GTables& G, double rv) {
   double gg = 0.0;
 #pragma unroll
   for (int i = 0; i < NX_MAX_GTABLES; ++i)
-    if (i < G.n) gg += interp_fast(G.f[i], rv);
+    if (i < G.n) gg += interp_fast<false>(G.f[i], rv);
   return gg;
 }
 

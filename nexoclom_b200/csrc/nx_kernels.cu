@@ -73,18 +73,34 @@ __device__ __forceinline__ size_t stage_table(const InterpTable& g, InterpTable&
 
 // fast path: interval records in shared memory, the (large) bucket index stays in
 // global memory and is served by L1
+// with_bucket: small bucket indices (the g-value tables of K4: a few hundred buckets) are
+// staged too, so a lookup never leaves shared memory -- with a ~200 KB shared-memory
+// carve-out the L1 that would serve a global bucket index is down to a few KB.
+#define NX_SMEM_BUCKET_MAX 8192
 __device__ __forceinline__ void stage_fast_table(const FastTable& g, FastTable& s,
-                                                 unsigned char* base) {
+                                                 unsigned char* base, bool with_bucket = false) {
   double4* sr = reinterpret_cast<double4*>(base);
   const double4* gr = reinterpret_cast<const double4*>(g.rec);
   for (int i = threadIdx.x; i < g.nrec; i += blockDim.x) sr[i] = gr[i];   // 32 B per record
   s.rec = reinterpret_cast<const InterpRec*>(sr);
   s.bucket = g.bucket;
+  if (with_bucket && g.nbucket <= NX_SMEM_BUCKET_MAX) {
+    unsigned short* sb = reinterpret_cast<unsigned short*>(sr + g.nrec);
+    for (int i = threadIdx.x; i < g.nbucket; i += blockDim.x) sb[i] = g.bucket[i];
+    s.bucket = sb;
+  }
   s.nrec = g.nrec; s.nbucket = g.nbucket; s.blo = g.blo; s.binvw = g.binvw; s.boff = g.boff;
 }
 
-size_t fast_table_smem_bytes(const FastTable& g) {
-  return (size_t)g.nrec * 32;
+__device__ __forceinline__ size_t fast_table_smem_bytes_dev(const FastTable& g) {
+  size_t b = (size_t)g.nrec * 32;
+  if (g.nbucket <= NX_SMEM_BUCKET_MAX) b += ((size_t)g.nbucket * 2 + 15) & ~(size_t)15;
+  return b;
+}
+size_t fast_table_smem_bytes(const FastTable& g, bool with_bucket = false) {
+  size_t b = (size_t)g.nrec * 32;
+  if (with_bucket && g.nbucket <= NX_SMEM_BUCKET_MAX) b += ((size_t)g.nbucket * 2 + 15) & ~(size_t)15;
+  return b;
 }
 
 size_t table_smem_bytes(const InterpTable& g) {
@@ -854,7 +870,9 @@ __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& 
 #define NX_BOUNCE_MAXWAIT 10
 #endif
 // MODE as in k_integrate_adaptive: -1 strict, else fast with MODE = GR*8 + RP*4 + LOSS.
-template <int MODE>
+// ROWS: compile the row sink in (a separate instantiation keeps the plain kernel's hot loop
+// as small as it was: the loop is instruction-cache bound).
+template <int MODE, bool ROWS>
 __global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
 k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, InterpTable Tg,
                      FastTable Fg, Spline2D S, uint64_t seed, uint64_t first_id, int nsteps,
@@ -953,7 +971,7 @@ k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, Interp
       }
       if (image) image_add(ip, G, isteps, s, image, counts);
     }
-    if (rows.cursor) {
+    if (ROWS) {
       // Row sink: what the reference keeps of a constant-step run (Output.py:434-449 flattens
       // results[N, 8, nsteps]; Output.save drops the frac == 0 rows and rounds to float32),
       // appended to a device table with one warp-aggregated atomic per iteration
@@ -1033,7 +1051,7 @@ k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
   size_t off = 0;
 #pragma unroll
   for (int t = 0; t < NX_MAX_GTABLES; ++t)
-    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off); off += (size_t)Gg.f[t].nrec * 32; }
+    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off, true); off += fast_table_smem_bytes_dev(Gg.f[t]); }
   __syncthreads();
   const ImageSteps isteps = image_steps(ip);
   const long long npair = n >> 1;
@@ -1090,7 +1108,7 @@ k_image_accumulate_tile(StateCols P, long long n, ImageParams ip, GTables Gg, Im
   size_t off = 0;
 #pragma unroll
   for (int t = 0; t < NX_MAX_GTABLES; ++t)
-    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off); off += (size_t)Gg.f[t].nrec * 32; }
+    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off, true); off += fast_table_smem_bytes_dev(Gg.f[t]); }
   unsigned* __restrict__ tcnt = reinterpret_cast<unsigned*>(smem_raw + off);
   const int tsize = tile.w * tile.h;
   for (int i = threadIdx.x; i < tsize; i += blockDim.x) tcnt[i] = 0u;
@@ -1450,13 +1468,23 @@ static cudaError_t launch_constant_mode(cudaStream_t st, int device, StateCols I
   const size_t tbytes = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
   const size_t smem = tbytes + (size_t)(NX_INT_THREADS / 32) * NX_FEED_BYTES_PER_WARP;
   int blocks = 0;
-  cudaError_t e = persistent_grid(k_integrate_constant<MODE>, device, smem, &blocks);
-  if (e != cudaSuccess) return e;
   const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
-  if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-  k_integrate_constant<MODE><<<blocks, NX_INT_THREADS, smem, st>>>(
-      In, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, rows, queue,
-      totals, status, (unsigned)tbytes);
+  cudaError_t e;
+  if (rows.cursor) {
+    e = persistent_grid(k_integrate_constant<MODE, true>, device, smem, &blocks);
+    if (e != cudaSuccess) return e;
+    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+    k_integrate_constant<MODE, true><<<blocks, NX_INT_THREADS, smem, st>>>(
+        In, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, rows, queue,
+        totals, status, (unsigned)tbytes);
+  } else {
+    e = persistent_grid(k_integrate_constant<MODE, false>, device, smem, &blocks);
+    if (e != cudaSuccess) return e;
+    if (need < blocks) blocks = (int)(need > 0 ? need : 1);
+    k_integrate_constant<MODE, false><<<blocks, NX_INT_THREADS, smem, st>>>(
+        In, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, rows, queue,
+        totals, status, (unsigned)tbytes);
+  }
   return cudaGetLastError();
 }
 
@@ -1495,10 +1523,9 @@ cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, lo
                                     const ImageParams& ip, const GTables& G, double* image,
                                     unsigned long long* counts, int mode) {
   size_t smem = 0;
-  for (int t = 0; t < G.n; ++t) smem += fast_table_smem_bytes(G.f[t]);
-  // privatised counts (mode 2; mode 0 = auto: when there are enough packets to amortise the
-  // tile flush): a square tile around the pixel of the projected planet centre
-  const bool tiled = mode == 2 || (mode == 0 && n >= (1LL << 22));
+  for (int t = 0; t < G.n; ++t) smem += fast_table_smem_bytes(G.f[t], true);
+  // privatised counts (mode 2): a square tile around the pixel of the projected planet centre
+  const bool tiled = mode == 2;
   if (tiled) {
     const size_t budget = 227 * 1024 - 1024 - smem;
     int side = (int)std::sqrt((double)(budget / 4));

@@ -169,8 +169,8 @@ long long compact_tiles(long long n);
 cudaError_t launch_compact_count(cudaStream_t st, const double* frac, long long n, int skip_dead,
                                  unsigned* tile_count, unsigned long long* total);
 cudaError_t launch_compact_scatter(cudaStream_t st, StateCols P, long long n, int skip_dead,
-                                   int to_f32, const unsigned* tile_offset, double* out,
-                                   size_t out_stride, unsigned* index);
+                                   int to_f32, int have_step, const unsigned* tile_offset,
+                                   double* out, size_t out_stride, unsigned* index);
 cudaError_t launch_to_f32(cudaStream_t st, const double* src, size_t src_stride, long long n,
                           int ncols, float* dst);
 }  // namespace nx

@@ -174,11 +174,15 @@ struct FastTable {
 // np.interp through the record table: bucket -> record, then at most two steps to the
 // following records (guaranteed by the table builder, nx_tables.h); clamp records make
 // the ends branch-free and pad records keep +inf in bounds.
+// GLOBAL_BUCKET: the bucket index is known to live in global memory (read through the
+// read-only path); false when it may have been staged in shared memory (K4's g tables).
+template <bool GLOBAL_BUCKET = true>
 NX_HD double interp_fast(const FastTable& T, double v) {
 #if defined(__CUDA_ARCH__)
   int b = __double2int_rz(fma(v, T.binvw, T.boff));    // boff = -blo*binvw; NaN -> 0
   b = max(0, min(b, T.nbucket - 1));
-  int idx = __ldg(T.bucket + b);                       // 64 KB index, L1-resident
+  int idx = GLOBAL_BUCKET ? (int)__ldg(T.bucket + b)   // 64 KB index, L1-resident
+                          : (int)T.bucket[b];
 #else
   int b = (v == v) ? (int)fmax(fmin((v - T.blo) * T.binvw, 2e9), -2e9) : 0;
   b = b < 0 ? 0 : (b >= T.nbucket ? T.nbucket - 1 : b);

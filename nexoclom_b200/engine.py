@@ -105,6 +105,7 @@ class Engine:
     def upload_tables(self, params, radpres_v=None, radpres_a=None, spline_tck=None):
         """params: RunParams; radpres_* in R_p/s, R_p/s^2; spline_tck = (tx, ty, c)."""
         self.params = params
+        self._uploaded_setup = self._uploaded_gtables = None     # caches of RunSetup.upload
         if radpres_v is not None:
             rv, ra = as_f64(radpres_v), as_f64(radpres_a)
             nrp = len(rv)
@@ -121,6 +122,7 @@ class Engine:
 
     def upload_gtables(self, tables):
         """tables: list of (velocity [R_p/s], g [1/s]) arrays, one per emission line."""
+        self._uploaded_gtables = None
         sizes = (C.c_int * len(tables))(*[len(v) for v, _ in tables])
         v = as_f64(np.concatenate([t[0] for t in tables])) if tables else np.zeros(1)
         g = as_f64(np.concatenate([t[1] for t in tables])) if tables else np.zeros(1)
@@ -237,8 +239,6 @@ class Engine:
         """K4 / K5 read ``table`` (None: the context's own slab) until the next bind."""
         self._check(self.lib.nx_packets_bind(self.ctx, table.handle if table is not None else None),
                     'nx_packets_bind')
-        if table is not None:
-            self.n = table.n
 
     # -- hot kernels ----------------------------------------------------------
     def integrate_adaptive(self, n=None):
@@ -297,6 +297,29 @@ class Engine:
                                                  cnt.ctypes.data_as(_lib.c_i64_p)),
                     'nx_image_accumulate')
         return img, cnt
+
+    def image_begin(self, nx, nz):
+        """Zero the context-owned device image (nx x nz, f64 + u64 counts)."""
+        self._check(self.lib.nx_image_begin(self.ctx, int(nx), int(nz)), 'nx_image_begin')
+
+    def image_add(self, image_params, n=None):
+        """K4 of the bound packet table (or the slab) into the context-owned image."""
+        n = self.n if n is None else n
+        self._check(self.lib.nx_image_add(self.ctx, int(n), C.byref(image_params)),
+                    'nx_image_add')
+
+    def image_fetch(self, nx, nz):
+        img = np.empty((nx, nz))
+        cnt = np.empty((nx, nz), dtype=np.int64)
+        self._check(self.lib.nx_image_fetch(self.ctx, dptr(img),
+                                            cnt.ctypes.data_as(_lib.c_i64_p)), 'nx_image_fetch')
+        return img, cnt
+
+    def image_device_ptrs(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.nx_image_device_ptrs(self.ctx, C.byref(a), C.byref(b)),
+                    'nx_image_device_ptrs')
+        return a.value, b.value
 
     def image_accumulate_dev(self, image_params, image_dev, counts_dev, n=None):
         n = self.n if n is None else n
@@ -394,19 +417,47 @@ class PacketTable:
     def export(self, with_step=False):
         """(dict of float32 columns, int32 packet index[, uint16 step]): the D2H copy of a
         save."""
-        cols = np.empty((8, self.n), dtype=np.float32)
+        cols = np.full((9, self.n), 1000.0, dtype=np.float32)
         index = np.empty(self.n, dtype=np.int32)
         step = np.zeros(self.n, dtype=np.uint16)
         if self.n:
             fp = C.POINTER(C.c_float)
-            ptrs = (fp * 8)(*[cols[k].ctypes.data_as(fp) for k in range(8)])
+            ptrs = (fp * 9)(*[cols[k].ctypes.data_as(fp) for k in range(9)])
             eng = self.engine
             eng._check(eng.lib.nx_packets_export(
                 eng.ctx, self.handle, ptrs, index.ctypes.data_as(C.POINTER(C.c_int32)),
                 step.ctypes.data_as(C.POINTER(C.c_uint16)) if with_step else None),
                 'nx_packets_export')
-        out = {c: cols[k] for k, c in enumerate(STATE_COLS)}
+        out = {c: cols[k] for k, c in enumerate(STATE_COLS + ('step_size',))}
         return (out, index, step) if with_step else (out, index)
+
+    def index_host(self):
+        """int64 packet index of every row (cached; 4 B per row over PCIe)."""
+        if getattr(self, '_index', None) is None:
+            self._index = self.export_index()
+        return self._index
+
+    def export_index(self):
+        index = np.empty(self.n, dtype=np.int32)
+        if self.n:
+            eng = self.engine
+            fp = C.POINTER(C.c_float)
+            ptrs = (fp * 9)(*([None] * 9))
+            eng._check(eng.lib.nx_packets_export(eng.ctx, self.handle, ptrs,
+                                                 index.ctypes.data_as(C.POINTER(C.c_int32)), None),
+                       'nx_packets_export')
+        return index.astype(np.int64)
+
+    def export_steps(self):
+        step = np.zeros(self.n, dtype=np.uint16)
+        if self.n:
+            eng = self.engine
+            fp = C.POINTER(C.c_float)
+            ptrs = (fp * 9)(*([None] * 9))
+            eng._check(eng.lib.nx_packets_export(eng.ctx, self.handle, ptrs, None,
+                                                 step.ctypes.data_as(C.POINTER(C.c_uint16))),
+                       'nx_packets_export')
+        return step
 
     def free(self):
         if self.handle is not None and getattr(self.engine, 'ctx', None):

@@ -117,7 +117,12 @@ class RunSetup:
         return self.surfaceint.tck if self.surfaceint is not None else None
 
     def upload(self, engine):
+        """Upload the per-run tables unless this very setup is what the engine holds."""
+        if getattr(engine, '_uploaded_setup', None) is self:
+            return
         engine.upload_tables(self.params, self.radpres_v, self.radpres_a, self.spline_tck)
+        engine._uploaded_setup = self
+        engine._uploaded_gtables = None
 
     # ---- g-value tables for radiance weighting (ModelResult.py:152-157) ----
     def gtables(self, wavelengths):
@@ -281,3 +286,22 @@ class RunSetup:
         else:
             assert 0, 'Angular Distribution not defined.'
         return sp
+
+
+_setups = {}
+
+
+def get_setup(inputs, strict_math=False):
+    """RunSetup of `inputs`, cached on the CONTENT of the inputs (they are mutable): building
+    the radiation-pressure / accommodation tables costs tens of milliseconds of host time,
+    more than integrating a million packets."""
+    from .catalogue import input_key
+    key = (input_key(inputs), bool(strict_math))
+    setup = _setups.get(key)
+    if setup is None:
+        if len(_setups) > 32:
+            _setups.pop(next(iter(_setups)))
+        setup = _setups[key] = RunSetup(inputs, strict_math=strict_math)
+    else:
+        setup.inputs = inputs
+    return setup
