@@ -3,13 +3,17 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--packets P] [--impl reference]
 
-A "step" is one pass of the hot path over one batch of synthetic packets:
-restore the resident initial state, K2 adaptive integration, K4 radiance image
-(800x800) -- BASELINE.json configs[1] (Na at Mercury, Maxwellian surface source,
-radiation pressure + photoionisation, 1e7 packets per GPU).  Metric:
-packet-steps/s = attempted Dormand-Prince steps / time, whole job over all GPUs.
-Packets are sharded over ranks by global id (weak scaling, no data-path
-collective); per-GPU images are combined with one NCCL all-reduce per step.
+A "step" is one pass of the hot path over one batch of synthetic packets: rewind the
+resident initial state, K2 adaptive integration, K4 radiance image (800x800) --
+BASELINE.json configs[1] (Na at Mercury, Maxwellian surface source, radiation pressure +
+photoionisation, 1e7 packets per GPU).  Metric: packet-steps/s = attempted Dormand-Prince
+steps / time, whole job over all GPUs.  Packets are sharded over ranks by global id (weak
+scaling, no data-path collective); the per-GPU images are combined with ONE NCCL all-reduce
+per run (inside the timed region).  `e2e` is the same work through the public API with host
+buffers: Output(inputs, n, X0=<pinned host columns>) -> ModelImage.  The other kernels of the
+path ride along as flat `config` keys: K1 (warm), K4 on an all-live state, K3 on configs[2],
+K5 for 1e5 lines of sight incl. its host preparation, and -- at N > 1 -- an assertion that
+the all-reduced product of two shards equals the single-rank product.
 """
 import argparse
 import json
@@ -163,14 +167,54 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
+FP64_LANES_PER_SM = 64       # DFMA per clock per SM on B200
+
+
+def image_params(setup, quantity=1, round_f32=1, skip_dead=1, dims=800, width=8.0):
+    """ImageParams of the default ModelImage view (ModelImage.py:53-68: from the north pole,
+    800 x 800 pixels over 8 x 8 R_p)."""
+    from nexoclom_b200._lib import ImageParams
+    from nexoclom_b200.ModelImage import image_rotation
+    M = np.asarray(image_rotation(0.0, np.pi / 2))
+    ip = ImageParams()
+    for k in range(9):
+        ip.M[k] = float(M.flat[k])
+    ip.x0, ip.x1, ip.z0, ip.z1 = -width / 2, width / 2, -width / 2, width / 2
+    ip.nx = ip.nz = dims
+    rcm = setup.radius_km * 1e5
+    ip.apix = (width / dims * rcm) * (width / dims * rcm)
+    ip.vrplanet = setup.vrplanet
+    ip.quantity, ip.round_f32, ip.skip_dead = quantity, round_f32, skip_dead
+    return ip, M
+
+
+def synthetic_los(nlos, seed=1):
+    """MESSENGER-UVVS-like sweep (BASELINE configs[4]): spacecraft on an eccentric polar
+    ellipse 1.1 - 6 R_p, boresights towards points 1 - 4 R_p from the planet centre."""
+    g = np.random.default_rng(seed)
+    th = g.random(nlos) * 2 * np.pi
+    rr = 1.1 + 4.9 * g.random(nlos)
+    x_sc = np.stack([0.3 * rr * np.cos(th), 0.2 * rr * np.cos(th) - 0.5, rr * np.sin(th)])
+    nrm = np.linalg.norm(x_sc, axis=0)
+    x_sc *= np.maximum(nrm, 1.1) / nrm
+    tgt = g.standard_normal((3, nlos))
+    tgt *= (1 + 3 * g.random(nlos)) / np.linalg.norm(tgt, axis=0)
+    bore = tgt - x_sc
+    bore /= np.linalg.norm(bore, axis=0)
+    dplan = np.linalg.norm(x_sc, axis=0)
+    ang = np.arccos(-(x_sc * bore).sum(axis=0) / dplan)
+    dplan = np.where(ang > np.arcsin(1. / dplan), 1e30, dplan)      # compute_iteration.py:105-115
+    return np.ascontiguousarray(np.concatenate([x_sc, bore])), np.ascontiguousarray(dplan)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
     from common import workload
-    from nexoclom_b200._lib import ImageParams
-    from nexoclom_b200.engine import Engine
-    from nexoclom_b200.runsetup import RunSetup
-    from nexoclom_b200.ModelImage import image_rotation
+    from nexoclom_b200 import Output, ModelImage, sharding
+    from nexoclom_b200._lib import LosParams
+    from nexoclom_b200.engine import get_engine
+    from nexoclom_b200.runsetup import get_setup
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -179,89 +223,72 @@ def run_gpu(args):
         raise RuntimeError('bench.py needs a CUDA device: nexoclom_b200 has no CPU fallback')
     torch.cuda.set_device(local)
     try:
-        # run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU:
-        # at 8 ranks the end-to-end path moves 8 x 640 MB per step out of host memory
+        # run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU
         import pynvml
         pynvml.nvmlInit()
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
     except Exception:
         pass
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    sharding.init()                                   # NCCL process group under torchrun
+    comm = sharding.nccl_comm()                       # (lib, nx_comm) or None
 
-    eng = Engine(local)
+    eng = get_engine(local)                           # the engine the product classes use
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
 
     n = args.packets
-    setup = RunSetup(workload(WORKLOAD))
+    inputs = workload(WORKLOAD)
+    setup = get_setup(inputs)
     setup.upload(eng)
     gt = setup.gtables([5891, 5897])
     eng.upload_gtables(gt)
     sp = setup.source_params(eng)
     first_id = rank * n
-    eng.init_state(sp, args.seed, first_id, n)           # resident inputs
-    eng.sync()
-    init_ms = eng.last_kernel_ms()
-    # keep a pristine device copy of the 8 state columns
-    cap_cols = [eng.state_device_ptr(k) for k in range(9)]
-    x0_dev = torch.empty((8, n), dtype=torch.float64, device='cuda')
-
-    class _DevArray:
-        """Zero-copy torch view of a library-owned device column."""
-
-        def __init__(self, ptr, count):
-            self.__cuda_array_interface__ = {'shape': (count,), 'typestr': '<f8',
-                                             'data': (ptr, False), 'version': 2}
-
-    state_cols = [torch.as_tensor(_DevArray(p, n), device='cuda') for p in cap_cols]
-
-    def restore_state():
-        for k in range(8):
-            state_cols[k].copy_(x0_dev[k])
-        state_cols[8].fill_(1000.0)
-
-    for k in range(8):
-        x0_dev[k].copy_(state_cols[k])
-
-    M = np.asarray(image_rotation(0.0, np.pi / 2))
-    ip = ImageParams()
-    for k in range(9):
-        ip.M[k] = float(M.flat[k])
-    ip.x0, ip.x1, ip.z0, ip.z1 = -4., 4., -4., 4.
-    ip.nx = ip.nz = 800
-    rcm = setup.radius_km * 1e5
-    ip.apix = (8 / 800 * rcm) * (8 / 800 * rcm)
-    ip.vrplanet = setup.vrplanet
-    ip.quantity = 1
-    ip.round_f32 = 1
-    ip.skip_dead = 1
-    image = torch.zeros((800, 800), dtype=torch.float64, device='cuda')
-    counts = torch.zeros((800, 800), dtype=torch.int64, device='cuda')
-
-    k2_ms, k4_ms, steps_total = [], [], []
-
-    def one_step(record):
-        restore_state()
-        image.zero_()
-        counts.zero_()
-        att, _ = eng.integrate_adaptive(n)
-        if record:
-            k2_ms.append(eng.last_kernel_ms())
-        eng.image_accumulate_dev(ip, image.data_ptr(), counts.data_ptr(), n)
-        if record:
-            eng.sync()
-            k4_ms.append(eng.last_kernel_ms())
-        if world > 1:
-            dist.all_reduce(image)
-            dist.all_reduce(counts)
-        if record:
-            steps_total.append(att)
+    ip, M = image_params(setup)
+    extras = {}
 
     def fence():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def best_ms(fn, reps=3):
+        b = 1e30
+        for _ in range(reps):
+            fn()
+            eng.sync()
+            b = min(b, eng.last_kernel_ms())
+        return b
+
+    peaks, peak_kind = measured_peaks()
+
+    # ---- K1 (warm) and K4 on the ALL-LIVE initial state ---------------------------------
+    eng.init_state(sp, args.seed, first_id, n)
+    eng.sync()
+    extras['k1_first_launch_ms'] = eng.last_kernel_ms()
+    k1 = best_ms(lambda: eng.init_state(sp, args.seed, first_id, n))
+    extras.update(k1_ms=k1, k1_bytes_per_packet=112, k1_hbm_gbs=112.0 * n / k1 / 1e6,
+                  k1_hbm_frac=112.0 * n / k1 / 1e6 / peaks['hbm_gbs'])
+    eng.image_begin(800, 800)
+    for name, quantity in (('column', 0), ('radiance', 1)):
+        ipa, _ = image_params(setup, quantity=quantity, skip_dead=0)
+        t = best_ms(lambda: eng.image_add(ipa, n))
+        extras[f'k4_alllive_{name}_ms_per_1e8'] = t * 1e8 / n
+        extras[f'k4_alllive_{name}_hbm_frac'] = 40.0 * n / t / 1e6 / peaks['hbm_gbs']
+
+    # ---- the step: rewind the resident X0 -> K2 -> K4 into the context-owned image -----
+    k2_ms, k4_ms, steps_total = [], [], []
+
+    def one_step(record):
+        eng.rewind_state()                          # the resident X0 is the input again
+        att, _ = eng.integrate_adaptive(n)
+        if record:
+            k2_ms.append(eng.last_kernel_ms())
+        eng.image_add(ip, n)
+        if record:
+            eng.sync()
+            k4_ms.append(eng.last_kernel_ms())
+            steps_total.append(att)
 
     for _ in range(args.warmup):
         one_step(False)
@@ -269,16 +296,20 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    eng.image_begin(800, 800)
     launches0 = eng.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         one_step(True)
+    if comm is not None:
+        eng.image_allreduce(comm[1])                # ONE all-reduce per product (image + counts)
     ev1.record(stream)
     fence()
     launches = eng.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)
+    img_run, cnt_run = eng.image_fetch(800, 800)
     t = torch.tensor([elapsed_ms, float(sum(steps_total))], dtype=torch.float64, device='cuda')
     if world > 1:
         tmax = t.clone()
@@ -289,85 +320,176 @@ def run_gpu(args):
     else:
         all_steps = float(t[1])
     value = all_steps / (elapsed_ms * 1e-3)
+    # the image accumulated over K steps of the same packets is K x one run's image
+    live_hits = int(cnt_run.sum())
+    extras['image_hits_per_step_all_ranks'] = live_hits // args.steps
+    x0_dev_cols = None
 
-    # ---- end-to-end through the host-buffer C ABI (H2D + kernels + D2H) ----
-    host_in = torch.empty((8, n), dtype=torch.float64).pin_memory()
-    host_in.copy_(x0_dev.cpu())
-    host_np = host_in.numpy()
-    cols = [host_np[k] for k in range(8)]
-    img_host = torch.empty((800, 800), dtype=torch.float64).pin_memory()
-    e2e_steps, e2e_ms = 0, 0.0
-    for it in range(0 if args.no_e2e else 1 + max(1, min(args.steps, 3))):
-        fence()
-        t0 = time.perf_counter()
-        # reference-facing host-buffer call: pinned H2D (64 B/packet) pipelined with K2
-        att, _ = eng.integrate_adaptive_host(cols, nchunks=args.e2e_chunks)
-        image.zero_()
-        counts.zero_()
-        eng.image_accumulate_dev(ip, image.data_ptr(), counts.data_ptr(), n)
-        if world > 1:
-            dist.all_reduce(image)
-        img_host.copy_(image, non_blocking=False)          # D2H result
-        fence()
-        if it > 0:
-            e2e_ms += (time.perf_counter() - t0) * 1e3
-            e2e_steps += att
-    te = torch.tensor([e2e_ms, float(e2e_steps)], dtype=torch.float64, device='cuda')
+    # ---- multi-rank product check: all-reduced == recomputed on rank 0 ------------------
     if world > 1:
-        tm = te.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = te.clone()
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        e2e_ms, e2e_steps = float(tm[0]), float(ts[1])
-    e2e_value = e2e_steps / (e2e_ms * 1e-3) if e2e_ms > 0 else None
+        m = args.check_packets
+        ipc, _ = image_params(setup, dims=200)
+        img = np.zeros((200, 200))
+        cnt = np.zeros((200, 200), dtype=np.int64)
+        if rank < 2:
+            eng.init_state(sp, args.seed + 7, rank * m, m)
+            eng.integrate_adaptive(m)
+            img, cnt = eng.image_accumulate(ipc, m)
+        sharding.allreduce_sum(img, cnt)
+        if rank == 0:
+            eng.init_state(sp, args.seed + 7, 0, 2 * m)        # both shards as ONE run
+            eng.integrate_adaptive(2 * m)
+            img1, cnt1 = eng.image_accumulate(ipc, 2 * m)
+            if not np.array_equal(cnt, cnt1):
+                raise AssertionError('all-reduced packet counts differ from the single-rank run')
+            nz = img1 > 0
+            err = float(np.max(np.abs(img[nz] - img1[nz]) / img1[nz]))
+            if not (np.array_equal(nz, img > 0) and err < 1e-12):
+                raise AssertionError(f'all-reduced image differs from the single-rank run: {err}')
+            extras['multirank_check'] = (f'2 shards x {m} packets: counts exact '
+                                         f'({int(cnt.sum())} hits), image max rel diff {err:.1e}')
+        eng.init_state(sp, args.seed, first_id, n)             # the bench state again
 
-    # ---- line-of-sight sweep over the resident final state (not part of `value`) ----
-    los_info = None
+    # ---- end to end through the public API, HOST buffers (import mode) ------------------
+    # Output(inputs, n, X0=<host columns>) -> ModelImage(inputs, params): pinned H2D of the
+    # initial state (64 B/packet) streamed behind K2, device-side Output.save (compaction +
+    # float32), K4 over the resident table, one all-reduce, D2H of image + packet image.
+    e2e = None
+    params = {'quantity': 'radiance'}
+    if not args.no_e2e:
+        host_in = torch.empty((8, n), dtype=torch.float64).pin_memory()
+        x0h = eng.export_x0()[:8]
+        host_in.copy_(torch.from_numpy(x0h))
+        del x0h
+        host_np = host_in.numpy()
+        cols = {c: host_np[k] for k, c in enumerate(
+            ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac'))}
+        reps = max(1, min(args.steps, 3))
+        e2e_steps, e2e_ms = 0, 0.0
+        for it in range(1 + reps):
+            inputs.delete_files()
+            fence()
+            t0 = time.perf_counter()
+            out = Output(inputs, n, X0=cols, first_id=first_id)
+            im = ModelImage(inputs, params)
+            checksum = float(im.image.sum())                   # the result is on the host
+            fence()
+            if it > 0:
+                e2e_ms += (time.perf_counter() - t0) * 1e3
+                e2e_steps += out.attempted_steps
+        inputs.delete_files()
+        te = torch.tensor([e2e_ms, float(e2e_steps)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            tm, ts = te.clone(), te.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            e2e_ms, e2e_steps = float(tm[0]), float(ts[1])
+        e2e = {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': 'packet-steps/s',
+               'h2d_bytes_per_step': 64 * n, 'd2h_bytes_per_step': 2 * 8 * 800 * 800,
+               'ms_per_step': e2e_ms / reps,
+               'call': 'Output(inputs, n, X0=<pinned host columns>, first_id) -> '
+                       'ModelImage(inputs, {quantity: radiance}) -> image on the host',
+               'image_checksum': checksum}
+
+        # the product's normal path draws the packets on the device (K1): Input.run -> ModelImage
+        api_ms, api_steps = 0.0, 0
+        for it in range(1 + reps):
+            inputs.delete_files()
+            fence()
+            t0 = time.perf_counter()
+            inputs.run(n * world, seed=args.seed, overwrite=True)
+            im = ModelImage(inputs, params)
+            float(im.image.sum())
+            fence()
+            if it > 0:
+                api_ms += (time.perf_counter() - t0) * 1e3
+                _, files, _, _ = inputs.search()
+                from nexoclom_b200 import catalogue
+                api_steps += sum(catalogue.fetch(f).attempted_steps for f in files)
+        inputs.delete_files()
+        ta = torch.tensor([api_ms, float(api_steps)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            tm, ts = ta.clone(), ta.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            api_ms, api_steps = float(tm[0]), float(ts[1])
+        extras['api_device_drawn_steps_per_s'] = api_steps / (api_ms * 1e-3)
+        extras['api_device_drawn_ms_per_step'] = api_ms / reps
+        extras['api_device_drawn_call'] = 'Input.run(n) -> ModelImage(inputs, params)'
+        del host_in, host_np, cols
+
+    # ---- K5: line-of-sight sweep over the resident final state (configs[4]) -------------
     if not args.no_los:
-        from nexoclom_b200._lib import LosParams
+        setup.upload(eng)
+        eng.upload_gtables(gt)
+        eng.init_state(sp, args.seed, first_id, n)
+        eng.integrate_adaptive(n)                              # the final state of the run
         nlos = args.los
-        g = torch.Generator(device='cpu').manual_seed(1)
-        th = torch.rand(nlos, generator=g, dtype=torch.float64) * 2 * np.pi
-        rr = 1.1 + 4.9 * torch.rand(nlos, generator=g, dtype=torch.float64)
-        x_sc = torch.stack([0.3 * rr * torch.cos(th), 0.2 * rr * torch.cos(th) - 0.5,
-                            rr * torch.sin(th)], dim=0)
-        x_sc *= torch.clamp(x_sc.norm(dim=0), min=1.1) / x_sc.norm(dim=0)
-        tgt = torch.randn(3, nlos, generator=g, dtype=torch.float64)
-        tgt *= (1 + 3 * torch.rand(nlos, generator=g, dtype=torch.float64)) / tgt.norm(dim=0)
-        bore = tgt - x_sc
-        bore /= bore.norm(dim=0)
-        dplan = x_sc.norm(dim=0)
-        ang = torch.arccos(-(x_sc * bore).sum(dim=0) / dplan)
-        dplan = torch.where(ang > torch.arcsin(1. / dplan), torch.full_like(dplan, 1e30), dplan)
-        los_host = torch.cat([x_sc, bore], dim=0).T.contiguous().numpy()
-        los_dev = torch.cat([x_sc, bore], dim=0).contiguous().cuda()
-        dist_dev = dplan.contiguous().cuda()
-        rad_dev = torch.zeros(nlos, dtype=torch.float64, device='cuda')
-        npk_dev = torch.zeros(nlos, dtype=torch.int64, device='cuda')
-        inc_dev = torch.zeros(n, dtype=torch.uint8, device='cuda')
+        los, dplan = synthetic_los(nlos)
         lp = LosParams()
         lp.dphi, lp.outeredge = float(np.radians(1.0)), 25.0
         lp.vrplanet, lp.rp_cm = setup.vrplanet, setup.radius_km * 1e5
         lp.quantity, lp.round_f32, lp.skip_dead = 1, 1, 0
-        los_ms = []
+        wall, kern = [], []
         for it in range(3):
-            rad_dev.zero_(); npk_dev.zero_(); inc_dev.zero_()
-            eng.los_accumulate_dev(nlos, los_dev.data_ptr(), dist_dev.data_ptr(), lp,
-                                   rad_dev.data_ptr(), npk_dev.data_ptr(), inc_dev.data_ptr(), n)
-            if world > 1:
-                dist.all_reduce(rad_dev)
-                dist.all_reduce(npk_dev)
             torch.cuda.synchronize()
-            los_ms.append(eng.last_kernel_ms())
-        los_info = {'lines_of_sight': nlos, 'packets_per_gpu': n, 'dphi_deg': 1.0,
-                    'ms': float(min(los_ms)), 'ms_per_1e8_packets': float(min(los_ms)) * 1e8 / n,
-                    'hits': int(npk_dev.sum().item()),
-                    'note': 'K5 cell-grid path over all resident packets (skip_dead=0), '
-                            'grid build included'}
+            t0 = time.perf_counter()
+            rad, npk, inc = eng.los_accumulate(los, dplan, lp, n=n)   # host prep + kernels + D2H
+            wall.append((time.perf_counter() - t0) * 1e3)
+            kern.append(eng.last_kernel_ms())
+        hits = np.array([float(npk.sum())])
+        if world > 1:
+            sharding.allreduce_sum(rad, npk)
+        extras.update(k5_lines_of_sight=nlos, k5_packets_per_gpu=n, k5_dphi_deg=1.0,
+                      k5_ms_incl_host_prep=float(min(wall)), k5_kernel_ms=float(min(kern)),
+                      k5_ms_per_1e8_packets=float(min(wall)) * 1e8 / n,
+                      k5_hits=int(hits[0]),
+                      k5_effective_pairs_per_s=float(nlos) * n / (min(wall) * 1e-3))
+
+    # ---- K3: configs[2] physics (bounce, T-dependent sticking), image fused -------------
+    if not args.no_k3:
+        n3 = args.k3_packets
+        setup3 = get_setup(workload('Na.bounce.input'))
+        setup3.upload(eng)
+        eng.upload_gtables(setup3.gtables([5891, 5897]))
+        sp3 = setup3.source_params(eng)
+        ip3, _ = image_params(setup3)
+        res3 = {}
+        for fused in (False, True):
+            ms = []
+            for it in range(2):
+                eng.init_state(sp3, args.seed, rank * n3, n3)
+                if fused:
+                    eng.image_begin(800, 800)
+                    a, b = eng.image_device_ptrs()
+                    _, nsteps, psteps = eng.integrate_constant(
+                        seed=args.seed + 1, first_id=rank * n3, image_params=ip3, image_dev=a,
+                        counts_dev=b, n=n3)
+                else:
+                    _, nsteps, psteps = eng.integrate_constant(seed=args.seed + 1,
+                                                               first_id=rank * n3, n=n3)
+                eng.sync()
+                ms.append(eng.last_kernel_ms())
+            res3[fused] = (min(ms), psteps, nsteps)
+        sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
+        nominal = 148 * FP64_LANES_PER_SM * 2 * sm_mhz * 1e6 / 1e12
+        for fused, tag in ((False, 'k3'), (True, 'k3_fused_image')):
+            ms, psteps, nsteps = res3[fused]
+            sps = psteps / (ms * 1e-3)
+            extras[f'{tag}_steps_per_s'] = sps
+            extras[f'{tag}_ms'] = ms
+            extras[f'{tag}_fp64_frac'] = sps * 626 / 1e12 / nominal
+        extras.update(k3_packets_per_gpu=n3, k3_nsteps=int(res3[False][2]),
+                      k3_flop_per_packet_step=626,
+                      k3_workload='Na.bounce.input (BASELINE configs[2])')
+        setup.upload(eng)                                      # back to the configs[1] tables
+        eng.upload_gtables(gt)
+        sp = setup.source_params(eng)
 
     if rank == 0:
-        fp64_peak = eng.measure_fp64_peak()
-        peaks, peak_kind = measured_peaks()
+        fp64_micro = eng.measure_fp64_peak()
+        sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
+        nominal = 148 * FP64_LANES_PER_SM * 2 * sm_mhz * 1e6 / 1e12
         k2 = float(np.mean(k2_ms))
         k4 = float(np.mean(k4_ms))
         steps_per_launch = float(np.mean(steps_total))
@@ -377,67 +499,62 @@ def run_gpu(args):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get('dram_bytes_per_launch')
+        config = {
+            'workload': 'BASELINE configs[1]: Na at Mercury, Maxwellian 1200 K surface source, '
+                        'radiation pressure + photoionisation, adaptive RK5(4), 800x800 '
+                        'radiance image',
+            'inputfile': WORKLOAD, 'packets_per_gpu': n, 'packets_total': n * world,
+            'attempted_steps_per_packet': steps_per_launch / n,
+            'l2': 'inputs (640 MB state per 1e7 packets) exceed the 126 MB L2; no flush',
+            'step': 'rewind resident X0 -> K2 adaptive integrate -> K4 image'
+                    + ('; ONE NCCL all-reduce(image, counts) per run' if world > 1 else ''),
+            'k2_integrate_ms': k2, 'k4_image_ms': k4,
+            'k4_benchstate_ms_per_1e8_packets': k4 * 1e8 / n,
+            'fp64_peak_microbenchmark_tflops': fp64_micro,
+        }
+        config.update(extras)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'packet-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {
-                'workload': 'Na at Mercury, Maxwellian 1200 K surface source, radiation '
-                            'pressure + photoionisation, adaptive RK5(4), + 800x800 radiance '
-                            'image (BASELINE configs[1])',
-                'inputfile': WORKLOAD, 'packets_per_gpu': n, 'packets_total': n * world,
-                'attempted_steps_per_packet': steps_per_launch / n,
-                'l2': 'inputs (640 MB state per 1e7 packets) exceed the 126 MB L2; no flush',
-                'step': 'restore resident X0 -> K2 adaptive integrate -> K4 image'
-                        + (' -> NCCL all-reduce(image, counts)' if world > 1 else ''),
-                'k1_init_ms': init_ms, 'k2_integrate_ms': k2, 'k4_image_ms': k4,
-                'image_ms_per_1e8_packets': k4 * 1e8 / n,
-                'image_hbm_gbs': 40.0 * n / (k4 * 1e-3) / 1e9,
-                'image_hbm_frac_of_' + peak_kind: 40.0 * n / (k4 * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                'los_sweep': los_info,
-            },
+            'config': config,
             'roofline': {
                 'bound': 'fp64', 'kernel': 'k_integrate_adaptive', 'achieved': achieved,
-                'peak': fp64_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
+                'peak': nominal, 'unit': 'TFLOP/s', 'frac': achieved / nominal,
                 'traffic': traffic,
-                'peak_source': 'DFMA-chain microbenchmark run live by bench.py '
-                               '(MEASURED_PEAKS.json has no FP64 entry); nominal 37.2',
+                'peak_source': f'nominal 148 SM x 64 DFMA/clk x 2 at the SM clock observed '
+                               f'during the timed region ({sm_mhz:.0f} MHz); MEASURED_PEAKS.json '
+                               f'has no FP64 entry; live DFMA microbenchmark reads '
+                               f'{fp64_micro:.1f}',
                 'flop_per_packet_step': FLOP_PER_STEP,
             },
-            # second kernel of the step, in the task's own schema (HBM-bound image accumulation;
-            # 40 B per packet = x, y, z, vy, frac; ncu: DRAM traffic == algorithmic bytes)
-            'roofline_hbm': {
-                'bound': 'hbm', 'kernel': 'k_image_accumulate',
-                'achieved': 40.0 * n / (k4 * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'],
-                'unit': 'GB/s', 'frac': 40.0 * n / (k4 * 1e-3) / 1e9 / peaks['hbm_gbs'],
-                'traffic': int(40.18 * n), 'peak_source': peak_kind + ' (MEASURED_PEAKS.json)',
-                'bytes_per_packet': 40},
-            'e2e': {'value': e2e_value, 'unit': 'packet-steps/s',
-                    'h2d_bytes_per_step': 64 * n, 'd2h_bytes_per_step': 8 * 800 * 800,
-                    'ms_per_step': e2e_ms / max(1, min(args.steps, 3)),
-                    'call': f'nx_integrate_adaptive_host(nchunks={args.e2e_chunks}) -> '
-                            'nx_image_accumulate_dev -> D2H image'},
+            'e2e': e2e,
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
         if world == 1 and not args.no_cpu:
-            X0h = np.ascontiguousarray(host_np[:, :args.cpu_packets].T)
+            eng.init_state(sp, args.seed, first_id, args.cpu_packets)
+            X0h = np.ascontiguousarray(eng.export_x0()[:8].T)
             sps, steps, wall = cpu_steps_per_s(X0h, 1)
             line['cpu_baseline'] = {
                 'value': sps, 'unit': 'packet-steps/s', 'cores': 1, 'kind': 'port',
-                'sample': f'first {args.cpu_packets} packets of the same resident X0, '
+                'sample': f'first {args.cpu_packets} packets of the same X0, '
                           f'{steps} steps in {wall:.1f} s, NumPy oracle port of the '
                           'reference driver, 1 process (host has '
                           f'{os.cpu_count()} cores)'}
-            # the image / line-of-sight products on the same final state (SURVEY 8d ii-iii)
             m = min(n, args.cpu_product_packets)
-            fin = torch.stack([state_cols[k][:m] for k in (1, 2, 3, 5, 7)]).cpu().numpy()
-            line['config']['cpu_products'] = cpu_products(
-                fin, setup, gt, M, ip.apix,
-                los_host[:args.cpu_product_los] if los_info is not None else None)
+            eng.init_state(sp, args.seed, first_id, m)
+            eng.integrate_adaptive(m)
+            fin = eng.export_state()[[1, 2, 3, 5, 7]]
+            cp = cpu_products(fin, setup, gt, M, ip.apix,
+                              synthetic_los(args.cpu_product_los)[0].T.copy()
+                              if not args.no_los else None)
+            config['cpu_image_ms_per_1e8_packets'] = cp['image']['ms_per_1e8_packets']
+            if 'los' in cp:
+                config['cpu_los_ms_per_line_of_sight_1e6_packets'] = cp['los']['ms_per_line_of_sight']
         emit(line)
-    eng.close()
+    fence()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -466,108 +583,8 @@ def cpu_products(fin, setup, gtables, M, apix, los):
         t_los = time.time() - t0
         out['los'] = {'packets': m, 'lines_of_sight': int(len(los)), 's': t_los,
                       'ms_per_line_of_sight': t_los * 1e3 / len(los), 'hits': int(npk.sum()),
-                      'kind': 'port', 'cores': 1,
-                      'note': 'KD-tree build included; the GPU los_sweep above is '
-                              '1e5 lines of sight over 10x the packets'}
+                      'kind': 'port', 'cores': 1}
     return out
-
-
-def run_gpu_config3(args):
-    """Extra measurement (not the driver's contract line): BASELINE configs[2] -- Na at
-    Mercury, surface-bound packets with temperature-dependent sticking, bounce and thermal
-    accommodation, constant 30 s step, the 800x800 radiance image accumulated per step
-    INSIDE the integrator (K1 -> K3 fused), packets sharded over the ranks, one NCCL
-    all-reduce of the image per step.  `--packets` per GPU (1.25e7 x 8 = the 1e8 run)."""
-    import torch
-    import torch.distributed as dist
-    from common import workload
-    from nexoclom_b200._lib import ImageParams
-    from nexoclom_b200.engine import Engine
-    from nexoclom_b200.runsetup import RunSetup
-    from nexoclom_b200.ModelImage import image_rotation
-
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    eng = Engine(local)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
-    n = args.packets
-    setup = RunSetup(workload('Na.bounce.input'))
-    setup.upload(eng)
-    eng.upload_gtables(setup.gtables([5891, 5897]))
-    sp = setup.source_params(eng)
-    M = np.asarray(image_rotation(0.0, np.pi / 2))
-    ip = ImageParams()
-    for k in range(9):
-        ip.M[k] = float(M.flat[k])
-    ip.x0, ip.x1, ip.z0, ip.z1 = -4., 4., -4., 4.
-    ip.nx = ip.nz = 800
-    rcm = setup.radius_km * 1e5
-    ip.apix = (8 / 800 * rcm) * (8 / 800 * rcm)
-    ip.vrplanet = setup.vrplanet
-    ip.quantity, ip.round_f32, ip.skip_dead = 1, 1, 1
-    image = torch.zeros((800, 800), dtype=torch.float64, device='cuda')
-    counts = torch.zeros((800, 800), dtype=torch.int64, device='cuda')
-    steps_done = []
-
-    def one_step(record):
-        image.zero_()
-        counts.zero_()
-        eng.init_state(sp, args.seed, rank * n, n)                    # K1
-        _, nsteps, psteps = eng.integrate_constant(                   # K3 + fused image
-            seed=args.seed + 1, first_id=rank * n, image_params=ip, image_dev=image.data_ptr(),
-            counts_dev=counts.data_ptr())
-        if world > 1:
-            dist.all_reduce(image)
-            dist.all_reduce(counts)
-        if record:
-            steps_done.append(psteps)
-        return nsteps
-
-    def fence():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        nsteps = one_step(False)
-    fence()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        one_step(True)
-    ev1.record(stream)
-    fence()
-    t = torch.tensor([ev0.elapsed_time(ev1), float(sum(steps_done))], dtype=torch.float64,
-                     device='cuda')
-    rows = counts.sum().item()
-    if world > 1:
-        tmax, tsum = t.clone(), t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        elapsed_ms, all_steps = float(tmax[0]), float(tsum[1])
-    else:
-        elapsed_ms, all_steps = float(t[0]), float(t[1])
-    if rank == 0:
-        emit({
-            'metric': 'packet-steps/s (FP64), constant step + bounce + fused image',
-            'value': all_steps / (elapsed_ms * 1e-3), 'unit': 'packet-steps/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE configs[2]: Na at Mercury, T-dependent sticking + '
-                                   'bounce + accommodation, 30 s step, image fused into K3',
-                       'inputfile': 'Na.bounce.input', 'packets_per_gpu': n,
-                       'packets_total': n * world, 'nsteps': int(nsteps),
-                       'rows_in_image_per_step': int(rows),
-                       'step': 'K1 init -> K3 constant-step integrate with fused radiance '
-                               'image' + (' -> NCCL all-reduce(image, counts)' if world > 1 else '')}})
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
 
 
 _OUT = None
@@ -611,16 +628,15 @@ def main():
     ap.add_argument('--no-e2e', action='store_true',
                     help='skip the end-to-end leg (its streaming kernel waits for concurrent '
                          'copies, which a serialising profiler never runs)')
-    ap.add_argument('--e2e-chunks', type=int, default=16,
-                    help='segments of the streamed H2D copy of the end-to-end path')
     ap.add_argument('--los', type=int, default=100_000, help='lines of sight of the K5 sweep')
-    ap.add_argument('--config3', action='store_true',
-                    help='extra: the constant-step / bounce / fused-image workload (configs[2])')
+    ap.add_argument('--no-k3', action='store_true', help='skip the configs[2] (K3) leg')
+    ap.add_argument('--k3-packets', type=int, default=2_000_000,
+                    help='packets per GPU of the configs[2] leg (361 steps each)')
+    ap.add_argument('--check-packets', type=int, default=200_000,
+                    help='packets per shard of the multi-rank product check')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
-    if args.config3:
-        return run_gpu_config3(args)
     return run_gpu(args)
 
 

@@ -131,6 +131,8 @@ int nx_ctx_create(int device, nx_ctx** out);
 int nx_ctx_destroy(nx_ctx* ctx);
 /* adopt a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) */
 int nx_ctx_set_stream(nx_ctx* ctx, void* cuda_stream);
+/* the cudaStream_t the context enqueues on (its own, or the adopted one) */
+int nx_ctx_stream(nx_ctx* ctx, void** cuda_stream);
 int nx_ctx_sync(nx_ctx* ctx);
 /* tuning switches: "order_packets" (cost model of the K2 work queue: 0 natural order,
  * 1 ballistic flight time (default), 2 + radiation-pressure perturbation);
@@ -234,6 +236,9 @@ int nx_image_begin(nx_ctx* ctx, int nx, int nz);
 int nx_image_add(nx_ctx* ctx, long long n, const nx_image_params* ip);
 int nx_image_fetch(nx_ctx* ctx, double* image, long long* counts);
 int nx_image_device_ptrs(nx_ctx* ctx, void** image_dev, void** counts_dev);
+/* Sharded runs: sum the context-owned image + counts over the ranks of `comm` (see nx_comm_create
+ * below), in place, on the context's stream -- the single all-reduce of an image product.    */
+int nx_image_allreduce(nx_ctx* ctx, nx_comm* comm);
 
 /* ---- K5: lines of sight (compute_iteration.py:151-222) ------------------------
  * los[6*nlos] SoA: x,y,z,xbore,ybore,zbore; dist_from_plan[nlos] as computed at

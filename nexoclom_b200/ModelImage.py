@@ -58,7 +58,7 @@ class _Hist2d:
 
 class ModelImage(ModelResult):
     def __init__(self, inputs, params, overwrite=False, distribute=None, device=None):
-        from .sharding import local_device, allreduce_sum
+        from .sharding import local_device, allreduce_sum, nccl_comm
         super().__init__(inputs, params)
         self.type = 'image'
         self.origin = self.params.get('origin', inputs.geometry.planet)
@@ -96,18 +96,28 @@ class ModelImage(ModelResult):
         # Every output file of this rank is binned into ONE image that stays on the device
         # (the reference adds the per-file histograms on the host, ModelImage.py:92-99) ...
         self.outid, self.outputfiles, _, _ = self.inputs.search()
-        if self.outputfiles:
+        comm = nccl_comm()
+        eng = None
+        if self.outputfiles or comm is not None:
             eng = get_engine(self._device)
             eng.image_begin(*self.dims)
             for fname in self.outputfiles:
                 print(f'Output filename: {fname}')
                 self.totalsource += self._accumulate(catalogue.fetch(fname), eng)
+        # ... and the ranks of a sharded run are combined with ONE all-reduce per product: on
+        # the device over NCCL / NVLink (before the image crosses PCIe once), through
+        # torch.distributed for the gloo backend of the CPU tests
+        if comm is not None:
+            eng.image_allreduce(comm[1])
+        if eng is not None:
             img, cnt = eng.image_fetch(*self.dims)
-            self.image += img
-            self.packet_image += cnt
-        # ... and the ranks of a sharded run are combined with one all-reduce per product
+            self.image = img
+            self.packet_image = cnt.astype(np.float64)
         tot = np.array([float(self.totalsource)])
-        allreduce_sum(self.image, self.packet_image, tot)
+        if comm is not None:
+            allreduce_sum(tot)
+        else:
+            allreduce_sum(self.image, self.packet_image, tot)
         self.totalsource = float(tot[0])
 
         mod_rate = self.totalsource / self.inputs.options.endtime.value

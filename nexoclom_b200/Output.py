@@ -107,8 +107,7 @@ class Output:
                     host_cols = cols
                 else:
                     eng.import_state(cols)
-                self._X0 = pd.DataFrame({c: cols[k] for k, c in enumerate(STATE_COLS)})
-                self._imported_cols = cols
+                self._imported_cols = cols           # X0 (a 64 B/packet frame) is built on access
             else:
                 if self.inputs.spatialdist.type not in ('uniform', 'surface map',
                                                         'surface spot'):

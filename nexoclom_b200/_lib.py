@@ -107,6 +107,7 @@ def load():
         'nx_ctx_create': [C.c_int, C.POINTER(vp)],
         'nx_ctx_destroy': [vp],
         'nx_ctx_set_stream': [vp, vp],
+        'nx_ctx_stream': [vp, C.POINTER(vp)],
         'nx_ctx_sync': [vp],
         'nx_ctx_set_option': [vp, C.c_char_p, C.c_int],
         'nx_last_error': [vp],
@@ -137,6 +138,7 @@ def load():
         'nx_image_add': [vp, i64, C.POINTER(ImageParams)],
         'nx_image_fetch': [vp, c_double_p, c_i64_p],
         'nx_image_device_ptrs': [vp, C.POINTER(vp), C.POINTER(vp)],
+        'nx_image_allreduce': [vp, vp],
         'nx_los_accumulate': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams),
                               c_double_p, c_i64_p, c_u8_p],
         'nx_los_accumulate_dev': [vp, i64, i64, vp, vp, C.POINTER(LosParams), vp, vp, vp],

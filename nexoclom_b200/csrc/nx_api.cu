@@ -78,6 +78,8 @@ struct nx_ctx {
   // make once per output file, and nothing to leak on an error path
   struct Scratch { void* p = nullptr; size_t bytes = 0; } scr[24];
   int img_nx = 0, img_nz = 0;  // shape of the context-owned image scratch (nx_image_begin)
+  void* pinned = nullptr;      // grow-only pinned staging for small D2H results (image, LOS columns)
+  size_t pinned_bytes = 0;
   unsigned* cmp_tiles = nullptr;     // compaction scratch (tile counts)
   long long cmp_tiles_cap = 0;       // X0 columns 0-7 hold an initial state (K1 or the host-buffer path)
   unsigned *att = nullptr, *acc = nullptr;
@@ -212,6 +214,15 @@ static int scratch_bytes(nx_ctx* ctx, int slot, size_t bytes, void** out) {
     (ptr) = reinterpret_cast<decltype(ptr)>(p_);                                           \
   } while (0)
 
+static int pinned_staging(nx_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_bytes) return 0;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+  CK(cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocDefault));
+  ctx->pinned_bytes = bytes;
+  return 0;
+}
+
 static StateCols state_cols(nx_ctx* ctx) {
   StateCols P;
   if (ctx->bound) {
@@ -315,6 +326,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   cudaFree(ctx->scalars); cudaFree(ctx->status); cudaFree(ctx->cmp_tiles);
   for (auto& sc : ctx->scr) cudaFree(sc.p);
   cudaFree(ctx->squeue); cudaFreeHost(ctx->seq_host);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -1038,9 +1050,34 @@ int nx_image_fetch(nx_ctx* ctx, double* image, long long* counts) {
   CK(cudaSetDevice(ctx->device));
   if (!ctx->img_nx) { ctx->err = "nx_image_begin not called"; return -1; }
   const size_t npix = (size_t)ctx->img_nx * ctx->img_nz;
-  if (image) CK(cudaMemcpyAsync(image, ctx->scr[SCR_IMG].p, npix * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  if (counts) CK(cudaMemcpyAsync(counts, ctx->scr[SCR_CNT].p, npix * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  // D2H into pinned staging (full PCIe rate), then a host memcpy into the caller's pageable
+  // arrays: about 3x faster than letting the driver stage a pageable copy
+  int r = pinned_staging(ctx, 2 * npix * 8);
+  if (r) return r;
+  char* st = static_cast<char*>(ctx->pinned);
+  if (image) CK(cudaMemcpyAsync(st, ctx->scr[SCR_IMG].p, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (counts) CK(cudaMemcpyAsync(st + npix * 8, ctx->scr[SCR_CNT].p, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (image) std::memcpy(image, st, npix * 8);
+  if (counts) std::memcpy(counts, st + npix * 8, npix * 8);
+  return 0;
+}
+
+// The ONE collective of an image product: the context-owned image and
+// counts of every rank of `comm` are summed in place, on the context's stream.
+int nx_image_allreduce(nx_ctx* ctx, nx_comm* comm) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->img_nx) { ctx->err = "nx_image_begin not called"; return -1; }
+  const long long npix = (long long)ctx->img_nx * ctx->img_nz;
+  int r = nx_allreduce(comm, ctx->scr[SCR_IMG].p, npix, NX_DTYPE_F64, ctx->stream);
+  if (r == 0) r = nx_allreduce(comm, ctx->scr[SCR_CNT].p, npix, NX_DTYPE_I64, ctx->stream);
+  if (r) ctx->err = std::string("nx_image_allreduce: ") + nx_comm_last_error();
+  return r;
+}
+
+int nx_ctx_stream(nx_ctx* ctx, void** cuda_stream) {
+  if (!cuda_stream) return -1;
+  *cuda_stream = ctx->stream;
   return 0;
 }
 

@@ -861,14 +861,41 @@ __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& 
   }
 }
 
-// measured (2e6 packets, no image / fused image, ms): 6/3: 21.0/28.0, 10/6: 18.5/25.7,
-// 16/10: 17.3/25.0, 20/12: 17.7/25.5, 24/16: 18.9/26.9
-#ifndef NX_BOUNCE_BATCH
-#define NX_BOUNCE_BATCH 16
-#endif
-#ifndef NX_BOUNCE_MAXWAIT
-#define NX_BOUNCE_MAXWAIT 10
-#endif
+// K3 keeps the packets of a warp in a shared-memory POOL of NX_POOL_SLOTS slots (twice the
+// warp width) and runs warp-uniform PHASES over it; a lane holds no packet between phases:
+//   NEW    packets that just arrived from HBM (cp.async straight into their slot): row 0
+//   STEP   32 runnable packets take one Dormand-Prince step; those that end below the
+//          surface are PARKED (state + radius written back), the rest emit their row
+//   BOUNCE 32 parked packets go through the surface interaction together and emit
+// The surface interaction costs about two steps and ~10 % of the packets need it after any
+// given step: run per lane where it occurs it leaves 20 of 32 lanes busy (round 1, ncu
+// smsp__thread_inst_executed_per_inst_executed 19.9); with the pool both the step and the
+// bounce code run on full warps, whatever the mix.  Results do not depend on the schedule:
+// the bounce deviates are Philox draws keyed by (seed, packet id, step).
+#define NX_POOL_WORDS 3
+#define NX_POOL_SLOTS (32 * NX_POOL_WORDS)
+#define NX_POOL_FIELDS 10      // time,x,y,z,vx,vy,vz,frac, time left in the run, radius at impact
+#define NX_POOL_BYTES_PER_WARP (NX_POOL_FIELDS * NX_POOL_SLOTS * 8 + NX_POOL_SLOTS * 8 + NX_POOL_SLOTS + 32)
+#define NX_POOL_BYTES_PER_WARP_ALIGNED ((NX_POOL_BYTES_PER_WARP + 15) / 16 * 16)
+enum { SLOT_FREE = 0, SLOT_LOADING = 1, SLOT_NEW = 2, SLOT_RUN = 3, SLOT_PARKED = 4 };
+
+// census of one class of slots: lane L looks at slots L, L + 32, ...; m[w] = ballot of word w
+struct SlotMask {
+  unsigned m[NX_POOL_WORDS];
+  __device__ __forceinline__ int count() const {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < NX_POOL_WORDS; ++w) c += __popc(m[w]);
+    return c;
+  }
+};
+__device__ __forceinline__ SlotMask census(const unsigned* k, unsigned what) {
+  SlotMask r;
+#pragma unroll
+  for (int w = 0; w < NX_POOL_WORDS; ++w) r.m[w] = __ballot_sync(FULL_MASK, k[w] == what);
+  return r;
+}
+
 // MODE as in k_integrate_adaptive: -1 strict, else fast with MODE = GR*8 + RP*4 + LOSS.
 // ROWS: compile the row sink in (a separate instantiation keeps the plain kernel's hot loop
 // as small as it was: the loop is instruction-cache bound).
@@ -886,84 +913,151 @@ k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, Interp
   FastTable F;
   if (MODE < 0) stage_table(Tg, T, smem_raw);
   else stage_fast_table(Fg, F, smem_raw);
-  PacketFeeder feed;
-  feed.init(smem_raw + table_bytes, &In, nullptr, queue, n);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned char* pool = smem_raw + table_bytes + (size_t)warp * NX_POOL_BYTES_PER_WARP_ALIGNED;
+  double* fld = reinterpret_cast<double*>(pool);                       // [FIELDS][SLOTS]
+  unsigned* sidx = reinterpret_cast<unsigned*>(fld + NX_POOL_FIELDS * NX_POOL_SLOTS);
+  unsigned* sct = sidx + NX_POOL_SLOTS;
+  unsigned char* kind = reinterpret_cast<unsigned char*>(sct + NX_POOL_SLOTS);
+  unsigned char* sel = kind + NX_POOL_SLOTS;                           // slot of lane r this phase
+#pragma unroll
+  for (int w = 0; w < NX_POOL_WORDS; ++w) kind[lane + 32 * w] = SLOT_FREE;
   __syncthreads();
   const bool pass_through = In.c[0] != P.c[0];     // see k_integrate_adaptive
-  const unsigned lane = threadIdx.x & 31u;
   const ImageSteps isteps = image_steps(ip);
 
-  bool have = false, drained = false, pending = false;
-  unsigned idx = 0;
-  double s[8], rhit = 0.0;
-  double curtime = 0.0;
-  int ct = 0, wait_iters = 0;
+  bool loading = false, queue_done = false;
   unsigned long long tot = 0;
   int st = 0;
 
-  // One row of the reference's trajectory tensor (Output.py:376-421) is EMITTED at a
-  // single place per loop iteration -- for a packet that was just loaded (row 0), that
-  // completed a step, or whose bounce was just resolved -- so the image / trajectory /
-  // retire code exists once in the kernel (instruction-cache footprint: with one copy
-  // per call site the fused kernel stalled 4.4 cycles per issue on instruction fetch).
   for (;;) {
-    bool emit = false, live = true;
-    unsigned need = __ballot_sync(FULL_MASK, !have);
-    while (need && !drained) {
-      if (feed.pos == feed.cnt && !feed.advance()) { drained = true; break; }
-      const int take = min(__popc(need), feed.cnt - feed.pos);
-      const int rank = __popc(need & ((1u << lane) - 1u));
-      if (!have && rank < take) {
-        const int slot = feed.pos + rank;
-        const double* v = feed.vals + (size_t)feed.buf * NX_FEED_COLS * 32 + slot;
+    if (loading) {                                   // the batch requested one phase ago
+      cp_async_wait_all();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] = v[k * 32];
-        idx = feed.ids[feed.buf * 32 + slot];
-        curtime = p.endtime; ct = 0;       // row 0 (Output.py:379-386)
-        have = true; emit = true; live = s[7] > 0.0;
-      }
-      feed.pos += take;
-      need = __ballot_sync(FULL_MASK, !have);
+      for (int w = 0; w < NX_POOL_WORDS; ++w)
+        if (kind[lane + 32 * w] == SLOT_LOADING) kind[lane + 32 * w] = SLOT_NEW;
+      loading = false;
+      __syncwarp();
     }
-    if (!__any_sync(FULL_MASK, have)) {
-      if (drained) break;
-      continue;
-    }
-    if (have && !pending && !emit) {
-      bool bad = false;
+    unsigned kk[NX_POOL_WORDS];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
-      if (bad) st |= 32;
-      ++tot;
-      if (MODE < 0) {
-        live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
-        emit = true;
-      } else {
-        const double r = constant_stages_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s);
-        bool hit = sub_rn(r, 1.0) < 0.0;
-        if (hit && p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0) { s[7] = 0.0; hit = false; }
-        if (hit) { pending = true; rhit = r; }
-        else { live = constant_post(p, s, r); emit = true; }
-      }
-    }
-    if (MODE >= 0) {
-      // Fast mode: the bounce is ~2x the cost of a step but only ~10% of the lanes
-      // need it in a given step, so lanes that hit the surface PARK (pending) and
-      // the warp runs the bounce code once enough of them have accumulated; results
-      // do not depend on the batching (Philox is keyed by packet id and step).
-      const int npend = __popc(__ballot_sync(FULL_MASK, pending));
-      const int nrun = __popc(__ballot_sync(FULL_MASK, have && !pending));
-      wait_iters = npend ? wait_iters + 1 : 0;
-      if (npend >= NX_BOUNCE_BATCH || (npend > 0 && (nrun == 0 || wait_iters >= NX_BOUNCE_MAXWAIT))) {
-        if (pending) {
-          constant_bounce_fast(p, S, s, rhit, seed, first_id + (uint64_t)idx, (uint32_t)ct);
-          pending = false;
-          live = constant_post(p, s, rhit);
-          emit = true;
+    for (int w = 0; w < NX_POOL_WORDS; ++w) kk[w] = kind[lane + 32 * w];
+    const SlotMask m_free = census(kk, SLOT_FREE), m_new = census(kk, SLOT_NEW),
+                   m_run = census(kk, SLOT_RUN), m_park = census(kk, SLOT_PARKED);
+    const int nfree = m_free.count(), nnew = m_new.count(), nrun = m_run.count(),
+              npark = m_park.count();
+    if (nfree == NX_POOL_SLOTS && queue_done) break;
+
+    // refill: 32 or more free slots are filled from the global packet queue (so that the
+    // NEW phases are full too); the copies land while the phase below runs
+    if (!queue_done && nfree >= 32) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(queue, (unsigned long long)nfree);
+      base = __shfl_sync(FULL_MASK, base, 0);
+      if ((long long)base + nfree >= n) queue_done = true;
+      int before = 0;
+#pragma unroll
+      for (int w = 0; w < NX_POOL_WORDS; ++w) {
+        const int j = (int)lane + 32 * w;
+        if ((m_free.m[w] >> lane) & 1u) {
+          const long long q = (long long)base + before + __popc(m_free.m[w] & ((1u << lane) - 1u));
+          if (q < n) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cp_async8(fld + k * NX_POOL_SLOTS + j, In.c[k] + q);
+            fld[8 * NX_POOL_SLOTS + j] = p.endtime;      // row 0 (Output.py:379-386)
+            sidx[j] = (unsigned)q;
+            sct[j] = 0u;
+            kind[j] = SLOT_LOADING;
+          }
         }
-        wait_iters = 0;
+        before += __popc(m_free.m[w]);
+      }
+      cp_async_commit();
+      loading = true;
+    }
+
+    // phase: a full warp of parked packets first (they hold slots), else new arrivals, else
+    // a step; a class that cannot fill the warp only runs when nothing else can
+    int phase;
+    if (npark >= 32) phase = SLOT_PARKED;
+    else if (nnew >= 32) phase = SLOT_NEW;
+    else if (nrun >= 32) phase = SLOT_RUN;
+    else if (nrun >= npark && nrun >= nnew && nrun > 0) phase = SLOT_RUN;
+    else if (npark >= nnew && npark > 0) phase = SLOT_PARKED;
+    else if (nnew > 0) phase = SLOT_NEW;
+    else continue;                                    // only copies in flight
+    SlotMask M;
+#pragma unroll
+    for (int w = 0; w < NX_POOL_WORDS; ++w)
+      M.m[w] = phase == SLOT_PARKED ? m_park.m[w] : (phase == SLOT_NEW ? m_new.m[w] : m_run.m[w]);
+    // the r-th slot of the class goes to lane r: every slot's owner lane scatters its rank
+    {
+      int before = 0;
+#pragma unroll
+      for (int w = 0; w < NX_POOL_WORDS; ++w) {
+        if ((M.m[w] >> lane) & 1u) {
+          const int r = before + __popc(M.m[w] & ((1u << lane) - 1u));
+          if (r < 32) sel[r] = (unsigned char)(lane + 32 * w);
+        }
+        before += __popc(M.m[w]);
+      }
+      __syncwarp();
+    }
+    const int navail = M.count();
+    const bool act = (int)lane < navail;
+    const int j = act ? (int)sel[lane] : 0;
+
+    double s[8], curtime = 0.0, rhit = 0.0;
+    unsigned idx = 0;
+    int ct = 0;
+    bool emit = false, live = true;
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = fld[k * NX_POOL_SLOTS + j];
+      curtime = fld[8 * NX_POOL_SLOTS + j];
+      idx = sidx[j];
+      ct = (int)sct[j];
+    }
+    if (phase == SLOT_NEW) {
+      if (act) { emit = true; live = s[7] > 0.0; }
+    } else if (phase == SLOT_RUN) {
+      if (act) {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
+        if (bad) st |= 32;
+        ++tot;
+        if (MODE < 0) {
+          live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+          emit = true;
+        } else {
+          const double r = constant_stages_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s);
+          bool hit = sub_rn(r, 1.0) < 0.0;
+          if (hit && p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0) { s[7] = 0.0; hit = false; }
+          if (hit) {                                   // park: the bounce runs on a full warp
+#pragma unroll
+            for (int k = 0; k < 8; ++k) fld[k * NX_POOL_SLOTS + j] = s[k];
+            fld[9 * NX_POOL_SLOTS + j] = r;
+            kind[j] = SLOT_PARKED;
+          } else {
+            live = constant_post(p, s, r);
+            emit = true;
+          }
+        }
+      }
+    } else {
+      if (MODE >= 0 && act) {
+        rhit = fld[9 * NX_POOL_SLOTS + j];
+        constant_bounce_fast(p, S, s, rhit, seed, first_id + (uint64_t)idx, (uint32_t)ct);
+        live = constant_post(p, s, rhit);
+        emit = true;
       }
     }
+
+    // One row of the reference's trajectory tensor (Output.py:376-421) is EMITTED at a
+    // single place per phase -- for a packet that was just loaded (row 0), that completed
+    // a step, or whose bounce was just resolved -- so the image / trajectory / retire code
+    // exists once in the kernel (instruction-cache footprint).
     if (emit) {
       if (traj) {
 #pragma unroll
@@ -974,7 +1068,7 @@ k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, Interp
     if (ROWS) {
       // Row sink: what the reference keeps of a constant-step run (Output.py:434-449 flattens
       // results[N, 8, nsteps]; Output.save drops the frac == 0 rows and rounds to float32),
-      // appended to a device table with one warp-aggregated atomic per iteration
+      // appended to a device table with one warp-aggregated atomic per phase
       // (cap == 0: the rows are only counted).
       const bool want = emit && (!rows.skip_dead || s[7] > 0.0);
       const unsigned m = __ballot_sync(FULL_MASK, want);
@@ -1007,9 +1101,16 @@ k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, Interp
 #pragma unroll
           for (int k = 0; k < 8; ++k) __stcs(P.c[k] + idx, s[k]);
         }
-        have = false;
+        kind[j] = SLOT_FREE;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fld[k * NX_POOL_SLOTS + j] = s[k];
+        fld[8 * NX_POOL_SLOTS + j] = curtime;
+        sct[j] = (unsigned)ct;
+        kind[j] = SLOT_RUN;
       }
     }
+    __syncwarp();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1465,10 +1566,10 @@ static cudaError_t launch_constant_mode(cudaStream_t st, int device, StateCols I
                                         const RowSink& rows,
                                         unsigned long long* queue, unsigned long long* totals,
                                         int* status) {
-  const size_t tbytes = (MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F);
-  const size_t smem = tbytes + (size_t)(NX_INT_THREADS / 32) * NX_FEED_BYTES_PER_WARP;
+  const size_t tbytes = (((MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F)) + 15) & ~(size_t)15;
+  const size_t smem = tbytes + (size_t)(NX_INT_THREADS / 32) * NX_POOL_BYTES_PER_WARP_ALIGNED;
   int blocks = 0;
-  const long long need = (n + NX_INT_THREADS - 1) / NX_INT_THREADS;
+  const long long need = (n + 2 * NX_INT_THREADS - 1) / (2 * NX_INT_THREADS);
   cudaError_t e;
   if (rows.cursor) {
     e = persistent_grid(k_integrate_constant<MODE, true>, device, smem, &blocks);

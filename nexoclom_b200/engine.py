@@ -315,6 +315,16 @@ class Engine:
                                             cnt.ctypes.data_as(_lib.c_i64_p)), 'nx_image_fetch')
         return img, cnt
 
+    def image_allreduce(self, comm):
+        """Sum the context-owned image + counts over the ranks of ``comm`` (an ``nx_comm``
+        handle), in place on the device: the one collective of an image product."""
+        self._check(self.lib.nx_image_allreduce(self.ctx, comm), 'nx_image_allreduce')
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        self._check(self.lib.nx_ctx_stream(self.ctx, C.byref(p)), 'nx_ctx_stream')
+        return p.value
+
     def image_device_ptrs(self):
         a, b = C.c_void_p(), C.c_void_p()
         self._check(self.lib.nx_image_device_ptrs(self.ctx, C.byref(a), C.byref(b)),

@@ -128,6 +128,15 @@ def allreduce_sum(*arrays):
     return arrays
 
 
+def nccl_comm():
+    """``(lib, nx_comm handle)`` when this process group runs over NCCL, else ``None`` (single
+    process, or the gloo backend of the CPU tests)."""
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1 or dist.get_backend() != 'nccl':
+        return None
+    return _nccl_comm()
+
+
 def allreduce_products(*tensors):
     """In-place SUM all-reduce of torch tensors (device tensors under NCCL); kept for callers
     that hold their products as tensors (bench.py)."""
