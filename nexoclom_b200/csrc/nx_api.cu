@@ -163,6 +163,7 @@ static void free_los_work(LosGridWork& w) {
   cudaFree(w.sorted.pos);
   cudaFree(w.sorted.frac); cudaFree(w.sorted.idx); cudaFree(w.cell_id); cudaFree(w.count);
   cudaFree(w.start); cudaFree(w.block_sum); cudaFree(w.total); cudaFree(w.extent_bits);
+  cudaFree(w.pairs); cudaFree(w.pair_cursor);
   const int G = w.G_fixed;
   const double scale = w.scale;
   w = LosGridWork{};
@@ -186,6 +187,17 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
   CK(cudaMalloc(&w.block_sum, ((ncell + 4095) / 4096 + 1) * sizeof(unsigned)));
   CK(cudaMalloc(&w.total, sizeof(unsigned)));
   CK(cudaMalloc(&w.extent_bits, 2 * sizeof(unsigned long long)));
+  // pair buffer: 32 pairs per packet, between 4 M and 512 M entries (4 GB of the 180), never
+  // less than one line of sight can produce (every packet once); lines of sight are batched
+  // when it cannot hold all pairs (launch_los_grid)
+  unsigned long long pc = 32ull * (unsigned long long)n;
+  if (pc < (1ull << 22)) pc = 1ull << 22;
+  if (pc > (1ull << 29)) pc = 1ull << 29;
+  if (pc < (unsigned long long)n + 1024) pc = (unsigned long long)n + 1024;
+  CK(cudaMalloc(&w.pairs, pc * sizeof(uint2)));
+  CK(cudaMalloc(&w.pair_cursor, 2 * sizeof(unsigned long long)));   // pairs written, line-of-sight ticket
+  w.pairs_cap = pc;
+  w.batch_hint = 0;
   w.cap = n;
   return 0;
 }
@@ -1306,6 +1318,7 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
   SCR(SCR_LADDER, d_ladder, ladder.size());
   SCR(SCR_WID2, d_wid2, wid2.size());
   SCR(SCR_NUSED, d_nused, (size_t)nlos);
+  CK(cudaMemsetAsync(d_nused, 0, (size_t)nlos * sizeof(unsigned long long), ctx->stream));
   CK(cudaMemcpyAsync(d_los, los, 6 * (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_dist, dist_from_plan, (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(d_nball, nball.data(), (size_t)nlos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

@@ -184,13 +184,17 @@ NX_HD void sincos_small(double d, double& sn, double& cs) {
 // MO = 1: one moon (the extension of RunParams) acts on the packets: its phase at the stage
 // time tau - c_n h is phi_0 + omega c_n h, evaluated by angle addition from one sincos per
 // step; `moon_end` receives the moon's position at the end of the step (impact test).
+// `hc` (constant-step driver: h is the same for every packet and step): the products
+// h * A2_mj (index m * 8 + j) and h * GM (index 56) formed once on the host -- the same
+// correctly rounded products, 16 fewer FP64 multiplies per step.
+#define NX_STEPCOEF_COUNT 57
 template <int GR, int RP, int LOSS, bool ERR, int MO = 0>
 NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, double h,
                        double* nx, double& fn, double* d, double& delta_f,
-                       double* moon_end = nullptr) {
+                       double* moon_end = nullptr, const double* hc = nullptr) {
   double K[6][3];                      // K_j = h * accel_j  (the only per-stage storage)
   const double hv0 = h * s[4], hv1 = h * s[5], hv2 = h * s[6];
-  const double hGM = h * p.GM;
+  const double hGM = hc ? hc[56] : h * p.GM;
   double ms0 = 0.0, mc0 = 1.0, hGMm = 0.0, hGMi = 0.0, mx = 0.0, my = 0.0;
   if (MO) {
     const double phi0 = p.moon_phi[0] - p.moon_omega[0] * s[0];
@@ -249,7 +253,7 @@ NX_HD void fast_stages(const RunParams& p, const FastTable& T, const double* s, 
         av0 = fma(a, K[j][0], av0); av1 = fma(a, K[j][1], av1); av2 = fma(a, K[j][2], av2);
       }
       if (j < n) {
-        const double ha2 = h * dp_a2(m, j);
+        const double ha2 = hc ? hc[m * 8 + j] : h * dp_a2(m, j);
         ap0 = fma(ha2, K[j][0], ap0); ap1 = fma(ha2, K[j][1], ap1); ap2 = fma(ha2, K[j][2], ap2);
       }
     }

@@ -877,6 +877,12 @@ __device__ __forceinline__ void image_add(const ImageParams& ip, const GTables& 
 #define NX_POOL_FIELDS 10      // time,x,y,z,vx,vy,vz,frac, time left in the run, radius at impact
 #define NX_POOL_BYTES_PER_WARP (NX_POOL_FIELDS * NX_POOL_SLOTS * 8 + NX_POOL_SLOTS * 8 + NX_POOL_SLOTS + 32)
 #define NX_POOL_BYTES_PER_WARP_ALIGNED ((NX_POOL_BYTES_PER_WARP + 15) / 16 * 16)
+// measured (8e6 packets of configs[2], plain / fused image, 1e10 packet-steps/s):
+// 512 threads (120 registers) 2.38 / 1.69; 640 threads (96 registers, 68 B of spills) 2.47 / 1.71
+#ifndef NX_K3_THREADS
+#define NX_K3_THREADS 640
+#endif
+struct StepCoef { double v[NX_STEPCOEF_COUNT]; };    // h-scaled tableau products (nx_fast.cuh)
 enum { SLOT_FREE = 0, SLOT_LOADING = 1, SLOT_NEW = 2, SLOT_RUN = 3, SLOT_PARKED = 4 };
 
 // census of one class of slots: lane L looks at slots L, L + 32, ...; m[w] = ballot of word w
@@ -900,14 +906,14 @@ __device__ __forceinline__ SlotMask census(const unsigned* k, unsigned what) {
 // ROWS: compile the row sink in (a separate instantiation keeps the plain kernel's hot loop
 // as small as it was: the loop is instruction-cache bound).
 template <int MODE, bool ROWS>
-__global__ void __launch_bounds__(NX_INT_THREADS, NX_INT_MINBLOCKS)
+__global__ void __launch_bounds__(NX_K3_THREADS, 1)
 k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, InterpTable Tg,
                      FastTable Fg, Spline2D S, uint64_t seed, uint64_t first_id, int nsteps,
                      ImageParams ip, GTables G, double* image, unsigned long long* counts,
                      double* traj, RowSink rows,
                      unsigned long long* __restrict__ queue,
                      unsigned long long* __restrict__ totals, int* __restrict__ status,
-                     unsigned table_bytes) {
+                     unsigned table_bytes, StepCoef hc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   InterpTable T;
   FastTable F;
@@ -1022,16 +1028,17 @@ k_integrate_constant(StateCols In, StateCols P, long long n, RunParams p, Interp
       if (act) { emit = true; live = s[7] > 0.0; }
     } else if (phase == SLOT_RUN) {
       if (act) {
-        bool bad = false;
+        // non-finite state (Output.py:388-389): exponent field all ones in any component
+        unsigned worst = 0u;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) bad |= !(fabs(s[k]) <= 1.7976931348623157e308);
-        if (bad) st |= 32;
+        for (int k = 0; k < 8; ++k) worst = max(worst, (unsigned)__double2hiint(s[k]) & 0x7fffffffu);
+        if (worst >= 0x7ff00000u) st |= 32;
         ++tot;
         if (MODE < 0) {
           live = constant_step<true>(p, T, S, s, seed, first_id + (uint64_t)idx, (uint32_t)ct);
           emit = true;
         } else {
-          const double r = constant_stages_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s);
+          const double r = constant_stages_fast<(MODE >> 3) & 1, (MODE >> 2) & 1, MODE & 3>(p, F, s, hc.v);
           bool hit = sub_rn(r, 1.0) < 0.0;
           if (hit && p.sticktype == STICK_CONSTANT && p.stickcoef == 1.0) { s[7] = 0.0; hit = false; }
           if (hit) {                                   // park: the bounce runs on a full warp
@@ -1387,13 +1394,14 @@ cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v) {
 }
 
 template <typename K>
-static cudaError_t persistent_grid(K kernel, int device, size_t smem, int* blocks) {
+static cudaError_t persistent_grid(K kernel, int device, size_t smem, int* blocks,
+                                   int threads = NX_INT_THREADS) {
   cudaError_t e = cudaSuccess;
   if (smem > 48 * 1024)
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NX_INT_THREADS, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   *blocks = per_sm * sm_count(device);
@@ -1567,24 +1575,28 @@ static cudaError_t launch_constant_mode(cudaStream_t st, int device, StateCols I
                                         unsigned long long* queue, unsigned long long* totals,
                                         int* status) {
   const size_t tbytes = (((MODE < 0) ? table_smem_bytes(T) : fast_table_smem_bytes(F)) + 15) & ~(size_t)15;
-  const size_t smem = tbytes + (size_t)(NX_INT_THREADS / 32) * NX_POOL_BYTES_PER_WARP_ALIGNED;
+  const size_t smem = tbytes + (size_t)(NX_K3_THREADS / 32) * NX_POOL_BYTES_PER_WARP_ALIGNED;
+  StepCoef hc;
+  for (int m = 0; m < 7; ++m)
+    for (int j = 0; j < 8; ++j) hc.v[m * 8 + j] = p.step_size * h_dp_a2[m * 8 + j];
+  hc.v[56] = p.step_size * p.GM;
   int blocks = 0;
-  const long long need = (n + 2 * NX_INT_THREADS - 1) / (2 * NX_INT_THREADS);
+  const long long need = (n + 2 * NX_K3_THREADS - 1) / (2 * NX_K3_THREADS);
   cudaError_t e;
   if (rows.cursor) {
-    e = persistent_grid(k_integrate_constant<MODE, true>, device, smem, &blocks);
+    e = persistent_grid(k_integrate_constant<MODE, true>, device, smem, &blocks, NX_K3_THREADS);
     if (e != cudaSuccess) return e;
     if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-    k_integrate_constant<MODE, true><<<blocks, NX_INT_THREADS, smem, st>>>(
+    k_integrate_constant<MODE, true><<<blocks, NX_K3_THREADS, smem, st>>>(
         In, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, rows, queue,
-        totals, status, (unsigned)tbytes);
+        totals, status, (unsigned)tbytes, hc);
   } else {
-    e = persistent_grid(k_integrate_constant<MODE, false>, device, smem, &blocks);
+    e = persistent_grid(k_integrate_constant<MODE, false>, device, smem, &blocks, NX_K3_THREADS);
     if (e != cudaSuccess) return e;
     if (need < blocks) blocks = (int)(need > 0 ? need : 1);
-    k_integrate_constant<MODE, false><<<blocks, NX_INT_THREADS, smem, st>>>(
+    k_integrate_constant<MODE, false><<<blocks, NX_K3_THREADS, smem, st>>>(
         In, P, n, p, T, F, S, seed, first_id, nsteps, ip, G, image, counts, traj, rows, queue,
-        totals, status, (unsigned)tbytes);
+        totals, status, (unsigned)tbytes, hc);
   }
   return cudaGetLastError();
 }

@@ -69,10 +69,15 @@ struct LosGridWork {
            *total = nullptr;
   unsigned long long* extent_bits = nullptr;
   long long cap = 0;
+  // candidate (line of sight, sorted packet) pairs between k_los_candidates and k_los_resolve
+  uint2* pairs = nullptr;
+  unsigned long long pairs_cap = 0;
+  unsigned long long* pair_cursor = nullptr;
+  long long batch_hint = 0;    // lines of sight per batch that half-filled `pairs` last time
 };
 cudaError_t launch_los_grid_build(cudaStream_t st, int device, StateCols P, long long n,
                                   const LosParams& lp, LosGridWork& w);
-cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlos,
+cudaError_t launch_los_grid(cudaStream_t st, LosGridWork& w, long long nlos,
                             const double* los, const double* dist_plan, const int* nball,
                             const double* ladder, const double* wid2, const LosParams& lp,
                             const LosConsts& lc, const GTables& G, double* radiance,

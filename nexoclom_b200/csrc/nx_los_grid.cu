@@ -170,6 +170,9 @@ k_scan_add(unsigned* __restrict__ out, const unsigned* __restrict__ block_sum, i
   if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
 }
 
+// F32: the packets are float32-rounded (what a saved Output holds, quirk Q14), so x, y, z, vy
+// and frac are stored as floats -- a candidate costs 16 bytes instead of 32
+template <bool F32>
 __global__ void __launch_bounds__(256)
 k_los_cell_scatter(StateCols P, long long n, int round32, const unsigned* __restrict__ cell_id,
                    const unsigned* __restrict__ start, unsigned* __restrict__ cursor,
@@ -181,62 +184,106 @@ k_los_cell_scatter(StateCols P, long long n, int round32, const unsigned* __rest
     const unsigned pos = start[id] + atomicAdd(&cursor[id], 1u);
     double x = P.c[1][i], y = P.c[2][i], z = P.c[3][i], vy = P.c[5][i], fr = P.c[7][i];
     if (round32) { x = round_f32(x); y = round_f32(y); z = round_f32(z); vy = round_f32(vy); fr = round_f32(fr); }
-    S.pos[pos] = make_double4(x, y, z, vy); S.frac[pos] = fr;
+    if (F32) {
+      reinterpret_cast<float4*>(S.pos)[pos] = make_float4((float)x, (float)y, (float)z, (float)vy);
+      reinterpret_cast<float*>(S.frac)[pos] = (float)fr;
+    } else {
+      S.pos[pos] = make_double4(x, y, z, vy); S.frac[pos] = fr;
+    }
     S.idx[pos] = (unsigned)i;
   }
 }
 
-// ---- 3. one warp per line of sight ------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long nlos,
-           const double* __restrict__ los, const double* __restrict__ dist_plan,
-           const int* __restrict__ nball, const double* __restrict__ ladder,
-           const double* __restrict__ wid2, LosParams lp, LosConsts lc, GTables G,
-           double* __restrict__ radiance, unsigned long long* __restrict__ npack,
-           unsigned char* __restrict__ included,
-           unsigned long long* __restrict__ nused, const long long* __restrict__ used_off,
-           unsigned long long* __restrict__ used_cursor, unsigned* __restrict__ used_idx,
-           const unsigned* __restrict__ order) {
-  const long long w_ = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w_ >= nlos) return;
+// ---- 3. candidates: one warp per line of sight, lean ------------------------------------
+// The march only decides which (line of sight, packet) pairs deserve the exact test: segment
+// ownership, the cone with a safety margin and the planet cut -- the first rejects of los_hit,
+// in the same arithmetic.  Survivors go to a global pair list (through a per-warp
+// shared-memory buffer: one atomic per ~100 pairs) and are resolved by k_los_resolve, one
+// THREAD per pair.  Keeping acos / log / the ball search / the g-value lookups out of this
+// kernel matters because it is bound by DRAM latency (round 1 ncu: long_scoreboard 9.3 cycles
+// per issue, 72 registers -> 17 resident warps per SM): at ~40 registers three times as many
+// warps are in flight, and the exact test runs on full warps instead of on the ~15 % of the
+// lanes that hit.
+__device__ __forceinline__ float4 load_rec(const float4* p) { return __ldg(p); }
+__device__ __forceinline__ double4 load_rec(const double4* p) { return *p; }
+template <bool F32> struct LosRec { typedef double4 type; };
+template <> struct LosRec<true> { typedef float4 type; };
+#define NX_LOS_WARPS 8              // warps per block of the candidate kernel
+#define NX_LOS_BUF 128              // pairs buffered per warp
+#ifndef NX_LOS_MINBLOCKS
+#define NX_LOS_MINBLOCKS 4          // 64 registers: 32 resident warps per SM
+#endif
+
+template <bool F32>
+__global__ void __launch_bounds__(32 * NX_LOS_WARPS, NX_LOS_MINBLOCKS)
+k_los_candidates(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long nlos,
+                 long long first, long long count, const double* __restrict__ los,
+                 const double* __restrict__ dist_plan, const int* __restrict__ nball,
+                 const double* __restrict__ ladder, double dphi, double cos_margin2,
+                 const unsigned* __restrict__ order, uint2* __restrict__ pairs,
+                 unsigned long long* __restrict__ cursor, unsigned long long cap) {
+  typedef typename LosRec<F32>::type RecT;
+  __shared__ unsigned buf_all[NX_LOS_WARPS][NX_LOS_BUF];
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned* buf = buf_all[threadIdx.x >> 5];
+  const RecT* __restrict__ recs = reinterpret_cast<const RecT*>(S.pos);
+  const double s2 = sin(2.0 * dphi);
+  const double tan_phi = tan(dphi) * (1.0 + 1e-9);
+  // persistent warps: a line of sight costs anything between a few and thousands of
+  // iterations, so every warp takes the next one from a ticket counter when it is done
+  for (;;) {
+  long long w_ = 0;
+  if (lane == 0) w_ = (long long)atomicAdd(cursor + 1, 1ull);
+  w_ = __shfl_sync(FULL_MASK, w_, 0);
+  if (w_ >= count) return;
   // lines of sight are processed in a spatially coherent order (host: Morton order of the
   // points of closest approach) so that neighbouring warps stream the same cells out of L2
-  const long long l = order ? (long long)order[w_] : w_;
-  const unsigned lane = threadIdx.x & 31u;
-  LosRay L;
-  L.xs = los[l]; L.ys = los[nlos + l]; L.zs = los[2 * nlos + l];
-  L.bx = los[3 * nlos + l]; L.by = los[4 * nlos + l]; L.bz = los[5 * nlos + l];
-  L.dist_plan = dist_plan[l];
-  L.nball = nball[l];
+  const long long l = order ? (long long)order[first + w_] : first + w_;
+  const double xs = los[l], ys = los[nlos + l], zs = los[2 * nlos + l];
+  const double bx = los[3 * nlos + l], by = los[4 * nlos + l], bz = los[5 * nlos + l];
+  const double dplan = dist_plan[l];
 
   // farthest axial distance at which a packet can still be a member: planet
   // truncation, last KD ball, and the far side of the packet cube
-  const double s2 = sin(2.0 * lp.dphi);
-  double t_end = ladder[L.nball - 1] * (1.0 + s2);
-  if (L.dist_plan < t_end) t_end = L.dist_plan;
-  const double reach = sqrt(L.xs * L.xs + L.ys * L.ys + L.zs * L.zs) + 1.7320508075688772 * g.half;
+  double t_end = ladder[nball[l] - 1] * (1.0 + s2);
+  if (dplan < t_end) t_end = dplan;
+  const double reach = sqrt(xs * xs + ys * ys + zs * zs) + 1.7320508075688772 * g.half;
   if (reach < t_end) t_end = reach;
-  const double tan_phi = tan(lp.dphi) * (1.0 + 1e-9);
 
-  double rad = 0.0;
-  unsigned long long cnt = 0, used = 0;
-  double t1 = 0.0;
+  int nbuf = 0;                                       // warp-uniform
+  auto flush = [&]() {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(cursor, (unsigned long long)nbuf);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    for (int i = (int)lane; i < nbuf; i += 32)
+      if (base + i < cap) pairs[base + i] = make_uint2((unsigned)l, buf[i]);
+    nbuf = 0;
+    __syncwarp();
+  };
+  double t0 = 0.0, t1 = 0.0;
+  auto keep = [&](double px, double py, double pz) {
+    // same arithmetic as los_hit, so that every packet has exactly one owner segment and no
+    // member is lost
+    const double rx = sub_rn(px, xs), ry = sub_rn(py, ys), rz = sub_rn(pz, zs);
+    const double lr = add_rn(add_rn(mul_rn(rx, bx), mul_rn(ry, by)), mul_rn(rz, bz));
+    const double d2 = add_rn(add_rn(mul_rn(rx, rx), mul_rn(ry, ry)), mul_rn(rz, rz));
+    return (lr >= t0 && lr < t1) && (lr > 0.0) && !(mul_rn(lr, lr) < mul_rn(d2, cos_margin2)) &&
+           (lr < dplan);
+  };
   while (t1 < t_end) {
     // segment [t0, t1): about one cell of the finest axis long, never shorter than the
     // cone is wide there; t1 of one segment IS t0 of the next (same double)
-    const double t0 = t1;
-    const double cx = L.xs + L.bx * t0, cy = L.ys + L.by * t0, cz = L.zs + L.bz * t0;
+    t0 = t1;
+    const double cx = xs + bx * t0, cy = ys + by * t0, cz = zs + bz * t0;
     const double dt = fmax(NX_LOS_SEG_CELLS *
                                fmin(cell_width(cx, g), fmin(cell_width(cy, g), cell_width(cz, g))),
                            2.0 * t0 * tan_phi);
     t1 = t0 + dt;
     const double rho = t1 * tan_phi + 1e-9 * (1.0 + t1);
-    const double ax = L.xs + L.bx * t0, bx = L.xs + L.bx * t1;
-    const double ay = L.ys + L.by * t0, by = L.ys + L.by * t1;
-    const double az = L.zs + L.bz * t0, bz = L.zs + L.bz * t1;
-    const double xlo = fmin(ax, bx) - rho, xhi = fmax(ax, bx) + rho;
-    const double ylo = fmin(ay, by) - rho, yhi = fmax(ay, by) + rho;
-    const double zlo = fmin(az, bz) - rho, zhi = fmax(az, bz) + rho;
+    const double ex = xs + bx * t1, ey = ys + by * t1, ez = zs + bz * t1;
+    const double xlo = fmin(cx, ex) - rho, xhi = fmax(cx, ex) + rho;
+    const double ylo = fmin(cy, ey) - rho, yhi = fmax(cy, ey) + rho;
+    const double zlo = fmin(cz, ez) - rho, zhi = fmax(cz, ez) + rho;
     // boxes entirely outside the packet cube hold nothing
     if (xlo > g.half || xhi < -g.half || ylo > g.half || yhi < -g.half || zlo > g.half ||
         zhi < -g.half)
@@ -244,45 +291,116 @@ k_los_grid(LosSorted S, LosGrid g, const unsigned* __restrict__ start, long long
     const int ix0 = cell_of(xlo, g), ix1 = cell_of(xhi, g);
     const int iy0 = cell_of(ylo, g), iy1 = cell_of(yhi, g);
     const int iz0 = cell_of(zlo, g), iz1 = cell_of(zhi, g);
-    for (int ix = ix0; ix <= ix1; ++ix) {
-      for (int iy = iy0; iy <= iy1; ++iy) {
+    // the (ix, iy) columns of the box: every lane fetches the packet range of one column (the
+    // dependent index loads of up to 32 columns are in flight together), then the warp
+    // streams the ranges one after the other, two records per lane in flight
+    const int nyr = iy1 - iy0 + 1, ncol = (ix1 - ix0 + 1) * nyr;
+    for (int c0 = 0; c0 < ncol; c0 += 32) {
+      const int c = c0 + (int)lane;
+      unsigned p0v = 0u, p1v = 0u;
+      if (c < ncol) {
+        const int ix = ix0 + c / nyr, iy = iy0 + c % nyr;
         const unsigned row = (unsigned)((ix * g.G + iy) * g.G);
-        const unsigned p0 = start[row + iz0], p1 = start[row + iz1 + 1];
-        for (unsigned q = p0 + lane; q < p1; q += 32) {
-          const double4 rec = S.pos[q];
-          const double px = rec.x, py = rec.y, pz = rec.z;
-          // ownership: the segment that contains the packet's axial coordinate
-          // (same arithmetic as los_hit so that every packet has one owner)
-          const double rx = sub_rn(px, L.xs), ry = sub_rn(py, L.ys), rz = sub_rn(pz, L.zs);
-          const double lr = add_rn(add_rn(mul_rn(rx, L.bx), mul_rn(ry, L.by)), mul_rn(rz, L.bz));
-          if (!(lr >= t0 && lr < t1)) continue;
-          double losrad, dist;
-          if (los_hit(L, lp.dphi, lc.cos_margin2, lc.cos_accept2, lc.cover, ladder, wid2,
-                    lc.inv_log_ratio, lc.log_t0,
-                      lc.kwin, px, py, pz, losrad, dist)) {
-            ++cnt;
-            const double w = los_weight(L, lp, G, lc.sin_dphi, S.frac[q], rec.w, losrad, dist);
-            rad += w;
-            if (included) included[S.idx[q]] = 1;
-            if (w > 0.0) {                    // `used` packets (compute_iteration.py:210-211)
-              ++used;
-              if (used_idx) used_idx[used_off[l] + atomicAdd(&used_cursor[l], 1ull)] = S.idx[q];
-            }
+        p0v = __ldg(start + row + iz0); p1v = __ldg(start + row + iz1 + 1);
+      }
+      const int nc = min(32, ncol - c0);
+      for (int k = 0; k < nc; ++k) {
+        const unsigned p0 = __shfl_sync(FULL_MASK, p0v, k), p1 = __shfl_sync(FULL_MASK, p1v, k);
+        for (unsigned qb = p0; qb < p1; qb += 64) {
+          const unsigned q0 = qb + lane, q1 = q0 + 32u;
+          const bool in0 = q0 < p1, in1 = q1 < p1;
+          RecT a, b;
+          if (in0) a = load_rec(recs + q0);
+          if (in1) b = load_rec(recs + q1);
+          const bool k0 = in0 && keep(a.x, a.y, a.z);
+          const bool k1 = in1 && keep(b.x, b.y, b.z);
+          const unsigned m0 = __ballot_sync(FULL_MASK, k0), m1 = __ballot_sync(FULL_MASK, k1);
+          if (m0 | m1) {
+            if (k0) buf[nbuf + __popc(m0 & ((1u << lane) - 1u))] = q0;
+            nbuf += __popc(m0);
+            if (k1) buf[nbuf + __popc(m1 & ((1u << lane) - 1u))] = q1;
+            nbuf += __popc(m1);
+            __syncwarp();
+            if (nbuf > NX_LOS_BUF - 64) flush();
           }
         }
       }
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    rad += __shfl_xor_sync(FULL_MASK, rad, o);
-    cnt += __shfl_xor_sync(FULL_MASK, cnt, o);
-    used += __shfl_xor_sync(FULL_MASK, used, o);
+  if (nbuf) flush();
   }
-  if (lane == 0) {
-    if (radiance) radiance[l] += rad;
-    if (npack) npack[l] += cnt;
-    if (nused) nused[l] = used;
+}
+
+// ---- 4. exact membership + weight, one thread per candidate pair -----------------------
+template <bool F32>
+__global__ void __launch_bounds__(256)
+k_los_resolve(LosSorted S, const uint2* __restrict__ pairs, unsigned long long npairs,
+              long long nlos, const double* __restrict__ los,
+              const double* __restrict__ dist_plan, const int* __restrict__ nball,
+              const double* __restrict__ ladder, const double* __restrict__ wid2, LosParams lp,
+              LosConsts lc, GTables G, double* __restrict__ radiance,
+              unsigned long long* __restrict__ npack, unsigned char* __restrict__ included,
+              unsigned long long* __restrict__ nused, const long long* __restrict__ used_off,
+              unsigned long long* __restrict__ used_cursor, unsigned* __restrict__ used_idx) {
+  typedef typename LosRec<F32>::type RecT;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // whole warps iterate together (the tail is padded with inactive lanes) so that the
+  // per-warp aggregation below can use full-mask collectives
+  const unsigned long long rounded = (npairs + 31ull) & ~31ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+       i < rounded; i += stride) {
+    const bool valid = i < npairs;
+    unsigned l = 0xffffffffu;
+    double w = 0.0;
+    bool hit = false;
+    if (valid) {
+      const uint2 pr = pairs[i];
+      l = pr.x;
+      const unsigned q = pr.y;
+      LosRay L;
+      L.xs = los[l]; L.ys = los[nlos + l]; L.zs = los[2 * nlos + l];
+      L.bx = los[3 * nlos + l]; L.by = los[4 * nlos + l]; L.bz = los[5 * nlos + l];
+      L.dist_plan = dist_plan[l];
+      L.nball = nball[l];
+      const RecT r = load_rec(reinterpret_cast<const RecT*>(S.pos) + q);
+      double losrad, dist;
+      if (los_hit(L, lp.dphi, lc.cos_margin2, lc.cos_accept2, lc.cover, ladder, wid2,
+                  lc.inv_log_ratio, lc.log_t0, lc.kwin, r.x, r.y, r.z, losrad, dist)) {
+        hit = true;
+        const double fr = F32 ? (double)reinterpret_cast<const float*>(S.frac)[q] : S.frac[q];
+        w = los_weight(L, lp, G, lc.sin_dphi, fr, r.w, losrad, dist);
+        const unsigned pidx = S.idx[q];
+        if (included) included[pidx] = 1;
+        if (w > 0.0 && used_idx)               // `used` packets (compute_iteration.py:210-211)
+          used_idx[used_off[l] + atomicAdd(&used_cursor[l], 1ull)] = pidx;
+      }
+    }
+    // pairs of one line of sight sit next to each other in the list: one atomic per run of
+    // equal l within the warp (segmented reduction over the lanes, in lane order)
+    const unsigned prev = __shfl_up_sync(FULL_MASK, l, 1);
+    const bool head = lane == 0 || prev != l;
+    const unsigned heads = __ballot_sync(FULL_MASK, head);
+    const unsigned hitm = __ballot_sync(FULL_MASK, hit);
+    const unsigned usedm = __ballot_sync(FULL_MASK, hit && w > 0.0);
+    // end of my run = next head after my lane
+    const unsigned after = heads & ~((2u << lane) - 1u);
+    const int run_end = after ? __ffs(after) - 1 : 32;
+    // the head of a run adds up its weights in lane order (every lane takes part in the shuffles)
+    double acc = 0.0;
+    for (int k = 0; k < 32; ++k) {
+      const double wk = __shfl_sync(FULL_MASK, w, k);
+      if (head && k >= (int)lane && k < run_end) acc += wk;
+    }
+    if (head && valid) {
+      const unsigned runmask = (run_end >= 32 ? 0xffffffffu : ((1u << run_end) - 1u)) & ~((1u << lane) - 1u);
+      const unsigned nh = __popc(hitm & runmask), nu = __popc(usedm & runmask);
+      if (nh) {
+        if (npack) atomicAdd(&npack[l], (unsigned long long)nh);
+        if (radiance && acc != 0.0) atomicAdd(&radiance[l], acc);
+        if (nused && nu) atomicAdd(&nused[l], (unsigned long long)nu);
+      }
+    }
   }
 }
 
@@ -324,11 +442,14 @@ cudaError_t launch_los_grid_build(cudaStream_t st, int device, StateCols P, long
   k_scan_top<<<1, 1024, 0, st>>>(w.block_sum, nb, w.total);
   k_scan_add<<<nb, 1024, 0, st>>>(w.start, w.block_sum, ncell, w.total);
   if ((e = cudaMemsetAsync(w.count, 0, (size_t)ncell * sizeof(unsigned), st)) != cudaSuccess) return e;
-  k_los_cell_scatter<<<blocks, 256, 0, st>>>(P, n, lp.round_f32, w.cell_id, w.start, w.count, w.sorted);
+  if (lp.round_f32)
+    k_los_cell_scatter<true><<<blocks, 256, 0, st>>>(P, n, lp.round_f32, w.cell_id, w.start, w.count, w.sorted);
+  else
+    k_los_cell_scatter<false><<<blocks, 256, 0, st>>>(P, n, lp.round_f32, w.cell_id, w.start, w.count, w.sorted);
   return cudaGetLastError();
 }
 
-cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlos,
+cudaError_t launch_los_grid(cudaStream_t st, LosGridWork& w, long long nlos,
                             const double* los, const double* dist_plan, const int* nball,
                             const double* ladder, const double* wid2, const LosParams& lp,
                             const LosConsts& lc, const GTables& G, double* radiance,
@@ -336,11 +457,56 @@ cudaError_t launch_los_grid(cudaStream_t st, const LosGridWork& w, long long nlo
                             unsigned long long* nused, const long long* used_off,
                             unsigned long long* used_cursor, unsigned* used_idx,
                             const unsigned* order) {
-  const long long threads = nlos * 32;
-  const long long blocks = (threads + 127) / 128;
-  k_los_grid<<<(unsigned)blocks, 128, 0, st>>>(w.sorted, w.grid, w.start, nlos, los, dist_plan,
-                                               nball, ladder, wid2, lp, lc, G, radiance, npack,
-                                               included, nused, used_off, used_cursor, used_idx, order);
+  // Lines of sight go through in batches sized so that the candidate pairs of a batch fit the
+  // pair buffer (about half full: the size of the next batch follows the pairs per line of
+  // sight seen so far); a batch that overflows is repeated with half as many lines.
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned long long cap = w.pairs_cap;
+  long long batch = w.batch_hint > 0 ? w.batch_hint : nlos;
+  long long first = 0;
+  cudaError_t e;
+  while (first < nlos) {
+    long long cnt = batch < nlos - first ? batch : nlos - first;
+    if ((e = cudaMemsetAsync(w.pair_cursor, 0, 2 * sizeof(unsigned long long), st)) != cudaSuccess) return e;
+    long long blocks = (cnt + NX_LOS_WARPS - 1) / NX_LOS_WARPS;
+    if (blocks > (long long)sms * NX_LOS_MINBLOCKS) blocks = (long long)sms * NX_LOS_MINBLOCKS;
+    if (lp.round_f32)
+      k_los_candidates<true><<<(unsigned)blocks, 32 * NX_LOS_WARPS, 0, st>>>(
+          w.sorted, w.grid, w.start, nlos, first, cnt, los, dist_plan, nball, ladder, lp.dphi,
+          lc.cos_margin2, order, w.pairs, w.pair_cursor, cap);
+    else
+      k_los_candidates<false><<<(unsigned)blocks, 32 * NX_LOS_WARPS, 0, st>>>(
+          w.sorted, w.grid, w.start, nlos, first, cnt, los, dist_plan, nball, ladder, lp.dphi,
+          lc.cos_margin2, order, w.pairs, w.pair_cursor, cap);
+    unsigned long long np = 0;
+    if ((e = cudaMemcpyAsync(&np, w.pair_cursor, sizeof(np), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (np > cap) {
+      if (cnt == 1) return cudaErrorMemoryAllocation;     // cannot happen: cap >= packets + slack
+      batch = cnt / 2 > 1 ? cnt / 2 : 1;
+      continue;
+    }
+    if (np) {
+      long long rb = (long long)((np + 255) / 256);
+      if (rb > (long long)sms * 16) rb = (long long)sms * 16;
+      if (lp.round_f32)
+        k_los_resolve<true><<<(unsigned)rb, 256, 0, st>>>(w.sorted, w.pairs, np, nlos, los, dist_plan, nball,
+                                                          ladder, wid2, lp, lc, G, radiance, npack, included,
+                                                          nused, used_off, used_cursor, used_idx);
+      else
+        k_los_resolve<false><<<(unsigned)rb, 256, 0, st>>>(w.sorted, w.pairs, np, nlos, los, dist_plan, nball,
+                                                           ladder, wid2, lp, lc, G, radiance, npack, included,
+                                                           nused, used_off, used_cursor, used_idx);
+    }
+    first += cnt;
+    const double per = (double)np / (double)cnt;
+    long long next = per > 0.0 ? (long long)(0.9 * (double)cap / per) : nlos;
+    if (next < 256) next = 256;
+    batch = next;
+    w.batch_hint = batch;
+  }
   return cudaGetLastError();
 }
 

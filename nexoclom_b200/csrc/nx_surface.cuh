@@ -317,9 +317,10 @@ NX_HD bool constant_step_fast(const RunParams& p, const FastTable& T, const Spli
 // --- split form of the fast constant step, for kernels that batch the bounces ---
 // stage part: s <- post-step state (before any surface interaction); returns r.
 template <int GR, int RP, int LOSS>
-NX_HD double constant_stages_fast(const RunParams& p, const FastTable& T, double* s) {
+NX_HD double constant_stages_fast(const RunParams& p, const FastTable& T, double* s,
+                                  const double* hc = nullptr) {
   double q[6], d[6], fn, df;
-  fast_stages<GR, RP, LOSS, false>(p, T, s, p.step_size, q, fn, d, df);
+  fast_stages<GR, RP, LOSS, false>(p, T, s, p.step_size, q, fn, d, df, nullptr, hc);
   s[0] -= p.step_size;
 #pragma unroll
   for (int k = 0; k < 6; ++k) s[1 + k] = q[k];
