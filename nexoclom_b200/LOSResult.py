@@ -161,6 +161,8 @@ class LOSResult(ModelResult):
         self.masking = kwargs.get('masking', None)
         self.fit_method = kwargs.get('fit_method', None)
         self.label = kwargs.get('label', 'LOSResult')
+        # True: make_mask / determine_source_rate behave exactly like the reference
+        self.reference_exact = kwargs.get('reference_exact', True)
         from .sharding import local_device
         self._device = local_device() if device is None else device
         self._iterations = {}
@@ -180,11 +182,15 @@ fit_method = {self.fit_method}
 fitted = {self.fitted}'''
 
     def make_mask(self, data):
-        """reference LOSResult.py:171-200.  `middleNN`: the reference hands the WHOLE data
-        frame to astropy's PercentileInterval.get_limits (:181-182), which ravel()s every
-        column (positions, boresights, sigma, ...) into one sample -- and fails on the
-        non-numeric columns a MESSENGERuvvs frame carries; here the limits are the
-        percentiles of the radiances, which the comparison on :183-185 is then applied to."""
+        """reference LOSResult.py:171-200, keyword by keyword.
+
+        `middleNN` as the reference does it (``reference_exact``, the default): the WHOLE
+        data frame goes to astropy's ``PercentileInterval.get_limits`` (:181-182), which
+        ravel()s every column -- positions, boresights, sigma, ... -- into one sample, drops
+        the non-finite values and takes the two percentiles; the radiances are then compared
+        with those limits (:183-185).  A frame with a non-numeric column fails there, as it
+        does in the reference.  ``reference_exact=False`` takes the percentiles of the
+        radiances themselves.  Pinned by tests/golden/source_rate.npz (the unmodified method)."""
         mask = np.array([True for _ in data.radiance])
         sigmalimit = None
         if self.masking is not None:
@@ -192,9 +198,14 @@ fitted = {self.fitted}'''
                 masktype = masktype.strip().lower()
                 if masktype.startswith('middle'):
                     perinterval = float(masktype[6:])
-                    lo = np.percentile(data.radiance, (100 - perinterval) / 2)
-                    hi = np.percentile(data.radiance, 100 - (100 - perinterval) / 2)
-                    mask = mask & (data.radiance >= lo) & (data.radiance <= hi)
+                    lower = (100 - perinterval) * 0.5
+                    if getattr(self, 'reference_exact', True):
+                        values = np.asarray(data).ravel()
+                        values = values[np.isfinite(values)]
+                    else:
+                        values = np.asarray(data.radiance)
+                    lim = np.percentile(values, (lower, 100 - lower))
+                    mask = mask & (data.radiance >= lim[0]) & (data.radiance <= lim[1])
                 elif masktype.startswith('minalt'):
                     mask = mask & (data.alttan >= float(masktype[6:]))
                 elif masktype.startswith('minsnr'):
@@ -257,30 +268,40 @@ fitted = {self.fitted}'''
         print(self.totalsource, self.atoms_per_packet)
 
     def determine_source_rate(self, scdata, use_weight=True):
-        """Linear least-squares scale factor model -> data (reference
-        LOSResult.py:278-308).  astropy's LinearLSQFitter (5.3, pinned by the reference's
-        poetry.lock) multiplies both sides of the design equation by `weights` before
-        np.linalg.lstsq, i.e. it minimises sum((w (d - f m))**2): on a Multiply model that is
-        the closed form f = sum(w^2 m d) / sum(w^2 m m).  The reference passes
-        w = 1/sigma**2 (:281), so its weighted fit is a 1/sigma^4 fit -- kept.  With
-        `siglimit` the reference refits with the weights of the FIRST mask (:296-298, astropy
-        raises on the length mismatch whenever a point was clipped); here the weights follow
-        the clipped mask."""
+        """Linear least-squares scale factor model -> data (reference LOSResult.py:278-308).
+        astropy's LinearLSQFitter (5.3, pinned by the reference's poetry.lock) multiplies both
+        sides of the design equation by `weights` before np.linalg.lstsq, i.e. it minimises
+        sum((w (d - f m))**2): on a Multiply model that is the closed form
+        f = sum(w^2 m d) / sum(w^2 m m).  The reference passes w = 1/sigma**2 (:281), so its
+        weighted fit is a 1/sigma^4 fit -- kept.
+
+        `siglimit`: the reference refits the clipped points with the weights of the FIRST
+        mask (:296-298); astropy raises on the length mismatch whenever a point was clipped.
+        ``reference_exact`` (default) does the same -- ValueError, message of the NumPy
+        broadcast that fails inside astropy --; ``reference_exact=False`` lets the weights
+        follow the clipped mask.  Pinned by tests/golden/source_rate.npz."""
         mask, sigmalimit = self.make_mask(scdata.data)
         d = scdata.data.radiance.values
         m = self.radiance.values
+        sigma = scdata.data.sigma.values
+        exact = getattr(self, 'reference_exact', True)
 
-        def fit(msk):
-            w = (1. / scdata.data.sigma.values[msk]**2 if use_weight
-                 else np.ones_like(scdata.data.sigma.values[msk]))
+        def weights_of(msk):
+            return 1. / sigma[msk]**2 if use_weight else np.ones_like(sigma[msk])
+
+        def fit(msk, w):
+            if len(w) != int(np.sum(msk)):
+                raise ValueError(f'operands could not be broadcast together with shapes '
+                                 f'({int(np.sum(msk))},1) ({len(w)},1) (ufunc \'multiply\')')
             return np.sum(w * w * m[msk] * d[msk]) / np.sum(w * w * m[msk] * m[msk])
 
         if not np.all(m == 0):
-            factor = fit(mask)
+            weights = weights_of(mask)
+            factor = fit(mask, weights)
             if sigmalimit is not None:
-                diff = np.abs((d - factor * m) / scdata.data.sigma.values)
+                diff = np.abs((d - factor * m) / sigma)
                 mask = mask & (diff < sigmalimit)
-                factor = fit(mask)
+                factor = fit(mask, weights if exact else weights_of(mask))
             self.radiance *= factor
             self.sourcerate = Quantity(factor, '')      # x 10**23 atoms/s
         else:

@@ -59,6 +59,7 @@ struct nx_ctx {
   DevInterp speed;
   DevInterp lon1d;             // inverse CDF of a longitude-only source map
   DevInterp gtab[NX_MAX_GTABLES];
+  DevInterp gsum;              // sum of the g-value tables on the union of their nodes
   GTables gtables{};
   double *spl_tx = nullptr, *spl_ty = nullptr, *spl_c = nullptr;
   Spline2D spline{};
@@ -327,6 +328,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
   free_interp(ctx->speed);
   free_interp(ctx->lon1d);
   for (auto& g : ctx->gtab) free_interp(g);
+  free_interp(ctx->gsum);
   cudaFree(ctx->spl_tx); cudaFree(ctx->spl_ty); cudaFree(ctx->spl_c);
   cudaFree(ctx->srcmap);
   cudaFree(ctx->state); cudaFree(ctx->x0); cudaFree(ctx->att); cudaFree(ctx->acc);
@@ -516,6 +518,37 @@ int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* 
     off += sizes[t];
   }
   ctx->gtables.n = ntables;
+  ctx->gtables.has_sum = 0;
+  if (ntables > 1) {
+    // union grid and the sum of the np.interp values there (ModelResult.py:152-157 adds the
+    // lines up per packet; the kernels look the sum up once)
+    std::vector<double> xs(v, v + off);
+    std::sort(xs.begin(), xs.end());
+    xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
+    std::vector<double> fs(xs.size(), 0.0);
+    size_t o = 0;
+    for (int t = 0; t < ntables; ++t) {
+      const double* x = v + o;
+      const double* f = g + o;
+      const int m = sizes[t];
+      for (size_t k = 0; k < xs.size(); ++k) {
+        const double q = xs[k];
+        double val;
+        if (m == 1 || q <= x[0]) val = f[0];
+        else if (q >= x[m - 1]) val = f[m - 1];
+        else {
+          const int j = (int)(std::upper_bound(x, x + m, q) - x) - 1;
+          val = (x[j] == q) ? f[j] : (f[j + 1] - f[j]) / (x[j + 1] - x[j]) * (q - x[j]) + f[j];
+        }
+        fs[k] = fs[k] + val;
+      }
+      o += m;
+    }
+    int r = upload_interp(ctx, ctx->gsum, xs.data(), fs.data(), (int)xs.size(), true, 256);
+    if (r) return r;
+    ctx->gtables.fsum = ctx->gsum.fast;
+    ctx->gtables.has_sum = 1;
+  }
   return 0;
 }
 

@@ -28,7 +28,12 @@ struct LosParams {
 struct GTables {
   InterpTable t[NX_MAX_GTABLES];
   FastTable f[NX_MAX_GTABLES];      // record form of the same tables (kernels)
+  // the SUM of the tables on the union of their nodes (built on upload when n > 1): a sum of
+  // piecewise-linear functions is piecewise linear on the union grid, so the fast path needs
+  // one lookup instead of n (values agree with the sum of n np.interp to rounding)
+  FastTable fsum;
   int n;
+  int has_sum;
 };
 
 NX_HD double round_f32(double v) { return (double)(float)v; }
@@ -85,6 +90,7 @@ NX_HD double gvalue_sum(const GTables& G, double rv) {
 // same sum through the record tables (value differs from np.interp by <= 1 ulp:
 // fma(slope, x - lo, f) instead of slope*(x - lo) + f)
 NX_HD double gvalue_sum_fast(const GTables& G, double rv) {
+  if (G.has_sum) return interp_fast<false>(G.fsum, rv);
   double gg = 0.0;
 #pragma unroll
   for (int i = 0; i < NX_MAX_GTABLES; ++i)

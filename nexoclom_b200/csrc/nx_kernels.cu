@@ -103,6 +103,26 @@ size_t fast_table_smem_bytes(const FastTable& g, bool with_bucket = false) {
   return b;
 }
 
+// g-value tables of K4 in shared memory: the sum table alone when there is one
+__device__ __forceinline__ size_t stage_gtables(const GTables& Gg, GTables& G, unsigned char* base) {
+  G.n = Gg.n; G.has_sum = Gg.has_sum;
+  size_t off = 0;
+  if (Gg.has_sum) {
+    stage_fast_table(Gg.fsum, G.fsum, base, true);
+    return fast_table_smem_bytes_dev(Gg.fsum);
+  }
+#pragma unroll
+  for (int t = 0; t < NX_MAX_GTABLES; ++t)
+    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], base + off, true); off += fast_table_smem_bytes_dev(Gg.f[t]); }
+  return off;
+}
+static size_t gtables_smem_bytes(const GTables& G) {
+  if (G.has_sum) return fast_table_smem_bytes(G.fsum, true);
+  size_t b = 0;
+  for (int t = 0; t < G.n; ++t) b += fast_table_smem_bytes(G.f[t], true);
+  return b;
+}
+
 size_t table_smem_bytes(const InterpTable& g) {
   if (g.n == 0) return 0;
   size_t bytes = (size_t)g.n * 24 + (size_t)g.nbucket * 2;
@@ -1155,11 +1175,7 @@ k_image_accumulate(StateCols P, long long n, ImageParams ip, GTables Gg,
                    double* __restrict__ image, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GTables G;
-  G.n = Gg.n;
-  size_t off = 0;
-#pragma unroll
-  for (int t = 0; t < NX_MAX_GTABLES; ++t)
-    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off, true); off += fast_table_smem_bytes_dev(Gg.f[t]); }
+  stage_gtables(Gg, G, smem_raw);
   __syncthreads();
   const ImageSteps isteps = image_steps(ip);
   const long long npair = n >> 1;
@@ -1212,11 +1228,7 @@ k_image_accumulate_tile(StateCols P, long long n, ImageParams ip, GTables Gg, Im
                         double* __restrict__ image, unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GTables G;
-  G.n = Gg.n;
-  size_t off = 0;
-#pragma unroll
-  for (int t = 0; t < NX_MAX_GTABLES; ++t)
-    if (t < Gg.n) { stage_fast_table(Gg.f[t], G.f[t], smem_raw + off, true); off += fast_table_smem_bytes_dev(Gg.f[t]); }
+  const size_t off = stage_gtables(Gg, G, smem_raw);
   unsigned* __restrict__ tcnt = reinterpret_cast<unsigned*>(smem_raw + off);
   const int tsize = tile.w * tile.h;
   for (int i = threadIdx.x; i < tsize; i += blockDim.x) tcnt[i] = 0u;
@@ -1635,8 +1647,7 @@ cudaError_t launch_integrate_constant(cudaStream_t st, int device, StateCols In,
 cudaError_t launch_image_accumulate(cudaStream_t st, int device, StateCols P, long long n,
                                     const ImageParams& ip, const GTables& G, double* image,
                                     unsigned long long* counts, int mode) {
-  size_t smem = 0;
-  for (int t = 0; t < G.n; ++t) smem += fast_table_smem_bytes(G.f[t], true);
+  size_t smem = gtables_smem_bytes(G);
   // privatised counts (mode 2): a square tile around the pixel of the projected planet centre
   const bool tiled = mode == 2;
   if (tiled) {

@@ -98,7 +98,8 @@ def test_determine_source_rate_is_astropy_linear_lsq(use_weight, masking):
     model = rng.random(n) * (rng.random(n) > 0.1)
     data = pd.DataFrame({'radiance': 2.5 * model + rng.normal(0, 0.05, n),
                          'sigma': 0.02 + 0.2 * rng.random(n), 'alttan': rng.random(n) * 2})
-    me = types.SimpleNamespace(masking=masking, radiance=pd.Series(model.copy()))
+    me = types.SimpleNamespace(masking=masking, radiance=pd.Series(model.copy()),
+                               reference_exact=False)      # weights follow the clipped mask
     me.make_mask = types.MethodType(LOSResult.make_mask, me)
     LOSResult.determine_source_rate(me, types.SimpleNamespace(data=data), use_weight=use_weight)
 
@@ -118,6 +119,45 @@ def test_determine_source_rate_is_astropy_linear_lsq(use_weight, masking):
     assert float(me.sourcerate) == pytest.approx(f, rel=1e-12)
     assert np.array_equal(np.asarray(me.mask), mask)
     assert np.allclose(me.radiance.values, model * f, rtol=1e-12)
+
+
+def test_make_mask_and_source_rate_vs_reference_golden():
+    """tests/golden/source_rate.npz: the UNMODIFIED reference LOSResult.make_mask /
+    determine_source_rate (LOSResult.py:171-200, 278-308) for every masking keyword --
+    `middleNN` over the whole data frame, the refit after `siglimit` that raises whenever a
+    point was clipped -- against the product methods in their default (reference_exact) mode."""
+    import os
+    import types
+    import pandas as pd
+    from common import GOLDEN
+    from nexoclom_b200.LOSResult import LOSResult
+    g = np.load(os.path.join(GOLDEN, 'source_rate.npz'))
+    data = pd.DataFrame({c[5:]: g[c] for c in g.files if c.startswith('data_')})
+    data = data[['radiance', 'sigma', 'alttan', 'x', 'xbore']]        # the generator's column order
+    nraise = 0
+    for ic, masking in enumerate(g['cases']):
+        masking = None if masking == 'None' else str(masking)
+        for w in (0, 1):
+            tag = f'c{ic}_w{w}'
+            me = types.SimpleNamespace(masking=masking, radiance=pd.Series(g['model'].copy()))
+            me.make_mask = types.MethodType(LOSResult.make_mask, me)
+            mask0, _ = me.make_mask(data)
+            assert np.array_equal(mask0, g[tag + '_mask0']), tag
+            if tag + '_raises' in g.files:
+                with pytest.raises(ValueError, match='could not be broadcast'):
+                    LOSResult.determine_source_rate(me, types.SimpleNamespace(data=data),
+                                                    use_weight=bool(w))
+                nraise += 1
+                continue
+            LOSResult.determine_source_rate(me, types.SimpleNamespace(data=data), use_weight=bool(w))
+            assert np.array_equal(np.asarray(me.mask), g[tag + '_mask']), tag
+            assert float(me.sourcerate) == pytest.approx(float(g[tag + '_factor']), rel=1e-12)
+            assert np.allclose(me.radiance.values, g[tag + '_radiance'], rtol=1e-12, atol=0)
+    assert nraise == 4
+    # the non-default variant: percentiles of the radiances only
+    me = types.SimpleNamespace(masking='middle50', radiance=None, reference_exact=False)
+    mask, _ = LOSResult.make_mask(me, data)
+    assert 0.45 < mask.mean() < 0.55
 
 
 @pytest.mark.parametrize('tag, normalize', [('norm', True), ('raw', False)])

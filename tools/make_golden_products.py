@@ -583,6 +583,105 @@ def golden_losresult_source_map():
     print('losresult_source_map.npz')
 
 
+class _PercentileInterval:
+    """astropy.visualization.PercentileInterval as astropy 5.3 defines it (the version the
+    reference pins, poetry.lock:33-34; astropy itself is absent here): get_limits() ravels
+    WHATEVER it is given, drops the non-finite values and returns
+    np.percentile(values, ((100 - p) / 2, 100 - (100 - p) / 2))."""
+
+    def __init__(self, percentile, n_samples=None):
+        self.lower = (100 - percentile) * 0.5
+        self.upper = 100 - self.lower
+
+    def get_limits(self, values):
+        values = np.asarray(values).ravel()
+        values = values[np.isfinite(values)]
+        vmin, vmax = np.percentile(values, (self.lower, self.upper))
+        return vmin, vmax
+
+
+class _Multiply:
+    """astropy.modeling.models.Multiply: y = factor * x, one linear parameter."""
+
+    def __init__(self, factor=1.0):
+        self.factor = u.Quantity(factor, u.dimensionless_unscaled) \
+            if hasattr(u, 'dimensionless_unscaled') else types.SimpleNamespace(value=factor)
+
+
+class _LinearLSQFitter:
+    """astropy.modeling.fitting.LinearLSQFitter on a one-parameter linear model, as astropy
+    5.3 does it: the design matrix column (d model / d factor = x) and the data are BOTH
+    multiplied by `weights` (a length mismatch raises, as numpy broadcasting does there),
+    the columns are scaled to unit norm and np.linalg.lstsq solves the system."""
+
+    def __call__(self, model, x, y, weights=None):
+        lhs = np.asarray(x, dtype=float)[:, np.newaxis].copy()
+        rhs = np.asarray(y, dtype=float).copy()
+        if weights is not None:
+            weights = np.asarray(weights, dtype=float)
+            lhs *= weights[:, np.newaxis]
+            rhs = rhs * weights
+        scl = (lhs * lhs).sum(0)
+        lhs /= scl
+        lacoef, *_ = np.linalg.lstsq(lhs, rhs, rcond=len(x) * np.finfo(float).eps)
+        factor = float((lacoef.T / scl).T[0])
+        fitted = _Multiply()
+        fitted.factor = types.SimpleNamespace(value=factor, __float__=lambda: factor)
+        fitted.factor = _Factor(factor)
+        return fitted
+
+
+class _Factor(float):
+    """best_fit.factor: usable as a number and through .value (LOSResult.py:293, 301)."""
+    @property
+    def value(self):
+        return float(self)
+
+
+def golden_source_rate():
+    """Execute the UNMODIFIED reference LOSResult.make_mask / determine_source_rate
+    (LOSResult.py:171-200, 278-308) on synthetic spectra for every masking keyword, with
+    astropy's PercentileInterval / LinearLSQFitter restated above -> tests/golden/source_rate.npz
+    (masks, scale factors, scaled radiances; 'raises' where the reference itself fails)."""
+    from nexoclom.data_simulation import LOSResult as lr
+    lr.PercentileInterval = _PercentileInterval
+    lr.models = types.SimpleNamespace(Multiply=_Multiply)
+    lr.fitting = types.SimpleNamespace(LinearLSQFitter=_LinearLSQFitter)
+    ns = types.SimpleNamespace
+    rng = np.random.default_rng(12)
+    n = 240
+    model = rng.random(n) * (rng.random(n) > 0.1)
+    data = pd.DataFrame({'radiance': 2.5 * model + rng.normal(0, 0.05, n),
+                         'sigma': 0.02 + 0.2 * rng.random(n),
+                         'alttan': rng.random(n) * 2,
+                         'x': rng.normal(0, 2, n), 'xbore': rng.normal(0, 1, n)})
+    out = {'model': model}
+    for c in data.columns:
+        out['data_' + c] = data[c].values
+    cases = [None, 'middle90', 'middle50; minalt0.3', 'minsnr3', 'minalt0.5; minsnr2',
+             'siglimit2', 'siglimit50', 'minsnr3; siglimit3']
+    out['cases'] = np.array([str(c) for c in cases])
+    for ic, masking in enumerate(cases):
+        for use_weight in (False, True):
+            tag = f'c{ic}_w{int(use_weight)}'
+            me = ns(masking=masking, radiance=pd.Series(model.copy()))
+            me.make_mask = types.MethodType(lr.LOSResult.make_mask, me)
+            mask0, siglimit = me.make_mask(data)
+            out[tag + '_mask0'] = np.asarray(mask0, dtype=bool)
+            try:
+                lr.LOSResult.determine_source_rate(me, ns(data=data), use_weight=use_weight)
+            except ValueError as err:            # the refit with the first mask's weights
+                out[tag + '_raises'] = np.array(str(err)[:60])
+                print(tag, masking, 'raises', str(err)[:60])
+                continue
+            out[tag + '_mask'] = np.asarray(me.mask, dtype=bool)
+            out[tag + '_factor'] = float(me.sourcerate.value)
+            out[tag + '_radiance'] = me.radiance.values
+            print(tag, masking, float(me.sourcerate.value), int(np.sum(me.mask)))
+    np.savez_compressed(os.path.join(GOLD, 'source_rate.npz'), **out)
+    print('source_rate.npz')
+
+
 if __name__ == '__main__':
     install()
     which = sys.argv[1:] or ['source', 'image', 'los', 'map']
@@ -598,3 +697,5 @@ if __name__ == '__main__':
         golden_losfit()
     if 'losmap' in which:
         golden_losresult_source_map()
+    if 'rate' in which:
+        golden_source_rate()
