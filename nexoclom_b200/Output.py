@@ -397,13 +397,33 @@ class Output:
         return d
 
     def __setstate__(self, d):
+        """Also the entry point for files written by the REFERENCE (``refpickle.load`` maps its
+        ``Output`` class here): whatever this package's own pickles carry beyond the
+        reference's attributes gets its default."""
         d = dict(d)
         self._X0 = d.pop('X0', None)
         self._X = d.pop('X', None)
         self._table = self._host = None
         self._upcast = False
         self.__dict__.update(d)
-        if getattr(self, 'imported_x0', False) and self._X0 is not None:
+        from .sharding import local_device
+        unit = self.__dict__.get('unit')
+        if unit is not None and not isinstance(unit, str) and hasattr(unit, 'name'):
+            name, dim, scale = unit.name()            # astropy unit of a reference file
+            self.unit = def_unit(name, dim, scale)
+        self.__dict__.setdefault('device', local_device())
+        self.__dict__.setdefault('first_id', 0)
+        self.__dict__.setdefault('strict_math', False)
+        self.__dict__.setdefault('trajectory_kept', True)
+        if 'imported_x0' not in self.__dict__:
+            # a reference file: its X0 was drawn from NumPy streams, it cannot be re-drawn here
+            self.imported_x0 = True
+            self.from_reference = True
+        opts = getattr(getattr(self, 'inputs', None), 'options', None)
+        if 'nsteps' not in self.__dict__ and opts is not None and getattr(opts, 'step_size', 0):
+            self.nsteps = int(np.ceil(float(np.asarray(opts.endtime)) / opts.step_size + 1))
+        if getattr(self, 'imported_x0', False) and self._X0 is not None and \
+                all(c in self._X0 for c in STATE_COLS):
             self._imported_cols = [np.ascontiguousarray(self._X0[c].values, dtype=np.float64)
                                    for c in STATE_COLS]
 

@@ -28,6 +28,7 @@ _outputs = {}       # filename -> Output
 _by_key = {}        # input key -> [filename, ...]
 _counter = [0]
 _resident = OrderedDict()   # filename -> bytes on the GPU, least recently used first
+_adopted = set()            # files written elsewhere (the reference's archive): never removed
 
 
 def input_key(inputs):
@@ -158,9 +159,26 @@ def fetch(filename):
     first use)."""
     if filename in _outputs:
         return _outputs[filename]
-    with open(filename, 'rb') as f:
-        output = pickle.load(f)
+    from . import refpickle
+    output = refpickle.load(filename)      # this package's files and the reference's alike
     _outputs[filename] = output
+    return output
+
+
+def adopt(filename):
+    """Make a run file that was written elsewhere -- by the REFERENCE (its PostgreSQL
+    `outputfile` table is not available here) or by another save path -- known to this
+    process: it is read (``refpickle``), and registered under the key of its own inputs so
+    that ``inputs.search()``, ``ModelImage`` and ``LOSResult`` find it.  Returns the Output."""
+    output = fetch(filename)
+    key = input_key(output.inputs)
+    output.filename = filename
+    _adopted.add(filename)
+    if getattr(output, 'idnum', None) is None:
+        _counter[0] += 1
+        output.idnum = _counter[0]
+    if filename not in _by_key.setdefault(key, []):
+        _by_key[key].append(filename)
     return output
 
 
@@ -175,6 +193,9 @@ def delete(inputs, filename=None):
             if out is not None and getattr(out, '_release_device', None) is not None:
                 out._release_device()
             _resident.pop(f, None)
+            if f in _adopted:                  # someone else's archive: only forgotten
+                _adopted.discard(f)
+                continue
             for path in (f, f[:-4] + '.json'):
                 if os.path.exists(path):
                     os.remove(path)
