@@ -224,6 +224,8 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     try:
         # run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU
+        if os.environ.get('NX_BENCH_NO_AFFINITY'):
+            raise RuntimeError('affinity disabled')
         import pynvml
         pynvml.nvmlInit()
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
@@ -285,22 +287,33 @@ def run_gpu(args):
         one_step(False)
     if comm is not None:
         eng.image_allreduce(comm[1])                # NCCL sets its channels up on first use
-    fence()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-    eng.image_begin(800, 800)
+        sampler.start()                             # (spawns nvidia-smi: before the fence, so
+    eng.image_begin(800, 800)                       #  that every rank starts at the same time)
+    fence()
     launches0 = eng.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(args.steps):
         one_step(True)
-    if comm is not None:
+    if comm is not None and not os.environ.get('NX_BENCH_SKIP_AR'):
         eng.image_allreduce(comm[1])                # ONE all-reduce per product (image + counts)
     ev1.record(stream)
     fence()
     launches = eng.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    if comm is not None:                            # the collective on its own
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ar = []
+        for _ in range(3):
+            fence()
+            ea.record(stream)
+            eng.image_allreduce(comm[1])
+            eb.record(stream)
+            torch.cuda.synchronize()
+            ar.append(ea.elapsed_time(eb))
+        extras['allreduce_image_counts_ms'] = float(min(ar))
     elapsed_ms = ev0.elapsed_time(ev1)
     img_run, cnt_run = eng.image_fetch(800, 800)
     t = torch.tensor([elapsed_ms, float(sum(steps_total))], dtype=torch.float64, device='cuda')
@@ -309,6 +322,10 @@ def run_gpu(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmin = t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        extras['rank_ms_per_step_min'] = float(tmin[0]) / args.steps
+        extras['rank_ms_per_step_max'] = float(tmax[0]) / args.steps
         elapsed_ms, all_steps = float(tmax[0]), float(tsum[1])
     else:
         all_steps = float(t[1])
@@ -357,8 +374,8 @@ def run_gpu(args):
         host_np = host_in.numpy()
         cols = {c: host_np[k] for k, c in enumerate(
             ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac'))}
-        reps = max(1, min(args.steps, 3))
-        e2e_steps, e2e_ms = 0, 0.0
+        reps = max(1, min(args.steps, 5))
+        rep_ms, rep_steps = [], []
         for it in range(1 + reps):
             inputs.delete_files()
             fence()
@@ -370,20 +387,26 @@ def run_gpu(args):
             t2 = time.perf_counter()
             fence()
             if it > 0:
-                e2e_ms += (time.perf_counter() - t0) * 1e3
-                e2e_steps += out.attempted_steps
+                rep_ms.append((time.perf_counter() - t0) * 1e3)
+                rep_steps.append(float(out.attempted_steps))
                 print(f'e2e rep {it}: Output {1e3 * (t1 - t0):.2f} ms (kernels {out.kernel_ms:.2f}), '
                       f'ModelImage {1e3 * (t2 - t1):.2f} ms', file=sys.stderr)
         inputs.delete_files()
-        te = torch.tensor([e2e_ms, float(e2e_steps)], dtype=torch.float64, device='cuda')
+        # per repetition: the slowest rank's time and the steps of all ranks; the line quotes
+        # the MEDIAN repetition (a single host hiccup on one of N ranks otherwise decides a
+        # 3-5 sample mean), the mean is reported next to it
+        tm = torch.tensor(rep_ms, dtype=torch.float64, device='cuda')
+        ts = torch.tensor(rep_steps, dtype=torch.float64, device='cuda')
         if world > 1:
-            tm, ts = te.clone(), te.clone()
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-            e2e_ms, e2e_steps = float(tm[0]), float(ts[1])
+        e2e_ms = float(tm.median())
+        e2e_steps = float(ts[0])
         e2e = {'value': e2e_steps / (e2e_ms * 1e-3), 'unit': 'packet-steps/s',
                'h2d_bytes_per_step': 64 * n, 'd2h_bytes_per_step': 2 * 8 * 800 * 800,
-               'ms_per_step': e2e_ms / reps,
+               'ms_per_step': e2e_ms, 'ms_per_step_mean': float(tm.mean()),
+               'ms_per_step_all': [round(float(v), 3) for v in tm],
+               'stat': f'median of {reps} repetitions, each = max over ranks',
                'call': 'Output(inputs, n, X0=<pinned host columns>, first_id) -> '
                        'ModelImage(inputs, {quantity: radiance}) -> image on the host',
                'image_checksum': checksum}
