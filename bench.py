@@ -297,7 +297,9 @@ def run_gpu(args):
     ev0.record(stream)
     for _ in range(args.steps):
         one_step(True)
-    if comm is not None and not os.environ.get('NX_BENCH_SKIP_AR'):
+    ev_pre = torch.cuda.Event(enable_timing=True)
+    ev_pre.record(stream)
+    if comm is not None:
         eng.image_allreduce(comm[1])                # ONE all-reduce per product (image + counts)
     ev1.record(stream)
     fence()
@@ -326,6 +328,15 @@ def run_gpu(args):
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         extras['rank_ms_per_step_min'] = float(tmin[0]) / args.steps
         extras['rank_ms_per_step_max'] = float(tmax[0]) / args.steps
+        # per rank, without the collective: own steps, mean K2 and the host gap between kernels
+        mine = torch.tensor([ev0.elapsed_time(ev_pre) / args.steps, float(np.mean(k2_ms)),
+                             float(np.mean(k4_ms)), float(np.max(k2_ms))],
+                            dtype=torch.float64, device='cuda')
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        extras['rank_own_ms_per_step'] = [round(float(v[0]), 3) for v in allr]
+        extras['rank_k2_ms'] = [round(float(v[1]), 3) for v in allr]
+        extras['rank_k2_max_ms'] = [round(float(v[3]), 3) for v in allr]
         elapsed_ms, all_steps = float(tmax[0]), float(tsum[1])
     else:
         all_steps = float(t[1])

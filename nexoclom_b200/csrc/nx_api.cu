@@ -87,7 +87,7 @@ struct nx_ctx {
   unsigned* perm = nullptr;          // longest-first processing order
   unsigned char* cost = nullptr;     // cost bucket per packet
   unsigned* hist = nullptr;          // 32 histogram + 32 cursors
-  int order_packets = 1;              // cost model: 0 none, 1 ballistic, 2 + radiation pressure
+  int order_packets = 3;              // cost model: 0 none, 1 ballistic, 2 / 3 + radiation pressure (3: lift-off threshold)
   int schedule = 1;                   // K2 queue: 1 class-ordered streaming passes, 0 sort + permutation
   unsigned long long* squeue = nullptr;   // NX_STREAM_CURSORS cursors, then the `arrived` word
   unsigned* seq_host = nullptr;           // pinned 0..32: source of the `arrived` updates

@@ -510,12 +510,12 @@ def test_packet_order_does_not_change_results(engine):
     setup.upload(engine)
     X0 = initial_state.draw_x0(setup, 20000, 4)[:, :8]
     out = []
-    for order in (0, 1, 2):
+    for order in (0, 1, 2, 3):
         engine.set_option('order_packets', order)
         engine.import_state(X0)
         att, acc = engine.integrate_adaptive()
         out.append((engine.export_state(), att, acc))
-    engine.set_option('order_packets', 1)
+    engine.set_option('order_packets', 3)
     for o in out[1:]:
         assert np.array_equal(o[0], out[0][0]) and o[1:] == out[0][1:]
     with pytest.raises(Exception):
