@@ -236,6 +236,12 @@ int nx_image_begin(nx_ctx* ctx, int nx, int nz);
 int nx_image_add(nx_ctx* ctx, long long n, const nx_image_params* ip);
 int nx_image_fetch(nx_ctx* ctx, double* image, long long* counts);
 int nx_image_device_ptrs(nx_ctx* ctx, void** image_dev, void** counts_dev);
+/* What ModelImage keeps (ModelImage.py:92-105): image * scale (scale = atoms_per_packet) and the
+ * packet image as float64, converted on the device, one copy.  Destinations obtained from
+ * nx_host_alloc (page-locked) receive the DMA directly, pageable ones are staged.            */
+int nx_image_fetch_scaled(nx_ctx* ctx, double scale, double* image, double* counts);
+int nx_host_alloc(long long bytes, void** out);
+int nx_host_free(void* p);
 /* Sharded runs: sum the context-owned image + counts over the ranks of `comm` (see nx_comm_create
  * below), in place, on the context's stream -- the single all-reduce of an image product.    */
 int nx_image_allreduce(nx_ctx* ctx, nx_comm* comm);

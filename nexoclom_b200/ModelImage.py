@@ -109,21 +109,20 @@ class ModelImage(ModelResult):
         # torch.distributed for the gloo backend of the CPU tests
         if comm is not None:
             eng.image_allreduce(comm[1])
-        if eng is not None:
-            img, cnt = eng.image_fetch(*self.dims)
-            self.image = img
-            self.packet_image = cnt.astype(np.float64)
         tot = np.array([float(self.totalsource)])
-        if comm is not None:
-            allreduce_sum(tot)
-        else:
-            allreduce_sum(self.image, self.packet_image, tot)
+        allreduce_sum(tot)
         self.totalsource = float(tot[0])
 
         mod_rate = self.totalsource / self.inputs.options.endtime.value
         self.atoms_per_packet = 1e23 / mod_rate
         self.sourcerate = Quantity(1e23, '1/s')
-        self.image *= self.atoms_per_packet
+        if eng is not None:
+            # `image *= atoms_per_packet` and the float packet image (ModelImage.py:92-105)
+            # are formed on the device; the two planes arrive in page-locked arrays
+            self.image, self.packet_image = eng.image_fetch_scaled(
+                *self.dims, self.atoms_per_packet)
+        if comm is None:
+            allreduce_sum(self.image, self.packet_image)       # gloo (CPU tests of the host logic)
 
     def image_rotation(self):
         return image_rotation(self.subobslongitude, self.subobslatitude)

@@ -138,6 +138,9 @@ def load():
         'nx_image_add': [vp, i64, C.POINTER(ImageParams)],
         'nx_image_fetch': [vp, c_double_p, c_i64_p],
         'nx_image_device_ptrs': [vp, C.POINTER(vp), C.POINTER(vp)],
+        'nx_image_fetch_scaled': [vp, C.c_double, c_double_p, c_double_p],
+        'nx_host_alloc': [i64, C.POINTER(vp)],
+        'nx_host_free': [vp],
         'nx_image_allreduce': [vp, vp],
         'nx_los_accumulate': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams),
                               c_double_p, c_i64_p, c_u8_p],

@@ -9,6 +9,9 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../../include/nexoclom_b200.h"
 #include "nx_kernels.h"
@@ -37,10 +40,48 @@ struct nx_packets {
   double* cols = nullptr;            // ncols columns time..frac[, step_size]
   unsigned* index = nullptr;         // original packet index of every row
   unsigned short* step = nullptr;    // constant-step rows: step number (else nullptr)
+  void* block = nullptr;             // the one stream-ordered allocation the three live in
 };
-static void free_packets(nx_packets* h) {
+
+// Packet tables come and go with every Output: they are carved from ONE block of the device's
+// stream-ordered memory pool (cudaMallocAsync, release threshold = keep everything), so that
+// creating / dropping a table costs microseconds instead of the implicit device
+// synchronisation of cudaMalloc / cudaFree.  Everything else (slabs, scratch) is cudaMalloc'ed
+// once and grows only; those sites trim the pool and retry when the device is full.
+static cudaError_t dev_malloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      cudaDeviceSynchronize();
+      cudaMemPoolTrimTo(pool, 0);
+      e = cudaMalloc(p, bytes);
+    }
+  }
+  return e;
+}
+template <class T> static cudaError_t dev_malloc(T** p, size_t bytes) {
+  return dev_malloc(reinterpret_cast<void**>(p), bytes);
+}
+static cudaError_t table_alloc(nx_packets* h, cudaStream_t st, int ncols, bool with_step) {
+  auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t bc = up((size_t)ncols * h->cap * sizeof(double));
+  const size_t bi = up((size_t)h->cap * sizeof(unsigned));
+  const size_t bs = with_step ? up((size_t)h->cap * sizeof(unsigned short)) : 0;
+  cudaError_t e = cudaMallocAsync(&h->block, bc + bi + bs, st);
+  if (e != cudaSuccess) { h->block = nullptr; return e; }
+  char* b = static_cast<char*>(h->block);
+  h->cols = reinterpret_cast<double*>(b);
+  h->index = reinterpret_cast<unsigned*>(b + bc);
+  h->step = with_step ? reinterpret_cast<unsigned short*>(b + bc + bi) : nullptr;
+  return cudaSuccess;
+}
+static void free_packets(nx_packets* h, cudaStream_t st) {
   if (!h) return;
-  cudaFree(h->cols); cudaFree(h->index); cudaFree(h->step);
+  if (h->block) cudaFreeAsync(h->block, st);        // in stream order: after its last reader
   delete h;
 }
 
@@ -179,10 +220,10 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
   const int gmax = w.G_fixed > NX_LOS_GRID_MAX ? w.G_fixed : NX_LOS_GRID_MAX;
   const size_t ncell = (size_t)gmax * gmax * gmax;
   const size_t nn = (size_t)n;
-  CK(cudaMalloc(&w.sorted.pos, nn * sizeof(double4)));
-  CK(cudaMalloc(&w.sorted.frac, nn * sizeof(double)));
-  CK(cudaMalloc(&w.sorted.idx, nn * sizeof(unsigned)));
-  CK(cudaMalloc(&w.cell_id, nn * sizeof(unsigned)));
+  CK(dev_malloc(&w.sorted.pos, nn * sizeof(double4)));
+  CK(dev_malloc(&w.sorted.frac, nn * sizeof(double)));
+  CK(dev_malloc(&w.sorted.idx, nn * sizeof(unsigned)));
+  CK(dev_malloc(&w.cell_id, nn * sizeof(unsigned)));
   CK(cudaMalloc(&w.count, ncell * sizeof(unsigned)));
   CK(cudaMalloc(&w.start, (ncell + 1) * sizeof(unsigned)));
   CK(cudaMalloc(&w.block_sum, ((ncell + 4095) / 4096 + 1) * sizeof(unsigned)));
@@ -195,7 +236,7 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
   if (pc < (1ull << 22)) pc = 1ull << 22;
   if (pc > (1ull << 29)) pc = 1ull << 29;
   if (pc < (unsigned long long)n + 1024) pc = (unsigned long long)n + 1024;
-  CK(cudaMalloc(&w.pairs, pc * sizeof(uint2)));
+  CK(dev_malloc(&w.pairs, pc * sizeof(uint2)));
   CK(cudaMalloc(&w.pair_cursor, 2 * sizeof(unsigned long long)));   // pairs written, line-of-sight ticket
   w.pairs_cap = pc;
   w.batch_hint = 0;
@@ -205,14 +246,15 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
 
 enum { SCR_IMG, SCR_CNT, SCR_LOS, SCR_DIST, SCR_RAD, SCR_NP, SCR_INC, SCR_NBALL, SCR_LADDER,
        SCR_WID2, SCR_ORDER, SCR_NUSED, SCR_CURSOR, SCR_OFF, SCR_IDX, SCR_SM_IN, SCR_SM_PTS,
-       SCR_SM_OUT, SCR_SM_CNT, SCR_TMP, SCR_NSLOTS };
+       SCR_SM_OUT, SCR_SM_CNT, SCR_TMP, SCR_IMG_OUT, SCR_DD, SCR_KEY, SCR_NSLOTS };
+static_assert(SCR_NSLOTS <= 24, "nx_ctx::scr is too small");
 static int scratch_bytes(nx_ctx* ctx, int slot, size_t bytes, void** out) {
   nx_ctx::Scratch& sc = ctx->scr[slot];
   if (bytes > sc.bytes) {
     cudaFree(sc.p);
     sc.p = nullptr; sc.bytes = 0;
     const size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMalloc(&sc.p, want);
+    cudaError_t e = dev_malloc(&sc.p, want);
     if (e != cudaSuccess) { ctx->err = std::string("scratch allocation: ") + cudaGetErrorString(e); return -(int)e; }
     sc.bytes = want;
   }
@@ -316,6 +358,14 @@ int nx_ctx_create(int device, nx_ctx** out) {
     return -2;
   }
   for (unsigned i = 0; i <= 32; ++i) ctx->seq_host[i] = i;
+  {
+    cudaMemPool_t pool;                       // keep freed packet tables for the next Output
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   *out = ctx;
   return 0;
 }
@@ -563,12 +613,12 @@ int nx_packets_resize(nx_ctx* ctx, long long n) {
   ctx->perm = nullptr; ctx->cost = nullptr;
   ctx->fresh = ctx->x0_valid = false;
   if (n >= (1LL << 32)) { ctx->err = "more than 2^32 packets per GPU"; return -1; }
-  CK(cudaMalloc(&ctx->state, (size_t)9 * cap * sizeof(double)));
-  CK(cudaMalloc(&ctx->x0, (size_t)14 * cap * sizeof(double)));
-  CK(cudaMalloc(&ctx->att, (size_t)cap * sizeof(unsigned)));
-  CK(cudaMalloc(&ctx->acc, (size_t)cap * sizeof(unsigned)));
-  CK(cudaMalloc(&ctx->perm, (size_t)cap * sizeof(unsigned)));
-  CK(cudaMalloc(&ctx->cost, (size_t)cap));
+  CK(dev_malloc(&ctx->state, (size_t)9 * cap * sizeof(double)));
+  CK(dev_malloc(&ctx->x0, (size_t)14 * cap * sizeof(double)));
+  CK(dev_malloc(&ctx->att, (size_t)cap * sizeof(unsigned)));
+  CK(dev_malloc(&ctx->acc, (size_t)cap * sizeof(unsigned)));
+  CK(dev_malloc(&ctx->perm, (size_t)cap * sizeof(unsigned)));
+  CK(dev_malloc(&ctx->cost, (size_t)cap));
   if (!ctx->hist) CK(cudaMalloc(&ctx->hist, 64 * sizeof(unsigned)));
   CK(cudaMemsetAsync(ctx->att, 0, (size_t)cap * sizeof(unsigned), ctx->stream));
   CK(cudaMemsetAsync(ctx->acc, 0, (size_t)cap * sizeof(unsigned), ctx->stream));
@@ -936,7 +986,7 @@ static int integrate_constant_core(nx_ctx* ctx, long long n, uint64_t seed, uint
   double* traj = nullptr;
   const size_t traj_bytes = (size_t)n * 8 * nsteps * sizeof(double);
   if (traj_host) {
-    CK(cudaMalloc(&traj, traj_bytes));
+    CK(dev_malloc(&traj, traj_bytes));
     cudaError_t e = cudaMemsetAsync(traj, 0, traj_bytes, ctx->stream);
     if (e != cudaSuccess) { cudaFree(traj); ctx->err = cudaGetErrorString(e); return -(int)e; }
   }
@@ -1007,12 +1057,10 @@ int nx_integrate_constant_rows(nx_ctx* ctx, long long n, uint64_t seed, uint64_t
   }
   nx_packets* h = new nx_packets();
   h->cap = (((long long)std::max<unsigned long long>(need, 1ull) + 31) / 32) * 32;
-  cudaError_t e = cudaMalloc(&h->cols, (size_t)8 * h->cap * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&h->index, (size_t)h->cap * sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMalloc(&h->step, (size_t)h->cap * sizeof(unsigned short));
+  cudaError_t e = table_alloc(h, ctx->stream, 8, true);
   if (e != cudaSuccess) {
     ctx->err = std::string("row table allocation (") + std::to_string(need) + " rows): " + cudaGetErrorString(e);
-    free_packets(h);
+    free_packets(h, ctx->stream);
     return -(int)e;
   }
   rows.cols = h->cols; rows.index = h->index; rows.step = h->step;
@@ -1020,13 +1068,13 @@ int nx_integrate_constant_rows(nx_ctx* ctx, long long n, uint64_t seed, uint64_t
   unsigned long long steps = 0;
   r = integrate_constant_core(ctx, n, seed, first_id, nullptr, nullptr, nullptr, nullptr, rows,
                               &steps);
-  if (r < 0) { free_packets(h); return r; }
+  if (r < 0) { free_packets(h, ctx->stream); return r; }
   unsigned long long got = 0;
   e = cudaMemcpyAsync(&got, cursor, sizeof(got), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess || got > (unsigned long long)h->cap) {
     ctx->err = e != cudaSuccess ? cudaGetErrorString(e) : "row table overflow";
-    free_packets(h);
+    free_packets(h, ctx->stream);
     return e != cudaSuccess ? -(int)e : -1;
   }
   h->n = (long long)got;
@@ -1108,6 +1156,55 @@ int nx_image_fetch(nx_ctx* ctx, double* image, long long* counts) {
   return 0;
 }
 
+// Page-locked host memory for results the caller wants at full PCIe rate and without a
+// staging copy (ModelImage's image / packet image live in such buffers).
+int nx_host_alloc(long long bytes, void** out) {
+  if (!out || bytes <= 0) return -1;
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault);
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+int nx_host_free(void* p) {
+  if (!p) return 0;
+  cudaError_t e = cudaFreeHost(p);
+  return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// image * scale and the packet counts as float64 (what ModelImage keeps: ModelImage.py:92-105),
+// converted on the device and copied once.  Destinations that are page-locked (nx_host_alloc)
+// receive the DMA directly; pageable ones go through the context's pinned staging buffer.
+int nx_image_fetch_scaled(nx_ctx* ctx, double scale, double* image, double* counts) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->img_nx) { ctx->err = "nx_image_begin not called"; return -1; }
+  if (!image || !counts) { ctx->err = "nx_image_fetch_scaled: null destination"; return -1; }
+  const size_t npix = (size_t)ctx->img_nx * ctx->img_nz;
+  double* d_out = nullptr;
+  SCR(SCR_IMG_OUT, d_out, 2 * npix);
+  CK(launch_image_finish(ctx->stream, static_cast<const double*>(ctx->scr[SCR_IMG].p),
+                         static_cast<const unsigned long long*>(ctx->scr[SCR_CNT].p), scale,
+                         d_out, d_out + npix, (long long)npix));
+  ctx->launches += 1;
+  auto pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  if (pinned(image) && pinned(counts)) {
+    CK(cudaMemcpyAsync(image, d_out, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(counts, d_out + npix, npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  int r = pinned_staging(ctx, 2 * npix * 8);
+  if (r) return r;
+  char* st = static_cast<char*>(ctx->pinned);
+  CK(cudaMemcpyAsync(st, d_out, 2 * npix * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(image, st, npix * 8);
+  std::memcpy(counts, st + npix * 8, npix * 8);
+  return 0;
+}
+
 // The ONE collective of an image product: the context-owned image and
 // counts of every rank of `comm` are summed in place, on the context's stream.
 int nx_image_allreduce(nx_ctx* ctx, nx_comm* comm) {
@@ -1135,22 +1232,12 @@ int nx_image_accumulate(nx_ctx* ctx, long long n, const nx_image_params* ip, dou
 }
 
 // Per-LOS ladder length and the shared geometric ladder (compute_iteration.py:158-171).
-static void los_prepare(const double* los, long long nlos, const LosParams& lp,
-                        std::vector<int>& nball, std::vector<double>& ladder,
-                        std::vector<double>& wid2, LosConsts& lc) {
+// Constants of a line-of-sight call and the ladder of KD-ball centres (compute_iteration.py:
+// 151-170), given the longest boresight distance `ddmax` to the outer edge.
+static void los_constants(const LosParams& lp, double ddmax, std::vector<double>& ladder,
+                          std::vector<double>& wid2, LosConsts& lc) {
   const double s = std::sin(lp.dphi);
   const double s2 = std::sin(lp.dphi * 2);
-  std::vector<double> dd(nlos);
-  double ddmax = 0.0;
-  for (long long i = 0; i < nlos; ++i) {
-    const double x = los[i], y = los[nlos + i], z = los[2 * nlos + i];
-    const double bx = los[3 * nlos + i], by = los[4 * nlos + i], bz = los[5 * nlos + i];
-    const double b = 2 * ((x * bx + y * by) + z * bz);
-    const double nrm = std::sqrt((x * x + y * y) + z * z);
-    const double c = nrm * nrm - lp.outeredge * lp.outeredge;
-    dd[i] = (-b + std::sqrt(b * b - 4 * 1 * c)) / 2;
-    if (dd[i] > ddmax) ddmax = dd[i];
-  }
   ladder.clear();
   ladder.push_back(s);
   while (ladder.back() < ddmax && ladder.size() < (1u << 20)) {
@@ -1159,16 +1246,6 @@ static void los_prepare(const double* los, long long nlos, const LosParams& lp,
   }
   wid2.resize(ladder.size());
   for (size_t k = 0; k < ladder.size(); ++k) { const double w = ladder[k] * s2; wid2[k] = w * w; }
-  nball.resize(nlos);
-  for (long long i = 0; i < nlos; ++i) {
-    // first k with t_k >= dd is the last ladder entry; NaN dd -> single entry
-    int k = 0;
-    if (dd[i] == dd[i]) {
-      k = (int)(std::lower_bound(ladder.begin(), ladder.end(), dd[i]) - ladder.begin());
-      if (k >= (int)ladder.size()) k = (int)ladder.size() - 1;
-    }
-    nball[i] = k + 1;
-  }
   lc.sin_dphi = s;
   const double cd = std::cos(lp.dphi);
   lc.cos_margin2 = (cd * (1 - 1e-9)) * (cd * (1 - 1e-9));
@@ -1187,65 +1264,85 @@ static void los_prepare(const double* los, long long nlos, const LosParams& lp,
   lc.nladder = (int)ladder.size();
 }
 
-// Processing order of the lines of sight for the cell-grid kernel: counting sort on the
-// 15-bit Morton code of the point of closest approach to the planet (0.4 R_p cells over
-// +-6.4 R_p), so that warps that run together stream the same near-planet cells.
-static std::vector<unsigned> los_order(const double* los, long long nlos) {
-  auto spread = [](unsigned v) {            // 5 bits -> every third bit
-    unsigned r = 0;
-    for (int b = 0; b < 5; ++b) r |= ((v >> b) & 1u) << (3 * b);
-    return r;
-  };
-  std::vector<unsigned> key(nlos), count(32768 + 1, 0), order(nlos);
+// Host version of the per-line preparation (nx_los_used; the accumulate calls do the same on
+// the device: k_los_prepare / k_los_finish in nx_los_grid.cu).
+static void los_prepare(const double* los, long long nlos, const LosParams& lp,
+                        std::vector<int>& nball, std::vector<double>& ladder,
+                        std::vector<double>& wid2, LosConsts& lc) {
+  std::vector<double> dd(nlos);
+  double ddmax = 0.0;
   for (long long i = 0; i < nlos; ++i) {
     const double x = los[i], y = los[nlos + i], z = los[2 * nlos + i];
     const double bx = los[3 * nlos + i], by = los[4 * nlos + i], bz = los[5 * nlos + i];
-    double t = -(x * bx + y * by + z * bz);
-    if (!(t > 0.0)) t = 0.0;
-    const double c[3] = {x + bx * t, y + by * t, z + bz * t};
-    unsigned q[3];
-    for (int a = 0; a < 3; ++a) {
-      double v = (c[a] + 6.4) / 0.4;
-      v = v < 0.0 ? 0.0 : (v > 31.0 ? 31.0 : v);
-      q[a] = (v == v) ? (unsigned)v : 0u;
-    }
-    key[i] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
-    ++count[key[i] + 1];
+    const double b = 2 * ((x * bx + y * by) + z * bz);
+    const double nrm = std::sqrt((x * x + y * y) + z * z);
+    const double c = nrm * nrm - lp.outeredge * lp.outeredge;
+    dd[i] = (-b + std::sqrt(b * b - 4 * 1 * c)) / 2;
+    if (dd[i] > ddmax) ddmax = dd[i];
   }
-  for (int k = 0; k < 32768; ++k) count[k + 1] += count[k];
-  for (long long i = 0; i < nlos; ++i) order[count[key[i]]++] = (unsigned)i;
-  return order;
+  los_constants(lp, ddmax, ladder, wid2, lc);
+  nball.resize(nlos);
+  for (long long i = 0; i < nlos; ++i) {
+    // first k with t_k >= dd is the last ladder entry; NaN dd -> single entry
+    int k = 0;
+    if (dd[i] == dd[i]) {
+      k = (int)(std::lower_bound(ladder.begin(), ladder.end(), dd[i]) - ladder.begin());
+      if (k >= (int)ladder.size()) k = (int)ladder.size() - 1;
+    }
+    nball[i] = k + 1;
+  }
 }
 
-static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_host,
-                   const double* los_dev, const double* dist_dev, const LosParams& lp,
-                   double* rad_dev, unsigned long long* np_dev, unsigned char* inc_dev) {
+static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_dev,
+                   const double* dist_dev, const LosParams& lp, double* rad_dev,
+                   unsigned long long* np_dev, unsigned char* inc_dev) {
   { int r0 = materialize(ctx); if (r0) return r0; }
-  std::vector<int> nball;
-  std::vector<double> ladder, wid2;
-  LosConsts lc;
-  los_prepare(los_host, nlos, lp, nball, ladder, wid2, lc);
-  int* d_nball = nullptr;
-  double *d_ladder = nullptr, *d_wid2 = nullptr;
-  SCR(SCR_NBALL, d_nball, nlos);
-  SCR(SCR_LADDER, d_ladder, ladder.size());
-  SCR(SCR_WID2, d_wid2, wid2.size());
-  CK(cudaMemcpyAsync(d_nball, nball.data(), nlos * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_ladder, ladder.data(), ladder.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_wid2, wid2.data(), wid2.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  static const bool timing = std::getenv("NX_LOS_TIMING") != nullptr;     // developer aid
+  const auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (timing)
+      std::fprintf(stderr, "[los_run] %s at %.3f ms\n", what,
+                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count());
+  };
   // candidate generation: brute force for small problems, cell grid otherwise
   const bool use_grid = ctx->los_mode == 2 ||
                         (ctx->los_mode == 0 && (double)n * (double)nlos > 2e9 && n < (1LL << 32));
+  const bool want_order = use_grid && ctx->los_order && nlos >= 1024;
+  // per-line preparation on the device; the host only turns the longest boresight distance
+  // (8 bytes back) into the common ladder
+  int* d_nball = nullptr;
+  double *d_ladder = nullptr, *d_wid2 = nullptr, *d_dd = nullptr;
+  unsigned *d_order = nullptr, *d_key = nullptr;
+  SCR(SCR_NBALL, d_nball, nlos);
+  SCR(SCR_DD, d_dd, nlos + 1);                       // [nlos]: the running maximum (bits)
+  if (want_order) {
+    SCR(SCR_ORDER, d_order, nlos);
+    SCR(SCR_KEY, d_key, nlos + NX_LOS_KEY_BINS);     // keys, then the key histogram / cursors
+  }
+  unsigned* d_hist = d_key ? d_key + nlos : nullptr;
+  unsigned long long* d_ddmax = reinterpret_cast<unsigned long long*>(d_dd + nlos);
+  CK(launch_los_prepare(ctx->stream, los_dev, nlos, lp.outeredge, d_dd, d_key, d_hist, d_ddmax));
+  double ddmax = 0.0;
+  CK(cudaMemcpyAsync(&ddmax, d_ddmax, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<double> ladder, wid2;
+  LosConsts lc;
+  los_constants(lp, ddmax, ladder, wid2, lc);
+  // ladder + wid2 through the context's pinned staging: the copies outlive this scope's vectors
+  { int r0 = pinned_staging(ctx, 2 * ladder.size() * sizeof(double)); if (r0) return r0; }
+  double* st_ladder = static_cast<double*>(ctx->pinned);
+  std::memcpy(st_ladder, ladder.data(), ladder.size() * sizeof(double));
+  std::memcpy(st_ladder + ladder.size(), wid2.data(), wid2.size() * sizeof(double));
+  SCR(SCR_LADDER, d_ladder, 2 * ladder.size());
+  d_wid2 = d_ladder + ladder.size();
+  CK(cudaMemcpyAsync(d_ladder, st_ladder, 2 * ladder.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(launch_los_finish(ctx->stream, d_dd, d_ladder, (int)ladder.size(), nlos, d_nball, d_key, d_hist,
+                       d_order));
+  ctx->launches += want_order ? 3 : 2;
+  lap("prepared");
   int nlaunch = 1;
   int r = 0;
-  unsigned* d_order = nullptr;
   if (use_grid) r = alloc_los_work(ctx, n);
-  if (r == 0 && use_grid && ctx->los_order && nlos >= 1024) {
-    const std::vector<unsigned> order = los_order(los_host, nlos);
-    SCR(SCR_ORDER, d_order, nlos);
-    CK(cudaMemcpyAsync(d_order, order.data(), nlos * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));       // `order` is a local vector
-  }
   if (r == 0) r = begin_timed(ctx);
   if (r == 0) {
     cudaError_t e;
@@ -1266,6 +1363,7 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_h
   if (r == 0) r = end_timed(ctx, nlaunch);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (r == 0 && e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  lap("kernels");
   return r;
 }
 
@@ -1279,11 +1377,8 @@ int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_de
   if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }   // compute_iteration.py:213
   if (ctx->gtables.n == 0) { ctx->err = "no g-value tables uploaded"; return -1; }
   if (n == 0 || nlos == 0) return 0;
-  std::vector<double> los_host((size_t)6 * nlos);
-  CK(cudaMemcpyAsync(los_host.data(), los_dev, los_host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return los_run(ctx, n, nlos, los_host.data(), (const double*)los_dev, (const double*)dist_dev,
-                 lp, (double*)radiance_dev, (unsigned long long*)npackets_dev,
+  return los_run(ctx, n, nlos, (const double*)los_dev, (const double*)dist_dev, lp,
+                 (double*)radiance_dev, (unsigned long long*)npackets_dev,
                  (unsigned char*)included_dev);
 }
 
@@ -1311,7 +1406,7 @@ int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* lo
   CK(cudaMemsetAsync(d_np, 0, nl * sizeof(unsigned long long), ctx->stream));
   CK(cudaMemsetAsync(d_inc, 0, nn, ctx->stream));
   int r = 0;
-  if (n > 0 && nlos > 0) r = los_run(ctx, n, nlos, los, d_los, d_dist, lp, d_rad, d_np, d_inc);
+  if (n > 0 && nlos > 0) r = los_run(ctx, n, nlos, d_los, d_dist, lp, d_rad, d_np, d_inc);
   if (r == 0) {
     cudaMemcpyAsync(radiance, d_rad, (size_t)nlos * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(npackets, d_np, (size_t)nlos * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
@@ -1415,8 +1510,7 @@ int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_
       h->n = (long long)total;
       h->cap = ((h->n + 31) / 32) * 32;
       h->ncols = 9;
-      e = cudaMalloc(&h->cols, (size_t)9 * h->cap * sizeof(double));
-      if (e == cudaSuccess) e = cudaMalloc(&h->index, (size_t)h->cap * sizeof(unsigned));
+      e = table_alloc(h, ctx->stream, 9, false);
       if (e == cudaSuccess)
         e = launch_compact_scatter(ctx->stream, P, n, skip_dead, round_f32,
                                    ctx->fresh ? 0 : 1, ctx->cmp_tiles, h->cols,
@@ -1424,10 +1518,10 @@ int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_
     }
     if (e != cudaSuccess) {
       ctx->err = std::string("nx_compact_state: ") + cudaGetErrorString(e);
-      free_packets(h);
+      free_packets(h, ctx->stream);
       return -(int)e;
     }
-    if ((r = end_timed(ctx, total > 0 ? 3 : 2))) { free_packets(h); return r; }
+    if ((r = end_timed(ctx, total > 0 ? 3 : 2))) { free_packets(h, ctx->stream); return r; }
   }
   *out = h;
   if (count) *count = h->n;
@@ -1441,8 +1535,7 @@ int nx_packets_upload(nx_ctx* ctx, long long n, const double* const* cols, const
   nx_packets* h = new nx_packets();
   h->n = n;
   h->cap = ((std::max(n, 1LL) + 31) / 32) * 32;
-  cudaError_t e = cudaMalloc(&h->cols, (size_t)8 * h->cap * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&h->index, (size_t)h->cap * sizeof(unsigned));
+  cudaError_t e = table_alloc(h, ctx->stream, 8, false);
   for (int k = 0; k < 8 && e == cudaSuccess && n > 0; ++k)
     e = cudaMemcpyAsync(h->cols + (size_t)k * h->cap, cols[k], (size_t)n * sizeof(double),
                         cudaMemcpyHostToDevice, ctx->stream);
@@ -1451,7 +1544,7 @@ int nx_packets_upload(nx_ctx* ctx, long long n, const double* const* cols, const
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     ctx->err = std::string("nx_packets_upload: ") + cudaGetErrorString(e);
-    free_packets(h);
+    free_packets(h, ctx->stream);
     return -(int)e;
   }
   *out = h;
@@ -1504,8 +1597,7 @@ int nx_packets_free(nx_ctx* ctx, nx_packets* h) {
   if (!h) return 0;
   cudaSetDevice(ctx->device);
   if (ctx->bound == h) ctx->bound = nullptr;
-  cudaStreamSynchronize(ctx->stream);
-  free_packets(h);
+  free_packets(h, ctx->stream);
   return 0;
 }
 

@@ -1413,6 +1413,27 @@ cudaError_t launch_init_from_deviates(cudaStream_t st, X0Cols X, long long n,
   return cudaGetLastError();
 }
 
+// ModelImage's last two host passes (ModelImage.py:104-105: image *= atoms_per_packet; the
+// packet image is a float histogram) done on the device before the image crosses PCIe
+__global__ void __launch_bounds__(256)
+k_image_finish(const double* __restrict__ img, const unsigned long long* __restrict__ cnt,
+               double scale, double* __restrict__ img_out, double* __restrict__ cnt_out,
+               long long npix) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+    img_out[i] = img[i] * scale;
+    cnt_out[i] = (double)cnt[i];
+  }
+}
+cudaError_t launch_image_finish(cudaStream_t st, const double* img, const unsigned long long* cnt,
+                                double scale, double* img_out, double* cnt_out, long long npix) {
+  if (npix <= 0) return cudaSuccess;
+  long long blocks = (npix + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_image_finish<<<(unsigned)blocks, 256, 0, st>>>(img, cnt, scale, img_out, cnt_out, npix);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v) {
   k_fill<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
   return cudaGetLastError();

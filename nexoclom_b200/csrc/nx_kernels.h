@@ -86,6 +86,15 @@ cudaError_t launch_los_grid(cudaStream_t st, LosGridWork& w, long long nlos,
                             unsigned long long* used_cursor = nullptr, unsigned* used_idx = nullptr,
                             const unsigned* order = nullptr);
 
+// per-call preparation of the lines of sight on the device (nx_los_grid.cu)
+#define NX_LOS_KEY_BINS 32768
+cudaError_t launch_los_prepare(cudaStream_t st, const double* los, long long nlos, double outeredge,
+                               double* dd, unsigned* key, unsigned* hist,
+                               unsigned long long* ddmax_bits);
+cudaError_t launch_los_finish(cudaStream_t st, const double* dd, const double* ladder, int nladder,
+                              long long nlos, int* nball, const unsigned* key, unsigned* hist,
+                              unsigned* order);
+
 size_t table_smem_bytes(const InterpTable& g);
 
 cudaError_t launch_init_state(cudaStream_t st, X0Cols X, long long n,
@@ -98,6 +107,8 @@ cudaError_t launch_init_from_deviates(cudaStream_t st, X0Cols X, long long n,
                                       const SourceParams& sp, const InterpTable& speed,
                                       const InterpTable& lon1d, const double* const* dev);
 cudaError_t launch_fill(cudaStream_t st, double* p, long long n, double v);
+cudaError_t launch_image_finish(cudaStream_t st, const double* img, const unsigned long long* cnt,
+                                double scale, double* img_out, double* cnt_out, long long npix);
 cudaError_t launch_cost_order(cudaStream_t st, int device, StateCols P, long long n,
                               const RunParams& p, int model, unsigned char* bucket,
                               unsigned* hist_cursor, unsigned* perm);

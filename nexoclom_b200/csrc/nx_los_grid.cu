@@ -510,4 +510,122 @@ cudaError_t launch_los_grid(cudaStream_t st, LosGridWork& w, long long nlos,
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Per-call preparation of the lines of sight, on the device (round 1 did this on the host:
+// 4 ms per 1e5 lines).  compute_iteration.py:151-170 builds, per spectrum, a ladder of KD-ball
+// centres t_0 = sin(dphi), t_{k+1} = t_k + t_k sin(dphi) up to the distance `dd` at which the
+// boresight leaves the outer edge; the ladder is common to all lines (the host builds its
+// ~430 entries once the longest `dd` is known), a line needs its own entry count only.
+//   k_los_prepare : dd per line (the reference's arithmetic order), the running maximum, and
+//                   the 15-bit Morton key of the point of closest approach to the planet
+//                   (0.4 R_p cells over +-6.4 R_p) + its histogram: lines of sight run in
+//                   Morton order, so that warps that run together stream the same
+//                   near-planet cells
+//   k_los_key_scan: exclusive scan of the 32768-bin histogram (one block)
+//   k_los_finish  : nball = lower_bound(ladder, dd) + 1 and the counting-sort scatter
+// ---------------------------------------------------------------------------
+#define NX_LOS_KEYS 32768
+__device__ __forceinline__ unsigned morton_spread5(unsigned v) {
+  unsigned r = 0;
+#pragma unroll
+  for (int b = 0; b < 5; ++b) r |= ((v >> b) & 1u) << (3 * b);
+  return r;
+}
+__global__ void __launch_bounds__(256)
+k_los_prepare(const double* __restrict__ los, long long nlos, double outeredge,
+              double* __restrict__ dd_out, unsigned* __restrict__ key_out,
+              unsigned* __restrict__ hist, unsigned long long* __restrict__ ddmax_bits) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double dd = 0.0;
+  if (i < nlos) {
+    const double x = los[i], y = los[nlos + i], z = los[2 * nlos + i];
+    const double bx = los[3 * nlos + i], by = los[4 * nlos + i], bz = los[5 * nlos + i];
+    const double b = 2 * ((x * bx + y * by) + z * bz);
+    const double nrm = sqrt((x * x + y * y) + z * z);
+    const double c = nrm * nrm - outeredge * outeredge;
+    dd = (-b + sqrt(b * b - 4 * 1 * c)) / 2;
+    dd_out[i] = dd;
+    if (key_out) {
+      double t = -(x * bx + y * by + z * bz);
+      if (!(t > 0.0)) t = 0.0;
+      const double cpa[3] = {x + bx * t, y + by * t, z + bz * t};
+      unsigned q[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        double v = (cpa[a] + 6.4) / 0.4;
+        v = v < 0.0 ? 0.0 : (v > 31.0 ? 31.0 : v);
+        q[a] = (v == v) ? (unsigned)v : 0u;
+      }
+      const unsigned key = morton_spread5(q[0]) | (morton_spread5(q[1]) << 1) | (morton_spread5(q[2]) << 2);
+      key_out[i] = key;
+      atomicAdd(&hist[key], 1u);
+    }
+  }
+  // block maximum of the positive, non-NaN dd (bit patterns of positive doubles are ordered)
+  unsigned long long bits = (dd > 0.0) ? (unsigned long long)__double_as_longlong(dd) : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+    bits = other > bits ? other : bits;
+  }
+  if ((threadIdx.x & 31) == 0 && bits) atomicMax(ddmax_bits, bits);
+}
+__global__ void __launch_bounds__(1024) k_los_key_scan(unsigned* __restrict__ hist) {
+  __shared__ unsigned part[1024];
+  const int per = NX_LOS_KEYS / 1024;
+  unsigned local[NX_LOS_KEYS / 1024];
+  unsigned run = 0;
+#pragma unroll
+  for (int k = 0; k < per; ++k) { local[k] = run; run += hist[threadIdx.x * per + k]; }
+  part[threadIdx.x] = run;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned v = threadIdx.x >= (unsigned)o ? part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  const unsigned base = part[threadIdx.x] - run;
+#pragma unroll
+  for (int k = 0; k < per; ++k) hist[threadIdx.x * per + k] = base + local[k];
+}
+__global__ void __launch_bounds__(256)
+k_los_finish(const double* __restrict__ dd, const double* __restrict__ ladder, int nladder,
+             long long nlos, int* __restrict__ nball, const unsigned* __restrict__ key,
+             unsigned* __restrict__ cursor, unsigned* __restrict__ order) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nlos) return;
+  const double d = dd[i];
+  int k = 0;
+  if (d == d) {                           // first k with t_k >= dd; NaN dd -> single entry
+    int lo = 0, hi = nladder;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (ladder[mid] < d) lo = mid + 1; else hi = mid;
+    }
+    k = lo >= nladder ? nladder - 1 : lo;
+  }
+  nball[i] = k + 1;
+  if (order) order[atomicAdd(&cursor[key[i]], 1u)] = (unsigned)i;
+}
+
+cudaError_t launch_los_prepare(cudaStream_t st, const double* los, long long nlos, double outeredge,
+                               double* dd, unsigned* key, unsigned* hist,
+                               unsigned long long* ddmax_bits) {
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(ddmax_bits, 0, sizeof(unsigned long long), st)) != cudaSuccess) return e;
+  if (key && (e = cudaMemsetAsync(hist, 0, NX_LOS_KEYS * sizeof(unsigned), st)) != cudaSuccess) return e;
+  k_los_prepare<<<(unsigned)((nlos + 255) / 256), 256, 0, st>>>(los, nlos, outeredge, dd, key, hist,
+                                                                  ddmax_bits);
+  return cudaGetLastError();
+}
+cudaError_t launch_los_finish(cudaStream_t st, const double* dd, const double* ladder, int nladder,
+                              long long nlos, int* nball, const unsigned* key, unsigned* hist,
+                              unsigned* order) {
+  if (order) k_los_key_scan<<<1, 1024, 0, st>>>(hist);
+  k_los_finish<<<(unsigned)((nlos + 255) / 256), 256, 0, st>>>(dd, ladder, nladder, nlos, nball, key,
+                                                                 hist, order);
+  return cudaGetLastError();
+}
+
 }  // namespace nx

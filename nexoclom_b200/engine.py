@@ -5,6 +5,7 @@ All arrays crossing this layer are plain NumPy float64 / int64 host buffers
 construction raises if the library or a CUDA device is missing.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -19,6 +20,49 @@ X0_COLS = ('time', 'x', 'y', 'z', 'vx', 'vy', 'vz', 'frac', 'v', 'longitude', 'l
 
 class NexoclomCudaError(RuntimeError):
     pass
+
+
+class _PinnedPool:
+    """Page-locked float64 result buffers (``nx_host_alloc``), handed out as NumPy arrays and
+    recycled once every array that views them has been garbage-collected: a device -> host copy
+    into fresh pageable memory pays a page fault per 4 KB and a staging copy (2.6 ms for the
+    two 800 x 800 planes of an image against 0.2 ms of DMA)."""
+    KEEP = 8                                     # idle buffers kept per size
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.idle = {}
+
+    def array(self, shape, dtype=np.float64):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        idle = self.idle.setdefault(nbytes, [])
+        if idle:
+            ptr = idle.pop()
+        else:
+            p = C.c_void_p()
+            if nbytes == 0 or self.lib.nx_host_alloc(nbytes, C.byref(p)) != 0 or not p.value:
+                return np.empty(shape, dtype=dtype)            # pageable: staged by the library
+            ptr = p.value
+        buf = (C.c_char * nbytes).from_address(ptr)
+        weakref.finalize(buf, self._release, nbytes, ptr)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def _release(self, nbytes, ptr):
+        idle = self.idle.setdefault(nbytes, [])
+        if len(idle) < self.KEEP:
+            idle.append(ptr)
+        else:
+            self.lib.nx_host_free(ptr)
+
+
+_POOL = None
+
+
+def _pinned_pool(lib):
+    global _POOL
+    if _POOL is None:
+        _POOL = _PinnedPool(lib)
+    return _POOL
 
 
 class Engine:
@@ -315,6 +359,16 @@ class Engine:
                                             cnt.ctypes.data_as(_lib.c_i64_p)), 'nx_image_fetch')
         return img, cnt
 
+    def image_fetch_scaled(self, nx, nz, scale):
+        """(image * scale, packet counts as float64): what ``ModelImage`` keeps
+        (ModelImage.py:92-105), converted on the device and copied ONCE into page-locked
+        result arrays (no staging copy, no host passes)."""
+        img = _pinned_pool(self.lib).array((nx, nz))
+        cnt = _pinned_pool(self.lib).array((nx, nz))
+        self._check(self.lib.nx_image_fetch_scaled(self.ctx, float(scale), dptr(img), dptr(cnt)),
+                    'nx_image_fetch_scaled')
+        return img, cnt
+
     def image_allreduce(self, comm):
         """Sum the context-owned image + counts over the ranks of ``comm`` (an ``nx_comm``
         handle), in place on the device: the one collective of an image product."""
@@ -344,15 +398,18 @@ class Engine:
         los = as_f64(los)
         nlos = los.shape[1]
         dist = as_f64(dist_from_plan)
-        rad = np.zeros(nlos)
-        npk = np.zeros(nlos, dtype=np.int64)
-        inc = np.zeros(max(n, 1), dtype=np.uint8)
+        # results land in page-locked arrays (direct DMA; the `included` mask is one byte per
+        # packet: 10 MB per 1e7 packets) and the mask is viewed, not converted
+        pool = _pinned_pool(self.lib)
+        rad = pool.array((nlos,))
+        npk = pool.array((nlos,), dtype=np.int64)
+        inc = pool.array((max(n, 1),), dtype=np.uint8)
         self._check(self.lib.nx_los_accumulate(self.ctx, n, nlos, dptr(los), dptr(dist),
                                                C.byref(los_params), dptr(rad),
                                                npk.ctypes.data_as(_lib.c_i64_p),
                                                inc.ctypes.data_as(_lib.c_u8_p)),
                     'nx_los_accumulate')
-        return rad, npk, inc[:n].astype(bool)
+        return rad, npk, inc[:n].view(np.bool_)
 
     def los_used(self, los, dist_from_plan, los_params, n=None):
         """CSR of the `used` packets (weight > 0) per line of sight:
