@@ -403,65 +403,77 @@ k_integrate_adaptive(StateCols In, StateCols P, long long n, RunParams p, Interp
 // ---------------------------------------------------------------------------
 #define NX_NBUCKET 32
 
-__device__ __forceinline__ int cost_bucket(const RunParams& p, int model, double t, double x, double y,
-                                           double z, double vx, double vy, double vz, double f) {
-  if (!(t > p.resolution) || !(f > 0.0)) return 0;
-  const double mu = fabs(p.GM);
-  const double r2 = x * x + y * y + z * z, r = sqrt(r2);
-  const double v2 = vx * vx + vy * vy + vz * vz;
-  const double rv = x * vx + y * vy + z * vz;
-  double tfl = t;
-  const double en = 0.5 * v2 - mu / r;
-  if (p.gravity && en < 0.0 && mu > 0.0) {
-    const double a = -mu / (2.0 * en);
-    const double l2 = fmax(r2 * v2 - rv * rv, 0.0);
-    const double e = sqrt(fmax(1.0 + 2.0 * en * l2 / (mu * mu), 0.0));
-    if (a * (1.0 - e) < 1.0 && e > 1e-12) {
-      // bound orbit that dips below the surface: time from here to r = 1 inbound
-      const double c1 = fmin(fmax((1.0 - 1.0 / a) / e, -1.0), 1.0);
-      const double c0 = fmin(fmax((1.0 - r / a) / e, -1.0), 1.0);
-      const double E1 = acos(c1);
-      double E0 = acos(c0);
-      if (rv < 0.0) E0 = 2.0 * NX_PI - E0;
-      const double Ei = 2.0 * NX_PI - E1;
-      const double dM = (Ei - e * sin(Ei)) - (E0 - e * sin(E0));
-      const double tk = dM * sqrt(a * a * a / mu);
-      // radiation pressure can turn a ballistic hop into a long excursion (Na at
-      // Mercury: up to half the surface gravity): if it can change the speed by
-      // more than ~15% during the hop, budget the full remaining time
-      bool perturbed = (model == 2) && p.radpres && (p.radpres_amax * tk > 0.15 * sqrt(v2));
+// Predicted attempted steps of a packet, in float (it only orders the queue): Kepler flight
+// time to the surface for bound orbits that dip below it, else the time the packet has left,
+// over the position-error step bound.
+__device__ __forceinline__ float cost_estimate_f(const RunParams& p, int model, float res, float mu,
+                                                float amax, double td, double xd, double yd,
+                                                double zd, double vxd, double vyd, double vzd) {
+  const float t = (float)td, x = (float)xd, y = (float)yd, z = (float)zd;
+  const float vx = (float)vxd, vy = (float)vyd, vz = (float)vzd;
+  const float r2 = x * x + y * y + z * z, r = sqrtf(r2);
+  const float v2 = vx * vx + vy * vy + vz * vz, v = sqrtf(v2);
+  const float rv = x * vx + y * vy + z * vz;
+  float tfl = t;
+  const float en = 0.5f * v2 - mu / r;
+  if (p.gravity && en < 0.0f && mu > 0.0f) {
+    const float a = -mu / (2.0f * en);
+    const float l2 = fmaxf(r2 * v2 - rv * rv, 0.0f);
+    const float e = sqrtf(fmaxf(1.0f + 2.0f * en * l2 / (mu * mu), 0.0f));
+    if (a * (1.0f - e) < 1.0f && e > 1e-6f) {
+      const float c1 = fminf(fmaxf((1.0f - 1.0f / a) / e, -1.0f), 1.0f);
+      const float c0 = fminf(fmaxf((1.0f - r / a) / e, -1.0f), 1.0f);
+      const float E1 = acosf(c1);
+      float E0 = acosf(c0);
+      if (rv < 0.0f) E0 = 6.2831853f - E0;
+      const float Ei = 6.2831853f - E1;
+      const float dM = (Ei - e * sinf(Ei)) - (E0 - e * sinf(E0));
+      const float tk = dM * sqrtf(a * a * a / mu);
+      bool perturbed = (model == 2) && p.radpres && (amax * tk > 0.15f * v);
       // model 3 (default): radiation pressure of the order of the local gravity lifts a hop
       // off the surface for good once the launch speed passes a sharp threshold (Na at
       // Mercury, amax = 0.98 g: v > 0.43 v_esc; those packets are 1 % of the run, 22 % of its
       // steps and held EVERY packet above 3000 steps, yet the ballistic hop predicted ~100).
       // With u = v / v_esc(r): flagged when 4.5 (amax / g) u^2 > (1 - u^2)^2  (u > 0.40 there)
       if (model == 3 && p.radpres) {
-        const double u2 = 0.5 * v2 * r / mu, w = 1.0 - u2;
-        perturbed = 4.5 * p.radpres_amax * r2 * u2 > mu * w * w;
+        const float u2 = 0.5f * v2 * r / mu, w = 1.0f - u2;
+        perturbed = 4.5f * amax * r2 * u2 > mu * w * w;
       }
-      if (tk > 0.0 && tk < tfl && !perturbed) tfl = tk;
+      if (tk > 0.0f && tk < tfl && !perturbed) tfl = tk;
     }
   }
-  const double est = tfl * sqrt(v2) / (40.0 * p.resolution * (1.0 + r)) + 4.0;
-  int b = (int)(2.0 * log2(est));
+  return tfl * v / (40.0f * res * (1.0f + r)) + 4.0f;
+}
+__device__ __forceinline__ int cost_bucket(const RunParams& p, int model, double t, double x, double y,
+                                           double z, double vx, double vy, double vz, double f) {
+  if (!(t > p.resolution) || !(f > 0.0)) return 0;
+  const float est = cost_estimate_f(p, model, (float)p.resolution, (float)fabs(p.GM),
+                                    (float)p.radpres_amax, t, x, y, z, vx, vy, vz);
+  const int b = (int)(2.0f * log2f(est));
   return b < 0 ? 0 : (b > NX_NBUCKET - 1 ? NX_NBUCKET - 1 : b);
 }
 
 __global__ void __launch_bounds__(256)
 k_cost_histogram(StateCols P, long long n, RunParams p, int model,
                  unsigned char* __restrict__ bucket, unsigned* __restrict__ hist) {
-  __shared__ unsigned sh[NX_NBUCKET];
-  if (threadIdx.x < NX_NBUCKET) sh[threadIdx.x] = 0;
+  __shared__ unsigned sh[8][NX_NBUCKET];            // one histogram per warp (most packets
+  sh[threadIdx.x >> 5][threadIdx.x & 31] = 0;       // share three or four buckets)
   __syncthreads();
+  unsigned* mine = sh[threadIdx.x >> 5];
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int b = cost_bucket(p, model, P.c[0][i], P.c[1][i], P.c[2][i], P.c[3][i], P.c[4][i],
                               P.c[5][i], P.c[6][i], P.c[7][i]);
     bucket[i] = (unsigned char)b;
-    atomicAdd(&sh[b], 1u);
+    atomicAdd(&mine[b], 1u);
   }
   __syncthreads();
-  if (threadIdx.x < NX_NBUCKET && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+  if (threadIdx.x < NX_NBUCKET) {
+    unsigned c = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) c += sh[w][threadIdx.x];
+    if (c) atomicAdd(&hist[threadIdx.x], c);
+  }
 }
 
 // cursor[b] = number of packets in buckets > b  (descending order of cost)
@@ -554,40 +566,12 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 #define NX_FEED_INLINE __forceinline__
-// float restatement of cost_bucket() folded into NX_NCLASS classes (0 = longest)
+// cost_estimate_f() folded into NX_NCLASS classes (0 = longest)
 __device__ NX_FEED_INLINE int cost_class(const RunParams& p, int model, float res, float mu,
                                           float amax, double td, double xd, double yd, double zd,
                                           double vxd, double vyd, double vzd, double fd) {
   if (!(td > p.resolution) || !(fd > 0.0)) return NX_NCLASS - 1;
-  const float t = (float)td, x = (float)xd, y = (float)yd, z = (float)zd;
-  const float vx = (float)vxd, vy = (float)vyd, vz = (float)vzd;
-  const float r2 = x * x + y * y + z * z, r = sqrtf(r2);
-  const float v2 = vx * vx + vy * vy + vz * vz, v = sqrtf(v2);
-  const float rv = x * vx + y * vy + z * vz;
-  float tfl = t;
-  const float en = 0.5f * v2 - mu / r;
-  if (p.gravity && en < 0.0f && mu > 0.0f) {
-    const float a = -mu / (2.0f * en);
-    const float l2 = fmaxf(r2 * v2 - rv * rv, 0.0f);
-    const float e = sqrtf(fmaxf(1.0f + 2.0f * en * l2 / (mu * mu), 0.0f));
-    if (a * (1.0f - e) < 1.0f && e > 1e-6f) {
-      const float c1 = fminf(fmaxf((1.0f - 1.0f / a) / e, -1.0f), 1.0f);
-      const float c0 = fminf(fmaxf((1.0f - r / a) / e, -1.0f), 1.0f);
-      const float E1 = acosf(c1);
-      float E0 = acosf(c0);
-      if (rv < 0.0f) E0 = 6.2831853f - E0;
-      const float Ei = 6.2831853f - E1;
-      const float dM = (Ei - e * sinf(Ei)) - (E0 - e * sinf(E0));
-      const float tk = dM * sqrtf(a * a * a / mu);
-      bool perturbed = (model == 2) && p.radpres && (amax * tk > 0.15f * v);
-      if (model == 3 && p.radpres) {            // see cost_bucket()
-        const float u2 = 0.5f * v2 * r / mu, w = 1.0f - u2;
-        perturbed = 4.5f * amax * r2 * u2 > mu * w * w;
-      }
-      if (tk > 0.0f && tk < tfl && !perturbed) tfl = tk;
-    }
-  }
-  const float est = tfl * v / (40.0f * res * (1.0f + r)) + 4.0f;
+  const float est = cost_estimate_f(p, model, res, mu, amax, td, xd, yd, zd, vxd, vyd, vzd);
   int cls = 0;
   float thr = NX_CLASS_TOP;
 #pragma unroll
