@@ -424,7 +424,7 @@ def run_gpu(args):
                'image_checksum': checksum}
 
         # the product's normal path draws the packets on the device (K1): Input.run -> ModelImage
-        api_ms, api_steps = 0.0, 0
+        api_ms, api_steps = [], []
         for it in range(1 + reps):
             inputs.delete_files()
             fence()
@@ -434,19 +434,20 @@ def run_gpu(args):
             float(im.image.sum())
             fence()
             if it > 0:
-                api_ms += (time.perf_counter() - t0) * 1e3
+                api_ms.append((time.perf_counter() - t0) * 1e3)
                 _, files, _, _ = inputs.search()
                 from nexoclom_b200 import catalogue
-                api_steps += sum(catalogue.fetch(f).attempted_steps for f in files)
+                api_steps.append(float(sum(catalogue.fetch(f).attempted_steps for f in files)))
         inputs.delete_files()
-        ta = torch.tensor([api_ms, float(api_steps)], dtype=torch.float64, device='cuda')
-        if world > 1:
-            tm, ts = ta.clone(), ta.clone()
+        tm = torch.tensor(api_ms, dtype=torch.float64, device='cuda')
+        ts = torch.tensor(api_steps, dtype=torch.float64, device='cuda')
+        if world > 1:                                  # per repetition: slowest rank, all steps
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-            api_ms, api_steps = float(tm[0]), float(ts[1])
-        extras['api_device_drawn_steps_per_s'] = api_steps / (api_ms * 1e-3)
-        extras['api_device_drawn_ms_per_step'] = api_ms / reps
+        api_med = float(tm.median())
+        extras['api_device_drawn_steps_per_s'] = float(ts[0]) / (api_med * 1e-3)
+        extras['api_device_drawn_ms_per_step'] = api_med
+        extras['api_device_drawn_ms_per_step_all'] = [round(float(v), 3) for v in tm]
         extras['api_device_drawn_call'] = 'Input.run(n) -> ModelImage(inputs, params)'
         del host_in, host_np, cols
 

@@ -245,6 +245,9 @@ int nx_host_free(void* p);
 /* Sharded runs: sum the context-owned image + counts over the ranks of `comm` (see nx_comm_create
  * below), in place, on the context's stream -- the single all-reduce of an image product.    */
 int nx_image_allreduce(nx_ctx* ctx, nx_comm* comm);
+/* The same with one scalar riding along (ModelImage's totalsource): *total is this rank's
+ * contribution on entry, the sum over the ranks on return.                                  */
+int nx_image_allreduce_total(nx_ctx* ctx, nx_comm* comm, double* total);
 
 /* ---- K5: lines of sight (compute_iteration.py:151-222) ------------------------
  * los[6*nlos] SoA: x,y,z,xbore,ybore,zbore; dist_from_plan[nlos] as computed at
@@ -264,6 +267,17 @@ int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_de
 int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
                 const double* dist_from_plan, const nx_los_params* lp,
                 const long long* used_offsets, long long* used_count, uint32_t* used_indices);
+/* nx_los_accumulate that also returns used_count[nlos] from the same pass and keeps its
+ * candidate pairs on the device; nx_los_used_fill then writes the CSR indices
+ * (used_offsets = prefix sums of used_count) by repeating only the exact test over those pairs
+ * when nothing happened in between, else by searching again.                                 */
+int nx_los_accumulate_counted(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                              const double* dist_from_plan, const nx_los_params* lp,
+                              double* radiance, long long* npackets, uint8_t* included,
+                              long long* used_count);
+int nx_los_used_fill(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                     const double* dist_from_plan, const nx_los_params* lp,
+                     const long long* used_offsets, uint32_t* used_indices);
 
 /* ---- K6: source maps (data_simulation/make_source_map.py:11-175) ----------------
  * Whole-planet and per-grid-point (haversine ball of radius smear_radius*cos(lat_point),

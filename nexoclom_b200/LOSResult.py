@@ -109,17 +109,25 @@ def compute_iteration(self, outputfile, scdata, delay=False):
         self._upload_weighting_tables(eng, setup)
         eng.bind_packets(table)
         try:
-            r_, n_, inc_ = eng.los_accumulate(los, dist_from_plan.values, lp, n=table.n)
+            want_used = resident and getattr(self, 'keep_used', True)
+            # `used` / `used0` (compute_iteration.py:143-144, 210-211): packets with weight
+            # > 0 per spectrum, as CSR (the sets the reference stores are built on demand by
+            # IterationResult.used_sets()).  Their counts come out of the accumulate pass, the
+            # indices from the candidate pairs that pass left on the device (nothing may touch
+            # the engine in between).
+            if want_used:
+                r_, n_, inc_, cnt_ = eng.los_accumulate(los, dist_from_plan.values, lp,
+                                                        n=table.n, count_used=True)
+                self.kernel_ms += eng.last_kernel_ms()
+                off, idx = eng.los_used_fill(los, dist_from_plan.values, lp, cnt_, n=table.n)
+            else:
+                r_, n_, inc_ = eng.los_accumulate(los, dist_from_plan.values, lp, n=table.n)
             self.kernel_ms += eng.last_kernel_ms()
             index = table.index_host() + first
             included_[index[inc_]] = True
             rad_ += r_
             npack_ += n_
-            # `used` / `used0` (compute_iteration.py:143-144, 210-211): packets with weight
-            # > 0 per spectrum, delivered by the kernel as CSR and kept in that form (the
-            # sets the reference stores are built on demand by IterationResult.used_sets())
-            if resident and getattr(self, 'keep_used', True):
-                off, idx = eng.los_used(los, dist_from_plan.values, lp, n=table.n)
+            if want_used:
                 used_csr = (off, index[idx], output.row_labels()[idx])
         finally:
             eng.bind_packets(None)

@@ -107,11 +107,12 @@ class ModelImage(ModelResult):
         # ... and the ranks of a sharded run are combined with ONE all-reduce per product: on
         # the device over NCCL / NVLink (before the image crosses PCIe once), through
         # torch.distributed for the gloo backend of the CPU tests
-        if comm is not None:
-            eng.image_allreduce(comm[1])
-        tot = np.array([float(self.totalsource)])
-        allreduce_sum(tot)
-        self.totalsource = float(tot[0])
+        if comm is not None:                       # (totalsource rides with the image)
+            self.totalsource = eng.image_allreduce_total(comm[1], float(self.totalsource))
+        else:
+            tot = np.array([float(self.totalsource)])
+            allreduce_sum(tot)
+            self.totalsource = float(tot[0])
 
         mod_rate = self.totalsource / self.inputs.options.endtime.value
         self.atoms_per_packet = 1e23 / mod_rate

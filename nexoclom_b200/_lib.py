@@ -142,9 +142,14 @@ def load():
         'nx_host_alloc': [i64, C.POINTER(vp)],
         'nx_host_free': [vp],
         'nx_image_allreduce': [vp, vp],
+        'nx_image_allreduce_total': [vp, vp, C.POINTER(C.c_double)],
         'nx_los_accumulate': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams),
                               c_double_p, c_i64_p, c_u8_p],
         'nx_los_accumulate_dev': [vp, i64, i64, vp, vp, C.POINTER(LosParams), vp, vp, vp],
+        'nx_los_accumulate_counted': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams),
+                                      c_double_p, c_i64_p, c_u8_p, c_i64_p],
+        'nx_los_used_fill': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams), c_i64_p,
+                             c_u32_p],
         'nx_los_used': [vp, i64, i64, c_double_p, c_double_p, C.POINTER(LosParams), c_i64_p,
                         c_i64_p, c_u32_p],
         'nx_source_map': [vp, i64, C.POINTER(SourceMapParams)] + [c_double_p] * 9 +

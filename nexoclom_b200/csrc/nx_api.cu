@@ -143,6 +143,16 @@ struct nx_ctx {
   unsigned long long* pipe_scalars = nullptr;  // 4 u64 per chunk
   unsigned* pipe_hist = nullptr;               // 64 u32 per chunk
   LosGridWork losw;
+  // candidate pairs of the last nx_los_accumulate_counted call, still in losw.pairs (np > 0):
+  // nx_los_used_fill resolves them again instead of repeating the whole search
+  struct LosKept {
+    unsigned long long np = 0;
+    long long n = 0, nlos = 0;
+    const void* bound = nullptr;
+    LosParams lp{};
+    LosConsts lc{};
+    size_t nladder = 0;
+  } los_kept;
   unsigned long long* scalars = nullptr;   // [0] queue, [1] total attempted, [2] total accepted
   int* status = nullptr;
   int status_host = 0;
@@ -155,6 +165,14 @@ struct nx_ctx {
       ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
       return -(int)e_;                                                                 \
     }                                                                                  \
+  } while (0)
+// Every entry point that can change what the line-of-sight kernels read starts with ENTER: it selects
+// the device and drops the candidate pairs a line-of-sight call may have left for
+// nx_los_used_fill (which alone keeps them).
+#define ENTER(ctx)                                                                     \
+  do {                                                                                 \
+    (ctx)->los_kept.np = 0;                                                            \
+    CK(cudaSetDevice((ctx)->device));                                                  \
   } while (0)
 
 static void free_interp(DevInterp& d) {
@@ -400,7 +418,7 @@ int nx_ctx_destroy(nx_ctx* ctx) {
 }
 
 int nx_ctx_set_stream(nx_ctx* ctx, void* cuda_stream) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->own_stream) CK(cudaStreamDestroy(ctx->stream));
   ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
@@ -415,6 +433,7 @@ int nx_ctx_sync(nx_ctx* ctx) {
 }
 
 int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
+  ENTER(ctx);
   if (name && std::strcmp(name, "order_packets") == 0) { ctx->order_packets = value; return 0; }
   if (name && std::strcmp(name, "schedule") == 0) { ctx->schedule = value; return 0; }
   if (name && std::strcmp(name, "los_mode") == 0) { ctx->los_mode = value; return 0; }
@@ -526,7 +545,7 @@ int nx_status(nx_ctx* ctx, int* bits) {
 int nx_tables_upload(nx_ctx* ctx, const nx_run_params* p, const double* rv, const double* ra,
                      int nrp, const double* tx, int ntx, const double* ty, int nty,
                      const double* c) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   std::memcpy(&ctx->params, p, sizeof(RunParams));
   ctx->have_params = true;
   if (ctx->params.radpres && nrp < 2) {
@@ -554,7 +573,7 @@ int nx_tables_upload(nx_ctx* ctx, const nx_run_params* p, const double* rv, cons
 
 int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* v,
                       const double* g) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (ntables < 0 || ntables > NX_MAX_GTABLES) { ctx->err = "too many g-value tables"; return -1; }
   ctx->gtables.n = 0;
   size_t off = 0;
@@ -603,7 +622,7 @@ int nx_gtables_upload(nx_ctx* ctx, int ntables, const int* sizes, const double* 
 }
 
 int nx_packets_resize(nx_ctx* ctx, long long n) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   ctx->bound = nullptr;
   if (n <= ctx->cap && ctx->state) return 0;
   const long long cap = ((std::max(n, 1LL) + 31) / 32) * 32;
@@ -627,6 +646,7 @@ int nx_packets_resize(nx_ctx* ctx, long long n) {
 }
 
 int nx_import_state(nx_ctx* ctx, long long n, const double* const* cols) {
+  ENTER(ctx);
   int r = nx_packets_resize(ctx, n);
   if (r) return r;
   ctx->fresh = false;
@@ -691,7 +711,7 @@ int nx_state_device_ptr(nx_ctx* ctx, int column, void** dev_ptr) {
 
 int nx_sourcemap_upload(nx_ctx* ctx, const double* fmap, int nx_, int ny_, const double* xaxis,
                         const double* yaxis) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   cudaFree(ctx->srcmap); ctx->srcmap = nullptr;
   CK(cudaMalloc(&ctx->srcmap, (size_t)nx_ * ny_ * sizeof(double)));
   CK(cudaMemcpyAsync(ctx->srcmap, fmap, (size_t)nx_ * ny_ * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -703,17 +723,18 @@ int nx_sourcemap_upload(nx_ctx* ctx, const double* fmap, int nx_, int ny_, const
 }
 
 int nx_speedtable_upload(nx_ctx* ctx, const double* cdf, const double* v, int n) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   return upload_interp(ctx, ctx->speed, cdf, v, n, false);
 }
 
 int nx_lontable_upload(nx_ctx* ctx, const double* cdf, const double* lon, int n) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   return upload_interp(ctx, ctx->lon1d, cdf, lon, n, false);
 }
 
 int nx_init_state(nx_ctx* ctx, const nx_source_params* sp_, uint64_t seed, uint64_t first_id,
                   long long n) {
+  ENTER(ctx);
   int r = nx_packets_resize(ctx, n);
   if (r) return r;
   SourceParams sp;
@@ -733,6 +754,7 @@ int nx_init_state_deviates(nx_ctx* ctx, const nx_source_params* sp_, long long n
                            const double* u_time, const double* u_sinlat, const double* u_lon,
                            const double* lon_in, const double* lat_in, const double* u_speed,
                            const double* z_normal, const double* u_alt, const double* u_az) {
+  ENTER(ctx);
   int r = nx_packets_resize(ctx, n);
   if (r) return r;
   SourceParams sp;
@@ -765,6 +787,7 @@ int nx_init_state_deviates(nx_ctx* ctx, const nx_source_params* sp_, long long n
 
 int nx_rewind_state(nx_ctx* ctx) {
   if (!ctx->x0_valid) { ctx->err = "no initial state resident (nx_init_state first)"; return -1; }
+  ctx->los_kept.np = 0;
   ctx->fresh = true;
   return 0;
 }
@@ -783,7 +806,7 @@ static int check_status(nx_ctx* ctx) {
 
 int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempted,
                           unsigned long long* accepted) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (!ctx->have_params) { ctx->err = "nx_tables_upload not called"; return -1; }
   ctx->bound = nullptr;            // integrators work on the slab
   if (n > ctx->cap) { ctx->err = "n exceeds resident packets"; return -1; }
@@ -848,6 +871,7 @@ int nx_integrate_adaptive(nx_ctx* ctx, long long n, unsigned long long* attempte
 #define NX_MAX_CHUNKS 16
 int nx_integrate_adaptive_host(nx_ctx* ctx, long long n, const double* const* cols, int nchunks,
                                unsigned long long* attempted, unsigned long long* accepted) {
+  ENTER(ctx);
   int r = nx_packets_resize(ctx, n);
   if (r) return r;
   if (!ctx->have_params) { ctx->err = "nx_tables_upload not called"; return -1; }
@@ -1024,6 +1048,7 @@ static int integrate_constant_core(nx_ctx* ctx, long long n, uint64_t seed, uint
 int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
                           const nx_image_params* img, void* image_dev, void* counts_dev,
                           double* traj_host, unsigned long long* packet_steps) {
+  ENTER(ctx);
   return integrate_constant_core(ctx, n, seed, first_id, img, image_dev, counts_dev, traj_host,
                                  RowSink{}, packet_steps);
 }
@@ -1031,7 +1056,7 @@ int nx_integrate_constant(nx_ctx* ctx, long long n, uint64_t seed, uint64_t firs
 int nx_integrate_constant_rows(nx_ctx* ctx, long long n, uint64_t seed, uint64_t first_id,
                                int skip_dead, int round_f32, nx_packets** out, long long* nrows,
                                unsigned long long* packet_steps) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (!out) { ctx->err = "nx_integrate_constant_rows: null output"; return -1; }
   *out = nullptr;
   if (!ctx->have_params || !(ctx->params.step_size > 0.0)) {
@@ -1116,9 +1141,9 @@ int nx_image_begin(nx_ctx* ctx, int nx_, int nz_) {
   const size_t npix = (size_t)nx_ * nz_;
   double* d_img = nullptr;
   unsigned long long* d_cnt = nullptr;
-  SCR(SCR_IMG, d_img, npix);
+  SCR(SCR_IMG, d_img, npix + 1);                // [npix]: a scalar that rides with the all-reduce
   SCR(SCR_CNT, d_cnt, npix);
-  CK(cudaMemsetAsync(d_img, 0, npix * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(d_img, 0, (npix + 1) * sizeof(double), ctx->stream));
   CK(cudaMemsetAsync(d_cnt, 0, npix * sizeof(unsigned long long), ctx->stream));
   ctx->img_nx = nx_; ctx->img_nz = nz_;
   return 0;
@@ -1217,6 +1242,24 @@ int nx_image_allreduce(nx_ctx* ctx, nx_comm* comm) {
   return r;
 }
 
+// The same with one scalar riding along (ModelImage's totalsource, ModelImage.py:92-99): *total
+// is this rank's contribution on entry and the sum over the ranks on return -- no second
+// collective for 8 bytes.
+int nx_image_allreduce_total(nx_ctx* ctx, nx_comm* comm, double* total) {
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->img_nx) { ctx->err = "nx_image_begin not called"; return -1; }
+  if (!total) return nx_image_allreduce(ctx, comm);
+  const long long npix = (long long)ctx->img_nx * ctx->img_nz;
+  double* d_img = static_cast<double*>(ctx->scr[SCR_IMG].p);
+  CK(cudaMemcpyAsync(d_img + npix, total, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  int r = nx_allreduce(comm, d_img, npix + 1, NX_DTYPE_F64, ctx->stream);
+  if (r == 0) r = nx_allreduce(comm, ctx->scr[SCR_CNT].p, npix, NX_DTYPE_I64, ctx->stream);
+  if (r) { ctx->err = std::string("nx_image_allreduce_total: ") + nx_comm_last_error(); return r; }
+  CK(cudaMemcpyAsync(total, d_img + npix, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int nx_ctx_stream(nx_ctx* ctx, void** cuda_stream) {
   if (!cuda_stream) return -1;
   *cuda_stream = ctx->stream;
@@ -1295,7 +1338,8 @@ static void los_prepare(const double* los, long long nlos, const LosParams& lp,
 
 static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_dev,
                    const double* dist_dev, const LosParams& lp, double* rad_dev,
-                   unsigned long long* np_dev, unsigned char* inc_dev) {
+                   unsigned long long* np_dev, unsigned char* inc_dev,
+                   unsigned long long* nused_dev = nullptr) {
   { int r0 = materialize(ctx); if (r0) return r0; }
   static const bool timing = std::getenv("NX_LOS_TIMING") != nullptr;     // developer aid
   const auto tp0 = std::chrono::steady_clock::now();
@@ -1305,7 +1349,7 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_d
                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count());
   };
   // candidate generation: brute force for small problems, cell grid otherwise
-  const bool use_grid = ctx->los_mode == 2 ||
+  const bool use_grid = ctx->los_mode == 2 || nused_dev ||      // (`used` counts: grid path only)
                         (ctx->los_mode == 0 && (double)n * (double)nlos > 2e9 && n < (1LL << 32));
   const bool want_order = use_grid && ctx->los_order && nlos >= 1024;
   // per-line preparation on the device; the host only turns the longest boresight distance
@@ -1348,10 +1392,17 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_d
     cudaError_t e;
     if (use_grid) {
       e = launch_los_grid_build(ctx->stream, ctx->device, state_cols(ctx), n, lp, ctx->losw);
+      unsigned long long kept = 0;
       if (e == cudaSuccess)
         e = launch_los_grid(ctx->stream, ctx->losw, nlos, los_dev, dist_dev, d_nball, d_ladder,
-                            d_wid2, lp, lc, ctx->gtables, rad_dev, np_dev, inc_dev, nullptr,
-                            nullptr, nullptr, nullptr, d_order);
+                            d_wid2, lp, lc, ctx->gtables, rad_dev, np_dev, inc_dev, nused_dev,
+                            nullptr, nullptr, nullptr, d_order, nused_dev ? &kept : nullptr);
+      if (e == cudaSuccess && kept) {
+        ctx->los_kept.np = kept; ctx->los_kept.n = n; ctx->los_kept.nlos = nlos;
+        ctx->los_kept.bound = ctx->bound; ctx->los_kept.lc = lc;
+        std::memcpy(&ctx->los_kept.lp, &lp, sizeof(lp));      // (bytes: compared with memcmp)
+        ctx->los_kept.nladder = ladder.size();
+      }
       nlaunch = 8;
     } else {
       e = launch_los_accumulate(ctx->stream, ctx->device, state_cols(ctx), n, nlos, los_dev,
@@ -1370,7 +1421,7 @@ static int los_run(nx_ctx* ctx, long long n, long long nlos, const double* los_d
 int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_dev, void* dist_dev,
                           const nx_los_params* lp_, void* radiance_dev, void* npackets_dev,
                           void* included_dev) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
   LosParams lp;
   std::memcpy(&lp, lp_, sizeof(lp));
@@ -1385,7 +1436,7 @@ int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_de
 int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* los,
                       const double* dist_from_plan, const nx_los_params* lp_, double* radiance,
                       long long* npackets, uint8_t* included) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
   LosParams lp;
   std::memcpy(&lp, lp_, sizeof(lp));
@@ -1417,10 +1468,98 @@ int nx_los_accumulate(nx_ctx* ctx, long long n, long long nlos, const double* lo
   return r;
 }
 
+// nx_los_accumulate that also counts, per line of sight, the `used` packets (weight > 0,
+// compute_iteration.py:210-211) in the same pass, and keeps the candidate pairs on the device
+// for nx_los_used_fill.
+int nx_los_accumulate_counted(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                              const double* dist_from_plan, const nx_los_params* lp_,
+                              double* radiance, long long* npackets, uint8_t* included,
+                              long long* used_count) {
+  if (!used_count)
+    return nx_los_accumulate(ctx, n, nlos, los, dist_from_plan, lp_, radiance, npackets, included);
+  ENTER(ctx);
+  if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
+  if (n >= (1LL << 32)) { ctx->err = "more than 2^32 packets per GPU"; return -1; }
+  LosParams lp;
+  std::memcpy(&lp, lp_, sizeof(lp));
+  if (lp.quantity != 1) { ctx->err = "Other quantities not set up."; return -1; }
+  if (ctx->gtables.n == 0) { ctx->err = "no g-value tables uploaded"; return -1; }
+  double *d_los = nullptr, *d_dist = nullptr, *d_rad = nullptr;
+  unsigned long long *d_np = nullptr, *d_nused = nullptr;
+  unsigned char* d_inc = nullptr;
+  const size_t nl = (size_t)(nlos > 0 ? nlos : 1), nn = (size_t)(n > 0 ? n : 1);
+  SCR(SCR_LOS, d_los, 6 * nl);
+  SCR(SCR_DIST, d_dist, nl);
+  SCR(SCR_RAD, d_rad, nl);
+  SCR(SCR_NP, d_np, nl);
+  SCR(SCR_INC, d_inc, nn);
+  SCR(SCR_NUSED, d_nused, nl);
+  CK(cudaMemcpyAsync(d_los, los, 6 * (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_dist, dist_from_plan, (size_t)nlos * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(d_rad, 0, nl * sizeof(double), ctx->stream));
+  CK(cudaMemsetAsync(d_np, 0, nl * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(d_nused, 0, nl * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(d_inc, 0, nn, ctx->stream));
+  int r = 0;
+  if (n > 0 && nlos > 0) r = los_run(ctx, n, nlos, d_los, d_dist, lp, d_rad, d_np, d_inc, d_nused);
+  if (r == 0) {
+    cudaMemcpyAsync(radiance, d_rad, (size_t)nlos * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(npackets, d_np, (size_t)nlos * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(used_count, d_nused, (size_t)nlos * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+    if (included) cudaMemcpyAsync(included, d_inc, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); r = -(int)e; }
+  }
+  return r;
+}
+
+// The indices of the `used` packets, CSR layout given by used_offsets (the prefix sums of the
+// counts nx_los_accumulate_counted returned).  When that call's candidate pairs are still on
+// the device (same packets, same lines of sight, nothing in between) only the exact test is
+// repeated over them; otherwise the whole search runs again (nx_los_used).
+int nx_los_used_fill(nx_ctx* ctx, long long n, long long nlos, const double* los,
+                     const double* dist_from_plan, const nx_los_params* lp_,
+                     const long long* used_offsets, uint32_t* used_indices) {
+  if (!used_offsets || !used_indices) { ctx->err = "nx_los_used_fill: null argument"; return -1; }
+  LosParams lp;
+  std::memcpy(&lp, lp_, sizeof(lp));
+  const nx_ctx::LosKept k = ctx->los_kept;
+  const bool reuse = k.np > 0 && k.n == n && k.nlos == nlos && k.bound == ctx->bound &&
+                     std::memcmp(&k.lp, &lp, sizeof(lp)) == 0;
+  if (!reuse) {
+    std::vector<long long> count((size_t)(nlos > 0 ? nlos : 1));
+    return nx_los_used(ctx, n, nlos, los, dist_from_plan, lp_, used_offsets, count.data(), used_indices);
+  }
+  CK(cudaSetDevice(ctx->device));
+  const long long total = used_offsets[nlos];
+  if (total <= 0) return 0;
+  unsigned long long* d_cursor = nullptr;
+  long long* d_off = nullptr;
+  unsigned* d_idx = nullptr;
+  SCR(SCR_CURSOR, d_cursor, (size_t)nlos);
+  SCR(SCR_OFF, d_off, (size_t)(nlos + 1));
+  SCR(SCR_IDX, d_idx, (size_t)total);
+  CK(cudaMemsetAsync(d_cursor, 0, (size_t)nlos * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemcpyAsync(d_off, used_offsets, (size_t)(nlos + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  const double* d_ladder = static_cast<const double*>(ctx->scr[SCR_LADDER].p);
+  int r = begin_timed(ctx);
+  if (r) return r;
+  CK(launch_los_resolve(ctx->stream, ctx->losw, k.np, nlos,
+                        static_cast<const double*>(ctx->scr[SCR_LOS].p),
+                        static_cast<const double*>(ctx->scr[SCR_DIST].p),
+                        static_cast<const int*>(ctx->scr[SCR_NBALL].p), d_ladder,
+                        d_ladder + k.nladder, k.lp, k.lc, ctx->gtables, nullptr, nullptr, nullptr,
+                        nullptr, d_off, d_cursor, d_idx));
+  if ((r = end_timed(ctx, 1))) return r;
+  CK(cudaMemcpyAsync(used_indices, d_idx, (size_t)total * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
                 const double* dist_from_plan, const nx_los_params* lp_, const long long* used_offsets,
                 long long* used_count, uint32_t* used_indices) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (n > resident_rows(ctx)) { ctx->err = "n exceeds resident packets"; return -1; }
   LosParams lp;
   std::memcpy(&lp, lp_, sizeof(lp));
@@ -1483,7 +1622,7 @@ int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
 // ---- resident packet tables (device-side Output.save, Output.py:522-543) -----------------
 int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_packets** out,
                      long long* count) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (!out) { ctx->err = "nx_compact_state: null output"; return -1; }
   *out = nullptr;
   ctx->bound = nullptr;
@@ -1530,7 +1669,7 @@ int nx_compact_state(nx_ctx* ctx, long long n, int skip_dead, int round_f32, nx_
 
 int nx_packets_upload(nx_ctx* ctx, long long n, const double* const* cols, const uint32_t* index,
                       nx_packets** out) {
-  CK(cudaSetDevice(ctx->device));
+  ENTER(ctx);
   if (!out) { ctx->err = "nx_packets_upload: null output"; return -1; }
   nx_packets* h = new nx_packets();
   h->n = n;
@@ -1552,6 +1691,7 @@ int nx_packets_upload(nx_ctx* ctx, long long n, const double* const* cols, const
 }
 
 int nx_packets_bind(nx_ctx* ctx, nx_packets* h) {
+  ctx->los_kept.np = 0;
   ctx->bound = h;
   return 0;
 }
@@ -1596,6 +1736,7 @@ int nx_packets_export(nx_ctx* ctx, nx_packets* h, float* const* cols, int32_t* i
 int nx_packets_free(nx_ctx* ctx, nx_packets* h) {
   if (!h) return 0;
   cudaSetDevice(ctx->device);
+  ctx->los_kept.np = 0;
   if (ctx->bound == h) ctx->bound = nullptr;
   free_packets(h, ctx->stream);
   return 0;

@@ -84,7 +84,14 @@ cudaError_t launch_los_grid(cudaStream_t st, LosGridWork& w, long long nlos,
                             unsigned long long* npack, unsigned char* included,
                             unsigned long long* nused = nullptr, const long long* used_off = nullptr,
                             unsigned long long* used_cursor = nullptr, unsigned* used_idx = nullptr,
-                            const unsigned* order = nullptr);
+                            const unsigned* order = nullptr, unsigned long long* kept_pairs = nullptr);
+cudaError_t launch_los_resolve(cudaStream_t st, LosGridWork& w, unsigned long long np, long long nlos,
+                               const double* los, const double* dist_plan, const int* nball,
+                               const double* ladder, const double* wid2, const LosParams& lp,
+                               const LosConsts& lc, const GTables& G, double* radiance,
+                               unsigned long long* npack, unsigned char* included,
+                               unsigned long long* nused, const long long* used_off,
+                               unsigned long long* used_cursor, unsigned* used_idx);
 
 // per-call preparation of the lines of sight on the device (nx_los_grid.cu)
 #define NX_LOS_KEY_BINS 32768

@@ -456,7 +456,7 @@ cudaError_t launch_los_grid(cudaStream_t st, LosGridWork& w, long long nlos,
                             unsigned long long* npack, unsigned char* included,
                             unsigned long long* nused, const long long* used_off,
                             unsigned long long* used_cursor, unsigned* used_idx,
-                            const unsigned* order) {
+                            const unsigned* order, unsigned long long* kept_pairs) {
   // Lines of sight go through in batches sized so that the candidate pairs of a batch fit the
   // pair buffer (about half full: the size of the next batch follows the pairs per line of
   // sight seen so far); a batch that overflows is repeated with half as many lines.
@@ -500,6 +500,8 @@ cudaError_t launch_los_grid(cudaStream_t st, LosGridWork& w, long long nlos,
                                                            ladder, wid2, lp, lc, G, radiance, npack, included,
                                                            nused, used_off, used_cursor, used_idx);
     }
+    // one batch covered every line of sight: its pairs stay valid in w.pairs
+    if (kept_pairs) *kept_pairs = (first == 0 && cnt == nlos) ? np : 0ull;
     first += cnt;
     const double per = (double)np / (double)cnt;
     long long next = per > 0.0 ? (long long)(0.9 * (double)cap / per) : nlos;
@@ -625,6 +627,32 @@ cudaError_t launch_los_finish(cudaStream_t st, const double* dd, const double* l
   if (order) k_los_key_scan<<<1, 1024, 0, st>>>(hist);
   k_los_finish<<<(unsigned)((nlos + 255) / 256), 256, 0, st>>>(dd, ladder, nladder, nlos, nball, key,
                                                                  hist, order);
+  return cudaGetLastError();
+}
+
+// The exact test + weights over a pair list that is already on the device (the pairs a
+// single-batch launch_los_grid left in w.pairs).
+cudaError_t launch_los_resolve(cudaStream_t st, LosGridWork& w, unsigned long long np, long long nlos,
+                               const double* los, const double* dist_plan, const int* nball,
+                               const double* ladder, const double* wid2, const LosParams& lp,
+                               const LosConsts& lc, const GTables& G, double* radiance,
+                               unsigned long long* npack, unsigned char* included,
+                               unsigned long long* nused, const long long* used_off,
+                               unsigned long long* used_cursor, unsigned* used_idx) {
+  if (!np) return cudaSuccess;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long rb = (long long)((np + 255) / 256);
+  if (rb > (long long)sms * 16) rb = (long long)sms * 16;
+  if (lp.round_f32)
+    k_los_resolve<true><<<(unsigned)rb, 256, 0, st>>>(w.sorted, w.pairs, np, nlos, los, dist_plan, nball,
+                                                      ladder, wid2, lp, lc, G, radiance, npack, included,
+                                                      nused, used_off, used_cursor, used_idx);
+  else
+    k_los_resolve<false><<<(unsigned)rb, 256, 0, st>>>(w.sorted, w.pairs, np, nlos, los, dist_plan, nball,
+                                                       ladder, wid2, lp, lc, G, radiance, npack, included,
+                                                       nused, used_off, used_cursor, used_idx);
   return cudaGetLastError();
 }
 

@@ -374,6 +374,13 @@ class Engine:
         handle), in place on the device: the one collective of an image product."""
         self._check(self.lib.nx_image_allreduce(self.ctx, comm), 'nx_image_allreduce')
 
+    def image_allreduce_total(self, comm, total):
+        """``image_allreduce`` with one scalar riding along; returns the summed scalar."""
+        v = C.c_double(float(total))
+        self._check(self.lib.nx_image_allreduce_total(self.ctx, comm, C.byref(v)),
+                    'nx_image_allreduce_total')
+        return v.value
+
     def stream_ptr(self):
         p = C.c_void_p()
         self._check(self.lib.nx_ctx_stream(self.ctx, C.byref(p)), 'nx_ctx_stream')
@@ -392,8 +399,11 @@ class Engine:
                                                      C.c_void_p(counts_dev)),
                     'nx_image_accumulate_dev')
 
-    def los_accumulate(self, los, dist_from_plan, los_params, n=None):
-        """los: (6, nlos) array x,y,z,xbore,ybore,zbore."""
+    def los_accumulate(self, los, dist_from_plan, los_params, n=None, count_used=False):
+        """los: (6, nlos) array x,y,z,xbore,ybore,zbore.  Returns (radiance, hit counts,
+        included mask); with ``count_used`` also the number of `used` packets (weight > 0) per
+        line of sight, counted in the same pass -- ``los_used_fill`` then delivers their
+        indices from the candidate pairs this call left on the device."""
         n = self.n if n is None else n
         los = as_f64(los)
         nlos = los.shape[1]
@@ -404,12 +414,36 @@ class Engine:
         rad = pool.array((nlos,))
         npk = pool.array((nlos,), dtype=np.int64)
         inc = pool.array((max(n, 1),), dtype=np.uint8)
+        if count_used:
+            cnt = np.zeros(nlos, dtype=np.int64)
+            self._check(self.lib.nx_los_accumulate_counted(
+                self.ctx, n, nlos, dptr(los), dptr(dist), C.byref(los_params), dptr(rad),
+                npk.ctypes.data_as(_lib.c_i64_p), inc.ctypes.data_as(_lib.c_u8_p),
+                cnt.ctypes.data_as(_lib.c_i64_p)), 'nx_los_accumulate_counted')
+            return rad, npk, inc[:n].view(np.bool_), cnt
         self._check(self.lib.nx_los_accumulate(self.ctx, n, nlos, dptr(los), dptr(dist),
                                                C.byref(los_params), dptr(rad),
                                                npk.ctypes.data_as(_lib.c_i64_p),
                                                inc.ctypes.data_as(_lib.c_u8_p)),
                     'nx_los_accumulate')
         return rad, npk, inc[:n].view(np.bool_)
+
+    def los_used_fill(self, los, dist_from_plan, los_params, used_count, n=None):
+        """CSR (offsets[nlos+1], packet indices) of the `used` packets, given the counts
+        ``los_accumulate(..., count_used=True)`` returned for the same arguments."""
+        n = self.n if n is None else n
+        los = as_f64(los)
+        nlos = los.shape[1]
+        dist = as_f64(dist_from_plan)
+        off = np.zeros(nlos + 1, dtype=np.int64)
+        np.cumsum(used_count, out=off[1:])
+        idx = np.zeros(max(int(off[-1]), 1), dtype=np.uint32)
+        if off[-1] > 0:
+            self._check(self.lib.nx_los_used_fill(
+                self.ctx, n, nlos, dptr(los), dptr(dist), C.byref(los_params),
+                off.ctypes.data_as(_lib.c_i64_p), idx.ctypes.data_as(_lib.c_u32_p)),
+                'nx_los_used_fill')
+        return off, idx[:int(off[-1])]
 
     def los_used(self, los, dist_from_plan, los_params, n=None):
         """CSR of the `used` packets (weight > 0) per line of sight:

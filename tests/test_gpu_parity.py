@@ -56,6 +56,30 @@ def test_adaptive_driver_vs_oracle(engine, wl, strict):
     assert np.all(Xg[dead, 0] == 0)                              # dead => time = 0 (Q8)
 
 
+def test_config0_at_its_named_size_vs_golden(engine):
+    """BASELINE configs[0] at the size it names (1e5 Ca packets): attempted / accepted step
+    counts of EVERY packet, the final state of every 16th packet and the column sums of all
+    final states against tests/golden/config0_1e5.npz (the oracle's port of the reference
+    driver, 3 min of CPU: tools/make_golden_config0.py)."""
+    g = np.load(os.path.join(GOLDEN, 'config0_1e5.npz'))
+    n, seed, stride = int(g['n']), int(g['seed']), int(g['stride'])
+    setup = RunSetup(workload('Ca.isotropic.flat.input'))
+    setup.upload(engine)
+    X0 = initial_state.draw_x0(setup, n, seed)[:, :8].astype(np.float32).astype(np.float64)
+    assert np.array_equal(X0.sum(axis=0), g['x0_sums'])          # the same initial state
+    engine.import_state(X0)
+    att, acc = engine.integrate_adaptive()
+    Xg = engine.export_state().T
+    a_g, c_g = engine.export_stats()
+    assert np.array_equal(a_g, g['attempted']) and np.array_equal(c_g, g['accepted'])
+    assert att == int(g['attempted'].astype(np.int64).sum())
+    par = state_parity(Xg[::stride], g['final_subset'])
+    assert par['alive_mismatch'] == 0, par
+    assert max(par['pos'], par['vel'], par['frac']) < STATE_TOL, par
+    assert np.allclose(Xg.sum(axis=0), g['final_sums'], rtol=0, atol=1e-9 * g['final_abs_sums'].max())
+    assert np.allclose(np.abs(Xg).sum(axis=0), g['final_abs_sums'], rtol=1e-10)
+
+
 def test_adaptive_import_mode_vs_reference_golden(engine):
     """Reference-generated initial states -> final state of the reference's own
     driver (tests/golden/adaptive_driver.npz)."""
@@ -298,6 +322,44 @@ def test_image_vs_reference_golden(engine, tag):
     assert nz.sum() > 1000
     assert np.max(np.abs(img[nz] - ref[nz]) / ref[nz]) < IMAGE_TOL
     assert np.all(img[~nz] == 0)
+
+
+def test_los_counted_pass_and_pair_reuse(engine):
+    """nx_los_accumulate_counted + nx_los_used_fill == nx_los_accumulate + the two-pass
+    nx_los_used, on the reference's own golden lines of sight: once re-resolving the candidate
+    pairs the counted pass left on the device, once after a call in between dropped them (the
+    fill then searches again), once with a pair buffer too small for one batch."""
+    from nexoclom_b200.LOSResult import dist_from_planet_cut
+    import pandas as pd
+    g = np.load(os.path.join(GOLDEN, 'los.npz'))
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    engine.upload_gtables(setup.gtables([5891, 5897]))
+    engine.import_state(g['X'])
+    los = g['los'].T.copy()
+    data = pd.DataFrame(g['los'], columns=['x', 'y', 'z', 'xbore', 'ybore', 'zbore'])
+    dist = np.asarray(dist_from_planet_cut(data), dtype=np.float64)
+    lp = LosParams()
+    lp.dphi, lp.outeredge = float(g['d3_dphi']), float(g['outeredge'])
+    lp.vrplanet, lp.rp_cm = setup.vrplanet, setup.radius_km * 1e5
+    lp.quantity = 1
+    rad0, npk0, inc0 = engine.los_accumulate(los, dist, lp)
+    off0, idx0 = engine.los_used(los, dist, lp)
+    assert off0[-1] > 1000
+
+    def same_sets(off, idx):
+        assert np.array_equal(off, off0)
+        for i in range(len(off) - 1):
+            assert np.array_equal(np.sort(idx[off[i]:off[i + 1]]), np.sort(idx0[off0[i]:off0[i + 1]]))
+
+    for between in (False, True):
+        rad, npk, inc, cnt = engine.los_accumulate(los, dist, lp, count_used=True)
+        assert np.array_equal(npk, npk0) and np.array_equal(inc, inc0)
+        assert np.array_equal(cnt, np.diff(off0))
+        assert np.allclose(rad, rad0, rtol=1e-12, atol=0)
+        if between:
+            engine.set_option('los_mode', 0)           # any state-changing call drops the pairs
+        same_sets(*engine.los_used_fill(los, dist, lp, cnt))
 
 
 @pytest.mark.parametrize('los_mode', [1, 2])

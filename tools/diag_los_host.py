@@ -26,3 +26,20 @@ for it in range(4):
     t0 = time.perf_counter()
     rad, npk, inc = eng.los_accumulate(los, dplan, lp, n=n)
     print(f'wall {(time.perf_counter() - t0) * 1e3:.2f} ms, kernels {eng.last_kernel_ms():.2f} ms, hits {int(npk.sum())}', flush=True)
+# `used` sets: counts from the accumulate pass + indices from its candidate pairs, against the
+# two extra searches of nx_los_used (1e4 lines of sight: the CSR is 4 B per used pair)
+los2, dplan2 = bench.synthetic_los(10_000)
+for it in range(2):
+    eng.sync(); t0 = time.perf_counter()
+    rad, npk, inc, cnt = eng.los_accumulate(los2, dplan2, lp, n=n, count_used=True)
+    t1 = time.perf_counter()
+    off, idx = eng.los_used_fill(los2, dplan2, lp, cnt, n=n)
+    t2 = time.perf_counter()
+    k_fill = eng.last_kernel_ms()
+    rad, npk, inc = eng.los_accumulate(los2, dplan2, lp, n=n)
+    t3 = time.perf_counter()
+    off_b, idx_b = eng.los_used(los2, dplan2, lp, n=n)
+    t4 = time.perf_counter()
+    assert np.array_equal(off, off_b)
+    print(f'counted accumulate {1e3 * (t1 - t0):.2f} ms + fill {1e3 * (t2 - t1):.2f} ms (kernel {k_fill:.2f}) | '
+          f'accumulate {1e3 * (t3 - t2):.2f} ms + two-pass used {1e3 * (t4 - t3):.2f} ms; {int(off[-1])} used pairs', flush=True)
