@@ -87,3 +87,19 @@ def test_philox_known_answers():
     assert [int(x) for x in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     out = f(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0)
     assert [int(x) for x in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_config0_named_size_fixture_is_the_oracles():
+    """tests/golden/config0_1e5.npz (tools/make_golden_config0.py): the oracle replayed on a
+    slice of the 1e5 packets reproduces the stored step counts and final states."""
+    g = np.load(os.path.join(GOLDEN, 'config0_1e5.npz'))
+    n, seed, stride = int(g['n']), int(g['seed']), int(g['stride'])
+    setup = RunSetup(workload(WL['ca']))
+    X0 = initial_state.draw_x0(setup, n, seed)[:, :8].astype(np.float32).astype(np.float64)
+    if not np.array_equal(X0.sum(axis=0), g['x0_sums']):
+        pytest.skip('initial state not bit-reproducible on this host (NumPy SIMD sin / cos)')
+    pick = np.arange(0, n, stride)[:240]
+    Xo, att, acc = tracking.integrate_adaptive(X0[pick], oracle_constants(setup))
+    assert np.array_equal(att, g['attempted'][pick]) and np.array_equal(acc, g['accepted'][pick])
+    ref = g['final_subset'][:240]
+    assert np.max(np.abs(Xo - ref)) < 1e-12 * max(1.0, np.abs(ref).max())
