@@ -28,7 +28,7 @@ namespace nx {
 
 #define FULL_MASK 0xffffffffu
 #ifndef NX_LOS_SEG_CELLS
-#define NX_LOS_SEG_CELLS 6.0      // march segment length in finest local cells (1: 41 ms, 4: 35.2, 8: 35.4, 16: 46.7)
+#define NX_LOS_SEG_CELLS 12.0     // march segment length in finest local cells (with the pieces below: 6: 17.7 ms, 8: 17.0, 12: 16.0, 16: 16.2)
 #endif
 
 // ---- 1. bounding cube: max |coordinate| over live packets ----------------------
@@ -210,6 +210,9 @@ template <bool F32> struct LosRec { typedef double4 type; };
 template <> struct LosRec<true> { typedef float4 type; };
 #define NX_LOS_WARPS 8              // warps per block of the candidate kernel
 #define NX_LOS_BUF 128              // pairs buffered per warp
+#ifndef NX_LOS_SUB
+#define NX_LOS_SUB 12               // pieces a march segment is cut into for the cell ranges (<= 31)
+#endif
 #ifndef NX_LOS_MINBLOCKS
 #define NX_LOS_MINBLOCKS 4          // 64 registers: 32 resident warps per SM
 #endif
@@ -224,6 +227,7 @@ k_los_candidates(LosSorted S, LosGrid g, const unsigned* __restrict__ start, lon
                  unsigned long long* __restrict__ cursor, unsigned long long cap) {
   typedef typename LosRec<F32>::type RecT;
   __shared__ unsigned buf_all[NX_LOS_WARPS][NX_LOS_BUF];
+  __shared__ __align__(16) int sub_all[NX_LOS_WARPS][NX_LOS_SUB * 8];
   const unsigned lane = threadIdx.x & 31u;
   unsigned* buf = buf_all[threadIdx.x >> 5];
   const RecT* __restrict__ recs = reinterpret_cast<const RecT*>(S.pos);
@@ -288,20 +292,58 @@ k_los_candidates(LosSorted S, LosGrid g, const unsigned* __restrict__ start, lon
     if (xlo > g.half || xhi < -g.half || ylo > g.half || yhi < -g.half || zlo > g.half ||
         zhi < -g.half)
       continue;
-    const int ix0 = cell_of(xlo, g), ix1 = cell_of(xhi, g);
-    const int iy0 = cell_of(ylo, g), iy1 = cell_of(yhi, g);
-    const int iz0 = cell_of(zlo, g), iz1 = cell_of(zhi, g);
-    // the (ix, iy) columns of the box: every lane fetches the packet range of one column (the
-    // dependent index loads of up to 32 columns are in flight together), then the warp
-    // streams the ranges one after the other, two records per lane in flight
+    // The axis-aligned box of a diagonal segment holds several times the cells its cone
+    // touches.  The segment is therefore cut into NX_LOS_SUB pieces: lane j takes the axis
+    // point at t0 + j dt / NX_LOS_SUB (the last one at t1), the cells of that point +- rho per
+    // axis; piece j is the hull of points j and j + 1 (cell_of is monotone, so the hull of the
+    // cell indices is the cell range of the hull).  A packet the segment owns sits within rho
+    // of the axis point at its own axial coordinate, i.e. inside one of the pieces.
+    int plo[3], phi[3];
+    {
+      const int j = min((int)lane, NX_LOS_SUB);
+      const double tj = j == NX_LOS_SUB ? t1 : t0 + dt * ((double)j * (1.0 / NX_LOS_SUB));
+      const double ax = xs + bx * tj, ay = ys + by * tj, az = zs + bz * tj;
+      plo[0] = cell_of(ax - rho, g); phi[0] = cell_of(ax + rho, g);
+      plo[1] = cell_of(ay - rho, g); phi[1] = cell_of(ay + rho, g);
+      plo[2] = cell_of(az - rho, g); phi[2] = cell_of(az + rho, g);
+    }
+    int* sb = sub_all[threadIdx.x >> 5];
+    __syncwarp();                                     // the previous segment's readers are done
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int nlo = __shfl_down_sync(FULL_MASK, plo[a], 1), nhi = __shfl_down_sync(FULL_MASK, phi[a], 1);
+      if (lane < NX_LOS_SUB) {
+        sb[lane * 8 + 2 * a] = min(plo[a], nlo);
+        sb[lane * 8 + 2 * a + 1] = max(phi[a], nhi);
+      }
+    }
+    __syncwarp();
+    const bool pt = lane <= NX_LOS_SUB;
+    const int ix0 = __reduce_min_sync(FULL_MASK, pt ? plo[0] : 0x7fffffff);
+    const int ix1 = __reduce_max_sync(FULL_MASK, pt ? phi[0] : -1);
+    const int iy0 = __reduce_min_sync(FULL_MASK, pt ? plo[1] : 0x7fffffff);
+    const int iy1 = __reduce_max_sync(FULL_MASK, pt ? phi[1] : -1);
+    // the (ix, iy) columns of the box: every lane finds the z cells the pieces reach in ITS
+    // column and fetches that packet range (the dependent index loads of up to 32 columns are
+    // in flight together), then the warp streams the ranges one after the other, two records
+    // per lane in flight; columns no piece touches stay empty
     const int nyr = iy1 - iy0 + 1, ncol = (ix1 - ix0 + 1) * nyr;
     for (int c0 = 0; c0 < ncol; c0 += 32) {
       const int c = c0 + (int)lane;
       unsigned p0v = 0u, p1v = 0u;
       if (c < ncol) {
         const int ix = ix0 + c / nyr, iy = iy0 + c % nyr;
-        const unsigned row = (unsigned)((ix * g.G + iy) * g.G);
-        p0v = __ldg(start + row + iz0); p1v = __ldg(start + row + iz1 + 1);
+        int iz0 = 0x7fffffff, iz1 = -1;
+#pragma unroll
+        for (int j = 0; j < NX_LOS_SUB; ++j) {
+          const int4 q = *reinterpret_cast<const int4*>(sb + j * 8);        // x lo, x hi, y lo, y hi
+          const int2 qz = *reinterpret_cast<const int2*>(sb + j * 8 + 4);   // z lo, z hi
+          if (ix >= q.x && ix <= q.y && iy >= q.z && iy <= q.w) { iz0 = min(iz0, qz.x); iz1 = max(iz1, qz.y); }
+        }
+        if (iz1 >= iz0) {
+          const unsigned row = (unsigned)((ix * g.G + iy) * g.G);
+          p0v = __ldg(start + row + iz0); p1v = __ldg(start + row + iz1 + 1);
+        }
       }
       const int nc = min(32, ncol - c0);
       for (int k = 0; k < nc; ++k) {
@@ -388,9 +430,16 @@ k_los_resolve(LosSorted S, const uint2* __restrict__ pairs, unsigned long long n
     const int run_end = after ? __ffs(after) - 1 : 32;
     // the head of a run adds up its weights in lane order (every lane takes part in the shuffles)
     double acc = 0.0;
-    for (int k = 0; k < 32; ++k) {
-      const double wk = __shfl_sync(FULL_MASK, w, k);
-      if (head && k >= (int)lane && k < run_end) acc += wk;
+    if (heads == 1u) {
+      // the usual case (a line of sight has thousands of pairs): the whole warp is one run
+      acc = w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+    } else {
+      for (int k = 0; k < 32; ++k) {
+        const double wk = __shfl_sync(FULL_MASK, w, k);
+        if (head && k >= (int)lane && k < run_end) acc += wk;
+      }
     }
     if (head && valid) {
       const unsigned runmask = (run_end >= 32 ? 0xffffffffu : ((1u << run_end) - 1u)) & ~((1u << lane) - 1u);
