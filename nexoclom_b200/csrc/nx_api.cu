@@ -745,7 +745,8 @@ int nx_init_state(nx_ctx* ctx, const nx_source_params* sp_, uint64_t seed, uint6
   if (n == 0) return 0;
   if ((r = begin_timed(ctx))) return r;
   CK(launch_init_state(ctx->stream, x0_cols(ctx), n, sp, ctx->map, ctx->speed.view,
-                       ctx->lon1d.view, seed, first_id));
+                       ctx->lon1d.view, seed, first_id,
+                       /*fast=*/!(ctx->have_params && ctx->params.strict_math)));
   ctx->fresh = ctx->x0_valid = true;
   return end_timed(ctx, 1);
 }

@@ -55,10 +55,11 @@ NX_HD double bilinear(const SourceMap& m, int nx, int ny, double x, double y) {
 
 // uniform surface band (source_distribution.py:47-62)
 NX_HD void uniform_lonlat(const SourceParams& sp, double u_sinlat, double u_lon, double& lon,
-                          double& lat) {
+                          double& lat, double* sinlat_out = nullptr) {
   const double sinlat = add_rn(sp.sinlat0, mul_rn(sub_rn(sp.sinlat1, sp.sinlat0), u_sinlat));
   lat = asin(sinlat);
   lon = fmod(add_rn(sp.lon0, mul_rn(sub_rn(sp.lon1, sp.lon0), u_lon)), NX_TWO_PI);
+  if (sinlat_out) *sinlat_out = sinlat;
 }
 
 // Everything after the surface point and the deviates are known: a pure transform
@@ -132,10 +133,74 @@ NX_HD void init_packet_finish(const SourceParams& sp, const InterpTable& speed, 
   }
 }
 
+// The same transform with the trigonometry folded (device K1 of the fast-arithmetic build; the
+// exact-order version above is what the reference's recorded deviates are replayed through):
+// sin(asin s) = s, cos(asin s) = sqrt(1 - s^2), one sincos per angle, the modulo of a value known
+// to lie in [12, 36) as a subtraction, reciprocals instead of the nine divisions of the local
+// frame.  Agrees with the exact version to a few ulp (gate of the parity tests: 1e-12).
+// sinlat: sin(lat) when the caller has it (uniform band, sin-latitude maps), else NaN.
+NX_HD void init_packet_finish_fast(const SourceParams& sp, const InterpTable& speed, double u_time,
+                                   double lon, double lat, double sinlat, double u_speed,
+                                   double z_normal, double u_alt, double u_az, double* x0) {
+  const double time = sp.random_time ? u_time * sp.endtime : sp.endtime;
+  double sl, cl, slon, clon;
+  if (sinlat == sinlat) { sl = sinlat; cl = sqrt(fmax(1.0 - sl * sl, 0.0)); }
+  else sincos(lat, &sl, &cl);
+  sincos(lon, &slon, &clon);
+  const double sx = sp.is_planet ? sp.exobase : -sp.exobase;
+  const double px = sx * slon * cl, py = -sp.exobase * clon * cl, pz = sp.exobase * sl;
+  double local_time = lon * 12.0 / NX_PI + 12.0;                  // lon in [0, 2 pi)
+  if (local_time >= 24.0) local_time -= 24.0;
+
+  double v;
+  if (sp.speed_type == SPEED_FLAT) v = u_speed * 2.0 * sp.delv + sp.vprob - sp.delv;
+  else if (sp.speed_type == SPEED_GAUSSIAN) v = (sp.vsigma == 0.0) ? sp.vprob : z_normal * sp.vsigma + sp.vprob;
+  else v = interp(speed, u_speed);
+  v *= sp.v_scale;
+
+  double alt, az, d[3];
+  if (sp.angular_type == ANGULAR_2D) {
+    const double cosalt = u_alt * (sp.sinalt1 - sp.sinalt0) + sp.sinalt0;
+    alt = acos(cosalt); az = 0.0;
+    const double v_rad = sqrt(fmax(1.0 - cosalt * cosalt, 0.0)), v_tan = cosalt;   // alt in [0, pi]
+    const double irn = 1.0 / sqrt(px * px + py * py);
+    const double rx = px * irn, ry = py * irn;
+    d[0] = v_tan * ry + v_rad * rx;
+    d[1] = -v_tan * rx + v_rad * ry;
+    d[2] = 0.0;
+  } else {
+    double v_rad, ca, saz = 0.0, caz = 1.0;
+    if (sp.angular_type == ANGULAR_RADIAL) {
+      alt = NX_PI / 2.; az = 0.0;
+      sincos(alt, &v_rad, &ca);                       // cos(pi/2) as the exact version rounds it
+    } else {
+      const double sinalt = u_alt * (sp.sinalt1 - sp.sinalt0) + sp.sinalt0;
+      alt = asin(sinalt);
+      az = sp.az0 + (sp.az1 - sp.az0) * u_az;
+      v_rad = sinalt; ca = sqrt(fmax(1.0 - sinalt * sinalt, 0.0));
+      sincos(az, &saz, &caz);
+    }
+    // local_direction (nx_surface.cuh): r = p / |p|, east = (y, -x, 0) / |.|, north = (-zx, -zy, x^2 + y^2) / |.|
+    const double v_tan0 = ca * caz, v_tan1 = ca * saz;
+    const double h2 = px * px + py * py;
+    const double irn = 1.0 / sqrt(h2 + pz * pz), ien = 1.0 / sqrt(h2);
+    const double nx_ = -pz * px, ny_ = -pz * py;
+    const double inn = 1.0 / sqrt(nx_ * nx_ + ny_ * ny_ + h2 * h2);
+    d[0] = v_tan0 * (nx_ * inn) + v_tan1 * (py * ien) + v_rad * (px * irn);
+    d[1] = v_tan0 * (ny_ * inn) + v_tan1 * (-px * ien) + v_rad * (py * irn);
+    d[2] = v_tan0 * (h2 * inn) + v_rad * (pz * irn);
+  }
+  x0[0] = time; x0[1] = px; x0[2] = py; x0[3] = pz;
+  x0[4] = d[0] * v; x0[5] = d[1] * v; x0[6] = d[2] * v;
+  x0[7] = 1.0; x0[8] = v; x0[9] = lon; x0[10] = lat; x0[11] = local_time;
+  x0[12] = alt; x0[13] = az;
+}
+
 // Fills x0[NCOL_X0] = time,x,y,z,vx,vy,vz,frac,v,longitude,latitude,local_time,
 // altitude,azimuth for packet `id`.
 // lon1d: inverse CDF of a longitude-only source map (source_distribution.py:72-76 ->
 // random_deviates_1d, randomdeviates.py:29-33); latitude is 0 for those maps.
+template <bool FAST = false>
 NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const InterpTable& speed,
                        uint64_t seed, uint64_t id, double* x0,
                        const InterpTable& lon1d = InterpTable{}) {
@@ -146,8 +211,9 @@ NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const Inter
 
   // ---- position (source_distribution.py:47-62, 96-121) ----
   double lon, lat;
+  double sinlat = __builtin_nan("");                  // sin(lat) where it is known without a sin()
   if (sp.spatial_type == SPATIAL_UNIFORM) {
-    uniform_lonlat(sp, u_sinlat, u_lon, lon, lat);
+    uniform_lonlat(sp, u_sinlat, u_lon, lon, lat, &sinlat);
   } else if (sp.spatial_type == SPATIAL_LON1D) {
     lon = interp(lon1d, u_lon);
     lat = 0.0;
@@ -164,6 +230,7 @@ NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const Inter
       if (mul_rn(uf, sp.map_fmax) < bilinear(map, sp.map_nx, sp.map_ny, x, y) || draw > 4000) {
         lon = x;
         lat = sp.map_lat_is_sin ? asin(y) : y;
+        if (sp.map_lat_is_sin) sinlat = y;
         break;
       }
     }
@@ -174,7 +241,12 @@ NX_HD void init_packet(const SourceParams& sp, const SourceMap& map, const Inter
     uniform_pair(seed, id, STREAM_INIT, 3, g0, g1);
     z = sqrt(-2.0 * log(1.0 - g0)) * cos(NX_TWO_PI * g1);     // Box-Muller on (1-g0) in (0,1]
   }
-  init_packet_finish(sp, speed, u_time, lon, lat, u_speed, z, u_alt, u_az, x0);
+  // the fast transform covers a planet's own surface (the moon frame and the time a packet of
+  // a map that reaches 2 pi would need stay on the exact path)
+  if (FAST && !sp.start_is_moon && lon >= 0.0 && lon < NX_TWO_PI)
+    init_packet_finish_fast(sp, speed, u_time, lon, lat, sinlat, u_speed, z, u_alt, u_az, x0);
+  else
+    init_packet_finish(sp, speed, u_time, lon, lat, u_speed, z, u_alt, u_az, x0);
 }
 
 }  // namespace nx

@@ -138,6 +138,7 @@ size_t table_smem_bytes(const InterpTable& g) {
 // packet; lanes 2j / 2j+1 then swap halves with one shuffle per column pair so that every
 // store is a 16-byte STG of two consecutive packets (even lanes: columns 0,2,..,12, odd
 // lanes: columns 1,3,..,13; 16 lanes x 16 B = one full 256-byte row segment per column).
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 k_init_state(X0Cols X, long long n, SourceParams sp, SourceMap map, InterpTable speed,
              InterpTable lon1d, uint64_t seed, uint64_t first_id) {
@@ -145,7 +146,7 @@ k_init_state(X0Cols X, long long n, SourceParams sp, SourceMap map, InterpTable 
   const long long ic = i < n ? i : n - 1;            // whole warps run the shuffles
   const unsigned lane = threadIdx.x & 31u;
   double x0[14];
-  init_packet(sp, map, speed, seed, first_id + (uint64_t)ic, x0, lon1d);
+  init_packet<FAST>(sp, map, speed, seed, first_id + (uint64_t)ic, x0, lon1d);
   const bool odd = lane & 1u;
   const long long pair0 = i & ~1LL;                  // first packet of this lane pair
   const bool full = pair0 + 1 < n;                   // both packets of the pair exist
@@ -1381,10 +1382,11 @@ static int sm_count(int device) {
 cudaError_t launch_init_state(cudaStream_t st, X0Cols X, long long n,
                               const SourceParams& sp, const SourceMap& map,
                               const InterpTable& speed, const InterpTable& lon1d, uint64_t seed,
-                              uint64_t first_id) {
+                              uint64_t first_id, bool fast) {
   const int threads = 256;
   const long long blocks = (n + threads - 1) / threads;
-  k_init_state<<<(unsigned)blocks, threads, 0, st>>>(X, n, sp, map, speed, lon1d, seed, first_id);
+  if (fast) k_init_state<true><<<(unsigned)blocks, threads, 0, st>>>(X, n, sp, map, speed, lon1d, seed, first_id);
+  else k_init_state<false><<<(unsigned)blocks, threads, 0, st>>>(X, n, sp, map, speed, lon1d, seed, first_id);
   return cudaGetLastError();
 }
 

@@ -107,7 +107,7 @@ size_t table_smem_bytes(const InterpTable& g);
 cudaError_t launch_init_state(cudaStream_t st, X0Cols X, long long n,
                               const SourceParams& sp, const SourceMap& map,
                               const InterpTable& speed, const InterpTable& lon1d, uint64_t seed,
-                              uint64_t first_id);
+                              uint64_t first_id, bool fast);
 // deviate columns: u_time, u_sinlat, u_lon, lon_in, lat_in (both null: uniform band), u_speed,
 // z_normal, u_alt, u_az
 cudaError_t launch_init_from_deviates(cudaStream_t st, X0Cols X, long long n,

@@ -21,11 +21,14 @@ lp = LosParams()
 lp.dphi, lp.outeredge = float(np.radians(1.0)), 25.0
 lp.vrplanet, lp.rp_cm = setup.vrplanet, setup.radius_km * 1e5
 lp.quantity, lp.round_f32, lp.skip_dead = 1, 1, 0
-for it in range(4):
+for G in [int(a) for a in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0]:
+  eng.set_option('los_grid', G)
+  print('los_grid', G)
+  for it in range(3):
     eng.sync()
     t0 = time.perf_counter()
     rad, npk, inc = eng.los_accumulate(los, dplan, lp, n=n)
-    print(f'wall {(time.perf_counter() - t0) * 1e3:.2f} ms, kernels {eng.last_kernel_ms():.2f} ms, hits {int(npk.sum())}', flush=True)
+    print(f'  wall {(time.perf_counter() - t0) * 1e3:.2f} ms, kernels {eng.last_kernel_ms():.2f} ms, hits {int(npk.sum())}', flush=True)
 # `used` sets: counts from the accumulate pass + indices from its candidate pairs, against the
 # two extra searches of nx_los_used (1e4 lines of sight: the CSR is 4 B per used pair)
 los2, dplan2 = bench.synthetic_los(10_000)
