@@ -196,6 +196,39 @@ NX_HD double interp_fast(const FastTable& T, double v) {
   return fma(r.slope, v - r.lo, r.f);
 }
 
+// The same lookup with a hint: `idx` is the record the previous lookup of this packet ended in.
+// The six stages of one step evaluate the table at nearly the same velocity, so the hinted
+// record almost always still holds v: two compares replace the bucket arithmetic and the
+// dependent index load.  The records partition the axis, so a hinted hit IS the record the
+// full lookup would return (bit-identical results).  TRY_HINT = false: plain lookup that
+// leaves its record in idx.
+template <bool TRY_HINT>
+NX_HD double interp_fast_hint(const FastTable& T, double v, int& idx) {
+  InterpRec r;
+  bool hit = false;
+  if (TRY_HINT) {
+    r = T.rec[idx];
+    hit = (v >= r.lo) && (v < r.hi);
+  }
+  if (!hit) {
+#if defined(__CUDA_ARCH__)
+    int b = __double2int_rz(fma(v, T.binvw, T.boff));
+    b = max(0, min(b, T.nbucket - 1));
+    idx = (int)__ldg(T.bucket + b);
+#else
+    int b = (v == v) ? (int)fmax(fmin((v - T.blo) * T.binvw, 2e9), -2e9) : 0;
+    b = b < 0 ? 0 : (b >= T.nbucket ? T.nbucket - 1 : b);
+    idx = T.bucket[b];
+#endif
+    r = T.rec[idx];
+    if (v >= r.hi) {
+      r = T.rec[++idx];
+      if (v >= r.hi) r = T.rec[++idx];
+    }
+  }
+  return fma(r.slope, v - r.lo, r.f);
+}
+
 // ---------------------------------------------------------------------------
 // RHS -- reference particle_tracking/state.py:17-74
 // ---------------------------------------------------------------------------
