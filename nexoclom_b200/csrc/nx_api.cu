@@ -44,7 +44,7 @@ struct nx_packets {
 };
 
 // Packet tables come and go with every Output: they are carved from ONE block of the device's
-// stream-ordered memory pool (cudaMallocAsync, release threshold = keep everything), so that
+// stream-ordered memory pool (cudaMallocAsync, release threshold 4 GB), so that
 // creating / dropping a table costs microseconds instead of the implicit device
 // synchronisation of cudaMalloc / cudaFree.  Everything else (slabs, scratch) is cudaMalloc'ed
 // once and grows only; those sites trim the pool and retry when the device is full.
@@ -379,7 +379,7 @@ int nx_ctx_create(int device, nx_ctx** out) {
   {
     cudaMemPool_t pool;                       // keep freed packet tables for the next Output
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
+      unsigned long long keep = 4ull << 30;   // beyond 4 GB freed blocks go back to the driver
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     cudaGetLastError();

@@ -23,34 +23,50 @@ class NexoclomCudaError(RuntimeError):
 
 
 class _PinnedPool:
-    """Page-locked float64 result buffers (``nx_host_alloc``), handed out as NumPy arrays and
-    recycled once every array that views them has been garbage-collected: a device -> host copy
-    into fresh pageable memory pays a page fault per 4 KB and a staging copy (2.6 ms for the
-    two 800 x 800 planes of an image against 0.2 ms of DMA)."""
-    KEEP = 8                                     # idle buffers kept per size
+    """Page-locked result buffers (``nx_host_alloc``), handed out as NumPy arrays and recycled
+    once every array that views them has been garbage-collected: a device -> host copy into
+    fresh pageable memory pays a page fault per 4 KB and a staging copy (2.6 ms for the two
+    800 x 800 planes of an image against 0.2 ms of DMA).  Capacities are rounded up to eighths
+    of an octave so that results of slightly different sizes share buffers; idle buffers are
+    kept up to ``IDLE_BYTES`` in total, the rest goes back to the driver."""
+    IDLE_BYTES = 1 << 30
 
     def __init__(self, lib):
         self.lib = lib
-        self.idle = {}
+        self.idle = {}                           # capacity -> [pointers]
+        self.idle_bytes = 0
+
+    @staticmethod
+    def _capacity(nbytes):
+        if nbytes <= 4096:
+            return 4096
+        step = 1 << max(12, nbytes.bit_length() - 4)
+        return (nbytes + step - 1) // step * step
 
     def array(self, shape, dtype=np.float64):
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        idle = self.idle.setdefault(nbytes, [])
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        nbytes = count * dtype.itemsize
+        if nbytes == 0:
+            return np.empty(shape, dtype=dtype)
+        cap = self._capacity(nbytes)
+        idle = self.idle.get(cap)
         if idle:
             ptr = idle.pop()
+            self.idle_bytes -= cap
         else:
             p = C.c_void_p()
-            if nbytes == 0 or self.lib.nx_host_alloc(nbytes, C.byref(p)) != 0 or not p.value:
+            if self.lib.nx_host_alloc(cap, C.byref(p)) != 0 or not p.value:
                 return np.empty(shape, dtype=dtype)            # pageable: staged by the library
             ptr = p.value
-        buf = (C.c_char * nbytes).from_address(ptr)
-        weakref.finalize(buf, self._release, nbytes, ptr)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+        buf = (C.c_char * cap).from_address(ptr)
+        weakref.finalize(buf, self._release, cap, ptr)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
-    def _release(self, nbytes, ptr):
-        idle = self.idle.setdefault(nbytes, [])
-        if len(idle) < self.KEEP:
-            idle.append(ptr)
+    def _release(self, cap, ptr):
+        if self.idle_bytes + cap <= self.IDLE_BYTES:
+            self.idle.setdefault(cap, []).append(ptr)
+            self.idle_bytes += cap
         else:
             self.lib.nx_host_free(ptr)
 

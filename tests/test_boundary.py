@@ -137,3 +137,20 @@ def test_workload_files_parse():
     for f in sorted(os.listdir(WORKLOADS)):
         inp = workload(f)
         assert inp.options.species in ('Na', 'Ca')
+
+
+def test_pinned_pool_capacities_and_fallback(built):
+    """Result buffers of the host side: capacities grow in eighths of an octave (buffers of
+    slightly different sizes are shared), and without a usable device ``nx_host_alloc`` fails
+    and the pool hands out ordinary NumPy arrays (the library then stages the copy)."""
+    from nexoclom_b200.engine import _PinnedPool
+    caps = [_PinnedPool._capacity(n) for n in (1, 4096, 4097, 10 ** 6, 10 ** 7, 10 ** 7 + 1, 10 ** 8)]
+    assert caps == sorted(caps) and caps[0] == 4096
+    for n, c in zip((10 ** 6, 10 ** 7, 10 ** 8), caps[3::1][0:1] + caps[4:5] + caps[6:7]):
+        assert n <= c <= 1.07 * n
+    pool = _PinnedPool(_lib.load())
+    a = pool.array((3, 5))
+    assert a.shape == (3, 5) and a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable
+    b = pool.array((7,), dtype=np.uint8)
+    assert b.shape == (7,) and b.dtype == np.uint8
+    assert pool.array((0,)).size == 0

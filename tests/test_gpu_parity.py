@@ -1284,3 +1284,25 @@ def test_privatised_image_counts_equal_global(engine, quantity):
         nz = img_g > 0
         assert np.array_equal(nz, img_t > 0)
         assert np.max(np.abs(img_t[nz] - img_g[nz]) / img_g[nz]) < 1e-10
+
+
+def test_pinned_result_buffers_are_recycled(engine):
+    """ModelImage's planes and the line-of-sight results live in pooled page-locked arrays: a
+    buffer returns to the pool when the last array viewing it dies and is handed out again."""
+    import gc
+    from nexoclom_b200.engine import _pinned_pool
+    pool = _pinned_pool(engine.lib)
+    a = pool.array((800, 800))
+    addr = a.ctypes.data
+    v = a[10:20]                       # a view keeps the buffer alive
+    del a
+    gc.collect()
+    b = pool.array((800, 800))
+    assert b.ctypes.data != addr
+    del v, b
+    gc.collect()
+    c = pool.array((800, 800))
+    d = pool.array((800, 800))
+    assert addr in (c.ctypes.data, d.ctypes.data)
+    c[:] = 1.0                          # writable, ordinary ndarray semantics
+    assert float(c.sum()) == 640000.0
