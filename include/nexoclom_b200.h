@@ -240,12 +240,15 @@ int nx_image_device_ptrs(nx_ctx* ctx, void** image_dev, void** counts_dev);
  * packet image as float64, converted on the device, one copy.  Destinations obtained from
  * nx_host_alloc (page-locked) receive the DMA directly, pageable ones are staged.            */
 int nx_image_fetch_scaled(nx_ctx* ctx, double scale, double* image, double* counts);
+/* Page-locked host memory for result arrays (no reference counterpart: the reference's results
+ * are NumPy arrays; these let the device write them without a staging copy).                  */
 int nx_host_alloc(long long bytes, void** out);
 int nx_host_free(void* p);
 /* Sharded runs: sum the context-owned image + counts over the ranks of `comm` (see nx_comm_create
  * below), in place, on the context's stream -- the single all-reduce of an image product.    */
 int nx_image_allreduce(nx_ctx* ctx, nx_comm* comm);
-/* The same with one scalar riding along (ModelImage's totalsource): *total is this rank's
+/* The same with one scalar riding along (ModelImage's totalsource, ModelImage.py:92-99 sums it
+ * over the output files; here also over the ranks): *total is this rank's
  * contribution on entry, the sum over the ranks on return.                                  */
 int nx_image_allreduce_total(nx_ctx* ctx, nx_comm* comm, double* total);
 
@@ -267,7 +270,8 @@ int nx_los_accumulate_dev(nx_ctx* ctx, long long n, long long nlos, void* los_de
 int nx_los_used(nx_ctx* ctx, long long n, long long nlos, const double* los,
                 const double* dist_from_plan, const nx_los_params* lp,
                 const long long* used_offsets, long long* used_count, uint32_t* used_indices);
-/* nx_los_accumulate that also returns used_count[nlos] from the same pass and keeps its
+/* The `used` / `used0` packet sets of compute_iteration.py:143-144, 210-211 without a second
+ * search: nx_los_accumulate that also returns used_count[nlos] from the same pass and keeps its
  * candidate pairs on the device; nx_los_used_fill then writes the CSR indices
  * (used_offsets = prefix sums of used_count) by repeating only the exact test over those pairs
  * when nothing happened in between, else by searching again.                                 */
