@@ -226,9 +226,11 @@ static void free_los_work(LosGridWork& w) {
   cudaFree(w.pairs); cudaFree(w.pair_cursor);
   const int G = w.G_fixed;
   const double scale = w.scale;
+  const unsigned long long pcf = w.pairs_cap_fixed;
   w = LosGridWork{};
   w.G_fixed = G;
   w.scale = scale;
+  w.pairs_cap_fixed = pcf;
 }
 
 static int alloc_los_work(nx_ctx* ctx, long long n) {
@@ -253,6 +255,8 @@ static int alloc_los_work(nx_ctx* ctx, long long n) {
   unsigned long long pc = 32ull * (unsigned long long)n;
   if (pc < (1ull << 22)) pc = 1ull << 22;
   if (pc > (1ull << 29)) pc = 1ull << 29;
+  if (n > 40000000LL) pc = 1ull << 30;              // 8 GB next to 40+ GB of packet slabs
+  if (w.pairs_cap_fixed) pc = w.pairs_cap_fixed;    // developer option "los_pair_cap"
   if (pc < (unsigned long long)n + 1024) pc = (unsigned long long)n + 1024;
   CK(dev_malloc(&w.pairs, pc * sizeof(uint2)));
   CK(cudaMalloc(&w.pair_cursor, 2 * sizeof(unsigned long long)));   // pairs written, line-of-sight ticket
@@ -441,6 +445,11 @@ int nx_ctx_set_option(nx_ctx* ctx, const char* name, int value) {
   if (name && std::strcmp(name, "los_order") == 0) { ctx->los_order = value; return 0; }
   if (name && std::strcmp(name, "class_cache") == 0) { ctx->class_cache = value; return 0; }
   if (name && std::strcmp(name, "los_grid") == 0) { ctx->losw.G_fixed = value; ctx->losw.cap = 0; return 0; }
+  if (name && std::strcmp(name, "los_pair_cap") == 0) {
+    ctx->losw.pairs_cap_fixed = value > 0 ? (unsigned long long)value : 0ull;
+    ctx->losw.cap = 0;
+    return 0;
+  }
   if (name && std::strcmp(name, "los_grid_scale_milli") == 0) { ctx->losw.scale = 1e-3 * value; return 0; }
   ctx->err = std::string("unknown option ") + (name ? name : "(null)");
   return -1;

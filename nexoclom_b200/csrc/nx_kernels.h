@@ -74,6 +74,7 @@ struct LosGridWork {
   unsigned long long pairs_cap = 0;
   unsigned long long* pair_cursor = nullptr;
   long long batch_hint = 0;    // lines of sight per batch that half-filled `pairs` last time
+  unsigned long long pairs_cap_fixed = 0;   // option "los_pair_cap" (tests: force several batches)
 };
 cudaError_t launch_los_grid_build(cudaStream_t st, int device, StateCols P, long long n,
                                   const LosParams& lp, LosGridWork& w);

@@ -354,6 +354,45 @@ def test_image_vs_reference_golden(engine, tag):
     assert np.all(img[~nz] == 0)
 
 
+def test_los_batches_when_the_pair_buffer_fills(engine):
+    """A pair buffer far too small for the sweep: the lines of sight go through in batches (an
+    overflowing batch is repeated with half as many lines) -- radiance, hit counts, `included`
+    and `used` sets as with one batch."""
+    setup = RunSetup(workload('Na.maxwellian.radpres.input'))
+    setup.upload(engine)
+    engine.upload_gtables(setup.gtables([5891, 5897]))
+    n = 300_000
+    engine.init_state(setup.source_params(engine), 3, 0, n)
+    from nexoclom_b200.LOSResult import dist_from_planet_cut
+    import pandas as pd
+    los6 = _synthetic_los(3000)
+    dist = np.asarray(dist_from_planet_cut(pd.DataFrame(
+        los6, columns=['x', 'y', 'z', 'xbore', 'ybore', 'zbore'])), dtype=np.float64)
+    los = los6.T.copy()
+    lp = LosParams()
+    lp.dphi, lp.outeredge = np.radians(3.0), 25.
+    lp.vrplanet, lp.rp_cm, lp.quantity = setup.vrplanet, setup.radius_km * 1e5, 1
+    engine.set_option('los_mode', 2)
+    try:
+        rad0, npk0, inc0, cnt0 = engine.los_accumulate(los, dist, lp, count_used=True)
+        off0, idx0 = engine.los_used_fill(los, dist, lp, cnt0)
+        assert npk0.sum() > 5 * (n + 1024)              # several batches with the small buffer
+        engine.set_option('los_pair_cap', n + 1024)
+        rad1, npk1, inc1, cnt1 = engine.los_accumulate(los, dist, lp, count_used=True)
+        off1, idx1 = engine.los_used_fill(los, dist, lp, cnt1)
+        off2, idx2 = engine.los_used(los, dist, lp)
+    finally:
+        engine.set_option('los_pair_cap', 0)
+        engine.set_option('los_mode', 0)
+    assert np.array_equal(npk1, npk0) and np.array_equal(inc1, inc0) and np.array_equal(cnt1, cnt0)
+    assert np.allclose(rad1, rad0, rtol=1e-12, atol=0)
+    assert np.array_equal(off1, off0) and np.array_equal(off2, off0)
+    for i in range(0, len(off0) - 1, 37):
+        ref = np.sort(idx0[off0[i]:off0[i + 1]])
+        assert np.array_equal(np.sort(idx1[off1[i]:off1[i + 1]]), ref)
+        assert np.array_equal(np.sort(idx2[off2[i]:off2[i + 1]]), ref)
+
+
 def test_los_counted_pass_and_pair_reuse(engine):
     """nx_los_accumulate_counted + nx_los_used_fill == nx_los_accumulate + the two-pass
     nx_los_used, on the reference's own golden lines of sight: once re-resolving the candidate
